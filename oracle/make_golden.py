@@ -1,0 +1,198 @@
+"""
+Mint golden vectors by running the UNMODIFIED reference in the build container.
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz
+
+TEST INFRASTRUCTURE.  This is the only file in the repo that imports
+/root/reference (which does not exist on the GPU box); the fixtures it writes
+are committed so that neither the tests nor the bench ever need it at run time.
+
+Method: numpy.random.{shuffle, uniform, rand, randn} are wrapped by a recorder
+while the reference's simulate_transmission / LSEstimator / MMSEEstimator /
+OFDMSystem / ChannelModel run, so each fixture holds (a) every random draw in
+call order (shuffle, uniform pilots, uniform data, P*ntx*nrx*2
+rand(20), 2 randn blocks) and (b) the reference's float64 outputs.
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("B2C_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+class Recorder:
+    """Wraps the four numpy.random entry points the hot path uses."""
+
+    def __init__(self):
+        self.log = []
+        self._orig = {}
+
+    def __enter__(self):
+        for name in ("shuffle", "uniform", "rand", "randn"):
+            self._orig[name] = getattr(np.random, name)
+        rec = self
+
+        def shuffle(a):
+            rec._orig["shuffle"](a)
+            rec.log.append(("shuffle", np.array(a, copy=True)))
+
+        def uniform(*a, **k):
+            v = rec._orig["uniform"](*a, **k)
+            rec.log.append(("uniform", np.array(v, copy=True)))
+            return v
+
+        def rand(*a):
+            v = rec._orig["rand"](*a)
+            rec.log.append(("rand", np.array(v, copy=True)))
+            return v
+
+        def randn(*a):
+            v = rec._orig["randn"](*a)
+            rec.log.append(("randn", np.array(v, copy=True)))
+            return v
+
+        np.random.shuffle, np.random.uniform = shuffle, uniform
+        np.random.rand, np.random.randn = rand, randn
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self._orig.items():
+            setattr(np.random, name, fn)
+
+
+def base_config(ntx, nrx):
+    return {
+        "ofdm": {"fft_size": 1024, "cp_length": 72, "num_symbols": 14,
+                 "useful_subcarriers": 600, "subcarrier_spacing": 15000},
+        "mimo": {"num_tx_antennas": ntx, "num_rx_antennas": nrx},
+        "channel": {"carrier_freq": 2.0e9},
+    }
+
+
+def slot_case(name, seed, ntx, nrx, model, doppler, snr, density, extra_methods=()):
+    import channel_simulator as cs
+    import baseline_estimators as be
+
+    np.random.seed(seed)
+    cfg = base_config(ntx, nrx)
+    with Recorder() as rec:
+        sim = cs.simulate_transmission(cfg, channel_type=model, doppler_hz=doppler,
+                                       snr_db=snr, pilot_density=density)
+    log = rec.log
+    P = len(cs.ChannelModel.CHANNEL_PROFILES[model]["delays"])
+    kinds = [k for k, _ in log]
+    assert kinds == ["shuffle", "uniform", "uniform"] + ["rand"] * (2 * P * ntx * nrx) + ["randn"] * 2, kinds
+    perm = log[0][1]
+    pilot_phase, data_phase = log[1][1], log[2][1]
+    jakes_u = np.stack([v for _, v in log[3:3 + 2 * P * ntx * nrx]]).reshape(P, ntx, nrx, 2, 20)
+    noise_re, noise_im = log[-2][1], log[-1][1]
+
+    rx, tx, H = sim["rx_symbols"], sim["tx_symbols"], sim["channel"]
+    pp = sim["pilot_pattern"]
+    rx4d = np.repeat(rx.reshape(rx.shape[0], nrx, 1, rx.shape[2]), ntx, axis=2)
+    H_ls = be.LSEstimator("linear").estimate(rx4d, sim["pilot_symbols"], pp.pilot_mask, pp.pilot_positions)
+    H_mm = be.MMSEEstimator().estimate(rx4d, sim["pilot_symbols"], pp.pilot_mask, pp.pilot_positions, snr_db=snr)
+    # the TX axis of the estimates is a pure replica; store tx=0 only
+    for t in range(1, ntx):
+        assert np.array_equal(H_ls[:, :, t], H_ls[:, :, 0]) and np.array_equal(H_mm[:, :, t], H_mm[:, :, 0])
+    assert all(np.array_equal(tx[:, t], tx[:, 0]) for t in range(ntx))
+    m_ls, m_mm = be.evaluate_estimator(H, H_ls), be.evaluate_estimator(H, H_mm)
+    out = dict(
+        ntx=ntx, nrx=nrx, model=model, doppler_hz=float(doppler), snr_db=float(snr), density=float(density),
+        perm=perm.astype(np.int32), pilot_phase=pilot_phase, data_phase=data_phase, jakes_u=jakes_u,
+        noise_re=noise_re, noise_im=noise_im,
+        pilot_indices=pp.pilot_indices.astype(np.int64), pilot_mask=pp.pilot_mask,
+        pilot_symbols=sim["pilot_symbols"], tx_grid=tx[:, 0], rx_symbols=rx, channel=H,
+        H_ls_tx0=H_ls[:, :, 0], H_mmse_tx0=H_mm[:, :, 0],
+        metrics_ls=np.array([m_ls["mse"], m_ls["nmse"], m_ls["nmse_db"]]),
+        metrics_mmse=np.array([m_mm["mse"], m_mm["nmse"], m_mm["nmse_db"]]),
+    )
+    for meth in extra_methods:
+        Hx = be.LSEstimator(meth).estimate(rx4d[:, :, :1], sim["pilot_symbols"], pp.pilot_mask, pp.pilot_positions)
+        out[f"H_ls_{meth}_tx0"] = Hx[:, :, 0]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: Np={pp.pilot_indices.size} LS {m_ls['nmse_db']:.2f} dB MMSE {m_mm['nmse_db']:.2f} dB")
+
+
+def dense_mmse_case(name, seed):
+    """Known-covariance branch (estimate_statistics=False), src/baseline_estimators.py:181-190."""
+    import channel_simulator as cs
+    import baseline_estimators as be
+
+    np.random.seed(seed)
+    ntx = nrx = 2
+    snr, density = 12.0, 0.02
+    with Recorder() as rec:
+        sim = cs.simulate_transmission(base_config(ntx, nrx), "EVA", 50, snr, density)
+    pp = sim["pilot_pattern"]
+    n_p = pp.pilot_indices.size
+    # exponential time/frequency correlation model, reproducible by formula in the tests
+    ds = pp.pilot_positions[0][:, None] - pp.pilot_positions[0][None, :]
+    dk = pp.pilot_positions[1][:, None] - pp.pilot_positions[1][None, :]
+    R = 0.4 * np.exp(-np.abs(ds) / 20.0 - np.abs(dk) / 60.0) * np.exp(1j * 2 * np.pi * dk * 3 / 1024)
+    rx = sim["rx_symbols"]
+    rx4d = np.repeat(rx.reshape(rx.shape[0], nrx, 1, rx.shape[2]), ntx, axis=2)
+    est = be.MMSEEstimator(channel_covariance=R, estimate_statistics=False)
+    H_mm = est.estimate(rx4d, sim["pilot_symbols"], pp.pilot_mask, pp.pilot_positions, snr_db=snr)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), ntx=ntx, nrx=nrx, snr_db=snr, density=density, n_p=n_p,
+        pilot_indices=pp.pilot_indices.astype(np.int64), pilot_mask=pp.pilot_mask,
+        pilot_symbols=sim["pilot_symbols"], rx_symbols=rx, H_mmse_tx0=H_mm[:, :, 0])
+    print(f"{name}: Np={n_p}")
+
+
+def ofdm_case(name, seed):
+    import channel_simulator as cs
+    rng = np.random.RandomState(seed)
+    sys_ = cs.OFDMSystem(cs.OFDMConfig())
+    sym = (rng.randn(14, 599) + 1j * rng.randn(14, 599)) / np.sqrt(2)
+    t = sys_.modulate(sym)
+    sig = (rng.randn(14, 1096) + 1j * rng.randn(14, 1096)) / np.sqrt(2)
+    f = sys_.demodulate(sig)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), symbols=sym, modulated=t, signal=sig,
+                        demodulated=f, used_indices=sys_.used_indices.astype(np.int64))
+    print(f"{name}: round trip {np.abs(sys_.demodulate(t) - sym).max():.2e}")
+
+
+def tdl_case(name, seed):
+    """generate_time_varying_channel standalone (src/channel_simulator.py:84-127) + profile tables."""
+    import channel_simulator as cs
+    out = {}
+    for model, fd, ntx, nrx, ns in (("EPA", 10.0, 1, 1, 3000), ("EVA", 50.0, 2, 1, 1500), ("ETU", 200.0, 1, 2, 1200)):
+        np.random.seed(seed)
+        cm = cs.ChannelModel(model, fd, 2.0e9, 15.36e6)
+        with Recorder() as rec:
+            h = cm.generate_time_varying_channel(ns, ntx, nrx)
+        ju = np.stack([v for _, v in rec.log]).reshape(cm.num_paths, ntx, nrx, 2, 20)
+        out[f"{model}_jakes_u"] = ju
+        out[f"{model}_h"] = h[::97]                   # every 97th time sample keeps the file small
+        out[f"{model}_shape"] = np.array(h.shape)
+        out[f"{model}_meta"] = np.array([fd, ntx, nrx, ns])
+        out[f"{model}_delay_samples"] = cm.delay_samples.astype(np.int64)
+        out[f"{model}_powers_linear"] = cm.powers_linear
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name)
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit(f"reference not found at {REF}; fixtures can only be minted in the build container")
+    sys.path.insert(0, os.path.join(REF, "src"))
+    os.makedirs(OUT, exist_ok=True)
+    slot_case("slot_siso_epa", 101, 1, 1, "EPA", 10, 20, 0.10, extra_methods=("nearest",))
+    slot_case("slot_2x2_eva", 202, 2, 2, "EVA", 50, 15, 0.10, extra_methods=("nearest",))
+    slot_case("slot_4x4_etu", 303, 4, 4, "ETU", 200, 10, 0.10)
+    slot_case("slot_2x2_etu_5pct", 404, 2, 2, "ETU", 100, 10, 0.05)
+    slot_case("slot_2x1_epa_1pct", 505, 2, 1, "EPA", 10, 0, 0.01)
+    dense_mmse_case("mmse_dense_2x2", 606)
+    ofdm_case("ofdm_modem", 707)
+    tdl_case("tdl_standalone", 808)
+
+
+if __name__ == "__main__":
+    main()
