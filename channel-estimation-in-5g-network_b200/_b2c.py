@@ -1,0 +1,114 @@
+"""ctypes binding of libb2c.so (include/b2c.h).  The product path has no CPU fallback: if the
+library is missing or a tensor is not a contiguous CUDA tensor, calls raise."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb2c.so")
+
+MAX_TAPS, MAX_ANT, MAX_SYM, N_OSC, N_STAT, N_BINSTAT = 16, 8, 16, 20, 3, 12
+EXPORTS = ["b2c_last_error_string", "b2c_abi_version", "b2c_tap_gains", "b2c_slot_pipeline",
+           "b2c_ls_interp", "b2c_pilot_vectors", "b2c_mmse_dense", "b2c_stats_bins",
+           "b2c_ofdm_modulate", "b2c_ofdm_demodulate", "b2c_apply_channel", "b2c_tdl_full"]
+
+
+class B2CError(RuntimeError):
+    pass
+
+
+class Geom(C.Structure):
+    _fields_ = [("nsym", C.c_int32), ("nsc", C.c_int32), ("ntx", C.c_int32), ("nrx", C.c_int32),
+                ("fft_size", C.c_int32), ("cp_length", C.c_int32), ("symbol_period_s", C.c_float)]
+
+
+class Profiles(C.Structure):
+    _fields_ = [("n_models", C.c_int32), ("ntaps", C.c_void_p), ("npaths", C.c_void_p),
+                ("tap_path", C.c_void_p), ("tap_amp", C.c_void_p), ("tap_tw", C.c_void_p),
+                ("tap_corr", C.c_void_p)]
+
+
+class Patterns(C.Structure):
+    _fields_ = [("n_patterns", C.c_int32), ("np_max", C.c_int32), ("npilots", C.c_void_p),
+                ("pilot_re", C.c_void_p), ("plan", C.c_void_p)]
+
+
+class Slots(C.Structure):
+    _fields_ = [("slot0", C.c_int64), ("seed", C.c_uint64), ("model_id", C.c_void_p),
+                ("doppler_hz", C.c_void_p), ("snr_db", C.c_void_p), ("pattern_id", C.c_void_p)]
+
+
+class Inject(C.Structure):
+    _fields_ = [("jakes_u", C.c_void_p), ("p_max", C.c_int32), ("sym_turns", C.c_void_p),
+                ("noise", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libb2c.so once.  Raises if it has not been built -- there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2CError(f"{LIB_PATH} not found: build it with "
+                           f"`python {os.path.join(HERE, 'build.py')}` (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        L.b2c_last_error_string.restype = C.c_char_p
+        L.b2c_abi_version.restype = C.c_int
+        P, I64, I32, F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+        sig = {
+            "b2c_tap_gains": [P, P, P, P, I64, P, P, P],
+            "b2c_slot_pipeline": [P, P, P, P, P, I64, P, P, P, P, P, P, P, P, P],
+            "b2c_ls_interp": [P, P, P, P, I64, P, P, I64, P, I32, P, P, P, P, P, P],
+            "b2c_pilot_vectors": [P, P, I64, I32, F, I32, P, P],
+            "b2c_mmse_dense": [P, I32, P, P, I64, I64, P],
+            "b2c_stats_bins": [P, P, P, I64, I32, P, P],
+            "b2c_ofdm_modulate": [P, P, P, I64, P],
+            "b2c_ofdm_demodulate": [P, P, P, I64, P],
+            "b2c_apply_channel": [P, P, P, I64, P, P, P, P, P],
+            "b2c_tdl_full": [P, P, I32, F, F, I64, I32, P, P, C.c_uint64, I64, P, P],
+        }
+        for name, argtypes in sig.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        if L.b2c_abi_version() != 1:
+            raise B2CError(f"libb2c ABI {L.b2c_abi_version()} != 1; rebuild")
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise B2CError(f"{what} failed ({rc}): {lib().b2c_last_error_string().decode()}")
+
+
+_DT = {"c64": torch.complex64, "f32": torch.float32, "f64": torch.float64, "i32": torch.int32, "u8": torch.uint8}
+
+
+def dptr(t, kind, optional=False):
+    """Device pointer of a contiguous CUDA tensor of the expected dtype."""
+    if t is None:
+        if optional:
+            return None
+        raise B2CError("required tensor is None")
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise B2CError("libb2c needs CUDA tensors (there is no CPU path)")
+    if t.dtype != _DT[kind]:
+        raise B2CError(f"expected dtype {_DT[kind]}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise B2CError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ref(struct):
+    return C.cast(C.pointer(struct), C.c_void_p) if struct is not None else None

@@ -1,0 +1,142 @@
+"""Host-side tables the kernels read: TDL profile tables and pilot-pattern interpolation plans.
+
+Built once per (profile set, geometry) / per pilot pattern in float64 and uploaded in the fp32
+layouts of include/b2c.h.  Plans use SciPy's Qhull Delaunay / KDTree -- the same third-party
+code scipy.interpolate.griddata runs inside the reference's LSEstimator.interpolate_channel
+(src/baseline_estimators.py:65-79) -- because only Qhull's own tie-breaking on the integer
+pilot lattice reproduces the reference's triangles.  The per-resource-element blend over the
+batch is done on the GPU (b2c_ls_interp / b2c_slot_pipeline); this module only builds indices.
+"""
+
+from __future__ import annotations
+
+import hashlib
+from collections import OrderedDict
+
+import numpy as np
+
+MAX_TAPS = 16
+N_OSC = 20
+
+# 3GPP TS 36.104 Annex B.2 power-delay profiles (delay ns, relative power dB); the reference keeps
+# the same tables at src/channel_simulator.py:41-54.
+PDP = {
+    "EPA": ((0, 30, 70, 90, 110, 190, 410), (0.0, -1.0, -2.0, -3.0, -8.0, -17.2, -20.8)),
+    "EVA": ((0, 30, 150, 310, 370, 710, 1090, 1730, 2510), (0.0, -1.5, -1.4, -3.6, -0.6, -9.1, -7.0, -12.0, -16.9)),
+    "ETU": ((0, 50, 120, 200, 230, 500, 1600, 2300, 5000), (-1.0, -1.0, -1.0, 0.0, 0.0, 0.0, -3.0, -5.0, -7.0)),
+}
+
+
+def path_tables(model_type: str, sampling_rate: float):
+    """delays [s], powers_db, normalised powers_linear, integer delay_samples
+    (ChannelModel.__init__, src/channel_simulator.py:72-82)."""
+    ns, db = PDP[model_type]          # KeyError for an unknown profile, like the reference (:72)
+    delays = np.array(ns, dtype=np.float64) * 1e-9
+    powers_db = np.array(db, dtype=np.float64)
+    lin = 10 ** (powers_db / 10)
+    lin = lin / np.sum(lin)
+    return delays, powers_db, lin, np.round(delays * sampling_rate).astype(int)
+
+
+def resolve_taps(delay_samples):
+    """(tap_delay, owner_path): later paths overwrite earlier ones that share a sample delay
+    (the tap write at src/channel_simulator.py:125 is an assignment)."""
+    last = {}
+    for p, d in enumerate(delay_samples):
+        last[int(d)] = p
+    d_sorted = sorted(last)
+    return d_sorted, [last[d] for d in d_sorted]
+
+
+def used_subcarriers(fft_size: int, useful: int):
+    """OFDMSystem.used_indices (src/channel_simulator.py:141-148)."""
+    dc = fft_size // 2
+    idx = np.arange(dc - useful // 2, dc + useful // 2)
+    return idx[idx != dc]
+
+
+def profile_tables(models, sampling_rate, fft_size, used):
+    """Numpy arrays for b2c_profiles."""
+    M, nsc = len(models), len(used)
+    ntaps = np.zeros(M, np.int32)
+    npaths = np.zeros(M, np.int32)
+    tap_path = np.zeros((M, MAX_TAPS), np.int32)
+    tap_delay = np.zeros((M, MAX_TAPS), np.int32)
+    tap_amp = np.zeros((M, MAX_TAPS), np.float32)
+    tap_tw = np.zeros((M, MAX_TAPS, nsc), np.complex64)
+    tap_corr = np.zeros((M, MAX_TAPS, MAX_TAPS), np.complex64)
+    f = (np.asarray(used, dtype=np.int64) - fft_size // 2)
+    for m, name in enumerate(models):
+        _, _, lin, dsamp = path_tables(name, sampling_rate)
+        delays, owners = resolve_taps(dsamp)
+        if len(delays) > MAX_TAPS:
+            raise ValueError(f"profile {name} has {len(delays)} taps > {MAX_TAPS}")
+        ntaps[m], npaths[m] = len(delays), len(dsamp)
+        tw = np.zeros((MAX_TAPS, nsc), np.complex128)
+        for t, (d, p) in enumerate(zip(delays, owners)):
+            tap_path[m, t], tap_delay[m, t] = p, d
+            tap_amp[m, t] = np.sqrt(lin[p]) / np.sqrt(2 * N_OSC)
+            # fftshift(fft(h, N))[i] = sum_d h[d] exp(-j 2 pi (i - N/2) d / N); exact integer phase index
+            tw[t] = np.exp(-2j * np.pi * ((f * d) % fft_size) / fft_size)
+        tap_tw[m] = tw
+        tap_corr[m] = tw @ tw.conj().T
+    return {"ntaps": ntaps, "npaths": npaths, "tap_path": tap_path, "tap_delay": tap_delay,
+            "tap_amp": tap_amp, "tap_tw": tap_tw, "tap_corr": tap_corr}
+
+
+PLAN_DTYPE = np.dtype([("i0", "<u2"), ("i1", "<u2"), ("i2", "<u2"), ("flags", "<u2"), ("w0", "<f4"), ("w1", "<f4")])
+assert PLAN_DTYPE.itemsize == 16
+
+
+def _queries(nsym, nsc):
+    s, k = np.divmod(np.arange(nsym * nsc), nsc)
+    return np.column_stack([s, k]).astype(np.float64)
+
+
+def interpolation_plan(pilot_positions, nsym, nsc, method="linear"):
+    """16-byte plan entries for every resource element (row-major), see b2c_patterns in b2c.h."""
+    pts = np.column_stack([np.asarray(pilot_positions[0]), np.asarray(pilot_positions[1])]).astype(np.float64)
+    if len(pts) > 65535:
+        raise ValueError("more than 65535 pilots")
+    plan = np.zeros(nsym * nsc, dtype=PLAN_DTYPE)
+    if method == "linear":
+        from scipy.spatial import Delaunay
+        tri = Delaunay(pts)                        # Qhull, same defaults as LinearNDInterpolator
+        q = _queries(nsym, nsc)
+        simplex = tri.find_simplex(q)
+        inside = simplex >= 0
+        sx = np.where(inside, simplex, 0)
+        T = tri.transform[sx]
+        b = np.einsum("nij,nj->ni", T[:, :2, :], q - T[:, 2, :])
+        v = tri.simplices[sx]
+        plan["i0"], plan["i1"], plan["i2"] = (np.where(inside, v[:, i], 0) for i in range(3))
+        plan["w0"], plan["w1"] = np.where(inside, b[:, 0], 0.0), np.where(inside, b[:, 1], 0.0)
+        plan["flags"] = inside.astype(np.uint16)
+    elif method == "nearest":
+        from scipy.spatial import KDTree            # NearestNDInterpolator's tree (leafsize 10)
+        _, i = KDTree(pts).query(_queries(nsym, nsc))
+        plan["i0"] = plan["i1"] = plan["i2"] = i
+        plan["w0"], plan["w1"], plan["flags"] = 1.0, 0.0, 1
+    else:
+        raise NotImplementedError(
+            f"interpolation method {method!r}: only 'linear' and 'nearest' are built "
+            "(Clough-Tocher 'cubic' is not a fixed linear map of the pilot values; see DESIGN.md)")
+    return plan
+
+
+_PLAN_CACHE: "OrderedDict[tuple, np.ndarray]" = OrderedDict()
+
+
+def cached_plan(pilot_indices, nsym, nsc, method="linear", cache_size=256):
+    """Plans are pure functions of the pilot set; cache them by content hash."""
+    idx = np.ascontiguousarray(np.asarray(pilot_indices, dtype=np.int64))
+    key = (hashlib.sha1(idx.tobytes()).hexdigest(), nsym, nsc, method)
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return hit
+    plan = interpolation_plan(np.unravel_index(idx, (nsym, nsc)), nsym, nsc, method)
+    _PLAN_CACHE[key] = plan
+    while len(_PLAN_CACHE) > cache_size:
+        _PLAN_CACHE.popitem(last=False)
+    return plan

@@ -1,0 +1,259 @@
+// K3: LS pilot division + plan interpolation (+ default MMSE, + squared-error statistics) on
+// caller-supplied received grids, and K5: folding per-slot statistics into per-bin accumulators.
+#include "b2c_common.cuh"
+
+namespace b2c {
+
+constexpr int EST_THREADS = 320;
+
+struct LsArgs {
+  b2c_geom g;
+  b2c_patterns pat;
+  const int32_t *pattern_id;
+  const float *snr_db;
+  const float2 *rx, *pilots, *hp_in, *H_true;
+  int64_t pilots_stride;
+  int mmse_mode;
+  float2 *H_ls, *H_mmse, *hp_out;
+  double *stats;
+};
+
+// One CTA per (slot, rx antenna).  The reference's rx_4d is rx replicated over tx
+// (src/dataset_generator.py:63-64), so the LS/MMSE grids are computed once per (slot, rx) and
+// written ntx times.
+template <int NTX>
+__global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *hp = reinterpret_cast<float2 *>(smem_raw);
+  __shared__ float red[33];
+  __shared__ float ssm[EST_THREADS / 32][NTX * 3];
+
+  const int nsc = a.g.nsc, nsym = a.g.nsym, ntx = a.g.ntx, nrx = a.g.nrx;
+  const int64_t b = blockIdx.x / nrx;
+  const int rx = blockIdx.x - (int)b * nrx;
+  const int pid = a.pattern_id[b];
+  const int np = a.pat.npilots[pid];
+  const int *pre = a.pat.pilot_re + (int64_t)pid * a.pat.np_max;
+
+  // h_p = y_p / (x_p + 1e-12), row-major pilot order (src/baseline_estimators.py:109-110)
+  float psum = 0.f;
+  for (int j = threadIdx.x; j < np; j += EST_THREADS) {
+    float2 h;
+    if (a.hp_in) {
+      h = __ldg(a.hp_in + (b * nrx + rx) * (int64_t)a.pat.np_max + j);
+    } else {
+      int e = __ldg(pre + j);
+      int s = e / nsc, k = e - s * nsc;
+      float2 y = __ldg(a.rx + ((b * nsym + s) * nrx + rx) * (int64_t)nsc + k);
+      h = ls_divide(y, __ldg(a.pilots + b * a.pilots_stride + j));
+    }
+    hp[j] = h;
+    if (a.hp_out) a.hp_out[(b * nrx + rx) * (int64_t)a.pat.np_max + j] = h;
+    psum += cabs2(h);
+  }
+  float P = block_sum(psum, red) / (float)np;   // barrier inside: hp[] complete past this point
+  float alpha = 0.f;
+  if (a.mmse_mode == 1) {
+    float sig2 = exp10f(-0.1f * a.snr_db[b]);    // noise_variance = 1/snr_linear (:174-175)
+    alpha = P / (P + sig2);
+  }
+
+  float st[NTX][3];
+#pragma unroll
+  for (int tx = 0; tx < NTX; ++tx) st[tx][0] = st[tx][1] = st[tx][2] = 0.f;
+
+  const uint4 *plan = reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)pid * nsym * nsc;
+  for (int k = threadIdx.x; k < nsc; k += EST_THREADS) {
+    for (int s = 0; s < nsym; ++s) {
+      PlanTap p = plan_decode(__ldg(plan + s * nsc + k));
+      float2 l = plan_apply(p, hp);
+      float2 m = cscale(alpha, l);
+      const int64_t row = ((b * nsym + s) * nrx + rx) * (int64_t)ntx * nsc + k;
+#pragma unroll
+      for (int tx = 0; tx < NTX; ++tx) {
+        if (tx < ntx) {
+          const int64_t o = row + (int64_t)tx * nsc;
+          if (a.H_ls) st_stream(a.H_ls + o, l);
+          if (a.H_mmse) st_stream(a.H_mmse + o, m);
+          if (a.H_true && a.stats) {
+            float2 h = __ldg(a.H_true + o);
+            st[tx][0] += cabs2(make_float2(h.x - l.x, h.y - l.y));
+            st[tx][1] += cabs2(make_float2(h.x - m.x, h.y - m.y));
+            st[tx][2] += cabs2(h);
+          }
+        }
+      }
+    }
+  }
+
+  if (a.stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int tx = 0; tx < NTX; ++tx)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float v = warp_sum(st[tx][j]);
+        if (lane == 0) ssm[warp][tx * 3 + j] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < ntx * 3) {
+      double acc = 0.0;
+      for (int w = 0; w < EST_THREADS / 32; ++w) acc += (double)ssm[w][threadIdx.x];
+      a.stats[(b * nrx + rx) * (int64_t)(ntx * 3) + threadIdx.x] = acc;
+    }
+  }
+}
+
+template <int NTX>
+static int launch_ls(const LsArgs &a, int64_t B, cudaStream_t stream) {
+  size_t smem = (size_t)a.pat.np_max * sizeof(float2);
+  auto kern = ls_interp_kernel<NTX>;
+  if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(B * a.g.nrx), EST_THREADS, smem, stream>>>(a);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+// LS / default-MMSE on bare pilot vectors (estimate_at_pilots, src/baseline_estimators.py:23-42,155-196):
+// out[v][:] = alpha_v * y[v][:] / (x[:] + 1e-12), alpha_v = 1 (mode 0) or P/(P + 10^(-snr/10)) (mode 1).
+__global__ void __launch_bounds__(256) pilot_vec_kernel(const float2 *__restrict__ y, const float2 *__restrict__ x,
+                                                        int n, float snr_db, int mode, float2 *__restrict__ out) {
+  __shared__ float red[33];
+  const int64_t v = blockIdx.x;
+  float psum = 0.f;
+  for (int j = threadIdx.x; j < n; j += 256) {
+    float2 h = ls_divide(__ldg(y + v * n + j), __ldg(x + j));
+    out[v * n + j] = h;
+    psum += cabs2(h);
+  }
+  if (mode == 0) return;
+  float P = block_sum(psum, red) / (float)n;
+  float alpha = P / (P + exp10f(-0.1f * snr_db));
+  for (int j = threadIdx.x; j < n; j += 256) out[v * n + j] = cscale(alpha, out[v * n + j]);
+}
+
+// ---- K5 ------------------------------------------------------------------------------------------
+constexpr int BIN_THREADS = 256;
+
+__global__ void __launch_bounds__(BIN_THREADS)
+stats_bins_kernel(b2c_geom g, const double *__restrict__ stats, const int32_t *__restrict__ bin_id,
+                  int64_t B, double *__restrict__ bins) {
+  __shared__ double sm[BIN_THREADS / 32][B2C_N_BINSTAT];
+  const int bin = blockIdx.x;
+  const int npair = g.nrx * g.ntx;
+  const double n_all = (double)g.nsym * g.nrx * g.ntx * g.nsc, n_pair = (double)g.nsym * g.nsc;
+  double acc[B2C_N_BINSTAT];
+#pragma unroll
+  for (int j = 0; j < B2C_N_BINSTAT; ++j) acc[j] = 0.0;
+  for (int64_t b = threadIdx.x; b < B; b += BIN_THREADS) {
+    if (bin_id[b] != bin) continue;
+    const double *s = stats + b * (int64_t)npair * 3;
+    double e_ls = 0, e_mm = 0, pw = 0;
+    for (int p = 0; p < npair; ++p) {
+      e_ls += s[p * 3];
+      e_mm += s[p * 3 + 1];
+      pw += s[p * 3 + 2];
+    }
+    // evaluate_estimator (src/baseline_estimators.py:326-331): means over the whole 4-D array
+    double mse_ls = e_ls / n_all, mse_mm = e_mm / n_all, pmean = pw / n_all;
+    double nm_ls = mse_ls / (pmean + 1e-12), nm_mm = mse_mm / (pmean + 1e-12);
+    // compute_nmse on pair (0,0) (run_phase8_pilot_optimization.py:32-37,149-154)
+    double p00 = s[2] / n_pair;
+    double n00_ls = (s[0] / n_pair) / (p00 + 1e-10), n00_mm = (s[1] / n_pair) / (p00 + 1e-10);
+    acc[0] += 1.0;
+    acc[1] += mse_ls;
+    acc[2] += mse_mm;
+    acc[3] += nm_ls;
+    acc[4] += nm_mm;
+    acc[5] += nm_ls * nm_ls;
+    acc[6] += nm_mm * nm_mm;
+    acc[7] += pmean;
+    acc[8] += n00_ls;
+    acc[9] += n00_ls * n00_ls;
+    acc[10] += n00_mm;
+    acc[11] += n00_mm * n00_mm;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < B2C_N_BINSTAT; ++j) {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < B2C_N_BINSTAT) {
+    double t = 0.0;
+    for (int w = 0; w < BIN_THREADS / 32; ++w) t += sm[w][threadIdx.x];
+    bins[bin * B2C_N_BINSTAT + threadIdx.x] += t;
+  }
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const int32_t *pattern_id,
+                             const float *snr_db, int64_t B, const float *rx, const float *pilots,
+                             int64_t pilots_stride, const float *hp_in, int32_t mmse_mode,
+                             const float *H_true, float *H_ls, float *H_mmse, float *hp_out, double *stats,
+                             void *stream) {
+  B2C_REQUIRE(g && pat && pattern_id, B2C_E_ARG, "b2c_ls_interp: null argument");
+  B2C_REQUIRE(g->nsym >= 1 && g->nsc >= 1 && g->nsym * (int64_t)g->nsc <= (1 << 22) && g->ntx >= 1 &&
+                  g->ntx <= B2C_MAX_ANT && g->nrx >= 1 && g->nrx <= B2C_MAX_ANT * B2C_MAX_ANT,
+              B2C_E_UNSUPPORTED, "b2c_ls_interp: geometry %dx%d grid, %dx%d antennas unsupported", g->nsym, g->nsc,
+              g->ntx, g->nrx);
+  B2C_REQUIRE(pat->plan && pat->pilot_re && pat->npilots, B2C_E_ARG, "b2c_ls_interp: incomplete pattern pool");
+  B2C_REQUIRE(hp_in || (rx && pilots), B2C_E_ARG, "b2c_ls_interp: need rx and pilots (or hp_in)");
+  B2C_REQUIRE(mmse_mode == 0 || (mmse_mode == 1 && snr_db), B2C_E_ARG, "b2c_ls_interp: mmse_mode=%d invalid or snr_db missing", mmse_mode);
+  B2C_REQUIRE(mmse_mode == 1 || !H_mmse, B2C_E_ARG, "b2c_ls_interp: H_mmse requested with mmse_mode=0");
+  B2C_REQUIRE(!stats || H_true, B2C_E_ARG, "b2c_ls_interp: stats need H_true");
+  B2C_REQUIRE(B >= 0 && B * g->nrx < (1ll << 31), B2C_E_ARG, "b2c_ls_interp: B=%lld out of range", (long long)B);
+  B2C_REQUIRE(pat->np_max >= 1 && pat->np_max <= 65535 && (size_t)pat->np_max * 8 <= 100 * 1024, B2C_E_UNSUPPORTED,
+              "b2c_ls_interp: np_max=%d unsupported", pat->np_max);
+  if (B == 0) return B2C_OK;
+  LsArgs a = {};
+  a.g = *g;
+  a.pat = *pat;
+  a.pattern_id = pattern_id;
+  a.snr_db = snr_db;
+  a.rx = reinterpret_cast<const float2 *>(rx);
+  a.pilots = reinterpret_cast<const float2 *>(pilots);
+  a.hp_in = reinterpret_cast<const float2 *>(hp_in);
+  a.H_true = reinterpret_cast<const float2 *>(H_true);
+  a.pilots_stride = pilots_stride;
+  a.mmse_mode = mmse_mode;
+  a.H_ls = reinterpret_cast<float2 *>(H_ls);
+  a.H_mmse = reinterpret_cast<float2 *>(H_mmse);
+  a.hp_out = reinterpret_cast<float2 *>(hp_out);
+  a.stats = stats;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g->ntx <= 1) return launch_ls<1>(a, B, st);
+  if (g->ntx <= 2) return launch_ls<2>(a, B, st);
+  if (g->ntx <= 4) return launch_ls<4>(a, B, st);
+  return launch_ls<8>(a, B, st);
+}
+
+extern "C" int b2c_stats_bins(const b2c_geom *g, const double *stats, const int32_t *bin_id, int64_t B,
+                              int32_t nbins, double *bins, void *stream) {
+  B2C_REQUIRE(g && stats && bin_id && bins, B2C_E_ARG, "b2c_stats_bins: null argument");
+  if (int rc = check_geom(g)) return rc;
+  B2C_REQUIRE(nbins >= 1 && B >= 0, B2C_E_ARG, "b2c_stats_bins: nbins=%d B=%lld", nbins, (long long)B);
+  if (B == 0) return B2C_OK;
+  stats_bins_kernel<<<nbins, BIN_THREADS, 0, (cudaStream_t)stream>>>(*g, stats, bin_id, B, bins);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_pilot_vectors(const float *y, const float *x, int64_t nvec, int32_t n, float snr_db,
+                                 int32_t mmse_mode, float *out, void *stream) {
+  B2C_REQUIRE(y && x && out, B2C_E_ARG, "b2c_pilot_vectors: null argument");
+  B2C_REQUIRE(n >= 1 && nvec >= 0 && nvec < (1ll << 31) && (mmse_mode == 0 || mmse_mode == 1), B2C_E_ARG,
+              "b2c_pilot_vectors: n=%d nvec=%lld mode=%d", n, (long long)nvec, mmse_mode);
+  if (nvec == 0) return B2C_OK;
+  pilot_vec_kernel<<<(unsigned)nvec, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2 *>(y), reinterpret_cast<const float2 *>(x), n, snr_db, mmse_mode,
+      reinterpret_cast<float2 *>(out));
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}

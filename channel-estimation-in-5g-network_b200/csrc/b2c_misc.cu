@@ -1,0 +1,258 @@
+// Stand-alone public-API kernels that are not on the fused path:
+//   b2c_apply_channel -- MIMOChannel.apply_channel for arbitrary tx / H (src/channel_simulator.py:313-345)
+//   b2c_tdl_full      -- ChannelModel.generate_time_varying_channel (:84-127), every time sample
+//   b2c_mmse_dense    -- W @ h_ls for the known-covariance MMSE branch (src/baseline_estimators.py:181-190)
+#include "b2c_common.cuh"
+#include "b2c_rng.cuh"
+
+namespace b2c {
+
+constexpr int MAXT = B2C_MAX_TAPS;
+constexpr int NOSC = B2C_N_OSC;
+
+// ---- apply_channel ---------------------------------------------------------------------------------
+// pass 1: y = H x per RE (:330-334) into rx, and the slot's sum |y|^2 (for :337).
+__global__ void __launch_bounds__(256) apply_hx_kernel(b2c_geom g, const float2 *__restrict__ tx,
+                                                       const float2 *__restrict__ H, float2 *__restrict__ rx,
+                                                       double *__restrict__ power, int chunks) {
+  __shared__ float red[33];
+  const int64_t b = blockIdx.x / chunks;
+  const int chunk = blockIdx.x - (int)b * chunks;
+  const int per = g.nsym * g.nrx * g.nsc;
+  const int e = chunk * 256 + threadIdx.x;
+  float p = 0.f;
+  if (e < per) {
+    int k = e % g.nsc, q = e / g.nsc;
+    int r = q % g.nrx, s = q / g.nrx;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int t = 0; t < g.ntx; ++t) {
+      float2 h = __ldg(H + (((b * g.nsym + s) * g.nrx + r) * g.ntx + t) * (int64_t)g.nsc + k);
+      float2 x = __ldg(tx + ((b * g.nsym + s) * g.ntx + t) * (int64_t)g.nsc + k);
+      acc = cadd(acc, cmul(h, x));
+    }
+    rx[b * per + e] = acc;
+    p = cabs2(acc);
+  }
+  float tot = block_sum(p, red);
+  if (threadIdx.x == 0) atomicAdd(power + b, (double)tot);
+}
+
+// pass 2: rx += noise_std * (n_re + j n_im)  (:338-343)
+__global__ void __launch_bounds__(256) apply_noise_kernel(b2c_geom g, b2c_slots slots, b2c_inject inj, int has_inj,
+                                                          float2 *__restrict__ rx, const double *__restrict__ power,
+                                                          int chunks) {
+  const int64_t b = blockIdx.x / chunks;
+  const int chunk = blockIdx.x - (int)b * chunks;
+  const int per = g.nsym * g.nrx * g.nsc;
+  const int e = chunk * 256 + threadIdx.x;
+  if (e >= per) return;
+  double p_sig = power[b] / (double)per;
+  float sigma = (float)sqrt(p_sig / pow(10.0, (double)slots.snr_db[b] / 10.0) / 2.0);
+  float2 n;
+  if (has_inj) {
+    n = __ldg(reinterpret_cast<const float2 *>(inj.noise) + b * per + e);
+  } else {
+    int k = e % g.nsc, q = e / g.nsc;
+    int r = q % g.nrx, s = q / g.nrx;
+    uint4 w = draw(make_key(slots.seed, slots.slot0 + b), STREAM_NOISE, (uint32_t)(((s >> 1) * g.nrx + r) * g.nsc + k));
+    n = (s & 1) ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
+  }
+  float2 y = rx[b * per + e];
+  rx[b * per + e] = make_float2(fmaf(sigma, n.x, y.x), fmaf(sigma, n.y, y.y));
+}
+
+// ---- tdl_full ---------------------------------------------------------------------------------------
+struct TdlArgs {
+  int ntaps, ntx, nrx, L;
+  int tap_delay[MAXT];
+  const int *tap_path;
+  const float *tap_amp;
+  const float *jakes_u;   // [npaths][ntx][nrx][2][20] or null
+  PhiloxKey key;
+  float doppler_hz, sample_period_s;
+  int64_t num_samples;
+  float2 *out;
+};
+
+// grid (time chunks, links); link = (tap, tx, rx)
+__global__ void __launch_bounds__(256) tdl_full_kernel(TdlArgs a) {
+  __shared__ float2 osc[NOSC];   // (phase turns, doppler shift in Hz)
+  const int link = blockIdx.y;
+  const int t = link / (a.ntx * a.nrx), rem = link - t * (a.ntx * a.nrx);
+  const int tx = rem / a.nrx, rx = rem - tx * a.nrx;
+  const int p = a.tap_path[t];
+  if (threadIdx.x < NOSC / 2) {
+    int pr = threadIdx.x;
+    float ua0, up0, ua1, up1;
+    if (a.jakes_u) {
+      const float *ju = a.jakes_u + (((int64_t)p * a.ntx + tx) * a.nrx + rx) * (2 * NOSC);
+      ua0 = ju[2 * pr];
+      ua1 = ju[2 * pr + 1];
+      up0 = ju[NOSC + 2 * pr];
+      up1 = ju[NOSC + 2 * pr + 1];
+    } else {
+      uint4 w = draw(a.key, STREAM_JAKES, (uint32_t)(((p * a.ntx + tx) * a.nrx + rx) * (NOSC / 2) + pr));
+      ua0 = u01(w.x);
+      up0 = u01(w.y);
+      ua1 = u01(w.z);
+      up1 = u01(w.w);
+    }
+    osc[2 * pr] = make_float2(up0, a.doppler_hz * cospif(2.0f * ua0));
+    osc[2 * pr + 1] = make_float2(up1, a.doppler_hz * cospif(2.0f * ua1));
+  }
+  __syncthreads();
+  const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (n >= a.num_samples) return;
+  // time in seconds as a double product rounded once: keeps the phase accurate for long records
+  const float tsec = (float)((double)n * (double)a.sample_period_s);
+  float ar = 0.f, ai = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < NOSC; ++i) {
+    float2 pd = osc[i];
+    float2 z = cis_turns(fmaf(tsec, pd.y, pd.x));
+    ar += z.x;
+    ai += z.y;
+  }
+  const float amp = a.tap_amp[t];
+  a.out[((n * a.nrx + rx) * a.ntx + tx) * (int64_t)a.L + a.tap_delay[t]] = make_float2(amp * ar, amp * ai);
+}
+
+// ---- dense Wiener apply: out[c][i] = sum_j W[i][j] in[c][j] -------------------------------------------
+// fp32 SIMT tiles: 64 (i) x 64 (c) outputs per CTA, 16-deep K steps, 4x4 complex per thread.
+constexpr int GM = 64, GN = 64, GK = 16;
+__global__ void __launch_bounds__(256) mmse_dense_kernel(const float2 *__restrict__ W, int np,
+                                                         const float2 *__restrict__ in, float2 *__restrict__ out,
+                                                         int64_t ncols, int64_t ld) {
+  __shared__ float2 sW[GK][GM + 1];   // [j][i]
+  __shared__ float2 sX[GK][GN + 1];   // [j][c]
+  const int i0 = blockIdx.x * GM;
+  const int64_t c0 = (int64_t)blockIdx.y * GN;
+  const int ti = threadIdx.x & 15, tc = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 outputs each
+  float2 acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = make_float2(0.f, 0.f);
+
+  for (int j0 = 0; j0 < np; j0 += GK) {
+    // W tile: rows i0.., cols j0..  (row-major, j contiguous)
+    for (int idx = threadIdx.x; idx < GM * GK; idx += 256) {
+      int jj = idx % GK, ii = idx / GK;
+      int i = i0 + ii, j = j0 + jj;
+      sW[jj][ii] = (i < np && j < np) ? __ldg(W + (int64_t)i * np + j) : make_float2(0.f, 0.f);
+    }
+    for (int idx = threadIdx.x; idx < GN * GK; idx += 256) {
+      int jj = idx % GK, cc = idx / GK;
+      int64_t c = c0 + cc;
+      int j = j0 + jj;
+      sX[jj][cc] = (c < ncols && j < np) ? __ldg(in + c * ld + j) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int jj = 0; jj < GK; ++jj) {
+      float2 w[4], x[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) w[a] = sW[jj][ti + 16 * a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) x[b] = sX[jj][tc + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          acc[a][b].x = fmaf(w[a].x, x[b].x, fmaf(-w[a].y, x[b].y, acc[a][b].x));
+          acc[a][b].y = fmaf(w[a].x, x[b].y, fmaf(w[a].y, x[b].x, acc[a][b].y));
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int i = i0 + ti + 16 * a;
+      int64_t c = c0 + tc + 16 * b;
+      if (i < np && c < ncols) out[c * ld + i] = acc[a][b];
+    }
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_apply_channel(const b2c_geom *g, const b2c_slots *slots, const b2c_inject *inj, int64_t B,
+                                 const float *tx, const float *H, float *rx, double *power_scratch, void *stream) {
+  B2C_REQUIRE(g && slots && tx && H && rx && power_scratch && slots->snr_db, B2C_E_ARG, "b2c_apply_channel: null argument");
+  if (int rc = check_geom(g)) return rc;
+  B2C_REQUIRE(!inj || inj->noise, B2C_E_ARG, "b2c_apply_channel: inject struct without noise");
+  if (B == 0) return B2C_OK;
+  const int per = g->nsym * g->nrx * g->nsc;
+  const int chunks = (per + 255) / 256;
+  B2C_REQUIRE(B > 0 && B * chunks < (1ll << 31), B2C_E_ARG, "b2c_apply_channel: B=%lld out of range", (long long)B);
+  cudaStream_t st = (cudaStream_t)stream;
+  B2C_CUDA(cudaMemsetAsync(power_scratch, 0, sizeof(double) * B, st));
+  apply_hx_kernel<<<(unsigned)(B * chunks), 256, 0, st>>>(*g, reinterpret_cast<const float2 *>(tx),
+                                                          reinterpret_cast<const float2 *>(H),
+                                                          reinterpret_cast<float2 *>(rx), power_scratch, chunks);
+  B2C_CUDA(cudaGetLastError());
+  b2c_inject ij = {};
+  if (inj) ij = *inj;
+  apply_noise_kernel<<<(unsigned)(B * chunks), 256, 0, st>>>(*g, *slots, ij, inj != nullptr,
+                                                             reinterpret_cast<float2 *>(rx), power_scratch, chunks);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_tdl_full(const b2c_geom *g, const b2c_profiles *prof, int32_t model_id, float doppler_hz,
+                            float sample_period_s, int64_t num_samples, int32_t L, const int32_t *tap_delay_host,
+                            const float *jakes_u, uint64_t seed, int64_t slot, float *out, void *stream) {
+  B2C_REQUIRE(g && prof && tap_delay_host && out, B2C_E_ARG, "b2c_tdl_full: null argument");
+  B2C_REQUIRE(g->ntx >= 1 && g->ntx <= B2C_MAX_ANT && g->nrx >= 1 && g->nrx <= B2C_MAX_ANT, B2C_E_UNSUPPORTED,
+              "b2c_tdl_full: antenna counts %dx%d", g->ntx, g->nrx);
+  B2C_REQUIRE(model_id >= 0 && model_id < prof->n_models, B2C_E_ARG, "b2c_tdl_full: model_id=%d", model_id);
+  B2C_REQUIRE(num_samples >= 0 && L >= 1, B2C_E_ARG, "b2c_tdl_full: num_samples=%lld L=%d", (long long)num_samples, L);
+  if (num_samples == 0) return B2C_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int ntaps = 0;
+  B2C_CUDA(cudaMemcpyAsync(&ntaps, prof->ntaps + model_id, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2C_CUDA(cudaStreamSynchronize(st));
+  B2C_REQUIRE(ntaps >= 1 && ntaps <= MAXT, B2C_E_ARG, "b2c_tdl_full: ntaps=%d", ntaps);
+  TdlArgs a = {};
+  a.ntaps = ntaps;
+  a.ntx = g->ntx;
+  a.nrx = g->nrx;
+  a.L = L;
+  for (int t = 0; t < ntaps; ++t) {
+    B2C_REQUIRE(tap_delay_host[t] >= 0 && tap_delay_host[t] < L, B2C_E_ARG, "b2c_tdl_full: tap delay %d outside L=%d",
+                tap_delay_host[t], L);
+    a.tap_delay[t] = tap_delay_host[t];
+  }
+  a.tap_path = prof->tap_path + model_id * MAXT;
+  a.tap_amp = prof->tap_amp + model_id * MAXT;
+  a.jakes_u = jakes_u;
+  a.key = make_key(seed, slot);
+  a.doppler_hz = doppler_hz;
+  a.sample_period_s = sample_period_s;
+  a.num_samples = num_samples;
+  a.out = reinterpret_cast<float2 *>(out);
+  B2C_CUDA(cudaMemsetAsync(out, 0, sizeof(float2) * (size_t)num_samples * g->nrx * g->ntx * L, st));
+  dim3 grid((unsigned)((num_samples + 255) / 256), (unsigned)(ntaps * g->ntx * g->nrx));
+  tdl_full_kernel<<<grid, 256, 0, st>>>(a);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_mmse_dense(const float *W, int32_t np, const float *in, float *out, int64_t ncols, int64_t ld,
+                              void *stream) {
+  B2C_REQUIRE(W && in && out, B2C_E_ARG, "b2c_mmse_dense: null argument");
+  B2C_REQUIRE(np >= 1 && ld >= np && ncols >= 0, B2C_E_ARG, "b2c_mmse_dense: np=%d ld=%lld ncols=%lld", np, (long long)ld,
+              (long long)ncols);
+  B2C_REQUIRE(in != out, B2C_E_ARG, "b2c_mmse_dense: in-place not supported");
+  if (ncols == 0) return B2C_OK;
+  dim3 grid((unsigned)((np + GM - 1) / GM), (unsigned)((ncols + GN - 1) / GN));
+  B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_mmse_dense: ncols=%lld too large for one launch", (long long)ncols);
+  mmse_dense_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(W), np,
+                                                            reinterpret_cast<const float2 *>(in),
+                                                            reinterpret_cast<float2 *>(out), ncols, ld);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}

@@ -1,0 +1,466 @@
+// K1a tap gains + the fused per-slot kernel (CFR, grid, y = Hx + n, LS, interpolation, MMSE, stats).
+//
+// Work decomposition: the channel is sampled once per OFDM symbol (src/channel_simulator.py:300-302),
+// so a slot's whole channel is nsym*nrx*ntx*ntaps complex tap gains (8 KB for 4x4 ETU).  K1a
+// evaluates those and the slot's noise scale; the slot kernel then runs one CTA per (slot, rx
+// antenna): it expands the gains to the CFR on the used bins by a direct ntaps-term DFT with
+// tabulated twiddles, and because every other quantity of the slot (grid symbols, noise, LS
+// pilots, interpolated estimates, errors) is a pure function of (gains, counters, plan) it never
+// re-reads anything it wrote: HBM traffic is the output arrays only.
+#include "b2c_common.cuh"
+#include "b2c_rng.cuh"
+
+namespace b2c {
+
+constexpr int MAXT = B2C_MAX_TAPS;
+constexpr int NOSC = B2C_N_OSC;
+constexpr int GAIN_THREADS = 256;
+constexpr int SLOT_THREADS = 320;   // 2 bins per thread cover the 599 used bins in one pass
+
+// ------------------------------------------------------------------------------------------
+// K1a: Jakes sum-of-sinusoids gains at the symbol-start instants (src/channel_simulator.py:102-125
+// evaluated only at the samples :301-302 consumes) and the AWGN scale of :337-340.
+// One CTA per slot.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GAIN_THREADS)
+tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj, int has_inj,
+                 float2 *__restrict__ gains, float *__restrict__ noise_std) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *osc = reinterpret_cast<float2 *>(smem_raw);   // [link][20] (phase turns, turns/symbol)
+  __shared__ double dred[GAIN_THREADS / 32];
+
+  const int64_t b = blockIdx.x;
+  const int m = slots.model_id[b];
+  const int ntaps = prof.ntaps[m];
+  const int ntx = g.ntx, nrx = g.nrx, nsym = g.nsym;
+  const int *tap_path = prof.tap_path + m * MAXT;
+  const float *tap_amp = prof.tap_amp + m * MAXT;
+  const float fdT = slots.doppler_hz[b] * g.symbol_period_s;   // Doppler turns per symbol at cos = 1
+  const PhiloxKey key = make_key(slots.seed, slots.slot0 + b);
+  const int nlinks = ntaps * ntx * nrx;                       // link = (tap, tx, rx)
+
+  // stage 1: one (phase, per-symbol phase step) pair per oscillator
+  for (int i = threadIdx.x; i < nlinks * (NOSC / 2); i += blockDim.x) {
+    int link = i / (NOSC / 2), pr = i - link * (NOSC / 2);
+    int t = link / (ntx * nrx), rem = link - t * (ntx * nrx);
+    int tx = rem / nrx, rx = rem - tx * nrx;
+    int p = tap_path[t];
+    float ua0, up0, ua1, up1;
+    if (has_inj) {
+      const float *ju = inj.jakes_u + ((((int64_t)b * inj.p_max + p) * ntx + tx) * nrx + rx) * (2 * NOSC);
+      ua0 = ju[2 * pr];
+      ua1 = ju[2 * pr + 1];
+      up0 = ju[NOSC + 2 * pr];
+      up1 = ju[NOSC + 2 * pr + 1];
+    } else {
+      uint4 w = draw(key, STREAM_JAKES, (uint32_t)(((p * ntx + tx) * nrx + rx) * (NOSC / 2) + pr));
+      ua0 = u01(w.x);
+      up0 = u01(w.y);
+      ua1 = u01(w.z);
+      up1 = u01(w.w);
+    }
+    // doppler_shift = fd * cos(theta), theta = 2 pi u  (:109, :119)
+    osc[link * NOSC + 2 * pr] = make_float2(up0, fdT * cospif(2.0f * ua0));
+    osc[link * NOSC + 2 * pr + 1] = make_float2(up1, fdT * cospif(2.0f * ua1));
+  }
+  __syncthreads();
+
+  // stage 2: gain[link][s] = amp * sum_n exp(j 2 pi (phase_n + s * step_n))
+  float2 *gout = gains + b * (int64_t)(nrx * nsym * ntx * MAXT);   // [rx][s][tx][MAXT]
+  const int nout = nrx * nsym * ntx * MAXT;
+  for (int o = threadIdx.x; o < nout; o += blockDim.x)
+    if ((o % MAXT) >= ntaps) gout[o] = make_float2(0.f, 0.f);
+  for (int i = threadIdx.x; i < nlinks * nsym; i += blockDim.x) {
+    int link = i / nsym, s = i - link * nsym;
+    int t = link / (ntx * nrx), rem = link - t * (ntx * nrx);
+    int tx = rem / nrx, rx = rem - tx * nrx;
+    const float2 *oc = osc + link * NOSC;
+    float fs = (float)s, ar = 0.f, ai = 0.f;
+#pragma unroll 4
+    for (int n = 0; n < NOSC; ++n) {
+      float2 pd = oc[n];
+      float2 z = cis_turns(fmaf(fs, pd.y, pd.x));
+      ar += z.x;
+      ai += z.y;
+    }
+    float a = tap_amp[t];
+    gout[((rx * nsym + s) * ntx + tx) * MAXT + t] = make_float2(a * ar, a * ai);
+  }
+  __syncthreads();   // this CTA's global writes are visible to its own threads past the barrier
+
+  // stage 3: mean |sum_tx H x|^2 over the slot as the quadratic form gs^H C gs (|x| = 1,
+  // same grid on every TX, :402-404), then noise_std of :338-340.  Tiny, done in double.
+  float2 *gs = osc;   // reuse: [rx*nsym + s][MAXT] sum over tx
+  for (int i = threadIdx.x; i < nrx * nsym * MAXT; i += blockDim.x) {
+    int t = i % MAXT, rs = i / MAXT;
+    float sr = 0.f, si = 0.f;
+    for (int tx = 0; tx < ntx; ++tx) {
+      float2 v = gout[(rs * ntx + tx) * MAXT + t];
+      sr += v.x;
+      si += v.y;
+    }
+    gs[i] = make_float2(sr, si);
+  }
+  __syncthreads();
+  const float2 *corr = reinterpret_cast<const float2 *>(prof.tap_corr) + m * MAXT * MAXT;
+  double part = 0.0;
+  for (int i = threadIdx.x; i < nrx * nsym * ntaps; i += blockDim.x) {
+    int p = i % ntaps, rs = i / ntaps;
+    float2 a = gs[rs * MAXT + p];
+    double accr = 0.0;
+    for (int q = 0; q < ntaps; ++q) {
+      float2 c = gs[rs * MAXT + q], k = corr[p * MAXT + q];
+      // Re( a * conj(c) * k )
+      double zr = (double)a.x * c.x + (double)a.y * c.y, zi = (double)a.y * c.x - (double)a.x * c.y;
+      accr += zr * k.x - zi * k.y;
+    }
+    part += accr;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) dred[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < GAIN_THREADS / 32; ++w) tot += dred[w];
+    double p_sig = tot / ((double)nsym * nrx * g.nsc);
+    double snr_lin = pow(10.0, (double)slots.snr_db[b] / 10.0);
+    noise_std[b] = (float)sqrt(p_sig / snr_lin / 2.0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused slot kernel.
+// ------------------------------------------------------------------------------------------
+struct SlotArgs {
+  b2c_geom g;
+  b2c_profiles prof;
+  b2c_patterns pat;
+  b2c_slots slots;
+  b2c_inject inj;
+  int has_inj;
+  const float2 *gains;
+  const float *noise_std;
+  float2 *H_true, *rx, *tx, *H_ls, *H_mmse;
+  double *stats;
+};
+
+struct SlotCtx {
+  int64_t b;
+  int rx, m, ntaps, pid;
+  float sigma, alpha;
+  PhiloxKey key;
+  const float4 *gsp;   // smem [nsym][ntx][MAXT] (gr, gr, gi, gi)
+  const float2 *hp;    // smem [np] LS estimates at the pilots
+};
+
+// Symbol and noise draws for resource element (s, k) of this CTA's rx antenna.
+__device__ __forceinline__ float2 draw_symbol(const SlotArgs &a, const SlotCtx &c, int s, int k) {
+  if (a.has_inj) return cis_turns(__ldg(a.inj.sym_turns + (c.b * a.g.nsym + s) * a.g.nsc + k));
+  uint4 w = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 2) * a.g.nsc + k));
+  return cis_turns(u01(pick(w, s & 3)));
+}
+__device__ __forceinline__ float2 draw_noise(const SlotArgs &a, const SlotCtx &c, int s, int k) {
+  if (a.has_inj)
+    return __ldg(reinterpret_cast<const float2 *>(a.inj.noise) +
+                 ((c.b * a.g.nsym + s) * a.g.nrx + c.rx) * a.g.nsc + k);
+  uint4 w = draw(c.key, STREAM_NOISE, (uint32_t)(((s >> 1) * a.g.nrx + c.rx) * a.g.nsc + k));
+  return (s & 1) ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
+}
+
+template <int T, int NTX, bool EST>
+__device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, float (&st)[NTX][3]) {
+  const int nsc = a.g.nsc, nsym = a.g.nsym, ntx = a.g.ntx, nrx = a.g.nrx;
+  const int k0 = threadIdx.x, k1 = threadIdx.x + SLOT_THREADS;
+  const bool v0 = k0 < nsc, v1 = k1 < nsc;
+  const int kk0 = v0 ? k0 : 0, kk1 = v1 ? k1 : 0;   // clamped: idle lanes compute on bin 0, store nothing
+
+  const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * nsc;
+  float2 tw0[T], tw1[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    tw0[t] = __ldg(tw + t * nsc + kk0);
+    tw1[t] = __ldg(tw + t * nsc + kk1);
+  }
+  const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * nsym * nsc : nullptr;
+
+  uint4 ws0 = make_uint4(0, 0, 0, 0), ws1 = ws0, wn0 = ws0, wn1 = ws0;
+  const bool need_draws = a.rx || a.tx;   // H-only calls (generate_channel_frequency_response) skip them
+  for (int s = 0; s < nsym; ++s) {
+    // ---- draws -----------------------------------------------------------------------------
+    float2 x0 = make_float2(0.f, 0.f), x1 = x0, n0 = x0, n1 = x0;
+    if (!need_draws) {
+    } else if (a.has_inj) {
+      x0 = draw_symbol(a, c, s, kk0);
+      x1 = draw_symbol(a, c, s, kk1);
+      n0 = draw_noise(a, c, s, kk0);
+      n1 = draw_noise(a, c, s, kk1);
+    } else {
+      if ((s & 3) == 0) {
+        ws0 = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 2) * nsc + kk0));
+        ws1 = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 2) * nsc + kk1));
+      }
+      x0 = cis_turns(u01(pick(ws0, s & 3)));
+      x1 = cis_turns(u01(pick(ws1, s & 3)));
+      if ((s & 1) == 0) {
+        wn0 = draw(c.key, STREAM_NOISE, (uint32_t)(((s >> 1) * nrx + c.rx) * nsc + kk0));
+        wn1 = draw(c.key, STREAM_NOISE, (uint32_t)(((s >> 1) * nrx + c.rx) * nsc + kk1));
+        n0 = normal_pair(wn0.x, wn0.y);
+        n1 = normal_pair(wn1.x, wn1.y);
+      } else {
+        n0 = normal_pair(wn0.z, wn0.w);
+        n1 = normal_pair(wn1.z, wn1.w);
+      }
+    }
+    // ---- LS interpolation + default MMSE for this RE (identical for every tx) -----------------
+    float2 l0 = make_float2(0.f, 0.f), l1 = l0, m0 = l0, m1 = l0;
+    if (EST) {
+      PlanTap p0 = plan_decode(__ldg(plan + s * nsc + kk0));
+      PlanTap p1 = plan_decode(__ldg(plan + s * nsc + kk1));
+      l0 = plan_apply(p0, c.hp);
+      l1 = plan_apply(p1, c.hp);
+      m0 = cscale(c.alpha, l0);
+      m1 = cscale(c.alpha, l1);
+    }
+    // ---- CFR per tx: H[s, rx, tx, k] = sum_t g[s, tx, t] * tw[t, k]  --------------------------
+    const int64_t rowH = ((c.b * nsym + s) * nrx + c.rx) * (int64_t)ntx * nsc;
+    float2 hs0 = make_float2(0.f, 0.f), hs1 = hs0;
+#pragma unroll
+    for (int tx = 0; tx < NTX; ++tx) {
+      if (tx < ntx) {
+        const float4 *gp = c.gsp + (s * ntx + tx) * MAXT;
+        float2 A0 = make_float2(0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          float4 gq = gp[t];
+          float2 gr = make_float2(gq.x, gq.y), gi = make_float2(gq.z, gq.w);
+          A0 = __ffma2_rn(gr, tw0[t], A0);
+          B0 = __ffma2_rn(gi, tw0[t], B0);
+          A1 = __ffma2_rn(gr, tw1[t], A1);
+          B1 = __ffma2_rn(gi, tw1[t], B1);
+        }
+        float2 h0 = make_float2(A0.x - B0.y, A0.y + B0.x);
+        float2 h1 = make_float2(A1.x - B1.y, A1.y + B1.x);
+        hs0 = cadd(hs0, h0);
+        hs1 = cadd(hs1, h1);
+        const int64_t o0 = rowH + (int64_t)tx * nsc + k0, o1 = rowH + (int64_t)tx * nsc + k1;
+        if (a.H_true) {
+          if (v0) st_stream(a.H_true + o0, h0);
+          if (v1) st_stream(a.H_true + o1, h1);
+        }
+        if (EST) {
+          if (a.H_ls) {
+            if (v0) st_stream(a.H_ls + o0, l0);
+            if (v1) st_stream(a.H_ls + o1, l1);
+          }
+          if (a.H_mmse) {
+            if (v0) st_stream(a.H_mmse + o0, m0);
+            if (v1) st_stream(a.H_mmse + o1, m1);
+          }
+          if (v0) {
+            st[tx][0] += cabs2(make_float2(h0.x - l0.x, h0.y - l0.y));
+            st[tx][1] += cabs2(make_float2(h0.x - m0.x, h0.y - m0.y));
+            st[tx][2] += cabs2(h0);
+          }
+          if (v1) {
+            st[tx][0] += cabs2(make_float2(h1.x - l1.x, h1.y - l1.y));
+            st[tx][1] += cabs2(make_float2(h1.x - m1.x, h1.y - m1.y));
+            st[tx][2] += cabs2(h1);
+          }
+        }
+      }
+    }
+    // ---- y = (sum_tx H) x + sigma n  (:330-343) ------------------------------------------------
+    if (a.rx) {
+      float2 y0 = cmul(hs0, x0), y1 = cmul(hs1, x1);
+      const int64_t r = ((c.b * nsym + s) * nrx + c.rx) * (int64_t)nsc;
+      if (v0) st_stream(a.rx + r + k0, make_float2(fmaf(c.sigma, n0.x, y0.x), fmaf(c.sigma, n0.y, y0.y)));
+      if (v1) st_stream(a.rx + r + k1, make_float2(fmaf(c.sigma, n1.x, y1.x), fmaf(c.sigma, n1.y, y1.y)));
+    }
+    if (a.tx && c.rx == 0) {
+      for (int tx = 0; tx < ntx; ++tx) {
+        const int64_t r = ((c.b * nsym + s) * ntx + tx) * (int64_t)nsc;
+        if (v0) st_stream(a.tx + r + k0, x0);
+        if (v1) st_stream(a.tx + r + k1, x1);
+      }
+    }
+  }
+}
+
+template <int NTX, bool EST>
+__global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nsc = a.g.nsc, nsym = a.g.nsym, ntx = a.g.ntx, nrx = a.g.nrx;
+  float4 *gsp = reinterpret_cast<float4 *>(smem_raw);                 // [nsym][ntx][MAXT]
+  float2 *gs = reinterpret_cast<float2 *>(gsp + nsym * ntx * MAXT);   // [nsym][MAXT] sum over tx
+  float2 *hp = gs + nsym * MAXT;                                      // [np_max]
+  __shared__ float red[33];
+  __shared__ float ssm[SLOT_THREADS / 32][NTX * 3];
+
+  SlotCtx c;
+  c.b = blockIdx.x / nrx;
+  c.rx = blockIdx.x - (int)c.b * nrx;
+  c.m = a.slots.model_id[c.b];
+  c.ntaps = a.prof.ntaps[c.m];
+  c.sigma = a.noise_std[c.b];
+  c.key = make_key(a.slots.seed, a.slots.slot0 + c.b);
+  c.gsp = gsp;
+  c.hp = hp;
+  c.alpha = 0.f;
+  c.pid = 0;
+
+  const float2 *gin = a.gains + (c.b * nrx + c.rx) * (int64_t)(nsym * ntx * MAXT);
+  for (int i = threadIdx.x; i < nsym * ntx * MAXT; i += SLOT_THREADS) {
+    float2 v = __ldg(gin + i);
+    gsp[i] = make_float4(v.x, v.x, v.y, v.y);
+  }
+  __syncthreads();
+
+  if (EST) {
+    // LS at the pilots: h_p = y_p / (x_p + 1e-12)  (src/baseline_estimators.py:109-110), with y_p
+    // evaluated directly at the pilot REs from the tx-summed gains.
+    for (int i = threadIdx.x; i < nsym * MAXT; i += SLOT_THREADS) {
+      int s = i / MAXT, t = i - s * MAXT;
+      float sr = 0.f, si = 0.f;
+      for (int tx = 0; tx < ntx; ++tx) {
+        float4 v = gsp[(s * ntx + tx) * MAXT + t];
+        sr += v.x;
+        si += v.z;
+      }
+      gs[i] = make_float2(sr, si);
+    }
+    __syncthreads();
+    c.pid = a.slots.pattern_id[c.b];
+    const int np = a.pat.npilots[c.pid];
+    const int *pre = a.pat.pilot_re + (int64_t)c.pid * a.pat.np_max;
+    const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * nsc;
+    float psum = 0.f;
+    for (int j = threadIdx.x; j < np; j += SLOT_THREADS) {
+      int e = __ldg(pre + j);
+      int s = e / nsc, k = e - s * nsc;
+      float2 hsum = make_float2(0.f, 0.f);
+      for (int t = 0; t < c.ntaps; ++t) hsum = cadd(hsum, cmul(gs[s * MAXT + t], __ldg(tw + t * nsc + k)));
+      float2 x = draw_symbol(a, c, s, k), n = draw_noise(a, c, s, k);
+      float2 y = cmul(hsum, x);
+      float2 h = ls_divide(make_float2(fmaf(c.sigma, n.x, y.x), fmaf(c.sigma, n.y, y.y)), x);
+      hp[j] = h;
+      psum += cabs2(h);
+    }
+    // default MMSE: R_h = P I  =>  W = P/(P + sigma^2) I  (src/baseline_estimators.py:174-190)
+    float P = block_sum(psum, red) / (float)np;
+    float sig2 = exp10f(-0.1f * a.slots.snr_db[c.b]);
+    c.alpha = P / (P + sig2);
+  }
+
+  float st[NTX][3];
+#pragma unroll
+  for (int tx = 0; tx < NTX; ++tx) st[tx][0] = st[tx][1] = st[tx][2] = 0.f;
+
+  if (c.ntaps <= 5) slot_body<5, NTX, EST>(a, c, st);
+  else if (c.ntaps <= 8) slot_body<8, NTX, EST>(a, c, st);
+  else if (c.ntaps <= 9) slot_body<9, NTX, EST>(a, c, st);
+  else slot_body<MAXT, NTX, EST>(a, c, st);
+
+  if (EST && a.stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int tx = 0; tx < NTX; ++tx)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float v = warp_sum(st[tx][j]);
+        if (lane == 0) ssm[warp][tx * 3 + j] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < ntx * 3) {
+      double acc = 0.0;
+      for (int w = 0; w < SLOT_THREADS / 32; ++w) acc += (double)ssm[w][threadIdx.x];
+      a.stats[(c.b * nrx + c.rx) * (int64_t)(ntx * 3) + threadIdx.x] = acc;
+    }
+  }
+}
+
+static size_t slot_smem_bytes(const b2c_geom *g, int np_max) {
+  return (size_t)g->nsym * g->ntx * MAXT * sizeof(float4) + (size_t)g->nsym * MAXT * sizeof(float2) +
+         (size_t)np_max * sizeof(float2);
+}
+
+template <int NTX, bool EST>
+static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
+  auto kern = slot_kernel<NTX, EST>;
+  if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(B * a.g.nrx), SLOT_THREADS, smem, stream>>>(a);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+template <bool EST>
+static int launch_slot_ntx(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
+  int ntx = a.g.ntx;
+  if (ntx <= 1) return launch_slot<1, EST>(a, B, smem, stream);
+  if (ntx <= 2) return launch_slot<2, EST>(a, B, smem, stream);
+  if (ntx <= 4) return launch_slot<4, EST>(a, B, smem, stream);
+  return launch_slot<8, EST>(a, B, smem, stream);
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_tap_gains(const b2c_geom *g, const b2c_profiles *prof, const b2c_slots *slots,
+                             const b2c_inject *inj, int64_t B, float *gains, float *noise_std,
+                             void *stream) {
+  B2C_REQUIRE(g && prof && slots && gains && noise_std, B2C_E_ARG, "b2c_tap_gains: null argument");
+  if (int rc = check_geom(g)) return rc;
+  B2C_REQUIRE(B >= 0 && B < (1ll << 31), B2C_E_ARG, "b2c_tap_gains: B=%lld out of range", (long long)B);
+  B2C_REQUIRE(!inj || inj->jakes_u, B2C_E_ARG, "b2c_tap_gains: inject struct without jakes_u");
+  if (B == 0) return B2C_OK;
+  b2c_inject ij = {};
+  if (inj) ij = *inj;
+  // stage-1 oscillators for up to MAXT taps; stage 3 reuses the buffer for the tx-summed gains
+  size_t osc = (size_t)MAXT * g->ntx * g->nrx * NOSC * sizeof(float2);
+  size_t gsb = (size_t)g->nrx * g->nsym * MAXT * sizeof(float2);
+  size_t smem = osc > gsb ? osc : gsb;
+  B2C_REQUIRE(smem <= 200 * 1024, B2C_E_UNSUPPORTED, "b2c_tap_gains: %zu B shared memory needed", smem);
+  if (smem > 48 * 1024)
+    B2C_CUDA(cudaFuncSetAttribute(tap_gains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tap_gains_kernel<<<(unsigned)B, GAIN_THREADS, smem, (cudaStream_t)stream>>>(
+      *g, *prof, *slots, ij, inj != nullptr, reinterpret_cast<float2 *>(gains), noise_std);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat,
+                                 const b2c_slots *slots, const b2c_inject *inj, int64_t B,
+                                 const float *gains, const float *noise_std, float *H_true, float *rx,
+                                 float *tx, float *H_ls, float *H_mmse, double *stats, void *stream) {
+  B2C_REQUIRE(g && prof && slots && gains && noise_std, B2C_E_ARG, "b2c_slot_pipeline: null argument");
+  if (int rc = check_geom(g)) return rc;
+  B2C_REQUIRE(B >= 0 && B * g->nrx < (1ll << 31), B2C_E_ARG, "b2c_slot_pipeline: B=%lld out of range",
+              (long long)B);
+  const bool est = H_ls || H_mmse || stats;
+  B2C_REQUIRE(!est || (pat && pat->plan && pat->pilot_re && pat->npilots && slots->pattern_id), B2C_E_ARG,
+              "b2c_slot_pipeline: estimation outputs requested without a pattern pool");
+  B2C_REQUIRE(!inj || !(est || rx || tx) || (inj->sym_turns && inj->noise), B2C_E_ARG,
+              "b2c_slot_pipeline: inject struct needs sym_turns and noise");
+  B2C_REQUIRE(!est || pat->np_max <= 65535, B2C_E_UNSUPPORTED, "b2c_slot_pipeline: more than 65535 pilots");
+  if (B == 0) return B2C_OK;
+  SlotArgs a = {};
+  a.g = *g;
+  a.prof = *prof;
+  if (pat) a.pat = *pat;
+  a.slots = *slots;
+  if (inj) a.inj = *inj;
+  a.has_inj = inj != nullptr;
+  a.gains = reinterpret_cast<const float2 *>(gains);
+  a.noise_std = noise_std;
+  a.H_true = reinterpret_cast<float2 *>(H_true);
+  a.rx = reinterpret_cast<float2 *>(rx);
+  a.tx = reinterpret_cast<float2 *>(tx);
+  a.H_ls = reinterpret_cast<float2 *>(H_ls);
+  a.H_mmse = reinterpret_cast<float2 *>(H_mmse);
+  a.stats = stats;
+  size_t smem = slot_smem_bytes(g, est ? pat->np_max : 0);
+  B2C_REQUIRE(smem <= 100 * 1024, B2C_E_UNSUPPORTED, "b2c_slot_pipeline: %zu B shared memory needed", smem);
+  return est ? launch_slot_ntx<true>(a, B, smem, (cudaStream_t)stream)
+             : launch_slot_ntx<false>(a, B, smem, (cudaStream_t)stream);
+}

@@ -1,0 +1,259 @@
+"""Batched host API over libb2c: device-resident tables, pattern pools and the slot pipeline.
+
+This is the layer the reference-shaped shims (channel_simulator.py, baseline_estimators.py,
+dataset_generator.py) and bench.py call.  Torch supplies device memory and streams; every
+computation is a libb2c kernel.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+import _b2c
+import _tables
+from _b2c import Geom, Inject, Patterns, Profiles, Slots, check, dptr, lib, ref, stream_ptr
+
+DEFAULT_MODELS = ("EPA", "EVA", "ETU")
+BIN_FIELDS = ("count", "sum_mse_ls", "sum_mse_mmse", "sum_nmse_ls", "sum_nmse_mmse", "sum_nmse_ls_sq",
+              "sum_nmse_mmse_sq", "sum_power", "sum_nmse00_ls", "sum_nmse00_ls_sq", "sum_nmse00_mmse",
+              "sum_nmse00_mmse_sq")
+
+
+def _cuda_device(device=None):
+    if not torch.cuda.is_available():
+        raise _b2c.B2CError("no CUDA device: this package runs on sm_100a only and has no CPU fallback")
+    return torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+
+
+class PatternPool:
+    """Device-resident pool of pilot patterns + interpolation plans (b2c_patterns)."""
+
+    def __init__(self, pilot_index_list, nsym, nsc, method="linear", device=None):
+        self.device = _cuda_device(device)
+        self.nsym, self.nsc, self.method = nsym, nsc, method
+        self.pilot_indices = [np.asarray(p, dtype=np.int64) for p in pilot_index_list]
+        n = len(self.pilot_indices)
+        self.npilots_host = np.array([len(p) for p in self.pilot_indices], dtype=np.int32)
+        self.np_max = int(self.npilots_host.max())
+        pre = np.zeros((n, self.np_max), dtype=np.int32)
+        plans = np.zeros((n, nsym * nsc), dtype=_tables.PLAN_DTYPE)
+        for i, p in enumerate(self.pilot_indices):
+            pre[i, :len(p)] = p
+            plans[i] = _tables.cached_plan(p, nsym, nsc, method)
+        self.npilots = torch.from_numpy(self.npilots_host).to(self.device)
+        self.pilot_re = torch.from_numpy(pre).to(self.device)
+        self.plan = torch.from_numpy(plans.view(np.uint8).reshape(n, nsym * nsc * 16)).to(self.device)
+        self.struct = Patterns(n, self.np_max, self.npilots.data_ptr(), self.pilot_re.data_ptr(), self.plan.data_ptr())
+
+    def __len__(self):
+        return len(self.pilot_indices)
+
+    def mask(self, i):
+        m = np.zeros(self.nsym * self.nsc, dtype=bool)
+        m[self.pilot_indices[i]] = True
+        return m.reshape(self.nsym, self.nsc)
+
+
+class SlotEngine:
+    """Geometry + TDL profile tables on one GPU, and launchers for every libb2c entry point."""
+
+    def __init__(self, config, models=DEFAULT_MODELS, device=None):
+        self.device = _cuda_device(device)
+        o, m = config["ofdm"], config["mimo"]
+        self.fft_size, self.cp = int(o["fft_size"]), int(o["cp_length"])
+        self.nsym, self.useful = int(o["num_symbols"]), int(o["useful_subcarriers"])
+        self.ntx, self.nrx = int(m["num_tx_antennas"]), int(m["num_rx_antennas"])
+        self.sampling_rate = self.fft_size * float(o["subcarrier_spacing"])
+        self.used = _tables.used_subcarriers(self.fft_size, self.useful)
+        self.nsc = len(self.used)
+        self.models = tuple(models)
+        self.geom = Geom(self.nsym, self.nsc, self.ntx, self.nrx, self.fft_size, self.cp,
+                         (self.fft_size + self.cp) / self.sampling_rate)
+        t = _tables.profile_tables(self.models, self.sampling_rate, self.fft_size, self.used)
+        self.host_tables = t
+        self._dev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in t.items()}
+        self.prof = Profiles(len(self.models), self._dev["ntaps"].data_ptr(), self._dev["npaths"].data_ptr(),
+                             self._dev["tap_path"].data_ptr(), self._dev["tap_amp"].data_ptr(),
+                             self._dev["tap_tw"].data_ptr(), self._dev["tap_corr"].data_ptr())
+        self.p_max = int(t["npaths"].max())
+
+    # ---- pools -------------------------------------------------------------------------------
+    def pool(self, pilot_index_list, method="linear"):
+        return PatternPool(pilot_index_list, self.nsym, self.nsc, method, self.device)
+
+    def random_pool(self, densities, per_density=1, seed=42, method="linear"):
+        """Fixed pool of scattered patterns (PilotPattern's rule, src/channel_simulator.py:223-229)
+        drawn from numpy RandomState(seed): pattern id = density_index * per_density + j."""
+        rs = np.random.RandomState(seed)
+        total = self.nsym * self.nsc
+        pats = []
+        for d in densities:
+            for _ in range(per_density):
+                perm = np.arange(total)
+                rs.shuffle(perm)
+                pats.append(np.sort(perm[:int(total * d)]))
+        return self.pool(pats, method)
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def _vec(self, v, B, dtype):
+        if isinstance(v, torch.Tensor):
+            return v.to(device=self.device, dtype=dtype).contiguous()
+        a = np.broadcast_to(np.asarray(v), (B,))
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dtype)
+
+    def _slots(self, B, model_id, doppler_hz, snr_db, pattern_id, slot0, seed):
+        keep = (self._vec(model_id, B, torch.int32), self._vec(doppler_hz, B, torch.float32),
+                self._vec(snr_db, B, torch.float32), self._vec(pattern_id, B, torch.int32))
+        s = Slots(int(slot0), int(seed) & 0xFFFFFFFFFFFFFFFF, *(k.data_ptr() for k in keep))
+        return s, keep
+
+    def _inject(self, inject):
+        if inject is None:
+            return None, ()
+        keep = []
+        ij = Inject()
+        if inject.get("jakes_u") is not None:
+            ju = inject["jakes_u"]
+            ij.jakes_u = dptr(ju, "f32").value
+            ij.p_max = ju.shape[1]
+            keep.append(ju)
+        if inject.get("sym_turns") is not None:
+            ij.sym_turns = dptr(inject["sym_turns"], "f32").value
+            ij.noise = dptr(inject["noise"], "c64").value
+            keep += [inject["sym_turns"], inject["noise"]]
+        return ij, keep
+
+    def workspace(self, B):
+        return {"gains": torch.empty((B, self.nrx, self.nsym, self.ntx, _b2c.MAX_TAPS), dtype=torch.complex64, device=self.device),
+                "noise_std": torch.empty((B,), dtype=torch.float32, device=self.device)}
+
+    def alloc_outputs(self, B, want):
+        shapes = {"H_true": (B, self.nsym, self.nrx, self.ntx, self.nsc), "H_ls": (B, self.nsym, self.nrx, self.ntx, self.nsc),
+                  "H_mmse": (B, self.nsym, self.nrx, self.ntx, self.nsc), "rx": (B, self.nsym, self.nrx, self.nsc),
+                  "tx": (B, self.nsym, self.ntx, self.nsc)}
+        out = {k: torch.empty(shapes[k], dtype=torch.complex64, device=self.device) for k in want if k in shapes}
+        if "stats" in want:
+            out["stats"] = torch.empty((B, self.nrx, self.ntx, _b2c.N_STAT), dtype=torch.float64, device=self.device)
+        return out
+
+    # ---- K1a + fused slot kernel -------------------------------------------------------------------
+    def run(self, B, model_id, doppler_hz, snr_db, pattern_id=0, pool=None, slot0=0, seed=42, inject=None,
+            want=("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), out=None, ws=None):
+        """Simulate B slots and (if any of H_ls/H_mmse/stats is wanted) estimate them.
+        Per-slot parameters are scalars or length-B arrays/tensors.  Returns dict of CUDA tensors."""
+        if out is None:
+            out = self.alloc_outputs(B, want)
+        if ws is None:
+            ws = self.workspace(B)
+        est = any(k in out for k in ("H_ls", "H_mmse", "stats"))
+        if est and pool is None:
+            raise ValueError("estimation outputs need a PatternPool")
+        slots, keep = self._slots(B, model_id, doppler_hz, snr_db, pattern_id, slot0, seed)
+        ij, keep_inj = self._inject(inject)
+        L = lib()
+        check(L.b2c_tap_gains(ref(self.geom), ref(self.prof), ref(slots), ref(ij), B,
+                              dptr(ws["gains"], "c64"), dptr(ws["noise_std"], "f32"), stream_ptr()), "b2c_tap_gains")
+        check(L.b2c_slot_pipeline(ref(self.geom), ref(self.prof), ref(pool.struct) if pool is not None else None,
+                                  ref(slots), ref(ij), B, dptr(ws["gains"], "c64"), dptr(ws["noise_std"], "f32"),
+                                  dptr(out.get("H_true"), "c64", True), dptr(out.get("rx"), "c64", True),
+                                  dptr(out.get("tx"), "c64", True), dptr(out.get("H_ls"), "c64", True),
+                                  dptr(out.get("H_mmse"), "c64", True), dptr(out.get("stats"), "f64", True),
+                                  stream_ptr()), "b2c_slot_pipeline")
+        out["_keepalive"] = (keep, keep_inj, ws)
+        return out
+
+    # ---- K3 ------------------------------------------------------------------------------------------
+    def ls_interp(self, rx, pilots, pool, pattern_id=0, snr_db=None, mmse=False, H_true=None, hp_in=None,
+                  want=("H_ls",), geom=None):
+        """rx [B,nsym,nrx,nsc] c64, pilots [B or 1, np_max] c64.  want subset of H_ls, H_mmse, hp, stats."""
+        g = geom if geom is not None else self.geom
+        B = rx.shape[0] if rx is not None else hp_in.shape[0]
+        pid = self._vec(pattern_id, B, torch.int32)
+        snr = self._vec(snr_db, B, torch.float32) if snr_db is not None else None
+        out = {}
+        shape = (B, g.nsym, g.nrx, g.ntx, g.nsc)
+        if "H_ls" in want:
+            out["H_ls"] = torch.empty(shape, dtype=torch.complex64, device=self.device)
+        if "H_mmse" in want:
+            out["H_mmse"] = torch.empty(shape, dtype=torch.complex64, device=self.device)
+        if "hp" in want:
+            out["hp"] = torch.zeros((B, g.nrx, pool.np_max), dtype=torch.complex64, device=self.device)
+        if "stats" in want:
+            out["stats"] = torch.empty((B, g.nrx, g.ntx, _b2c.N_STAT), dtype=torch.float64, device=self.device)
+        stride = pilots.shape[1] if (pilots is not None and pilots.shape[0] > 1) else 0
+        check(lib().b2c_ls_interp(ref(g), ref(pool.struct), dptr(pid, "i32"), dptr(snr, "f32", True), B,
+                                  dptr(rx, "c64", True), dptr(pilots, "c64", True), stride, dptr(hp_in, "c64", True),
+                                  1 if mmse else 0, dptr(H_true, "c64", True), dptr(out.get("H_ls"), "c64", True),
+                                  dptr(out.get("H_mmse"), "c64", True), dptr(out.get("hp"), "c64", True),
+                                  dptr(out.get("stats"), "f64", True), stream_ptr()), "b2c_ls_interp")
+        return out
+
+    def pilot_vectors(self, y, x, snr_db=0.0, mmse=False):
+        """y [nvec, n], x [n] complex64 CUDA -> alpha * y / (x + 1e-12)."""
+        out = torch.empty_like(y)
+        check(lib().b2c_pilot_vectors(dptr(y, "c64"), dptr(x, "c64"), y.shape[0], y.shape[1], float(snr_db),
+                                      1 if mmse else 0, dptr(out, "c64"), stream_ptr()), "b2c_pilot_vectors")
+        return out
+
+    def mmse_dense(self, W, h):
+        """W [np,np] c64, h [ncols, ld>=np] c64 -> W @ h[c, :np] per column set."""
+        out = torch.zeros_like(h)
+        check(lib().b2c_mmse_dense(dptr(W, "c64"), W.shape[0], dptr(h, "c64"), dptr(out, "c64"), h.shape[0],
+                                   h.shape[1], stream_ptr()), "b2c_mmse_dense")
+        return out
+
+    # ---- K5 ------------------------------------------------------------------------------------------
+    def stats_bins(self, stats, bin_id, nbins, bins=None, geom=None):
+        g = geom if geom is not None else self.geom
+        B = stats.shape[0]
+        if bins is None:
+            bins = torch.zeros((nbins, _b2c.N_BINSTAT), dtype=torch.float64, device=self.device)
+        bid = self._vec(bin_id, B, torch.int32)
+        check(lib().b2c_stats_bins(ref(g), dptr(stats, "f64"), dptr(bid, "i32"), B, nbins, dptr(bins, "f64"),
+                                   stream_ptr()), "b2c_stats_bins")
+        return bins
+
+    # ---- K2 ------------------------------------------------------------------------------------------
+    def ofdm_modulate(self, sym):
+        rows = sym.shape[0]
+        out = torch.empty((rows, self.fft_size + self.cp), dtype=torch.complex64, device=self.device)
+        check(lib().b2c_ofdm_modulate(ref(self.geom), dptr(sym, "c64"), dptr(out, "c64"), rows, stream_ptr()),
+              "b2c_ofdm_modulate")
+        return out
+
+    def ofdm_demodulate(self, sig):
+        rows = sig.shape[0]
+        out = torch.empty((rows, self.nsc), dtype=torch.complex64, device=self.device)
+        check(lib().b2c_ofdm_demodulate(ref(self.geom), dptr(sig, "c64"), dptr(out, "c64"), rows, stream_ptr()),
+              "b2c_ofdm_demodulate")
+        return out
+
+    # ---- a8 / a3 stand-alone -----------------------------------------------------------------------------
+    def apply_channel(self, tx, H, snr_db, noise=None, slot0=0, seed=42, geom=None):
+        g = geom if geom is not None else self.geom
+        B = tx.shape[0]
+        slots, keep = self._slots(B, 0, 0.0, snr_db, 0, slot0, seed)
+        ij, keep_inj = (None, ())
+        if noise is not None:
+            ij = Inject()
+            ij.noise = dptr(noise, "c64").value
+        rx = torch.empty((B, g.nsym, g.nrx, g.nsc), dtype=torch.complex64, device=self.device)
+        scratch = torch.empty((B,), dtype=torch.float64, device=self.device)
+        check(lib().b2c_apply_channel(ref(g), ref(slots), ref(ij), B, dptr(tx, "c64"), dptr(H, "c64"),
+                                      dptr(rx, "c64"), dptr(scratch, "f64"), stream_ptr()), "b2c_apply_channel")
+        return rx
+
+    def tdl_full(self, model, doppler_hz, num_samples, ntx, nrx, jakes_u=None, seed=42, slot=0):
+        m = self.models.index(model)
+        nt = int(self.host_tables["ntaps"][m])
+        delays = np.ascontiguousarray(self.host_tables["tap_delay"][m, :nt].astype(np.int32))
+        L = int(delays.max()) + 1
+        g = Geom(self.nsym, self.nsc, ntx, nrx, self.fft_size, self.cp, self.geom.symbol_period_s)
+        out = torch.empty((num_samples, nrx, ntx, L), dtype=torch.complex64, device=self.device)
+        check(lib().b2c_tdl_full(ref(g), ref(self.prof), m, float(doppler_hz), 1.0 / self.sampling_rate, num_samples, L,
+                                 delays.ctypes.data_as(C.c_void_p), dptr(jakes_u, "f32", True), int(seed), int(slot),
+                                 dptr(out, "c64"), stream_ptr()), "b2c_tdl_full")
+        return out

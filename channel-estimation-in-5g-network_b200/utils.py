@@ -1,0 +1,80 @@
+"""Hot-path helpers of the reference's src/utils.py (seeding, config, dB conversion, channel metrics,
+complex<->real packing).  The QAM mod/demod, BER and torch-checkpoint helpers of that file belong to
+the ML side / 'next' rows and are not provided here."""
+
+from __future__ import annotations
+
+import os
+import random
+from pathlib import Path
+from typing import Any, Dict
+
+import numpy as np
+
+_DEFAULT_CONFIG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs", "experiment_config.yaml")
+
+
+def set_seed(seed: int = 42):
+    """Seed python, numpy and torch generators (src/utils.py:13-22)."""
+    import torch
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def load_config(config_path: str = 'configs/experiment_config.yaml') -> Dict[str, Any]:
+    """YAML -> dict (src/utils.py:25-29).  Falls back to the copy shipped with this package when the
+    relative default path does not exist in the working directory."""
+    import yaml
+    path = config_path if os.path.exists(config_path) else _DEFAULT_CONFIG
+    with open(path, 'r') as fh:
+        return yaml.safe_load(fh)
+
+
+def default_config(ntx: int = 2, nrx: int = 2) -> Dict[str, Any]:
+    """The hot-path keys of configs/experiment_config.yaml (:4-42) without reading a file."""
+    return {
+        "ofdm": {"fft_size": 1024, "cp_length": 72, "subcarrier_spacing": 15000, "num_symbols": 14,
+                 "useful_subcarriers": 600},
+        "mimo": {"num_tx_antennas": ntx, "num_rx_antennas": nrx},
+        "channel": {"models": ["EPA", "EVA", "ETU"], "doppler_hz": [10, 50, 100, 200], "carrier_freq": 2.0e9},
+        "pilots": {"density": [0.01, 0.02, 0.05, 0.10]},
+        "simulation": {"snr_range": [-5, 0, 5, 10, 15, 20, 25, 30]},
+        "dataset": {"train_samples": 50000, "val_samples": 5000, "test_samples": 10000, "save_format": "npz"},
+    }
+
+
+def create_directories(config: Dict[str, Any]):
+    for value in config.get('paths', {}).values():
+        Path(value).mkdir(parents=True, exist_ok=True)
+
+
+def db2linear(db_value: float) -> float:
+    return 10 ** (db_value / 10)
+
+
+def linear2db(linear_value: float) -> float:
+    """10 log10(x + 1e-12) (src/utils.py:44-46)."""
+    return 10 * np.log10(linear_value + 1e-12)
+
+
+def calculate_mse(true_channel: np.ndarray, estimated_channel: np.ndarray) -> float:
+    """mean |H - H_est|^2 (src/utils.py:161-163), reduced on the GPU."""
+    from baseline_estimators import evaluate_estimator
+    return evaluate_estimator(true_channel, estimated_channel)['mse']
+
+
+def calculate_nmse(true_channel: np.ndarray, estimated_channel: np.ndarray) -> float:
+    """mse / (mean|H|^2 + 1e-12) (src/utils.py:166-170)."""
+    from baseline_estimators import evaluate_estimator
+    return evaluate_estimator(true_channel, estimated_channel)['nmse']
+
+
+def complex_to_real(complex_array: np.ndarray) -> np.ndarray:
+    return np.stack([complex_array.real, complex_array.imag], axis=-1)
+
+
+def real_to_complex(real_array: np.ndarray) -> np.ndarray:
+    return real_array[..., 0] + 1j * real_array[..., 1]

@@ -1,0 +1,217 @@
+/*
+ * b2c.h -- C ABI of libb2c.so: batched MIMO-OFDM channel simulation and LS/MMSE channel
+ * estimation on NVIDIA B200 (sm_100a).
+ *
+ * The reference (anish-dev09/CHANNEL-ESTIMATION-IN-5G-NETWORK) is pure Python and has no
+ * FFI of its own; the "plugin interface" this library sits behind is the Python surface of
+ * src/channel_simulator.py, src/baseline_estimators.py and src/dataset_generator.py.  Each entry
+ * point below names the reference function(s) it replaces (file:line into the reference) and
+ * is bound from Python with ctypes (see INTEGRATION.md and
+ * channel-estimation-in-5g-network_b200/_b2c.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host; complex64 arrays are interleaved (re, im) float pairs;
+ *   - nothing allocates, nothing synchronises: kernels are enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return value 0 = enqueued; negative = B2C_E_*; b2c_last_error_string() describes the
+ *     last failure on the calling thread;
+ *   - arrays are row-major with the reference's per-slot axis order, stacked over a leading
+ *     slot axis B:   H[B][nsym][nrx][ntx][nsc], rx[B][nsym][nrx][nsc], tx[B][nsym][ntx][nsc].
+ *
+ * Random draws.  Every kernel that consumes randomness has two modes:
+ *   injected  -- the caller supplies the draws (parity tests feed the reference's recorded
+ *                numpy draws);
+ *   Philox    -- Philox4x32-10 keyed by (seed, global slot index): results do not depend on
+ *                batch size, launch geometry or the number of GPUs the slots are sharded over.
+ *   Counter layout: key = (seed lo, seed hi); ctr = (index, stream, slot lo, slot hi)
+ *     stream 0 SYMBOLS: index = (s>>2)*nsc + k, word s&3           -> phase of RE (s,k), in turns
+ *     stream 1 JAKES  : index = ((p*ntx+tx)*nrx+rx)*10 + (n>>1), words (0,1) even n / (2,3) odd n
+ *                                                                  -> (arrival angle, phase) of oscillator n
+ *     stream 2 NOISE  : index = ((s>>1)*nrx+rx)*nsc + k, words (0,1) even s / (2,3) odd s
+ *                                                                  -> Box-Muller (u1,u2) of rx[s][rx][k]
+ *     uniform u = ((word>>9)+0.5)*2^-23.   oracle/philox.py is the bit-exact CPU twin.
+ */
+#ifndef B2C_H_
+#define B2C_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2C_ABI_VERSION 1
+#define B2C_MAX_TAPS 16     /* distinct sample delays per TDL profile (EPA 5, EVA 8, ETU 9)  */
+#define B2C_MAX_ANT 8       /* ntx, nrx <= 8                                                  */
+#define B2C_MAX_SYM 16      /* OFDM symbols per slot                                          */
+#define B2C_N_OSC 20        /* Jakes oscillators, src/channel_simulator.py:100                */
+#define B2C_N_STAT 3        /* per antenna pair: sum|H-H_ls|^2, sum|H-H_mmse|^2, sum|H|^2     */
+
+enum {
+  B2C_OK = 0,
+  B2C_E_ARG = -1,           /* invalid argument (null pointer, size out of range)             */
+  B2C_E_CUDA = -2,          /* a CUDA runtime call failed; see b2c_last_error_string()        */
+  B2C_E_UNSUPPORTED = -3    /* geometry beyond the compiled limits above                      */
+};
+
+/* Slot geometry.  OFDMConfig / MIMOConfig, src/channel_simulator.py:17-31; nsc is
+ * len(OFDMSystem.used_indices) (:141-148), 599 for the default 600 useful subcarriers. */
+typedef struct b2c_geom {
+  int32_t nsym;             /* OFDM symbols per slot (14)                                     */
+  int32_t nsc;              /* used subcarriers (599)                                         */
+  int32_t ntx, nrx;
+  int32_t fft_size;         /* 1024                                                           */
+  int32_t cp_length;        /* 72                                                             */
+  float symbol_period_s;    /* (fft_size+cp_length)/sampling_rate: spacing of the symbol-start
+                               instants the channel is sampled at (:300-302)                  */
+} b2c_geom;
+
+/* TDL profile tables, built on the host once per (profile set, geometry) by
+ * channel-estimation-in-5g-network_b200/_tables.py from ChannelModel.__init__ (:56-82) with the
+ * duplicate-delay overwrite of :125 resolved.  All device pointers, M = number of profiles.  */
+typedef struct b2c_profiles {
+  int32_t n_models;
+  const int32_t *ntaps;     /* [M]                    surviving taps                           */
+  const int32_t *npaths;    /* [M]                    paths in the profile (RNG draw order)    */
+  const int32_t *tap_path;  /* [M][B2C_MAX_TAPS]      path index that owns the tap             */
+  const float *tap_amp;     /* [M][B2C_MAX_TAPS]      sqrt(P_path) / sqrt(2*20)                */
+  const float *tap_tw;      /* [M][B2C_MAX_TAPS][nsc] complex: exp(-j 2 pi (i_k - N/2) d / N)  */
+  const float *tap_corr;    /* [M][B2C_MAX_TAPS][B2C_MAX_TAPS] complex: sum_k T[p,k] conj(T[q,k]) */
+} b2c_profiles;
+
+/* Pool of pilot patterns with their interpolation plans.  PilotPattern
+ * (src/channel_simulator.py:209-236) + the Delaunay/barycentric (or nearest) structure that
+ * scipy.interpolate.griddata builds inside LSEstimator.interpolate_channel
+ * (src/baseline_estimators.py:65-79); built once per pattern on the host.
+ * plan entry (16 bytes per resource element, row-major (sym, sc)):
+ *   uint16 i0, i1, i2, flags(bit0 = inside hull); float w0, w1;   w2 = 1 - w0 - w1
+ * value = inside ? w0*h[i0] + w1*h[i1] + w2*h[i2] : 0        (griddata fill_value=0.0)      */
+typedef struct b2c_patterns {
+  int32_t n_patterns;
+  int32_t np_max;           /* row stride of pilot_re                                         */
+  const int32_t *npilots;   /* [n_patterns]                                                   */
+  const int32_t *pilot_re;  /* [n_patterns][np_max]  sorted flat RE index of pilot j          */
+  const void *plan;         /* [n_patterns][nsym*nsc] 16-byte plan entries                    */
+} b2c_patterns;
+
+/* Per-slot parameters (device arrays of length B).  */
+typedef struct b2c_slots {
+  int64_t slot0;            /* global index of slot 0 of this batch (Philox counter)          */
+  uint64_t seed;
+  const int32_t *model_id;  /* index into b2c_profiles                                        */
+  const float *doppler_hz;
+  const float *snr_db;
+  const int32_t *pattern_id;/* index into b2c_patterns                                        */
+} b2c_slots;
+
+/* Injected draws (all nullable as a group: NULL struct pointer = Philox mode).
+ *   jakes_u  [B][P_max][ntx][nrx][2][20] float, raw U[0,1) (angles then phases), reference order
+ *            src/channel_simulator.py:102-110; P_max = max npaths over the profile set
+ *   sym_turns[B][nsym][nsc] float, phase/(2 pi) of each resource element's symbol (:394-399)
+ *   noise    [B][nsym][nrx][nsc] complex float, the two randn blocks of :342 interleaved      */
+typedef struct b2c_inject {
+  const float *jakes_u;
+  int32_t p_max;
+  const float *sym_turns;
+  const float *noise;
+} b2c_inject;
+
+const char *b2c_last_error_string(void);
+int b2c_abi_version(void);
+
+/* K1a.  Jakes tap gains at the nsym symbol-start instants + the slot's AWGN standard deviation.
+ * Replaces ChannelModel.generate_time_varying_channel as consumed by
+ * MIMOChannel.generate_channel_frequency_response (src/channel_simulator.py:84-127, 285-302)
+ * and the power/noise-scale arithmetic of apply_channel (:337-340).
+ *   gains    [B][nrx][nsym][ntx][B2C_MAX_TAPS] complex float (out)
+ *   noise_std[B] float (out): sqrt(mean|H x|^2 / 10^(snr/10) / 2); the mean is evaluated as the
+ *            quadratic form g^H C g (all TX send the same unit-modulus grid, :402-404).        */
+int b2c_tap_gains(const b2c_geom *g, const b2c_profiles *prof, const b2c_slots *slots,
+                  const b2c_inject *inj, int64_t B, float *gains, float *noise_std, void *stream);
+
+/* K1+K3+K5 fused.  One pass per slot: CFR from the tap gains, resource grid, y = Hx + n, LS at
+ * the pilots, plan interpolation, default MMSE (alpha * LS) and squared-error statistics.
+ * Replaces simulate_transmission (src/channel_simulator.py:348-421) followed by
+ * LSEstimator('linear'|'nearest').estimate (src/baseline_estimators.py:83-117),
+ * MMSEEstimator().estimate on its default branch (:232-270, :177-180) and evaluate_estimator
+ * (:315-337).  Every output pointer is optional (NULL = not written); estimation is skipped
+ * entirely when H_ls, H_mmse and stats are all NULL (then this is simulate_transmission alone).
+ *   H_true [B][nsym][nrx][ntx][nsc], rx [B][nsym][nrx][nsc], tx [B][nsym][ntx][nsc] complex
+ *   H_ls, H_mmse like H_true;  stats [B][nrx][ntx][B2C_N_STAT] double                          */
+int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat,
+                      const b2c_slots *slots, const b2c_inject *inj, int64_t B,
+                      const float *gains, const float *noise_std,
+                      float *H_true, float *rx, float *tx, float *H_ls, float *H_mmse,
+                      double *stats, void *stream);
+
+/* K3.  LS pilot division + plan interpolation on caller-supplied received grids.
+ * Replaces LSEstimator.estimate (src/baseline_estimators.py:83-117) and, with mmse_mode=1,
+ * MMSEEstimator.estimate's default branch (:232-270).
+ *   rx       [B][nsym][nrx][nsc] complex (the reference's rx_4d is this replicated over tx)
+ *   pilots   [B or 1][np_max] complex transmitted pilot symbols; pilots_stride = np_max or 0
+ *   hp_in    optional [B][nrx][np_max] complex: use these pilot-position values instead of
+ *            rx/pilots (the dense-Wiener path feeds W h_ls here)
+ *   mmse_mode 0: H_mmse not produced; 1: alpha = P/(P+10^(-snr/10)), P = mean|h_ls|^2 (:174-180)
+ *   H_true   optional, for stats.  hp_out optional [B][nrx][np_max]: h_ls at the pilots (:110). */
+int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const int32_t *pattern_id,
+                  const float *snr_db, int64_t B, const float *rx, const float *pilots,
+                  int64_t pilots_stride, const float *hp_in, int32_t mmse_mode,
+                  const float *H_true, float *H_ls, float *H_mmse, float *hp_out, double *stats,
+                  void *stream);
+
+/* LS / default-MMSE on bare pilot vectors: out[v][j] = alpha_v * y[v][j] / (x[j] + 1e-12).
+ * Replaces LSEstimator.estimate_at_pilots (src/baseline_estimators.py:23-42) with mmse_mode=0 and
+ * MMSEEstimator.estimate_at_pilots' default branch (:155-196) with mmse_mode=1
+ * (alpha_v = P/(P+10^(-snr_db/10)), P = mean_j |y/x|^2).   y, out [nvec][n]; x [n] complex.       */
+int b2c_pilot_vectors(const float *y, const float *x, int64_t nvec, int32_t n, float snr_db,
+                      int32_t mmse_mode, float *out, void *stream);
+
+/* K4.  Dense Wiener filter at the pilots: out[c][:] = W @ in[c][:], complex64, for ncols
+ * columns (slot x rx).  Replaces `mmse_matrix @ h_ls` of MMSEEstimator.estimate_at_pilots on its
+ * known-covariance branch (src/baseline_estimators.py:181-190); W = R (R + sigma^2 I)^-1 is
+ * built once per (pattern, SNR) on the host.
+ *   W [np][np] row-major complex; in/out [ncols][ld] complex.                                 */
+int b2c_mmse_dense(const float *W, int32_t np, const float *in, float *out, int64_t ncols,
+                   int64_t ld, void *stream);
+
+/* K5.  Fold per-slot statistics into per-bin float64 accumulators (deterministic order).
+ * Replaces the per-sample evaluate_estimator / compute_nmse + list aggregation of
+ * src/baseline_estimators.py:326-337 and run_phase8_pilot_optimization.py:32-37,186-206.
+ *   stats [B][nrx][ntx][3] (from the kernels above), bin_id [B] in [0, nbins) or <0 to skip
+ *   bins  [nbins][B2C_N_BINSTAT] double, ACCUMULATED INTO (zero it first):
+ *     0 count  1 sum mse_ls  2 sum mse_mmse  3 sum nmse_ls  4 sum nmse_mmse  5 sum nmse_ls^2
+ *     6 sum nmse_mmse^2  7 sum mean|H|^2  8 sum nmse00_ls  9 sum nmse00_ls^2  10 sum nmse00_mmse
+ *     11 sum nmse00_mmse^2       (nmse: /(pow+1e-12); nmse00: antenna pair (0,0), /(pow+1e-10)) */
+#define B2C_N_BINSTAT 12
+int b2c_stats_bins(const b2c_geom *g, const double *stats, const int32_t *bin_id, int64_t B,
+                   int32_t nbins, double *bins, void *stream);
+
+/* K2.  OFDM modulate / demodulate, batched over rows (one row = one OFDM symbol of one antenna).
+ * Replaces OFDMSystem.modulate (src/channel_simulator.py:150-178): map 599 -> 1024 bins,
+ * ifftshift, IFFT * sqrt(N), cyclic-prefix prepend; and OFDMSystem.demodulate (:180-203): CP
+ * strip, FFT / sqrt(N), fftshift, gather used bins.  fft_size must be 1024.
+ *   modulate:   in [rows][nsc] -> out [rows][fft_size+cp]      demodulate: the reverse          */
+int b2c_ofdm_modulate(const b2c_geom *g, const float *in, float *out, int64_t rows, void *stream);
+int b2c_ofdm_demodulate(const b2c_geom *g, const float *in, float *out, int64_t rows, void *stream);
+
+/* a8 generic.  MIMOChannel.apply_channel (src/channel_simulator.py:313-345) for arbitrary tx
+ * grids and channel responses: y = H x per RE, slot-mean power, AWGN.
+ *   tx [B][nsym][ntx][nsc], H [B][nsym][nrx][ntx][nsc], snr_db [B], rx [B][nsym][nrx][nsc] (out)
+ *   noise injected (inj->noise) or Philox stream 2; power_scratch [B] double (zeroed by call).  */
+int b2c_apply_channel(const b2c_geom *g, const b2c_slots *slots, const b2c_inject *inj, int64_t B,
+                      const float *tx, const float *H, float *rx, double *power_scratch,
+                      void *stream);
+
+/* a3 standalone.  ChannelModel.generate_time_varying_channel (src/channel_simulator.py:84-127):
+ * the full (num_samples, nrx, ntx, max_delay+1) CIR of ONE realisation, sample n at t = n/fs.
+ *   jakes_u [npaths][ntx][nrx][2][20] injected, or NULL for Philox (slot = slots->slot0)
+ *   out [num_samples][nrx][ntx][L] complex, L = max delay + 1 (written in full, zeros included) */
+int b2c_tdl_full(const b2c_geom *g, const b2c_profiles *prof, int32_t model_id, float doppler_hz,
+                 float sample_period_s, int64_t num_samples, int32_t L, const int32_t *tap_delay_host,
+                 const float *jakes_u, uint64_t seed, int64_t slot, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2C_H_ */

@@ -1,0 +1,163 @@
+"""CPU-only checks of the product's host logic: table construction against the oracle, plan
+construction against scipy.griddata semantics, Philox parameter choice, sharding, and the C-ABI
+library's exported symbols (no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import OFDM_CFG, PKG, ROOT, SLOT_CASES, load_golden, relerr
+from oracle import chanest_oracle as orc
+from oracle import philox as opx
+
+import _tables
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = opx.philox4x32_10(np.array(ctr, dtype=np.uint64), key)
+        assert tuple(int(x) for x in got) == want
+
+
+def test_philox_draw_statistics():
+    u = opx.symbol_u(42, 7, 14, 599)
+    assert u.min() > 0 and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+    re, im = opx.noise(42, 7, 14, 4, 599)
+    z = np.concatenate([re.ravel(), im.ravel()])
+    assert abs(z.mean()) < 0.01 and abs(z.var() - 1) < 0.02 and abs(np.mean(z ** 4) - 3) < 0.15
+    ju = opx.jakes_u(42, 7, 9, 4, 4)
+    assert ju.shape == (9, 4, 4, 2, 20) and len(np.unique(ju)) > 0.99 * ju.size
+
+
+def test_param_choice_matches_oracle_twin():
+    import dataset_generator as dg
+    sizes = (3, 4, 8, 2)
+    got = dg.philox_param_choice(42, 1000, 64, sizes)
+    for j in range(64):
+        assert tuple(int(g[j]) for g in got) == opx.param_choice(42, 1000 + j, *sizes)
+    for g, n in zip(dg.philox_param_choice(1, 0, 20000, sizes), sizes):
+        assert np.bincount(g, minlength=n).min() > 0.8 * 20000 / n
+
+
+@pytest.mark.parametrize("model", ["EPA", "EVA", "ETU"])
+def test_profile_tables_match_oracle(model):
+    used = _tables.used_subcarriers(1024, 600)
+    assert np.array_equal(used, orc.used_bins(1024, 600))
+    t = _tables.profile_tables([model], 15.36e6, 1024, used)
+    prof = orc.tdl_profile(model, 15.36e6)
+    d, own = orc.surviving_taps(prof["delay_samples"])
+    nt = int(t["ntaps"][0])
+    assert nt == len(d) and t["npaths"][0] == len(prof["delay_samples"])
+    assert t["tap_delay"][0, :nt].tolist() == d.tolist() and t["tap_path"][0, :nt].tolist() == own.tolist()
+    assert np.allclose(t["tap_amp"][0, :nt], np.sqrt(prof["powers_linear"][own] / 40), rtol=1e-6)
+    # twiddle table reproduces fftshift(fft(h, 1024))[used] for a random CIR on the surviving taps
+    rng = np.random.default_rng(0)
+    h = np.zeros(int(d.max()) + 1, complex)
+    g = rng.standard_normal(nt) + 1j * rng.standard_normal(nt)
+    h[d] = g
+    want = orc.cfr_from_cir(h[None, None, None, :], 1024, used)[0, 0, 0]
+    got = (g[:, None] * t["tap_tw"][0, :nt].astype(complex)).sum(0)
+    assert relerr(got, want) < 1e-6
+    # quadratic form equals the bin-summed power
+    c = t["tap_corr"][0, :nt, :nt].astype(complex)
+    assert abs((g @ c @ g.conj()).real / np.sum(np.abs(want) ** 2) - 1) < 1e-5
+
+
+@pytest.mark.parametrize("name", SLOT_CASES)
+def test_plan_reproduces_reference_interpolation(name):
+    """The 16-byte plan entries (fp32 weights) reproduce the reference's griddata output."""
+    g = load_golden(name)
+    plan = _tables.cached_plan(g["pilot_indices"], 14, 599, "linear")
+    assert plan.dtype.itemsize == 16 and plan.shape == (14 * 599,)
+    w0, w1 = plan["w0"].astype(np.float64), plan["w1"].astype(np.float64)
+    inside = plan["flags"].astype(bool)
+    for r in range(int(g["nrx"])):
+        h_p = orc.ls_at_pilots(g["rx_symbols"][:, r], g["pilot_symbols"], g["pilot_mask"])
+        val = w0 * h_p[plan["i0"]] + w1 * h_p[plan["i1"]] + (1 - w0 - w1) * h_p[plan["i2"]]
+        val = np.where(inside, val, 0).reshape(14, 599)
+        assert relerr(val, g["H_ls_tx0"][:, r]) < 1e-6
+        assert np.array_equal(val == 0, g["H_ls_tx0"][:, r] == 0)
+
+
+def test_nearest_plan_and_unknown_method():
+    g = load_golden("slot_2x2_eva")
+    plan = _tables.cached_plan(g["pilot_indices"], 14, 599, "nearest")
+    pos = np.unravel_index(g["pilot_indices"], (14, 599))
+    assert np.array_equal(plan["i0"], orc.nearest_plan(pos, 14, 599))
+    with pytest.raises(NotImplementedError):
+        _tables.interpolation_plan(pos, 14, 599, "cubic")
+    with pytest.raises(KeyError):
+        _tables.path_tables("XYZ", 15.36e6)
+
+
+def test_shard_ranges_partition_the_samples():
+    import dataset_generator as dg
+    for total in (0, 1, 7, 1000, 100003):
+        for ws in (1, 2, 3, 8):
+            r = [dg.shard_range(total, k, ws) for k in range(ws)]
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(r[k][1] == r[k + 1][0] for k in range(ws - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_summarize_bins_units():
+    import dataset_generator as dg
+    bins = np.zeros((2, 12))
+    bins[0] = [4, 4 * 0.5, 4 * 0.25, 4 * 1.0, 4 * 0.5, 0, 0, 4 * 0.5, 4 * 2.0, 4 * 5.0, 0, 0]
+    rows = dg.summarize_bins(bins)
+    assert rows[0]["count"] == 4 and abs(rows[0]["mse_ls"] - 0.5) < 1e-15
+    assert abs(rows[0]["nmse_ls_db"]) < 1e-9 and abs(rows[0]["nmse00_ls_std"] - 1.0) < 1e-12
+    assert rows[1]["count"] == 0
+
+
+def test_library_exports_every_declared_symbol():
+    """include/b2c.h is the contract: every function it declares is exported by libb2c.so."""
+    import _b2c
+    hdr = open(os.path.join(ROOT, "include", "b2c.h")).read()
+    declared = set(re.findall(r"\b(b2c_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_b2c.EXPORTS), declared ^ set(_b2c.EXPORTS)
+    if not os.path.exists(_b2c.LIB_PATH):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("b2c_build", os.path.join(PKG, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    L = _b2c.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.b2c_abi_version() == 1
+    # argument validation runs before any CUDA call: safe without a GPU
+    assert L.b2c_tap_gains(None, None, None, None, 1, None, None, None) == -1
+    assert b"null argument" in L.b2c_last_error_string()
+    g = _b2c.Geom(14, 599, 4, 4, 2048, 72, 7.1e-5)
+    buf = (ctypes.c_float * 8)()
+    assert L.b2c_ofdm_modulate(ctypes.byref(g), buf, buf, 1, None) == -3      # only fft 1024 is built
+
+
+def test_product_fails_loudly_without_cuda():
+    """No CPU fallback: constructing the engine without a GPU raises."""
+    import torch
+    import _b2c
+    import engine
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from utils import default_config
+    with pytest.raises(_b2c.B2CError):
+        engine.SlotEngine(default_config())
+    import channel_simulator as cs
+    with pytest.raises(_b2c.B2CError):
+        cs.simulate_transmission(default_config())
+
+
+def test_product_never_imports_the_oracle():
+    for fn in os.listdir(PKG):
+        if fn.endswith(".py"):
+            src = open(os.path.join(PKG, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
