@@ -151,6 +151,8 @@ class SlotEngine:
         est = any(k in out for k in ("H_ls", "H_mmse", "stats"))
         if est and pool is None:
             raise ValueError("estimation outputs need a PatternPool")
+        if B == 0:
+            return out
         slots, keep = self._slots(B, model_id, doppler_hz, snr_db, pattern_id, slot0, seed)
         ij, keep_inj = self._inject(inject)
         L = lib()

@@ -1,0 +1,67 @@
+"""Host-buffer front end of the slot pipeline: per-slot parameters come from pinned host memory,
+results land in pinned host buffers (what the reference's NumPy API hands its caller).
+
+Chunks are double-buffered over two CUDA streams so the device->host copy of chunk i overlaps the
+kernels of chunk i+1.  This is the end-to-end (`e2e`) path bench.py times; it is PCIe-bound:
+a 4x4 slot is 3.76 MB of results.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+ARRAYS = ("H_true", "rx", "tx", "H_ls", "H_mmse")
+
+
+class HostPipeline:
+    def __init__(self, engine, pool, chunk=512, want=ARRAYS + ("stats",)):
+        self.eng, self.pool, self.chunk, self.want = engine, pool, chunk, tuple(want)
+        self.dev = [engine.alloc_outputs(chunk, self.want) for _ in range(2)]
+        self.ws = [engine.workspace(chunk) for _ in range(2)]
+        self.host = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in d.items()} for d in self.dev]
+        self.par_host = [torch.empty((4, chunk), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        self.par_dev = [torch.empty((4, chunk), dtype=torch.float32, device=engine.device) for _ in range(2)]
+        self.compute = torch.cuda.Stream(device=engine.device)
+        self.copy = torch.cuda.Stream(device=engine.device)
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.ev_copied = [torch.cuda.Event() for _ in range(2)]
+        self.d2h_bytes_per_slot = sum(v[0].numel() * v.element_size() for v in self.dev[0].values())
+        self.h2d_bytes_per_slot = 16
+
+    def run(self, model_id, doppler_hz, snr_db, pattern_id, slot0=0, seed=42, consume=None):
+        """Process len(model_id) slots; `consume(first_slot, n, host_buffers)` is called once each
+        chunk's arrays are complete in pinned memory (buffers are reused two chunks later)."""
+        total = len(model_id)
+        pending = [None, None]
+        par = np.stack([np.asarray(model_id, np.float32), np.asarray(doppler_hz, np.float32),
+                        np.asarray(snr_db, np.float32), np.asarray(pattern_id, np.float32)])
+        for c, start in enumerate(range(0, total, self.chunk)):
+            i = c & 1
+            n = min(self.chunk, total - start)
+            if pending[i] is not None:                 # buffer i still owned by an earlier chunk
+                self.ev_copied[i].synchronize()
+                if consume is not None:
+                    consume(*pending[i], self.host[i])
+            self.par_host[i][:, :n] = torch.from_numpy(par[:, start:start + n])
+            with torch.cuda.stream(self.compute):
+                self.compute.wait_event(self.ev_copied[i])
+                self.par_dev[i].copy_(self.par_host[i], non_blocking=True)
+                p = self.par_dev[i]
+                out = {k: v[:n] for k, v in self.dev[i].items()}
+                ws = {k: v[:n] for k, v in self.ws[i].items()}
+                self.eng.run(n, p[0, :n].to(torch.int32), p[1, :n], p[2, :n], p[3, :n].to(torch.int32), self.pool,
+                             slot0=slot0 + start, seed=seed, want=self.want, out=out, ws=ws)
+                self.ev_done[i].record(self.compute)
+            with torch.cuda.stream(self.copy):
+                self.copy.wait_event(self.ev_done[i])
+                for k, v in self.dev[i].items():
+                    self.host[i][k][:n].copy_(v[:n], non_blocking=True)
+                self.ev_copied[i].record(self.copy)
+            pending[i] = (slot0 + start, n)
+        for i in sorted(range(2), key=lambda j: pending[j][0] if pending[j] is not None else -1):
+            if pending[i] is not None:
+                self.ev_copied[i].synchronize()
+                if consume is not None:
+                    consume(*pending[i], self.host[i])
+        return total

@@ -1,0 +1,208 @@
+"""GPU tests of the reference-shaped Python surface (channel_simulator, baseline_estimators,
+dataset_generator, utils): same calls as the reference's own test scripts
+(test_phase1_transmission.py, test_phase2_ls.py, test_phase2_mmse.py), but with numeric parity
+against the golden vectors because the shims consume numpy.random in the reference's order."""
+import numpy as np
+import pytest
+
+from conftest import OFDM_CFG, SLOT_CASES, full_config, load_golden, relerr
+from oracle import chanest_oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+SEEDS = {"slot_siso_epa": 101, "slot_2x2_eva": 202, "slot_4x4_etu": 303, "slot_2x2_etu_5pct": 404, "slot_2x1_epa_1pct": 505}
+
+
+@pytest.mark.parametrize("name", SLOT_CASES)
+def test_simulate_transmission_is_a_seeded_drop_in(name):
+    """np.random.seed(s); simulate_transmission(...) returns the reference's arrays."""
+    import channel_simulator as cs
+    g = load_golden(name)
+    ntx, nrx = int(g["ntx"]), int(g["nrx"])
+    np.random.seed(SEEDS[name])
+    sim = cs.simulate_transmission(full_config(ntx, nrx), channel_type=str(g["model"]), doppler_hz=float(g["doppler_hz"]),
+                                   snr_db=float(g["snr_db"]), pilot_density=float(g["density"]))
+    assert set(sim) == {"tx_symbols", "rx_symbols", "channel", "pilot_pattern", "pilot_symbols", "ofdm_config",
+                        "mimo_config", "snr_db"}
+    pp = sim["pilot_pattern"]
+    assert np.array_equal(pp.pilot_indices, g["pilot_indices"]) and np.array_equal(pp.pilot_mask, g["pilot_mask"])
+    assert np.array_equal(np.ravel_multi_index(pp.pilot_positions, (14, 599)), g["pilot_indices"])
+    assert sim["channel"].shape == (14, nrx, ntx, 599) and sim["channel"].dtype == np.complex128
+    assert sim["rx_symbols"].shape == (14, nrx, 599) and sim["tx_symbols"].shape == (14, ntx, 599)
+    assert relerr(sim["channel"], g["channel"]) < RTOL
+    assert relerr(sim["rx_symbols"], g["rx_symbols"]) < RTOL
+    assert relerr(sim["pilot_symbols"], g["pilot_symbols"]) < RTOL
+    for t in range(ntx):
+        assert relerr(sim["tx_symbols"][:, t], g["tx_grid"]) < RTOL
+    assert abs(np.mean(pp.pilot_mask) - float(g["density"])) < 0.05       # test_phase1_transmission.py:92-101
+
+
+@pytest.mark.parametrize("name", ["slot_siso_epa", "slot_2x2_eva", "slot_2x2_etu_5pct"])
+def test_ls_and_mmse_estimators(name):
+    """The calls of test_phase2_ls.py:67-98 / test_phase2_mmse.py on the reference's rx grids."""
+    import baseline_estimators as be
+    g = load_golden(name)
+    ntx, nrx = int(g["ntx"]), int(g["nrx"])
+    rx4d = np.repeat(g["rx_symbols"].reshape(14, nrx, 1, 599), ntx, axis=2)
+    pos = np.unravel_index(g["pilot_indices"], (14, 599))
+    H_ls = be.LSEstimator(interpolation_method='linear').estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos)
+    est = be.MMSEEstimator(estimate_statistics=True)
+    H_mm = est.estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos, snr_db=float(g["snr_db"]))
+    assert H_ls.shape == rx4d.shape and H_ls.dtype == np.complex128
+    assert abs(est.noise_variance - 10 ** (-float(g["snr_db"]) / 10)) < 1e-12      # state mutation (:175)
+    for t in range(ntx):
+        assert relerr(H_ls[:, :, t], g["H_ls_tx0"]) < RTOL
+        assert relerr(H_mm[:, :, t], g["H_mmse_tx0"]) < RTOL
+    if f"H_ls_nearest_tx0" in g:
+        H_n = be.LSEstimator('nearest').estimate(rx4d[:, :, :1], g["pilot_symbols"], g["pilot_mask"], pos)
+        assert relerr(H_n[:, :, 0], g["H_ls_nearest_tx0"]) < RTOL
+    m = be.evaluate_estimator(g["channel"], H_ls)
+    assert set(m) == {"mse", "nmse", "nmse_db"}
+    assert abs(m["nmse_db"] - g["metrics_ls"][2]) < 0.01 and abs(m["mse"] / g["metrics_ls"][0] - 1) < 2e-3
+    # independent (rx, tx) slices: a tx slice that differs from its replica is estimated on its own
+    rx_mod = rx4d.copy()
+    rx_mod[:, 0, -1] *= 2.0
+    H2 = be.LSEstimator().estimate(rx_mod, g["pilot_symbols"], g["pilot_mask"], pos)
+    assert relerr(H2[:, 0, -1], 2.0 * g["H_ls_tx0"][:, 0]) < RTOL
+    with pytest.raises(NotImplementedError):
+        be.LSEstimator('cubic').estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos)
+    with pytest.raises(ValueError):
+        be.equalize_channel(g["rx_symbols"], H_ls, method='bogus')
+
+
+def test_estimator_helper_methods():
+    import baseline_estimators as be
+    g = load_golden("slot_2x2_eva")
+    pos = np.unravel_index(g["pilot_indices"], (14, 599))
+    ls = be.LSEstimator()
+    h_p = ls.estimate_at_pilots(g["rx_symbols"][:, 1], g["pilot_symbols"], g["pilot_mask"])
+    want = orc.ls_at_pilots(g["rx_symbols"][:, 1], g["pilot_symbols"], g["pilot_mask"])
+    assert relerr(h_p, want) < RTOL
+    grid = ls.interpolate_channel(want, pos, (14, 599))
+    assert relerr(grid, g["H_ls_tx0"][:, 1]) < RTOL
+    mm = be.MMSEEstimator()
+    h_m = mm.estimate_at_pilots(g["rx_symbols"][:, 1][g["pilot_mask"]], g["pilot_symbols"],
+                                np.ones_like(g["pilot_symbols"], dtype=bool), float(g["snr_db"]))
+    assert relerr(h_m, orc.mmse_at_pilots(want, float(g["snr_db"]))) < RTOL
+    assert relerr(mm.interpolate_channel(orc.mmse_at_pilots(want, float(g["snr_db"])), pos, (14, 599)), g["H_mmse_tx0"][:, 1]) < RTOL
+
+
+def test_known_covariance_mmse_estimator():
+    import baseline_estimators as be
+    g = load_golden("mmse_dense_2x2")
+    pos = np.unravel_index(g["pilot_indices"], (14, 599))
+    ds = pos[0][:, None] - pos[0][None, :]
+    dk = pos[1][:, None] - pos[1][None, :]
+    R = 0.4 * np.exp(-np.abs(ds) / 20.0 - np.abs(dk) / 60.0) * np.exp(1j * 2 * np.pi * dk * 3 / 1024)
+    rx4d = np.repeat(g["rx_symbols"].reshape(14, 2, 1, 599), 2, axis=2)
+    est = be.MMSEEstimator(channel_covariance=R, estimate_statistics=False)
+    H = est.estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos, snr_db=float(g["snr_db"]))
+    for t in range(2):
+        assert relerr(H[:, :, t], g["H_mmse_tx0"]) < RTOL
+
+
+def test_channel_model_and_ofdm_classes():
+    """test_phase1_channels.py:60-88 shape / finiteness checks + numeric parity on recorded draws."""
+    import channel_simulator as cs
+    g = load_golden("tdl_standalone")
+    for model in ("EPA", "EVA", "ETU"):
+        fd, ntx, nrx, ns = (g[f"{model}_meta"][0], *(int(v) for v in g[f"{model}_meta"][1:]))
+        cm = cs.ChannelModel(model, float(fd), 2.0e9, 15.36e6)
+        assert np.array_equal(cm.delay_samples, g[f"{model}_delay_samples"]) and cm.num_paths == len(cm.delays)
+        assert np.allclose(cm.powers_linear, g[f"{model}_powers_linear"], rtol=1e-15)
+        np.random.seed(808)
+        h = cm.generate_time_varying_channel(ns, ntx, nrx)
+        assert h.shape == (ns, nrx, ntx, int(cm.delay_samples.max()) + 1) and np.isfinite(h).all() and np.abs(h).sum() > 0
+        assert relerr(h[::97], g[f"{model}_h"]) < RTOL
+    with pytest.raises(KeyError):
+        cs.ChannelModel("XYZ", 10, 2e9, 15.36e6)
+    o = load_golden("ofdm_modem")
+    sys_ = cs.OFDMSystem(cs.OFDMConfig())
+    assert np.array_equal(sys_.used_indices, o["used_indices"]) and sys_.dc_idx == 512 and sys_.sampling_rate == 15.36e6
+    assert relerr(sys_.modulate(o["symbols"]), o["modulated"]) < RTOL
+    assert relerr(sys_.demodulate(o["signal"]), o["demodulated"]) < RTOL
+
+
+def test_mimo_channel_methods():
+    """generate_channel_frequency_response / apply_channel called on their own, seeded like the reference."""
+    import channel_simulator as cs
+    g = load_golden("slot_2x2_eva")
+    ofdm, mimo = cs.OFDMConfig(), cs.MIMOConfig(2, 2)
+    cm = cs.ChannelModel("EVA", 50.0, 2e9, 15.36e6)
+    ch = cs.MIMOChannel(ofdm, mimo, cm)
+    np.random.seed(1)
+    ju = np.random.rand(9, 2, 2, 2, 20)
+    nz = np.random.randn(2, 14, 2, 599)
+    np.random.seed(1)
+    H = ch.generate_channel_frequency_response(14)
+    assert relerr(H, orc.channel_frequency_response("EVA", 50.0, OFDM_CFG, ju, 2, 2)) < RTOL
+    tx = np.repeat(g["tx_grid"][:, None, :], 2, axis=1)
+    rx = ch.apply_channel(tx, H, 12.0)
+    assert relerr(rx, orc.apply_channel(tx, H, 12.0, nz[0], nz[1])) < RTOL
+    pp = cs.PilotPattern(599, 14, 0.1)
+    grid = pp.insert_pilots(np.arange(8386 - 838) + 0j, np.full(838, -1 + 0j))
+    assert np.array_equal(pp.extract_pilots(grid), np.full(838, -1 + 0j)) and pp.get_pilot_positions() is pp.pilot_positions
+
+
+def test_dataset_generator_numpy_mode_follows_reference_draw_order(tmp_path):
+    import dataset_generator as dg
+    from utils import default_config, set_seed
+    cfg = default_config(2, 2)
+    set_seed(123)
+    gen = dg.ChannelEstimationDataset(cfg, batch_size=4)
+    data = gen.generate_dataset(5, split='val')
+    assert len(data) == 5
+    # replay the same global-RNG stream through the oracle (src/dataset_generator.py:112-121 order)
+    np.random.seed(123)
+    for s in data:
+        ch = np.random.choice(cfg["channel"]["models"])
+        fd = np.random.choice(cfg["channel"]["doppler_hz"])
+        snr = np.random.choice(cfg["simulation"]["snr_range"])
+        dens = np.random.choice(cfg["pilots"]["density"])
+        assert (s["channel_type"], s["doppler_hz"], s["snr_db"], s["pilot_density"]) == (ch, fd, snr, dens)
+        perm = np.arange(8386)
+        np.random.shuffle(perm)
+        n_p = int(8386 * dens)
+        draws = {"perm": perm, "pilot_phase": np.random.uniform(0, 2 * np.pi, n_p),
+                 "data_phase": np.random.uniform(0, 2 * np.pi, 8386 - n_p),
+                 "jakes_u": np.random.rand(len(orc.TDL_NS[ch]), 2, 2, 2, 20)}
+        z = np.random.randn(2, 14, 2, 599)
+        draws["noise_re"], draws["noise_im"] = z[0], z[1]
+        ref = orc.simulate(OFDM_CFG, 2, 2, ch, float(fd), float(snr), float(dens), draws)
+        rx4d = np.repeat(ref["rx_symbols"][:, :, None, :], 2, axis=2)
+        H_ls = orc.ls_estimate(rx4d, ref["pilot_symbols"], ref["pilot_mask"], ref["pilot_positions"])
+        assert np.array_equal(s["pilot_mask"], ref["pilot_mask"])
+        assert relerr(s["H_true"], ref["channel"]) < RTOL and relerr(s["rx_symbols"], ref["rx_symbols"]) < RTOL
+        assert relerr(s["tx_symbols"], ref["tx_symbols"]) < RTOL and relerr(s["H_ls"], H_ls) < RTOL
+    f = tmp_path / "val.npz"
+    gen.save_dataset(data, str(f), format='npz')
+    z = np.load(f)
+    assert set(z.files) == {"rx_symbols", "tx_symbols", "H_ls", "H_true", "pilot_mask", "snr_db", "channel_type",
+                            "doppler_hz", "pilot_density"}
+    assert z["H_true"].shape == (5, 14, 2, 2, 599) and z["rx_symbols"].shape == (5, 14, 2, 599)   # verify_phase3_datasets.py:68-74
+    with pytest.raises(ValueError):
+        gen.save_dataset(data, str(f), format='csv')
+
+
+def test_dataset_generator_philox_mode_and_sharding():
+    """Throughput mode: per-sample arrays and per-SNR statistics do not depend on how the global
+    sample range is split across ranks (emulated here as two half-range runs on one GPU)."""
+    import torch
+    import dataset_generator as dg
+    from utils import default_config
+    cfg = default_config(2, 2)
+    cfg["pilots"]["density"] = [0.05, 0.10]
+    N = 96
+    whole = dg.sharded_statistics(cfg, N, 0, 1, batch=40, seed=42)
+    halves = [dg.sharded_statistics(cfg, N, r, 2, batch=17, seed=42) for r in range(2)]
+    merged = halves[0] + halves[1]
+    assert torch.equal(whole[:, 0], merged[:, 0]) and whole[:, 0].sum().item() == N
+    assert torch.allclose(whole, merged, rtol=1e-12, atol=0)
+    rows = dg.summarize_bins(whole)
+    assert len(rows) == 8 and all(np.isfinite(r["nmse_ls_db"]) for r in rows if r["count"])
+    ds = dg.ChannelEstimationDataset(cfg, rng='philox', seed=42)
+    a, pa = ds.generate_batch(8, slot0=10)
+    b, pb = ds.generate_batch(3, slot0=13)
+    assert torch.equal(a["H_ls"][3:6], b["H_ls"]) and np.array_equal(pa["snr"][3:6], pb["snr"])
+    lst = ds.generate_dataset(6)
+    assert len(lst) == 6 and lst[0]["H_true"].shape == (14, 2, 2, 599) and lst[0]["pilot_mask"].dtype == bool

@@ -1,0 +1,375 @@
+"""GPU parity tests: the CUDA path (called through the C ABI via engine.SlotEngine / the
+reference-shaped shims) against the CPU oracle and the golden vectors recorded from the reference.
+
+Tolerances (north_star): bit-exact for integer / index data; float results within relative error
+1e-4 of the float64 reference, measured norm-wise as max|a-b| / max|b| over each array (RTOL);
+per-slot MSE/NMSE within 0.01 dB.  The observed errors are ~1e-6 (fp32 arithmetic).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import OFDM_CFG, ROOT, SLOT_CASES, full_config, golden_draws, load_golden, relerr
+from oracle import chanest_oracle as orc
+from oracle import philox as opx
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+DB_TOL = 0.01
+DIAG = os.path.join(ROOT, "gpurun_out", "parity_diag.jsonl")
+
+
+def diag(**kw):
+    os.makedirs(os.path.dirname(DIAG), exist_ok=True)
+    with open(DIAG, "a") as fh:
+        fh.write(json.dumps({k: (float(v) if isinstance(v, (np.floating, float)) else v) for k, v in kw.items()}) + "\n")
+
+
+@pytest.fixture(scope="module")
+def engines():
+    from engine import SlotEngine
+    cache = {}
+
+    def get(ntx, nrx):
+        if (ntx, nrx) not in cache:
+            cache[(ntx, nrx)] = SlotEngine(full_config(ntx, nrx))
+        return cache[(ntx, nrx)]
+    return get
+
+
+def inject_from_golden(eng, g):
+    """Recorded reference draws -> the injected-draw tensors of include/b2c.h."""
+    nsym, nsc = 14, 599
+    mask = g["pilot_mask"]
+    turns = np.empty((nsym, nsc))
+    turns[mask] = g["pilot_phase"] / (2 * np.pi)
+    turns[~mask] = g["data_phase"] / (2 * np.pi)
+    ju = np.zeros((eng.p_max,) + g["jakes_u"].shape[1:])
+    ju[:g["jakes_u"].shape[0]] = g["jakes_u"]
+    dev = eng.device
+    return {"jakes_u": torch.from_numpy(ju[None]).to(dev, torch.float32),
+            "sym_turns": torch.from_numpy(turns[None]).to(dev, torch.float32),
+            "noise": torch.from_numpy((g["noise_re"] + 1j * g["noise_im"])[None]).to(dev, torch.complex64)}
+
+
+def db(x):
+    return 10 * np.log10(x + 1e-12)
+
+
+@pytest.mark.parametrize("name", SLOT_CASES)
+def test_fused_pipeline_on_reference_draws(name, engines):
+    """simulate + LS + default MMSE + statistics, injected with the reference's own draws."""
+    g = load_golden(name)
+    ntx, nrx = int(g["ntx"]), int(g["nrx"])
+    eng = engines(ntx, nrx)
+    pool = eng.pool([g["pilot_indices"]])
+    out = eng.run(1, eng.models.index(str(g["model"])), float(g["doppler_hz"]), float(g["snr_db"]), 0, pool,
+                  inject=inject_from_golden(eng, g))
+    torch.cuda.synchronize()
+    H = out["H_true"][0].cpu().numpy()
+    rx = out["rx"][0].cpu().numpy()
+    tx = out["tx"][0].cpu().numpy()
+    H_ls = out["H_ls"][0].cpu().numpy()
+    H_mm = out["H_mmse"][0].cpu().numpy()
+    errs = {"H": relerr(H, g["channel"]), "rx": relerr(rx, g["rx_symbols"]),
+            "tx": max(relerr(tx[:, t], g["tx_grid"]) for t in range(ntx)),
+            "H_ls": max(relerr(H_ls[:, :, t], g["H_ls_tx0"]) for t in range(ntx)),
+            "H_mmse": max(relerr(H_mm[:, :, t], g["H_mmse_tx0"]) for t in range(ntx))}
+    diag(test="fused_injected", case=name, **errs)
+    for k, v in errs.items():
+        assert v < RTOL, (k, v)
+    # exact zeros outside the pilots' convex hull (griddata fill_value = 0.0)
+    assert np.array_equal(H_ls[:, :, 0] == 0, g["H_ls_tx0"] == 0)
+    # statistics vs evaluate_estimator on the reference's arrays
+    st = out["stats"][0].cpu().numpy().sum(axis=(0, 1))
+    n = H.size
+    mse_ls, mse_mm, pw = st[0] / n, st[1] / n, st[2] / n
+    d_ls = abs(db(mse_ls / (pw + 1e-12)) - g["metrics_ls"][2])
+    d_mm = abs(db(mse_mm / (pw + 1e-12)) - g["metrics_mmse"][2])
+    diag(test="fused_injected_stats", case=name, d_ls_db=d_ls, d_mm_db=d_mm)
+    assert d_ls < DB_TOL and d_mm < DB_TOL
+    assert abs(db(mse_ls) - db(g["metrics_ls"][0])) < DB_TOL and abs(db(mse_mm) - db(g["metrics_mmse"][0])) < DB_TOL
+
+
+def test_simulate_only_and_h_only_variants(engines):
+    """Optional outputs: simulate_transmission alone, and the CFR alone, equal the fused run."""
+    g = load_golden("slot_2x2_eva")
+    eng = engines(2, 2)
+    inj = inject_from_golden(eng, g)
+    args = (1, eng.models.index("EVA"), float(g["doppler_hz"]), float(g["snr_db"]))
+    full = eng.run(*args, 0, eng.pool([g["pilot_indices"]]), inject=inj)
+    sim = eng.run(*args, inject=inj, want=("H_true", "rx", "tx"))
+    h_only = eng.run(*args, inject={"jakes_u": inj["jakes_u"]}, want=("H_true",))
+    torch.cuda.synchronize()
+    for k in ("H_true", "rx", "tx"):
+        assert torch.equal(full[k], sim[k])
+    assert torch.equal(full["H_true"], h_only["H_true"])
+
+
+@pytest.mark.parametrize("ntx,nrx,model,fd,snr,dens", [(2, 2, "EVA", 50.0, 15.0, 0.10), (4, 4, "ETU", 200.0, 5.0, 0.10),
+                                                       (1, 1, "EPA", 10.0, 30.0, 0.05), (4, 2, "EPA", 100.0, -5.0, 0.02)])
+def test_philox_mode_matches_oracle_on_twin_draws(ntx, nrx, model, fd, snr, dens, engines):
+    """Throughput (Philox) mode: the oracle fed with oracle/philox.py's bit-exact twin of the device
+    draws must reproduce the GPU arrays."""
+    eng = engines(ntx, nrx)
+    pool = eng.random_pool([dens], seed=7)
+    seed, slot0, B = 1234, 2 ** 33 + 5, 3            # slot index beyond 32 bits exercises the counter words
+    out = eng.run(B, eng.models.index(model), fd, snr, 0, pool, slot0=slot0, seed=seed)
+    torch.cuda.synchronize()
+    mask = pool.mask(0)
+    pos = np.unravel_index(pool.pilot_indices[0], (14, 599))
+    P = len(orc.TDL_NS[model])
+    worst = {}
+    for i in range(B):
+        d = opx.slot_draws(seed, slot0 + i, 14, 599, P, ntx, nrx, mask)
+        d["perm"] = np.concatenate([pool.pilot_indices[0], np.setdiff1d(np.arange(14 * 599), pool.pilot_indices[0])])
+        ref = orc.slot_pipeline(OFDM_CFG, ntx, nrx, model, fd, snr, dens, d)
+        assert np.array_equal(ref["pilot_mask"], mask)
+        got = {k: out[k][i].cpu().numpy() for k in ("H_true", "rx", "tx", "H_ls", "H_mmse")}
+        e = {"H": relerr(got["H_true"], ref["channel"]), "rx": relerr(got["rx"], ref["rx_symbols"]),
+             "tx": relerr(got["tx"], ref["tx_symbols"]), "H_ls": relerr(got["H_ls"], ref["H_ls"]),
+             "H_mmse": relerr(got["H_mmse"], ref["H_mmse"])}
+        for k, v in e.items():
+            worst[k] = max(worst.get(k, 0), v)
+        st = out["stats"][i].cpu().numpy().sum(axis=(0, 1)) / ref["channel"].size
+        m_ls, m_mm = orc.evaluate(ref["channel"], ref["H_ls"]), orc.evaluate(ref["channel"], ref["H_mmse"])
+        assert abs(db(st[0] / (st[2] + 1e-12)) - m_ls["nmse_db"]) < DB_TOL
+        assert abs(db(st[1] / (st[2] + 1e-12)) - m_mm["nmse_db"]) < DB_TOL
+    diag(test="philox_twin", case=f"{ntx}x{nrx}_{model}", **worst)
+    for k, v in worst.items():
+        assert v < RTOL, (k, v)
+
+
+def test_results_do_not_depend_on_batching(engines):
+    """Counter-based draws: slot g is the same array whether it is generated alone or inside a batch,
+    which is what makes sharding over GPUs and resume exact."""
+    eng = engines(2, 2)
+    pool = eng.random_pool([0.05, 0.10], seed=3)
+    B = 8
+    model = np.array([0, 1, 2, 0, 1, 2, 0, 1], dtype=np.int32)
+    fd = np.array([10, 50, 100, 200, 10, 50, 100, 200], dtype=np.float32)
+    snr = np.array([-5, 0, 5, 10, 15, 20, 25, 30], dtype=np.float32)
+    pid = np.array([0, 1, 0, 1, 1, 0, 1, 0], dtype=np.int32)
+    big = eng.run(B, model, fd, snr, pid, pool, slot0=100, seed=9)
+    for i in (0, 3, 7):
+        one = eng.run(1, model[i:i + 1], fd[i:i + 1], snr[i:i + 1], pid[i:i + 1], pool, slot0=100 + i, seed=9)
+        torch.cuda.synchronize()
+        for k in ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"):
+            assert torch.equal(big[k][i], one[k][0]), (k, i)
+    other = eng.run(1, model[:1], fd[:1], snr[:1], pid[:1], pool, slot0=100, seed=10)
+    assert not torch.equal(other["H_true"][0], big["H_true"][0])
+
+
+def test_mixed_batch_against_oracle(engines):
+    """Mixed EPA/EVA/ETU, Doppler, SNR and density in one launch (dataset-generation shape)."""
+    eng = engines(2, 2)
+    dens = [0.05, 0.10]
+    pool = eng.random_pool(dens, seed=11)
+    models = ["ETU", "EPA", "EVA", "EPA"]
+    fd = [200.0, 10.0, 50.0, 100.0]
+    snr = [0.0, 30.0, 10.0, -5.0]
+    pid = [1, 0, 1, 0]
+    out = eng.run(4, [eng.models.index(m) for m in models], fd, snr, pid, pool, slot0=40, seed=5)
+    torch.cuda.synchronize()
+    for i in range(4):
+        mask = pool.mask(pid[i])
+        d = opx.slot_draws(5, 40 + i, 14, 599, len(orc.TDL_NS[models[i]]), 2, 2, mask)
+        d["perm"] = np.concatenate([pool.pilot_indices[pid[i]], np.setdiff1d(np.arange(8386), pool.pilot_indices[pid[i]])])
+        ref = orc.slot_pipeline(OFDM_CFG, 2, 2, models[i], fd[i], snr[i], dens[pid[i]], d)
+        for k, rk in (("H_true", "channel"), ("rx", "rx_symbols"), ("H_ls", "H_ls"), ("H_mmse", "H_mmse")):
+            assert relerr(out[k][i].cpu().numpy(), ref[rk]) < RTOL, (i, k)
+
+
+@pytest.mark.parametrize("name", ["slot_2x2_eva", "slot_4x4_etu", "slot_2x1_epa_1pct"])
+def test_standalone_ls_kernel(name, engines):
+    """b2c_ls_interp on the reference's rx grids: LS, default MMSE, pilot estimates, statistics."""
+    g = load_golden(name)
+    ntx, nrx = int(g["ntx"]), int(g["nrx"])
+    eng = engines(ntx, nrx)
+    pool = eng.pool([g["pilot_indices"]])
+    dev = eng.device
+    rx = torch.from_numpy(g["rx_symbols"][None]).to(dev, torch.complex64)
+    xp = torch.from_numpy(g["pilot_symbols"][None]).to(dev, torch.complex64)
+    Ht = torch.from_numpy(g["channel"][None]).to(dev, torch.complex64)
+    out = eng.ls_interp(rx, xp, pool, snr_db=float(g["snr_db"]), mmse=True, H_true=Ht,
+                        want=("H_ls", "H_mmse", "hp", "stats"))
+    torch.cuda.synchronize()
+    H_ls, H_mm = out["H_ls"][0].cpu().numpy(), out["H_mmse"][0].cpu().numpy()
+    for t in range(ntx):
+        assert relerr(H_ls[:, :, t], g["H_ls_tx0"]) < RTOL
+        assert relerr(H_mm[:, :, t], g["H_mmse_tx0"]) < RTOL
+    for r in range(nrx):
+        hp = orc.ls_at_pilots(g["rx_symbols"][:, r], g["pilot_symbols"], g["pilot_mask"])
+        assert relerr(out["hp"][0, r, :len(hp)].cpu().numpy(), hp) < RTOL
+    st = out["stats"][0].cpu().numpy().sum(axis=(0, 1)) / g["channel"].size
+    assert abs(db(st[0] / (st[2] + 1e-12)) - g["metrics_ls"][2]) < DB_TOL
+    assert abs(db(st[1] / (st[2] + 1e-12)) - g["metrics_mmse"][2]) < DB_TOL
+
+
+def test_stats_bins_against_numpy(engines):
+    eng = engines(2, 2)
+    pool = eng.random_pool([0.10], seed=1)
+    B = 64
+    snr_idx = np.arange(B) % 8
+    snr = np.array([-5, 0, 5, 10, 15, 20, 25, 30], dtype=np.float32)[snr_idx]
+    out = eng.run(B, 1, 50.0, snr, 0, pool, slot0=0, seed=77)
+    bin_id = snr_idx.astype(np.int32).copy()
+    bin_id[5] = -1                                        # skipped slot
+    bins = eng.stats_bins(out["stats"], bin_id, 8).cpu().numpy()
+    H, Hl, Hm = (out[k].cpu().numpy().astype(np.complex128) for k in ("H_true", "H_ls", "H_mmse"))
+    want = np.zeros((8, 12))
+    for b in range(B):
+        if bin_id[b] < 0:
+            continue
+        ls, mm = orc.evaluate(H[b], Hl[b]), orc.evaluate(H[b], Hm[b])
+        n00l, n00m = orc.nmse_pair00(Hl[b], H[b]), orc.nmse_pair00(Hm[b], H[b])
+        want[bin_id[b]] += [1, ls["mse"], mm["mse"], ls["nmse"], mm["nmse"], ls["nmse"] ** 2, mm["nmse"] ** 2,
+                            np.mean(np.abs(H[b]) ** 2), n00l, n00l ** 2, n00m, n00m ** 2]
+    assert np.array_equal(bins[:, 0], want[:, 0])
+    assert np.allclose(bins, want, rtol=2e-5), np.abs(bins / want - 1).max()
+    # accumulate-into semantics and determinism
+    again = eng.stats_bins(out["stats"], bin_id, 8, torch.from_numpy(bins).to(eng.device)).cpu().numpy()
+    assert np.array_equal(again, 2 * bins)
+
+
+def test_ofdm_modem(engines):
+    g = load_golden("ofdm_modem")
+    eng = engines(1, 1)
+    dev = eng.device
+    mod = eng.ofdm_modulate(torch.from_numpy(g["symbols"]).to(dev, torch.complex64))
+    dem = eng.ofdm_demodulate(torch.from_numpy(g["signal"]).to(dev, torch.complex64))
+    rt = eng.ofdm_demodulate(mod)
+    torch.cuda.synchronize()
+    e = {"mod": relerr(mod.cpu().numpy(), g["modulated"]), "demod": relerr(dem.cpu().numpy(), g["demodulated"]),
+         "roundtrip": relerr(rt.cpu().numpy(), g["symbols"])}
+    diag(test="ofdm", **e)
+    assert max(e.values()) < RTOL
+    # many rows (grid-stride path) + linearity
+    x = torch.randn(5000, 599, dtype=torch.complex64, device=dev)
+    y = eng.ofdm_modulate(x)
+    assert relerr(eng.ofdm_demodulate(y).cpu().numpy(), x.cpu().numpy()) < RTOL
+    assert relerr((eng.ofdm_modulate(2 * x[:64]) - 2 * y[:64]).abs().cpu().numpy() + 1, np.ones((64, 1096))) < 1e-5
+    assert torch.equal(y[:, :72], y[:, 1024:])            # cyclic prefix
+
+
+@pytest.mark.parametrize("model", ["EPA", "EVA", "ETU"])
+def test_tdl_standalone(model, engines):
+    g = load_golden("tdl_standalone")
+    fd, ntx, nrx, ns = (g[f"{model}_meta"][0], *(int(v) for v in g[f"{model}_meta"][1:]))
+    eng = engines(ntx, nrx)
+    ju = torch.from_numpy(g[f"{model}_jakes_u"]).to(eng.device, torch.float32)
+    h = eng.tdl_full(model, float(fd), ns, ntx, nrx, jakes_u=ju)
+    torch.cuda.synchronize()
+    assert tuple(h.shape) == tuple(g[f"{model}_shape"])
+    got = h.cpu().numpy()
+    assert relerr(got[::97], g[f"{model}_h"]) < RTOL
+    # untouched delays are exactly zero (the reference allocates zeros, :97)
+    delays = set(int(d) for d in g[f"{model}_delay_samples"])
+    for d in range(got.shape[-1]):
+        if d not in delays:
+            assert not got[..., d].any()
+
+
+def test_apply_channel_generic(engines):
+    eng = engines(2, 2)
+    rng = np.random.default_rng(5)
+    B = 3
+    tx = rng.standard_normal((B, 14, 2, 599)) + 1j * rng.standard_normal((B, 14, 2, 599))
+    H = rng.standard_normal((B, 14, 2, 2, 599)) + 1j * rng.standard_normal((B, 14, 2, 2, 599))
+    nz = rng.standard_normal((B, 14, 2, 599)) + 1j * rng.standard_normal((B, 14, 2, 599))
+    snr = np.array([0.0, 10.0, 25.0], dtype=np.float32)
+    dev = eng.device
+    rx = eng.apply_channel(torch.from_numpy(tx).to(dev, torch.complex64), torch.from_numpy(H).to(dev, torch.complex64),
+                           snr, noise=torch.from_numpy(nz).to(dev, torch.complex64))
+    torch.cuda.synchronize()
+    for b in range(B):
+        assert relerr(rx[b].cpu().numpy(), orc.apply_channel(tx[b], H[b], float(snr[b]), nz[b].real, nz[b].imag)) < RTOL
+    # Philox noise: empirical SNR close to the request
+    rx2 = eng.apply_channel(torch.from_numpy(tx).to(dev, torch.complex64), torch.from_numpy(H).to(dev, torch.complex64),
+                            snr, seed=3, slot0=0).cpu().numpy()
+    for b in range(B):
+        y = np.einsum("srtk,stk->srk", H[b], tx[b])
+        est = 10 * np.log10(np.mean(np.abs(y) ** 2) / np.mean(np.abs(rx2[b] - y) ** 2))
+        assert abs(est - snr[b]) < 0.2
+
+
+def test_dense_wiener_path(engines):
+    """Known-covariance MMSE: GPU LS at pilots -> dense W GEMM -> plan interpolation vs the reference."""
+    g = load_golden("mmse_dense_2x2")
+    eng = engines(2, 2)
+    pos = np.unravel_index(g["pilot_indices"], (14, 599))
+    ds = pos[0][:, None] - pos[0][None, :]
+    dk = pos[1][:, None] - pos[1][None, :]
+    R = 0.4 * np.exp(-np.abs(ds) / 20.0 - np.abs(dk) / 60.0) * np.exp(1j * 2 * np.pi * dk * 3 / 1024)
+    W = orc.wiener_matrix(R, float(g["snr_db"]))
+    dev = eng.device
+    pool = eng.pool([g["pilot_indices"]])
+    rx = torch.from_numpy(g["rx_symbols"][None]).to(dev, torch.complex64)
+    xp = torch.from_numpy(g["pilot_symbols"][None]).to(dev, torch.complex64)
+    hp = eng.ls_interp(rx, xp, pool, want=("hp",))["hp"]
+    hm = eng.mmse_dense(torch.from_numpy(W).to(dev, torch.complex64), hp.reshape(2, -1)).reshape(1, 2, -1)
+    H = eng.ls_interp(None, None, pool, hp_in=hm, want=("H_ls",))["H_ls"][0].cpu().numpy()
+    for t in range(2):
+        assert relerr(H[:, :, t], g["H_mmse_tx0"]) < RTOL
+    # GEMM alone at an awkward size against numpy
+    rng = np.random.default_rng(2)
+    n, c = 167, 77
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    X = rng.standard_normal((c, n)) + 1j * rng.standard_normal((c, n))
+    Y = eng.mmse_dense(torch.from_numpy(A).to(dev, torch.complex64), torch.from_numpy(X).to(dev, torch.complex64))
+    assert relerr(Y.cpu().numpy(), X @ A.T) < RTOL
+
+
+def test_error_reporting(engines):
+    import _b2c
+    eng = engines(2, 2)
+    with pytest.raises(ValueError):
+        eng.run(1, 0, 10.0, 10.0)                          # estimation outputs without a pattern pool
+    with pytest.raises(_b2c.B2CError):
+        eng.ofdm_modulate(torch.zeros((2, 599), dtype=torch.complex64))   # CPU tensor
+    out = eng.run(0, 0, 10.0, 10.0, want=("H_true",))       # empty batch is a no-op
+    assert out["H_true"].shape[0] == 0
+
+
+def test_full_size_properties(engines):
+    """BASELINE config 3 shape (4x4 ETU 200 Hz, 10 % pilots) at a batch too large for the oracle:
+    size-independent properties of the reference's algorithm."""
+    eng = engines(4, 4)
+    pool = eng.random_pool([0.10], seed=42)
+    B = 512
+    snr = np.array([-5, 0, 5, 10, 15, 20, 25, 30], dtype=np.float32)[np.arange(B) % 8]
+    out = eng.run(B, eng.models.index("ETU"), 200.0, snr, 0, pool, slot0=0, seed=42)
+    torch.cuda.synchronize()
+    H, rx, tx, Hl, Hm = (out[k] for k in ("H_true", "rx", "tx", "H_ls", "H_mmse"))
+    for t in (H, rx, tx, Hl, Hm):
+        assert torch.isfinite(torch.view_as_real(t)).all()
+    # unit-modulus symbols, the same grid on every TX antenna (:402-404)
+    assert (tx.abs() - 1).abs().max() < 1e-5
+    assert torch.equal(tx[:, :, 0], tx[:, :, 3])
+    # Jakes normalisation: E|H|^2 = sum of surviving path powers / 2 = 0.5 for ETU
+    assert abs(H.abs().pow(2).mean().item() - 0.5) < 0.02
+    # estimates are replicated over tx; MMSE is a positive real shrinkage of LS per (slot, rx)
+    assert torch.equal(Hl[:, :, :, 0], Hl[:, :, :, 2]) and torch.equal(Hm[:, :, :, 1], Hm[:, :, :, 3])
+    ratio = (Hm[:, :, :, 0] * Hl[:, :, :, 0].conj()).real.sum(dim=(1, 3)) / Hl[:, :, :, 0].abs().pow(2).sum(dim=(1, 3))
+    assert (ratio > 0).all() and (ratio < 1).all()
+    # zeros exactly where the plan says "outside the hull"
+    mask_out = torch.from_numpy(~pool_inside(pool)).to(eng.device)
+    assert (Hl[:, :, 0, 0][:, mask_out] == 0).all() and (Hl[:, :, 0, 0][:, ~mask_out] != 0).any()
+    # empirical SNR of rx against the noiseless sum_tx H x
+    y = (H.sum(dim=3) * tx[:, :, :1])
+    emp = 10 * torch.log10(y.abs().pow(2).mean(dim=(1, 2, 3)) / (rx - y).abs().pow(2).mean(dim=(1, 2, 3)))
+    assert (emp.cpu().numpy() - snr).__abs__().max() < 0.15
+    # LS at a pilot RE equals rx / x there
+    e = int(pool.pilot_indices[0][123])
+    s, k = divmod(e, 599)
+    assert relerr((rx[:, s, :, k] / tx[:, s, 0, k][:, None]).cpu().numpy(), Hl[:, s, :, 0, k].cpu().numpy()) < RTOL
+
+
+def pool_inside(pool):
+    import _tables
+    plan = _tables.cached_plan(pool.pilot_indices[0], pool.nsym, pool.nsc, pool.method)
+    return plan["flags"].astype(bool).reshape(pool.nsym, pool.nsc)
