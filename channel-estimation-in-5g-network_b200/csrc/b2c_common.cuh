@@ -61,12 +61,12 @@ struct PlanTap {
   int i0, i1, i2;
   float w0, w1, w2;
 };
-__device__ __forceinline__ PlanTap plan_decode(uint4 raw) {
+__device__ __forceinline__ PlanTap plan_decode(uint4 raw, bool valid = true) {
   PlanTap p;
   p.i0 = raw.x & 0xffffu;
   p.i1 = raw.x >> 16;
   p.i2 = raw.y & 0xffffu;
-  float inside = (raw.y >> 16) & 1u ? 1.0f : 0.0f;
+  float inside = (valid && ((raw.y >> 16) & 1u)) ? 1.0f : 0.0f;
   float w0 = __uint_as_float(raw.z), w1 = __uint_as_float(raw.w);
   p.w0 = inside * w0;
   p.w1 = inside * w1;

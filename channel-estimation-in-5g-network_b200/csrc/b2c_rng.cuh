@@ -49,7 +49,10 @@ __device__ __forceinline__ float u01(uint32_t w) {
 
 // Box-Muller pair -> one complex normal with unit variance per component.
 __device__ __forceinline__ float2 normal_pair(uint32_t w1, uint32_t w2) {
-  float r = sqrtf(-2.0f * logf(u01(w1)));
+  // r = sqrt(-2 ln u) on the SFU: lg2.approx (abs. error <= 2^-22 on [0.5, 2]) and rsqrt.approx; the
+  // clamp keeps r finite should the approximation round ln u to +0 for u within 1e-7 of 1.
+  float x = fmaxf(-1.3862943611198906f * __log2f(u01(w1)), 1e-30f);
+  float r = x * rsqrtf(x);
   float v = u01(w2) - 0.5f;           // cos(2 pi u) = -cos(2 pi (u - 1/2)), same for sin
   float s, c;
   __sincosf(6.283185307179586f * v, &s, &c);

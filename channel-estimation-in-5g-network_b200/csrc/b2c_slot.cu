@@ -168,129 +168,166 @@ __device__ __forceinline__ float2 draw_noise(const SlotArgs &a, const SlotCtx &c
   return (s & 1) ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
 }
 
-template <int T, int NTX, bool EST>
+// Main loop of the slot kernel.  Thread t owns used bins t and t + SLOT_THREADS for every symbol.
+//   T      compile-time tap count (>= the profile's surviving taps; absent taps have zero gain)
+//   NTX    compile-time TX bound; EXACT = (ntx == NTX) removes the per-tx predicate
+//   NSC    used bins when known at compile time (599 for the default grid), 0 = read from b2c_geom:
+//          with NSC fixed every store offset inside a symbol is an immediate.
+// Output addressing: one 64-bit base per slot (uniform) + 32-bit per-thread element offsets.
+template <int T, int NTX, bool EXACT, bool EST, int NSC>
 __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, float (&st)[NTX][3]) {
-  const int nsc = a.g.nsc, nsym = a.g.nsym, ntx = a.g.ntx, nrx = a.g.nrx;
-  const int k0 = threadIdx.x, k1 = threadIdx.x + SLOT_THREADS;
-  const bool v0 = k0 < nsc, v1 = k1 < nsc;
-  const int kk0 = v0 ? k0 : 0, kk1 = v1 ? k1 : 0;   // clamped: idle lanes compute on bin 0, store nothing
+  const int nsc = NSC ? NSC : a.g.nsc;
+  const int nsym = a.g.nsym, nrx = a.g.nrx;
+  const int ntx = EXACT ? NTX : a.g.ntx;
+  const int k0 = threadIdx.x;
+  const bool v0 = k0 < nsc, v1 = k0 + SLOT_THREADS < nsc;
+  const int kk0 = v0 ? k0 : 0, kk1 = v1 ? k0 + SLOT_THREADS : 0;   // idle lanes read bin 0, store nothing
 
+  // Twiddles.  Idle lanes get zeros, so their H, LS/MMSE values and error terms are exactly zero
+  // and need no predication in the loop.
   const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * nsc;
+  const float2 zero2 = make_float2(0.f, 0.f), neg1 = make_float2(-1.f, -1.f), nalpha = make_float2(-c.alpha, -c.alpha);
   float2 tw0[T], tw1[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    tw0[t] = __ldg(tw + t * nsc + kk0);
-    tw1[t] = __ldg(tw + t * nsc + kk1);
+    tw0[t] = v0 ? __ldg(tw + t * nsc + kk0) : zero2;
+    tw1[t] = v1 ? __ldg(tw + t * nsc + kk1) : zero2;
   }
-  const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * nsym * nsc : nullptr;
 
-  uint4 ws0 = make_uint4(0, 0, 0, 0), ws1 = ws0, wn0 = ws0, wn1 = ws0;
-  const bool need_draws = a.rx || a.tx;   // H-only calls (generate_channel_frequency_response) skip them
-  for (int s = 0; s < nsym; ++s) {
-    // ---- draws -----------------------------------------------------------------------------
-    float2 x0 = make_float2(0.f, 0.f), x1 = x0, n0 = x0, n1 = x0;
-    if (!need_draws) {
-    } else if (a.has_inj) {
-      x0 = draw_symbol(a, c, s, kk0);
-      x1 = draw_symbol(a, c, s, kk1);
-      n0 = draw_noise(a, c, s, kk0);
-      n1 = draw_noise(a, c, s, kk1);
-    } else {
-      if ((s & 3) == 0) {
-        ws0 = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 2) * nsc + kk0));
-        ws1 = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 2) * nsc + kk1));
-      }
-      x0 = cis_turns(u01(pick(ws0, s & 3)));
-      x1 = cis_turns(u01(pick(ws1, s & 3)));
-      if ((s & 1) == 0) {
-        wn0 = draw(c.key, STREAM_NOISE, (uint32_t)(((s >> 1) * nrx + c.rx) * nsc + kk0));
-        wn1 = draw(c.key, STREAM_NOISE, (uint32_t)(((s >> 1) * nrx + c.rx) * nsc + kk1));
-        n0 = normal_pair(wn0.x, wn0.y);
-        n1 = normal_pair(wn1.x, wn1.y);
-      } else {
-        n0 = normal_pair(wn0.z, wn0.w);
-        n1 = normal_pair(wn1.z, wn1.w);
+  const int64_t slot_h = (int64_t)nsym * nrx * ntx * nsc;
+  float2 *const Hb = a.H_true ? a.H_true + c.b * slot_h : nullptr;
+  float2 *const Lb = (EST && a.H_ls) ? a.H_ls + c.b * slot_h : nullptr;
+  float2 *const Mb = (EST && a.H_mmse) ? a.H_mmse + c.b * slot_h : nullptr;
+  float2 *const Rb = a.rx ? a.rx + c.b * (int64_t)nsym * nrx * nsc : nullptr;
+  float2 *const Tb = (a.tx && c.rx == 0) ? a.tx + c.b * (int64_t)nsym * ntx * nsc : nullptr;
+  const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * nsym * nsc : nullptr;
+  const float2 *inj_noise = a.has_inj ? reinterpret_cast<const float2 *>(a.inj.noise) + c.b * (int64_t)nsym * nrx * nsc : nullptr;
+  const float *inj_sym = a.has_inj ? a.inj.sym_turns + c.b * (int64_t)nsym * nsc : nullptr;
+
+  int oH = c.rx * ntx * nsc + k0;   // element offset of H[s][rx][0][k0] inside the slot
+  int oR = c.rx * nsc + k0;         //                   rx[s][rx][k0]
+  int oT = k0;                      //                   tx[s][0][k0]
+  int oP0 = kk0, oP1 = kk1;         // plan / injected-symbol offsets (clamped bins)
+  const int dH = nrx * ntx * nsc, dR = nrx * nsc, dT = ntx * nsc;
+  const float4 *gps = c.gsp;
+  const bool need_draws = Rb != nullptr || a.tx != nullptr;   // H-only calls skip the draws
+
+  uint4 ws0 = make_uint4(0, 0, 0, 0), ws1 = ws0;
+  for (int s2 = 0; s2 < nsym; s2 += 2) {
+    uint4 wn0 = make_uint4(0, 0, 0, 0), wn1 = wn0;
+    if (need_draws && !a.has_inj) {
+      const uint32_t base = (uint32_t)(((s2 >> 1) * nrx + c.rx) * nsc);
+      wn0 = draw(c.key, STREAM_NOISE, base + kk0);
+      wn1 = draw(c.key, STREAM_NOISE, base + kk1);
+      if ((s2 & 3) == 0) {
+        ws0 = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 2) * nsc + kk0));
+        ws1 = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 2) * nsc + kk1));
       }
     }
-    // ---- LS interpolation + default MMSE for this RE (identical for every tx) -----------------
-    float2 l0 = make_float2(0.f, 0.f), l1 = l0, m0 = l0, m1 = l0;
-    if (EST) {
-      PlanTap p0 = plan_decode(__ldg(plan + s * nsc + kk0));
-      PlanTap p1 = plan_decode(__ldg(plan + s * nsc + kk1));
-      l0 = plan_apply(p0, c.hp);
-      l1 = plan_apply(p1, c.hp);
-      m0 = cscale(c.alpha, l0);
-      m1 = cscale(c.alpha, l1);
-    }
-    // ---- CFR per tx: H[s, rx, tx, k] = sum_t g[s, tx, t] * tw[t, k]  --------------------------
-    const int64_t rowH = ((c.b * nsym + s) * nrx + c.rx) * (int64_t)ntx * nsc;
-    float2 hs0 = make_float2(0.f, 0.f), hs1 = hs0;
 #pragma unroll
-    for (int tx = 0; tx < NTX; ++tx) {
-      if (tx < ntx) {
-        const float4 *gp = c.gsp + (s * ntx + tx) * MAXT;
-        float2 A0 = make_float2(0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-          float4 gq = gp[t];
-          float2 gr = make_float2(gq.x, gq.y), gi = make_float2(gq.z, gq.w);
-          A0 = __ffma2_rn(gr, tw0[t], A0);
-          B0 = __ffma2_rn(gi, tw0[t], B0);
-          A1 = __ffma2_rn(gr, tw1[t], A1);
-          B1 = __ffma2_rn(gi, tw1[t], B1);
-        }
-        float2 h0 = make_float2(A0.x - B0.y, A0.y + B0.x);
-        float2 h1 = make_float2(A1.x - B1.y, A1.y + B1.x);
-        hs0 = cadd(hs0, h0);
-        hs1 = cadd(hs1, h1);
-        const int64_t o0 = rowH + (int64_t)tx * nsc + k0, o1 = rowH + (int64_t)tx * nsc + k1;
-        if (a.H_true) {
-          if (v0) st_stream(a.H_true + o0, h0);
-          if (v1) st_stream(a.H_true + o1, h1);
-        }
+    for (int j = 0; j < 2; ++j) {
+      const int s = s2 + j;
+      if (s < nsym) {
+        // ---- LS interpolation for this RE (identical for every tx); MMSE = alpha * LS ----------------
+        float2 l0 = zero2, l1 = zero2;
         if (EST) {
-          if (a.H_ls) {
-            if (v0) st_stream(a.H_ls + o0, l0);
-            if (v1) st_stream(a.H_ls + o1, l1);
-          }
-          if (a.H_mmse) {
-            if (v0) st_stream(a.H_mmse + o0, m0);
-            if (v1) st_stream(a.H_mmse + o1, m1);
-          }
-          if (v0) {
-            st[tx][0] += cabs2(make_float2(h0.x - l0.x, h0.y - l0.y));
-            st[tx][1] += cabs2(make_float2(h0.x - m0.x, h0.y - m0.y));
-            st[tx][2] += cabs2(h0);
-          }
-          if (v1) {
-            st[tx][0] += cabs2(make_float2(h1.x - l1.x, h1.y - l1.y));
-            st[tx][1] += cabs2(make_float2(h1.x - m1.x, h1.y - m1.y));
-            st[tx][2] += cabs2(h1);
+          l0 = plan_apply(plan_decode(__ldg(plan + oP0), v0), c.hp);
+          l1 = plan_apply(plan_decode(__ldg(plan + oP1), v1), c.hp);
+        }
+        // ---- CFR per tx: H[s, rx, tx, k] = sum_t g[s, tx, t] * tw[t, k] ---------------------------
+        float2 hs0 = zero2, hs1 = zero2;
+#pragma unroll
+        for (int tx = 0; tx < NTX; ++tx) {
+          if (EXACT || tx < ntx) {
+            const float4 *gp = gps + tx * MAXT;
+            float2 A0 = zero2, B0 = zero2, A1 = zero2, B1 = zero2;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const float4 gq = gp[t];
+              const float2 gr = make_float2(gq.x, gq.y), gi = make_float2(gq.z, gq.w);
+              A0 = __ffma2_rn(gr, tw0[t], A0);
+              B0 = __ffma2_rn(gi, tw0[t], B0);
+              A1 = __ffma2_rn(gr, tw1[t], A1);
+              B1 = __ffma2_rn(gi, tw1[t], B1);
+            }
+            const float2 h0 = make_float2(A0.x - B0.y, A0.y + B0.x);
+            const float2 h1 = make_float2(A1.x - B1.y, A1.y + B1.x);
+            hs0 = __fadd2_rn(hs0, h0);
+            hs1 = __fadd2_rn(hs1, h1);
+            const int o = oH + tx * nsc;
+            if (Hb) {
+              if (v0) st_stream(Hb + o, h0);
+              if (v1) st_stream(Hb + o + SLOT_THREADS, h1);
+            }
+            if (EST) {
+              if (Lb) {
+                if (v0) st_stream(Lb + o, l0);
+                if (v1) st_stream(Lb + o + SLOT_THREADS, l1);
+              }
+              if (Mb) {
+                if (v0) st_stream(Mb + o, cscale(c.alpha, l0));
+                if (v1) st_stream(Mb + o + SLOT_THREADS, cscale(c.alpha, l1));
+              }
+              // squared errors: d = h - l and h - alpha*l as one packed FMA each; idle lanes add zeros
+              float2 d = __ffma2_rn(l0, neg1, h0);
+              st[tx][0] += cabs2(d);
+              d = __ffma2_rn(l1, neg1, h1);
+              st[tx][0] += cabs2(d);
+              d = __ffma2_rn(l0, nalpha, h0);
+              st[tx][1] += cabs2(d);
+              d = __ffma2_rn(l1, nalpha, h1);
+              st[tx][1] += cabs2(d);
+              st[tx][2] += cabs2(h0) + cabs2(h1);
+            }
           }
         }
-      }
-    }
-    // ---- y = (sum_tx H) x + sigma n  (:330-343) ------------------------------------------------
-    if (a.rx) {
-      float2 y0 = cmul(hs0, x0), y1 = cmul(hs1, x1);
-      const int64_t r = ((c.b * nsym + s) * nrx + c.rx) * (int64_t)nsc;
-      if (v0) st_stream(a.rx + r + k0, make_float2(fmaf(c.sigma, n0.x, y0.x), fmaf(c.sigma, n0.y, y0.y)));
-      if (v1) st_stream(a.rx + r + k1, make_float2(fmaf(c.sigma, n1.x, y1.x), fmaf(c.sigma, n1.y, y1.y)));
-    }
-    if (a.tx && c.rx == 0) {
-      for (int tx = 0; tx < ntx; ++tx) {
-        const int64_t r = ((c.b * nsym + s) * ntx + tx) * (int64_t)nsc;
-        if (v0) st_stream(a.tx + r + k0, x0);
-        if (v1) st_stream(a.tx + r + k1, x1);
+        // ---- draws (after the tx loop: keeps them out of its register budget) ---------------------------------------------------------------------------
+        float2 x0 = zero2, x1 = zero2, n0 = zero2, n1 = zero2;
+        if (need_draws) {
+          if (a.has_inj) {
+            x0 = cis_turns(__ldg(inj_sym + oP0));
+            x1 = cis_turns(__ldg(inj_sym + oP1));
+            n0 = __ldg(inj_noise + (oR - k0) + kk0);
+            n1 = __ldg(inj_noise + (oR - k0) + kk1);
+          } else {
+            const bool hi = (s2 & 2) != 0;
+            x0 = cis_turns(u01(hi ? (j ? ws0.w : ws0.z) : (j ? ws0.y : ws0.x)));
+            x1 = cis_turns(u01(hi ? (j ? ws1.w : ws1.z) : (j ? ws1.y : ws1.x)));
+            n0 = j ? normal_pair(wn0.z, wn0.w) : normal_pair(wn0.x, wn0.y);
+            n1 = j ? normal_pair(wn1.z, wn1.w) : normal_pair(wn1.x, wn1.y);
+          }
+        }
+        // ---- y = (sum_tx H) x + sigma n  (:330-343) ------------------------------------------------
+        if (Rb) {
+          const float2 y0 = cmul(hs0, x0), y1 = cmul(hs1, x1);
+          if (v0) st_stream(Rb + oR, make_float2(fmaf(c.sigma, n0.x, y0.x), fmaf(c.sigma, n0.y, y0.y)));
+          if (v1) st_stream(Rb + oR + SLOT_THREADS, make_float2(fmaf(c.sigma, n1.x, y1.x), fmaf(c.sigma, n1.y, y1.y)));
+        }
+        if (Tb) {   // the rx-0 CTA writes the (tx-replicated) grid
+#pragma unroll
+          for (int tx = 0; tx < NTX; ++tx) {
+            if (EXACT || tx < ntx) {
+              if (v0) st_stream(Tb + oT + tx * nsc, x0);
+              if (v1) st_stream(Tb + oT + tx * nsc + SLOT_THREADS, x1);
+            }
+          }
+        }
+        oH += dH;
+        oR += dR;
+        oT += dT;
+        oP0 += nsc;
+        oP1 += nsc;
+        gps += ntx * MAXT;
       }
     }
   }
 }
 
-template <int NTX, bool EST>
+template <int NTX, bool EXACT, bool EST, int NSC>
 __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nsc = a.g.nsc, nsym = a.g.nsym, ntx = a.g.ntx, nrx = a.g.nrx;
+  const int nsc = NSC ? NSC : a.g.nsc;
+  const int nsym = a.g.nsym, ntx = a.g.ntx, nrx = a.g.nrx;
   float4 *gsp = reinterpret_cast<float4 *>(smem_raw);                 // [nsym][ntx][MAXT]
   float2 *gs = reinterpret_cast<float2 *>(gsp + nsym * ntx * MAXT);   // [nsym][MAXT] sum over tx
   float2 *hp = gs + nsym * MAXT;                                      // [np_max]
@@ -356,10 +393,10 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
 #pragma unroll
   for (int tx = 0; tx < NTX; ++tx) st[tx][0] = st[tx][1] = st[tx][2] = 0.f;
 
-  if (c.ntaps <= 5) slot_body<5, NTX, EST>(a, c, st);
-  else if (c.ntaps <= 8) slot_body<8, NTX, EST>(a, c, st);
-  else if (c.ntaps <= 9) slot_body<9, NTX, EST>(a, c, st);
-  else slot_body<MAXT, NTX, EST>(a, c, st);
+  if (c.ntaps <= 5) slot_body<5, NTX, EXACT, EST, NSC>(a, c, st);
+  else if (c.ntaps <= 8) slot_body<8, NTX, EXACT, EST, NSC>(a, c, st);
+  else if (c.ntaps <= 9) slot_body<9, NTX, EXACT, EST, NSC>(a, c, st);
+  else slot_body<MAXT, NTX, EXACT, EST, NSC>(a, c, st);
 
   if (EST && a.stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -384,22 +421,30 @@ static size_t slot_smem_bytes(const b2c_geom *g, int np_max) {
          (size_t)np_max * sizeof(float2);
 }
 
-template <int NTX, bool EST>
+template <int NTX, bool EXACT, bool EST, int NSC>
 static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
-  auto kern = slot_kernel<NTX, EST>;
+  auto kern = slot_kernel<NTX, EXACT, EST, NSC>;
   if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(B * a.g.nrx), SLOT_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }
 
+// Fast path: default grid (599 used bins) and a power-of-two TX count; everything else takes the
+// generic instantiation (runtime nsc, predicated tx loop).
 template <bool EST>
 static int launch_slot_ntx(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
-  int ntx = a.g.ntx;
-  if (ntx <= 1) return launch_slot<1, EST>(a, B, smem, stream);
-  if (ntx <= 2) return launch_slot<2, EST>(a, B, smem, stream);
-  if (ntx <= 4) return launch_slot<4, EST>(a, B, smem, stream);
-  return launch_slot<8, EST>(a, B, smem, stream);
+  const int ntx = a.g.ntx;
+  if (a.g.nsc == 599) {
+    if (ntx == 1) return launch_slot<1, true, EST, 599>(a, B, smem, stream);
+    if (ntx == 2) return launch_slot<2, true, EST, 599>(a, B, smem, stream);
+    if (ntx == 4) return launch_slot<4, true, EST, 599>(a, B, smem, stream);
+    if (ntx == 8) return launch_slot<8, true, EST, 599>(a, B, smem, stream);
+  }
+  if (ntx <= 1) return launch_slot<1, false, EST, 0>(a, B, smem, stream);
+  if (ntx <= 2) return launch_slot<2, false, EST, 0>(a, B, smem, stream);
+  if (ntx <= 4) return launch_slot<4, false, EST, 0>(a, B, smem, stream);
+  return launch_slot<8, false, EST, 0>(a, B, smem, stream);
 }
 
 }  // namespace b2c
