@@ -1,0 +1,66 @@
+"""N>1 host logic on CPU: two gloo ranks shard the global sample range exactly like the NCCL path
+(dataset_generator.shard_range + reduce_bins) and reduce their per-bin accumulators.  The GPU work
+itself is replaced by a deterministic stand-in keyed by the global sample index -- what is under
+test is the partition, the parameter draw per global index and the collective."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_bins(lo, hi, seed, sizes, nbins):
+    """Stand-in for sharded_statistics: per-slot 'nmse' is a pure function of the global index."""
+    import dataset_generator as dg
+    mi, di, si, pi = dg.philox_param_choice(seed, lo, hi - lo, sizes)
+    g = np.arange(lo, hi, dtype=np.float64)
+    nmse = 0.1 + (g % 97) / 97.0
+    bins = np.zeros((nbins, 12))
+    np.add.at(bins[:, 0], si, 1.0)
+    np.add.at(bins[:, 3], si, nmse)
+    np.add.at(bins[:, 5], si, nmse ** 2)
+    return torch.from_numpy(bins)
+
+
+def _worker(rank, world, port, total, out_dir):
+    import sys
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import dataset_generator as dg
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = dg.shard_range(total, rank, world)
+    bins = _fake_bins(lo, hi, 42, (3, 4, 8, 2), 8)
+    bins = dg.reduce_bins(bins)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "bins.npy"), bins.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_rank_sharding_and_reduction(world, tmp_path):
+    total = 1001
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, total, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "bins.npy")
+    want = _fake_bins(0, total, 42, (3, 4, 8, 2), 8).numpy()
+    assert np.array_equal(got[:, 0], want[:, 0]) and got[:, 0].sum() == total
+    assert np.allclose(got, want, rtol=1e-13, atol=0)
+
+
+def test_reduce_bins_is_identity_without_a_process_group():
+    import dataset_generator as dg
+    b = torch.arange(24, dtype=torch.float64).reshape(2, 12)
+    assert torch.equal(dg.reduce_bins(b.clone()), b)
