@@ -96,8 +96,8 @@ def _queries(nsym, nsc):
 def interpolation_plan(pilot_positions, nsym, nsc, method="linear"):
     """16-byte plan entries for every resource element (row-major), see b2c_patterns in b2c.h."""
     pts = np.column_stack([np.asarray(pilot_positions[0]), np.asarray(pilot_positions[1])]).astype(np.float64)
-    if len(pts) > 65535:
-        raise ValueError("more than 65535 pilots")
+    if len(pts) > 65534:
+        raise ValueError("more than 65534 pilots")
     plan = np.zeros(nsym * nsc, dtype=PLAN_DTYPE)
     if method == "linear":
         from scipy.spatial import Delaunay
@@ -122,6 +122,19 @@ def interpolation_plan(pilot_positions, nsym, nsc, method="linear"):
             f"interpolation method {method!r}: only 'linear' and 'nearest' are built "
             "(Clough-Tocher 'cubic' is not a fixed linear map of the pilot values; see DESIGN.md)")
     return plan
+
+
+def finalize_plan(plan, zero_slot):
+    """Device form of a plan (b2c_patterns in b2c.h): resource elements outside the hull point all
+    three taps at `zero_slot` (the zero entry the kernels append to the pilot vector, index np_max)
+    with weights (1, 0, 0), and one extra all-outside row is appended for the kernels' idle lanes."""
+    out = np.zeros(len(plan) + 1, dtype=PLAN_DTYPE)
+    out[:-1] = plan
+    outside = out["flags"] == 0
+    for f in ("i0", "i1", "i2"):
+        out[f][outside] = zero_slot
+    out["w0"][outside], out["w1"][outside] = 1.0, 0.0
+    return out
 
 
 _PLAN_CACHE: "OrderedDict[tuple, np.ndarray]" = OrderedDict()

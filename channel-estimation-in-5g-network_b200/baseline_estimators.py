@@ -183,7 +183,7 @@ def evaluate_estimator(H_true: np.ndarray, H_est: np.ndarray) -> dict:
     t = _c64(H_true.reshape(rows, 1, 1, 1, nsc), eng.device)
     e = _c64(H_est.reshape(rows, 1, 1, nsc), eng.device)
     stats = _sq_error_stats(eng, t, e, g)
-    tot = stats.sum(dim=(0, 1, 2)).cpu().numpy()
+    tot = stats[:, :, 1].sum(dim=(0, 1)).cpu().numpy()
     n = rows * nsc
     mse = tot[0] / n
     nmse = mse / (tot[2] / n + 1e-12)
@@ -203,12 +203,12 @@ def _sq_error_stats(eng, H_true, H_est_as_rx, g):
         pool.device, pool.nsym, pool.nsc, pool.method = eng.device, 1, nsc, "identity"
         pool.pilot_indices = [np.arange(nsc)]
         pool.np_max = nsc
-        plan = np.zeros(nsc, dtype=_tables.PLAN_DTYPE)
-        plan["i0"] = plan["i1"] = plan["i2"] = np.arange(nsc)
+        plan = np.zeros(2 * (nsc + 1), dtype=_tables.PLAN_DTYPE)
+        plan["i0"][:nsc + 1] = plan["i1"][:nsc + 1] = plan["i2"][:nsc + 1] = np.arange(nsc + 1)   # row nsc -> the zero slot
         plan["w0"], plan["flags"] = 1.0, 1
         pool.npilots = torch.tensor([nsc], dtype=torch.int32, device=eng.device)
         pool.pilot_re = torch.arange(nsc, dtype=torch.int32, device=eng.device).reshape(1, nsc)
-        pool.plan = torch.from_numpy(plan.view(np.uint8).reshape(1, nsc * 16)).to(eng.device)
+        pool.plan = torch.from_numpy(plan.view(np.uint8).reshape(2, (nsc + 1) * 16)).to(eng.device)
         from _b2c import Patterns
         pool.struct = Patterns(1, nsc, pool.npilots.data_ptr(), pool.pilot_re.data_ptr(), pool.plan.data_ptr())
         ones = torch.ones((1, nsc), dtype=torch.complex64, device=eng.device)

@@ -57,20 +57,21 @@ __device__ __forceinline__ float2 ls_divide(float2 y, float2 x) {
 }
 
 // ---- interpolation plan entry (16 B, see b2c_patterns in b2c.h) ----------------------------
+// value = w0*h[i0] + w1*h[i1] + (1-w0-w1)*h[i2].  Resource elements outside the pilots' convex hull
+// point all three indices at the zero slot h[np_max] that the kernels append to the pilot vector,
+// which yields griddata's fill_value = 0.0 exactly and needs no flag test.
 struct PlanTap {
   int i0, i1, i2;
   float w0, w1, w2;
 };
-__device__ __forceinline__ PlanTap plan_decode(uint4 raw, bool valid = true) {
+__device__ __forceinline__ PlanTap plan_decode(uint4 raw) {
   PlanTap p;
   p.i0 = raw.x & 0xffffu;
   p.i1 = raw.x >> 16;
   p.i2 = raw.y & 0xffffu;
-  float inside = (valid && ((raw.y >> 16) & 1u)) ? 1.0f : 0.0f;
-  float w0 = __uint_as_float(raw.z), w1 = __uint_as_float(raw.w);
-  p.w0 = inside * w0;
-  p.w1 = inside * w1;
-  p.w2 = inside * (1.0f - w0 - w1);
+  p.w0 = __uint_as_float(raw.z);
+  p.w1 = __uint_as_float(raw.w);
+  p.w2 = 1.0f - p.w0 - p.w1;
   return p;
 }
 __device__ __forceinline__ float2 plan_apply(const PlanTap &p, const float2 *__restrict__ hp) {
@@ -101,6 +102,8 @@ __device__ __forceinline__ float block_sum(float v, float *scratch) {
   __syncthreads();
   return scratch[32];
 }
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // streaming 8-byte store (outputs are written once and not re-read by this kernel)
 __device__ __forceinline__ void st_stream(float2 *p, float2 v) { __stcs(p, v); }

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *hp = reinterpret_cast<float2 *>(smem_raw);
   __shared__ float red[33];
-  __shared__ float ssm[EST_THREADS / 32][NTX * 3];
+  __shared__ float ssm[EST_THREADS / 32][6];
 
   const int nsc = a.g.nsc, nsym = a.g.nsym, ntx = a.g.ntx, nrx = a.g.nrx;
   const int64_t b = blockIdx.x / nrx;
@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
       h = ls_divide(y, __ldg(a.pilots + b * a.pilots_stride + j));
     }
     hp[j] = h;
+    if (j == 0) hp[a.pat.np_max] = make_float2(0.f, 0.f);   // zero slot for REs outside the hull
     if (a.hp_out) a.hp_out[(b * nrx + rx) * (int64_t)a.pat.np_max + j] = h;
     psum += cabs2(h);
   }
@@ -58,11 +59,9 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
     alpha = P / (P + sig2);
   }
 
-  float st[NTX][3];
-#pragma unroll
-  for (int tx = 0; tx < NTX; ++tx) st[tx][0] = st[tx][1] = st[tx][2] = 0.f;
+  float st[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // [0] antenna pair (rx, 0), [1] all tx of this rx
 
-  const uint4 *plan = reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)pid * nsym * nsc;
+  const uint4 *plan = reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)pid * (nsym * nsc + 1);
   for (int k = threadIdx.x; k < nsc; k += EST_THREADS) {
     for (int s = 0; s < nsym; ++s) {
       PlanTap p = plan_decode(__ldg(plan + s * nsc + k));
@@ -77,9 +76,17 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
           if (a.H_mmse) st_stream(a.H_mmse + o, m);
           if (a.H_true && a.stats) {
             float2 h = __ldg(a.H_true + o);
-            st[tx][0] += cabs2(make_float2(h.x - l.x, h.y - l.y));
-            st[tx][1] += cabs2(make_float2(h.x - m.x, h.y - m.y));
-            st[tx][2] += cabs2(h);
+            const float e_ls = cabs2(make_float2(h.x - l.x, h.y - l.y));
+            const float e_mm = cabs2(make_float2(h.x - m.x, h.y - m.y));
+            const float pw = cabs2(h);
+            st[1][0] += e_ls;
+            st[1][1] += e_mm;
+            st[1][2] += pw;
+            if (tx == 0) {
+              st[0][0] += e_ls;
+              st[0][1] += e_mm;
+              st[0][2] += pw;
+            }
           }
         }
       }
@@ -89,24 +96,24 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
   if (a.stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int tx = 0; tx < NTX; ++tx)
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        float v = warp_sum(st[tx][j]);
-        if (lane == 0) ssm[warp][tx * 3 + j] = v;
+        float v = warp_sum(st[q][j]);
+        if (lane == 0) ssm[warp][q * 3 + j] = v;
       }
     __syncthreads();
-    if (threadIdx.x < ntx * 3) {
+    if (threadIdx.x < 6) {
       double acc = 0.0;
       for (int w = 0; w < EST_THREADS / 32; ++w) acc += (double)ssm[w][threadIdx.x];
-      a.stats[(b * nrx + rx) * (int64_t)(ntx * 3) + threadIdx.x] = acc;
+      a.stats[(b * nrx + rx) * 6 + threadIdx.x] = acc;
     }
   }
 }
 
 template <int NTX>
 static int launch_ls(const LsArgs &a, int64_t B, cudaStream_t stream) {
-  size_t smem = (size_t)a.pat.np_max * sizeof(float2);
+  size_t smem = (size_t)(a.pat.np_max + 1) * sizeof(float2);
   auto kern = ls_interp_kernel<NTX>;
   if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(B * a.g.nrx), EST_THREADS, smem, stream>>>(a);
@@ -140,19 +147,18 @@ stats_bins_kernel(b2c_geom g, const double *__restrict__ stats, const int32_t *_
                   int64_t B, double *__restrict__ bins) {
   __shared__ double sm[BIN_THREADS / 32][B2C_N_BINSTAT];
   const int bin = blockIdx.x;
-  const int npair = g.nrx * g.ntx;
   const double n_all = (double)g.nsym * g.nrx * g.ntx * g.nsc, n_pair = (double)g.nsym * g.nsc;
   double acc[B2C_N_BINSTAT];
 #pragma unroll
   for (int j = 0; j < B2C_N_BINSTAT; ++j) acc[j] = 0.0;
   for (int64_t b = threadIdx.x; b < B; b += BIN_THREADS) {
     if (bin_id[b] != bin) continue;
-    const double *s = stats + b * (int64_t)npair * 3;
+    const double *s = stats + b * (int64_t)g.nrx * 6;   // [nrx][{pair (rx,0), all tx}][3]
     double e_ls = 0, e_mm = 0, pw = 0;
-    for (int p = 0; p < npair; ++p) {
-      e_ls += s[p * 3];
-      e_mm += s[p * 3 + 1];
-      pw += s[p * 3 + 2];
+    for (int r = 0; r < g.nrx; ++r) {
+      e_ls += s[r * 6 + 3];
+      e_mm += s[r * 6 + 4];
+      pw += s[r * 6 + 5];
     }
     // evaluate_estimator (src/baseline_estimators.py:326-331): means over the whole 4-D array
     double mse_ls = e_ls / n_all, mse_mm = e_mm / n_all, pmean = pw / n_all;
@@ -209,7 +215,7 @@ extern "C" int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const i
   B2C_REQUIRE(mmse_mode == 1 || !H_mmse, B2C_E_ARG, "b2c_ls_interp: H_mmse requested with mmse_mode=0");
   B2C_REQUIRE(!stats || H_true, B2C_E_ARG, "b2c_ls_interp: stats need H_true");
   B2C_REQUIRE(B >= 0 && B * g->nrx < (1ll << 31), B2C_E_ARG, "b2c_ls_interp: B=%lld out of range", (long long)B);
-  B2C_REQUIRE(pat->np_max >= 1 && pat->np_max <= 65535 && (size_t)pat->np_max * 8 <= 100 * 1024, B2C_E_UNSUPPORTED,
+  B2C_REQUIRE(pat->np_max >= 1 && pat->np_max <= 65534 && (size_t)pat->np_max * 8 <= 100 * 1024, B2C_E_UNSUPPORTED,
               "b2c_ls_interp: np_max=%d unsupported", pat->np_max);
   if (B == 0) return B2C_OK;
   LsArgs a = {};

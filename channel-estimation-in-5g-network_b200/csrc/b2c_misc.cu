@@ -54,8 +54,10 @@ __global__ void __launch_bounds__(256) apply_noise_kernel(b2c_geom g, b2c_slots 
   } else {
     int k = e % g.nsc, q = e / g.nsc;
     int r = q % g.nrx, s = q / g.nrx;
-    uint4 w = draw(make_key(slots.seed, slots.slot0 + b), STREAM_NOISE, (uint32_t)(((s >> 1) * g.nrx + r) * g.nsc + k));
-    n = (s & 1) ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
+    const int half = k >= B2C_RNG_LANES;
+    uint4 w = draw(make_key(slots.seed, slots.slot0 + b), STREAM_NOISE,
+                   (uint32_t)((s * g.nrx + r) * B2C_RNG_LANES + k - half * B2C_RNG_LANES));
+    n = half ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
   }
   float2 y = rx[b * per + e];
   rx[b * per + e] = make_float2(fmaf(sigma, n.x, y.x), fmaf(sigma, n.y, y.y));

@@ -16,6 +16,7 @@ constexpr int MAXT = B2C_MAX_TAPS;
 constexpr int NOSC = B2C_N_OSC;
 constexpr int GAIN_THREADS = 256;
 constexpr int SLOT_THREADS = 320;   // 2 bins per thread cover the 599 used bins in one pass
+constexpr int RNG_LANES = B2C_RNG_LANES;
 
 // ------------------------------------------------------------------------------------------
 // K1a: Jakes sum-of-sinusoids gains at the symbol-start instants (src/channel_simulator.py:102-125
@@ -154,37 +155,74 @@ struct SlotCtx {
   const float2 *hp;    // smem [np] LS estimates at the pilots
 };
 
-// Symbol and noise draws for resource element (s, k) of this CTA's rx antenna.
+// Symbol and noise draws for resource element (s, k) of this CTA's rx antenna (layout in b2c.h:
+// bins are drawn in two halves of B2C_RNG_LANES = 320, so that the thread owning bins k and k+320
+// gets both from one Philox call).
 __device__ __forceinline__ float2 draw_symbol(const SlotArgs &a, const SlotCtx &c, int s, int k) {
   if (a.has_inj) return cis_turns(__ldg(a.inj.sym_turns + (c.b * a.g.nsym + s) * a.g.nsc + k));
-  uint4 w = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 2) * a.g.nsc + k));
-  return cis_turns(u01(pick(w, s & 3)));
+  const int half = k >= RNG_LANES;
+  uint4 w = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 1) * RNG_LANES + k - half * RNG_LANES));
+  return cis_turns(u01(pick(w, (s & 1) * 2 + half)));
 }
 __device__ __forceinline__ float2 draw_noise(const SlotArgs &a, const SlotCtx &c, int s, int k) {
   if (a.has_inj)
     return __ldg(reinterpret_cast<const float2 *>(a.inj.noise) +
                  ((c.b * a.g.nsym + s) * a.g.nrx + c.rx) * a.g.nsc + k);
-  uint4 w = draw(c.key, STREAM_NOISE, (uint32_t)(((s >> 1) * a.g.nrx + c.rx) * a.g.nsc + k));
-  return (s & 1) ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
+  const int half = k >= RNG_LANES;
+  uint4 w = draw(c.key, STREAM_NOISE, (uint32_t)((s * a.g.nrx + c.rx) * RNG_LANES + k - half * RNG_LANES));
+  return half ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
+}
+
+// LS at the pilots: h_p = y_p / (x_p + 1e-12) (src/baseline_estimators.py:109-110), with y_p evaluated
+// directly at the pilot REs from the tx-summed gains, then the default-MMSE shrinkage factor.
+template <int T, int NSC>
+__device__ __forceinline__ void pilot_phase(const SlotArgs &a, SlotCtx &c, const float2 *gs, float2 *hp, float *red) {
+  const int nsc = NSC ? NSC : a.g.nsc;
+  const int np = a.pat.npilots[c.pid];
+  const int *pre = a.pat.pilot_re + (int64_t)c.pid * a.pat.np_max;
+  const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * nsc;
+  float psum = 0.f;
+  if (threadIdx.x == 0) hp[a.pat.np_max] = make_float2(0.f, 0.f);   // the plan's "outside the hull" slot
+  for (int j = threadIdx.x; j < np; j += SLOT_THREADS) {
+    const int e = __ldg(pre + j);
+    const int s = e / nsc, k = e - s * nsc;
+    float2 twk[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) twk[t] = __ldg(tw + t * nsc + k);   // issued together: one L2 round trip
+    float2 hsum = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < T; ++t) hsum = cadd(hsum, cmul(gs[s * MAXT + t], twk[t]));
+    const float2 x = draw_symbol(a, c, s, k), n = draw_noise(a, c, s, k);
+    const float2 y = cmul(hsum, x);
+    const float2 h = ls_divide(make_float2(fmaf(c.sigma, n.x, y.x), fmaf(c.sigma, n.y, y.y)), x);
+    hp[j] = h;
+    psum += cabs2(h);
+  }
+  // default MMSE: R_h = P I  =>  W = P/(P + sigma^2) I  (src/baseline_estimators.py:174-190)
+  const float P = block_sum(psum, red) / (float)np;
+  const float sig2 = exp10f(-0.1f * a.slots.snr_db[c.b]);
+  c.alpha = P / (P + sig2);
 }
 
 // Main loop of the slot kernel.  Thread t owns used bins t and t + SLOT_THREADS for every symbol.
 //   T      compile-time tap count (>= the profile's surviving taps; absent taps have zero gain)
 //   NTX    compile-time TX bound; EXACT = (ntx == NTX) removes the per-tx predicate
 //   NSC    used bins when known at compile time (599 for the default grid), 0 = read from b2c_geom:
-//          with NSC fixed every store offset inside a symbol is an immediate.
+//          with NSC fixed every store offset inside a symbol is an immediate
+//   FAST   the throughput configuration: Philox draws, every output requested, even nsym -- all
+//          the optional-output / injected-draw tests fold away
 // Output addressing: one 64-bit base per slot (uniform) + 32-bit per-thread element offsets.
-template <int T, int NTX, bool EXACT, bool EST, int NSC>
-__device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, float (&st)[NTX][3]) {
+template <int T, int NTX, bool EXACT, bool EST, int NSC, bool FAST>
+__device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, float (&st)[2][3]) {
   const int nsc = NSC ? NSC : a.g.nsc;
   const int nsym = a.g.nsym, nrx = a.g.nrx;
   const int ntx = EXACT ? NTX : a.g.ntx;
   const int k0 = threadIdx.x;
-  const bool v0 = k0 < nsc, v1 = k0 + SLOT_THREADS < nsc;
+  const bool v0 = (NSC >= SLOT_THREADS) || k0 < nsc, v1 = k0 + SLOT_THREADS < nsc;
   const int kk0 = v0 ? k0 : 0, kk1 = v1 ? k0 + SLOT_THREADS : 0;   // idle lanes read bin 0, store nothing
 
-  // Twiddles.  Idle lanes get zeros, so their H, LS/MMSE values and error terms are exactly zero
-  // and need no predication in the loop.
+  // Twiddles.  Idle lanes get zeros (and the plan's all-zero row below), so their H, LS/MMSE
+  // values and error terms are exactly zero and need no predication in the loop.
   const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * nsc;
   const float2 zero2 = make_float2(0.f, 0.f), neg1 = make_float2(-1.f, -1.f), nalpha = make_float2(-c.alpha, -c.alpha);
   float2 tw0[T], tw1[T];
@@ -195,44 +233,45 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
   }
 
   const int64_t slot_h = (int64_t)nsym * nrx * ntx * nsc;
-  float2 *const Hb = a.H_true ? a.H_true + c.b * slot_h : nullptr;
-  float2 *const Lb = (EST && a.H_ls) ? a.H_ls + c.b * slot_h : nullptr;
-  float2 *const Mb = (EST && a.H_mmse) ? a.H_mmse + c.b * slot_h : nullptr;
-  float2 *const Rb = a.rx ? a.rx + c.b * (int64_t)nsym * nrx * nsc : nullptr;
-  float2 *const Tb = (a.tx && c.rx == 0) ? a.tx + c.b * (int64_t)nsym * ntx * nsc : nullptr;
-  const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * nsym * nsc : nullptr;
-  const float2 *inj_noise = a.has_inj ? reinterpret_cast<const float2 *>(a.inj.noise) + c.b * (int64_t)nsym * nrx * nsc : nullptr;
-  const float *inj_sym = a.has_inj ? a.inj.sym_turns + c.b * (int64_t)nsym * nsc : nullptr;
+  const int nre = nsym * nsc;
+  float2 *const Hb = (FAST || a.H_true) ? a.H_true + c.b * slot_h : nullptr;
+  float2 *const Lb = (FAST || (EST && a.H_ls)) ? a.H_ls + c.b * slot_h : nullptr;
+  float2 *const Mb = (FAST || (EST && a.H_mmse)) ? a.H_mmse + c.b * slot_h : nullptr;
+  float2 *const Rb = (FAST || a.rx) ? a.rx + c.b * (int64_t)nsym * nrx * nsc : nullptr;
+  float2 *const Tb = ((FAST || a.tx) && c.rx == 0) ? a.tx + c.b * (int64_t)nsym * ntx * nsc : nullptr;
+  const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * (nre + 1) : nullptr;
+  const bool inj = !FAST && a.has_inj;
+  const float2 *inj_noise = inj ? reinterpret_cast<const float2 *>(a.inj.noise) + c.b * (int64_t)nsym * nrx * nsc : nullptr;
+  const float *inj_sym = inj ? a.inj.sym_turns + c.b * (int64_t)nsym * nsc : nullptr;
 
   int oH = c.rx * ntx * nsc + k0;   // element offset of H[s][rx][0][k0] inside the slot
   int oR = c.rx * nsc + k0;         //                   rx[s][rx][k0]
   int oT = k0;                      //                   tx[s][0][k0]
-  int oP0 = kk0, oP1 = kk1;         // plan / injected-symbol offsets (clamped bins)
+  int oP0 = v0 ? k0 : nre, oP1 = v1 ? k0 + SLOT_THREADS : nre;   // plan rows; row nre = "outside" for idle lanes
+  const int dP0 = v0 ? nsc : 0, dP1 = v1 ? nsc : 0;
   const int dH = nrx * ntx * nsc, dR = nrx * nsc, dT = ntx * nsc;
   const float4 *gps = c.gsp;
-  const bool need_draws = Rb != nullptr || a.tx != nullptr;   // H-only calls skip the draws
+  const bool need_draws = FAST || Rb != nullptr || a.tx != nullptr;   // H-only calls skip the draws
 
-  uint4 ws0 = make_uint4(0, 0, 0, 0), ws1 = ws0;
+  static_assert(SLOT_THREADS == RNG_LANES, "thread t owns bins t and t + RNG_LANES");
+  uint4 ws = make_uint4(0, 0, 0, 0);
   for (int s2 = 0; s2 < nsym; s2 += 2) {
-    uint4 wn0 = make_uint4(0, 0, 0, 0), wn1 = wn0;
-    if (need_draws && !a.has_inj) {
-      const uint32_t base = (uint32_t)(((s2 >> 1) * nrx + c.rx) * nsc);
-      wn0 = draw(c.key, STREAM_NOISE, base + kk0);
-      wn1 = draw(c.key, STREAM_NOISE, base + kk1);
-      if ((s2 & 3) == 0) {
-        ws0 = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 2) * nsc + kk0));
-        ws1 = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 2) * nsc + kk1));
-      }
-    }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int s = s2 + j;
-      if (s < nsym) {
+      if (FAST || s < nsym) {
         // ---- LS interpolation for this RE (identical for every tx); MMSE = alpha * LS ----------------
         float2 l0 = zero2, l1 = zero2;
         if (EST) {
-          l0 = plan_apply(plan_decode(__ldg(plan + oP0), v0), c.hp);
-          l1 = plan_apply(plan_decode(__ldg(plan + oP1), v1), c.hp);
+          l0 = plan_apply(plan_decode(__ldg(plan + oP0)), c.hp);
+          l1 = plan_apply(plan_decode(__ldg(plan + oP1)), c.hp);
+          oP0 += dP0;
+          oP1 += dP1;
+          // pull the next symbol's entries into L1 now: their L2 latency hides behind the tx loop and
+          // costs no registers (the last iteration touches the row after the pattern's plan: in bounds,
+          // the pool is padded by one pattern)
+          prefetch_l1(plan + oP0);
+          prefetch_l1(plan + oP1);
         }
         // ---- CFR per tx: H[s, rx, tx, k] = sum_t g[s, tx, t] * tw[t, k] ---------------------------
         float2 hs0 = zero2, hs1 = zero2;
@@ -255,50 +294,60 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
             hs0 = __fadd2_rn(hs0, h0);
             hs1 = __fadd2_rn(hs1, h1);
             const int o = oH + tx * nsc;
-            if (Hb) {
+            if (FAST || Hb) {
               if (v0) st_stream(Hb + o, h0);
               if (v1) st_stream(Hb + o + SLOT_THREADS, h1);
             }
             if (EST) {
-              if (Lb) {
+              if (FAST || Lb) {
                 if (v0) st_stream(Lb + o, l0);
                 if (v1) st_stream(Lb + o + SLOT_THREADS, l1);
               }
-              if (Mb) {
+              if (FAST || Mb) {
                 if (v0) st_stream(Mb + o, cscale(c.alpha, l0));
                 if (v1) st_stream(Mb + o + SLOT_THREADS, cscale(c.alpha, l1));
               }
-              // squared errors: d = h - l and h - alpha*l as one packed FMA each; idle lanes add zeros
+              // squared errors: d = h - l and h - alpha*l as one packed FMA each; idle lanes add zeros.
+              // Accumulated over all tx ([1]) and, for the pair-(0,0) NMSE of the pilot sweep, for tx 0 ([0]).
               float2 d = __ffma2_rn(l0, neg1, h0);
-              st[tx][0] += cabs2(d);
+              float e_ls = cabs2(d);
               d = __ffma2_rn(l1, neg1, h1);
-              st[tx][0] += cabs2(d);
+              e_ls += cabs2(d);
               d = __ffma2_rn(l0, nalpha, h0);
-              st[tx][1] += cabs2(d);
+              float e_mm = cabs2(d);
               d = __ffma2_rn(l1, nalpha, h1);
-              st[tx][1] += cabs2(d);
-              st[tx][2] += cabs2(h0) + cabs2(h1);
+              e_mm += cabs2(d);
+              const float pw = cabs2(h0) + cabs2(h1);
+              st[1][0] += e_ls;
+              st[1][1] += e_mm;
+              st[1][2] += pw;
+              if (tx == 0) {
+                st[0][0] += e_ls;
+                st[0][1] += e_mm;
+                st[0][2] += pw;
+              }
             }
           }
         }
-        // ---- draws (after the tx loop: keeps them out of its register budget) ---------------------------------------------------------------------------
+        // ---- draws (after the tx loop: keeps them out of its register budget) ------------------------
         float2 x0 = zero2, x1 = zero2, n0 = zero2, n1 = zero2;
         if (need_draws) {
-          if (a.has_inj) {
-            x0 = cis_turns(__ldg(inj_sym + oP0));
-            x1 = cis_turns(__ldg(inj_sym + oP1));
+          if (inj) {
+            x0 = cis_turns(__ldg(inj_sym + s * nsc + kk0));
+            x1 = cis_turns(__ldg(inj_sym + s * nsc + kk1));
             n0 = __ldg(inj_noise + (oR - k0) + kk0);
             n1 = __ldg(inj_noise + (oR - k0) + kk1);
           } else {
-            const bool hi = (s2 & 2) != 0;
-            x0 = cis_turns(u01(hi ? (j ? ws0.w : ws0.z) : (j ? ws0.y : ws0.x)));
-            x1 = cis_turns(u01(hi ? (j ? ws1.w : ws1.z) : (j ? ws1.y : ws1.x)));
-            n0 = j ? normal_pair(wn0.z, wn0.w) : normal_pair(wn0.x, wn0.y);
-            n1 = j ? normal_pair(wn1.z, wn1.w) : normal_pair(wn1.x, wn1.y);
+            if (j == 0) ws = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 1) * RNG_LANES + k0));
+            x0 = cis_turns(u01(j ? ws.z : ws.x));
+            x1 = cis_turns(u01(j ? ws.w : ws.y));
+            const uint4 wn = draw(c.key, STREAM_NOISE, (uint32_t)((s * nrx + c.rx) * RNG_LANES + k0));
+            n0 = normal_pair(wn.x, wn.y);
+            n1 = normal_pair(wn.z, wn.w);
           }
         }
         // ---- y = (sum_tx H) x + sigma n  (:330-343) ------------------------------------------------
-        if (Rb) {
+        if (FAST || Rb) {
           const float2 y0 = cmul(hs0, x0), y1 = cmul(hs1, x1);
           if (v0) st_stream(Rb + oR, make_float2(fmaf(c.sigma, n0.x, y0.x), fmaf(c.sigma, n0.y, y0.y)));
           if (v1) st_stream(Rb + oR + SLOT_THREADS, make_float2(fmaf(c.sigma, n1.x, y1.x), fmaf(c.sigma, n1.y, y1.y)));
@@ -315,24 +364,22 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
         oH += dH;
         oR += dR;
         oT += dT;
-        oP0 += nsc;
-        oP1 += nsc;
         gps += ntx * MAXT;
       }
     }
   }
 }
 
-template <int NTX, bool EXACT, bool EST, int NSC>
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST>
 __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nsc = NSC ? NSC : a.g.nsc;
   const int nsym = a.g.nsym, ntx = a.g.ntx, nrx = a.g.nrx;
   float4 *gsp = reinterpret_cast<float4 *>(smem_raw);                 // [nsym][ntx][MAXT]
   float2 *gs = reinterpret_cast<float2 *>(gsp + nsym * ntx * MAXT);   // [nsym][MAXT] sum over tx
-  float2 *hp = gs + nsym * MAXT;                                      // [np_max]
+  float2 *hp = gs + nsym * MAXT;                                      // [np_max + 1], last = 0
   __shared__ float red[33];
-  __shared__ float ssm[SLOT_THREADS / 32][NTX * 3];
+  __shared__ float ssm[SLOT_THREADS / 32][6];
 
   SlotCtx c;
   c.b = blockIdx.x / nrx;
@@ -368,83 +415,77 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
     }
     __syncthreads();
     c.pid = a.slots.pattern_id[c.b];
-    const int np = a.pat.npilots[c.pid];
-    const int *pre = a.pat.pilot_re + (int64_t)c.pid * a.pat.np_max;
-    const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * nsc;
-    float psum = 0.f;
-    for (int j = threadIdx.x; j < np; j += SLOT_THREADS) {
-      int e = __ldg(pre + j);
-      int s = e / nsc, k = e - s * nsc;
-      float2 hsum = make_float2(0.f, 0.f);
-      for (int t = 0; t < c.ntaps; ++t) hsum = cadd(hsum, cmul(gs[s * MAXT + t], __ldg(tw + t * nsc + k)));
-      float2 x = draw_symbol(a, c, s, k), n = draw_noise(a, c, s, k);
-      float2 y = cmul(hsum, x);
-      float2 h = ls_divide(make_float2(fmaf(c.sigma, n.x, y.x), fmaf(c.sigma, n.y, y.y)), x);
-      hp[j] = h;
-      psum += cabs2(h);
-    }
-    // default MMSE: R_h = P I  =>  W = P/(P + sigma^2) I  (src/baseline_estimators.py:174-190)
-    float P = block_sum(psum, red) / (float)np;
-    float sig2 = exp10f(-0.1f * a.slots.snr_db[c.b]);
-    c.alpha = P / (P + sig2);
   }
 
-  float st[NTX][3];
-#pragma unroll
-  for (int tx = 0; tx < NTX; ++tx) st[tx][0] = st[tx][1] = st[tx][2] = 0.f;
+  float st[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // [0] antenna pair (rx, 0), [1] all tx of this rx
 
-  if (c.ntaps <= 5) slot_body<5, NTX, EXACT, EST, NSC>(a, c, st);
-  else if (c.ntaps <= 8) slot_body<8, NTX, EXACT, EST, NSC>(a, c, st);
-  else if (c.ntaps <= 9) slot_body<9, NTX, EXACT, EST, NSC>(a, c, st);
-  else slot_body<MAXT, NTX, EXACT, EST, NSC>(a, c, st);
+  if (c.ntaps <= 5) {
+    if (EST) pilot_phase<5, NSC>(a, c, gs, hp, red);
+    slot_body<5, NTX, EXACT, EST, NSC, FAST>(a, c, st);
+  }
+  else if (c.ntaps <= 8) {
+    if (EST) pilot_phase<8, NSC>(a, c, gs, hp, red);
+    slot_body<8, NTX, EXACT, EST, NSC, FAST>(a, c, st);
+  }
+  else if (c.ntaps <= 9) {
+    if (EST) pilot_phase<9, NSC>(a, c, gs, hp, red);
+    slot_body<9, NTX, EXACT, EST, NSC, FAST>(a, c, st);
+  }
+  else {
+    if (EST) pilot_phase<MAXT, NSC>(a, c, gs, hp, red);
+    slot_body<MAXT, NTX, EXACT, EST, NSC, FAST>(a, c, st);
+  }
 
-  if (EST && a.stats) {
+  if (EST && (FAST || a.stats)) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int tx = 0; tx < NTX; ++tx)
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        float v = warp_sum(st[tx][j]);
-        if (lane == 0) ssm[warp][tx * 3 + j] = v;
+        float v = warp_sum(st[q][j]);
+        if (lane == 0) ssm[warp][q * 3 + j] = v;
       }
     __syncthreads();
-    if (threadIdx.x < ntx * 3) {
+    if (threadIdx.x < 6) {
       double acc = 0.0;
       for (int w = 0; w < SLOT_THREADS / 32; ++w) acc += (double)ssm[w][threadIdx.x];
-      a.stats[(c.b * nrx + c.rx) * (int64_t)(ntx * 3) + threadIdx.x] = acc;
+      a.stats[(c.b * nrx + c.rx) * 6 + threadIdx.x] = acc;
     }
   }
 }
 
 static size_t slot_smem_bytes(const b2c_geom *g, int np_max) {
   return (size_t)g->nsym * g->ntx * MAXT * sizeof(float4) + (size_t)g->nsym * MAXT * sizeof(float2) +
-         (size_t)np_max * sizeof(float2);
+         (size_t)(np_max + 1) * sizeof(float2);
 }
 
-template <int NTX, bool EXACT, bool EST, int NSC>
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST>
 static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
-  auto kern = slot_kernel<NTX, EXACT, EST, NSC>;
+  auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST>;
   if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(B * a.g.nrx), SLOT_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }
 
-// Fast path: default grid (599 used bins) and a power-of-two TX count; everything else takes the
-// generic instantiation (runtime nsc, predicated tx loop).
+// Fast path: the throughput configuration -- default grid (599 used bins), power-of-two TX count,
+// even symbol count, Philox draws, every output requested.  Everything else (parity runs with
+// injected draws, partial outputs, other geometries) takes the generic instantiation.
 template <bool EST>
 static int launch_slot_ntx(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
   const int ntx = a.g.ntx;
-  if (a.g.nsc == 599) {
-    if (ntx == 1) return launch_slot<1, true, EST, 599>(a, B, smem, stream);
-    if (ntx == 2) return launch_slot<2, true, EST, 599>(a, B, smem, stream);
-    if (ntx == 4) return launch_slot<4, true, EST, 599>(a, B, smem, stream);
-    if (ntx == 8) return launch_slot<8, true, EST, 599>(a, B, smem, stream);
+  const bool fast = EST && a.g.nsc == 599 && (a.g.nsym & 1) == 0 && !a.has_inj && a.H_true && a.rx && a.tx &&
+                    a.H_ls && a.H_mmse && a.stats;
+  if (fast) {
+    if (ntx == 1) return launch_slot<1, true, true, 599, true>(a, B, smem, stream);
+    if (ntx == 2) return launch_slot<2, true, true, 599, true>(a, B, smem, stream);
+    if (ntx == 4) return launch_slot<4, true, true, 599, true>(a, B, smem, stream);
+    if (ntx == 8) return launch_slot<8, true, true, 599, true>(a, B, smem, stream);
   }
-  if (ntx <= 1) return launch_slot<1, false, EST, 0>(a, B, smem, stream);
-  if (ntx <= 2) return launch_slot<2, false, EST, 0>(a, B, smem, stream);
-  if (ntx <= 4) return launch_slot<4, false, EST, 0>(a, B, smem, stream);
-  return launch_slot<8, false, EST, 0>(a, B, smem, stream);
+  if (ntx <= 1) return launch_slot<1, false, EST, 0, false>(a, B, smem, stream);
+  if (ntx <= 2) return launch_slot<2, false, EST, 0, false>(a, B, smem, stream);
+  if (ntx <= 4) return launch_slot<4, false, EST, 0, false>(a, B, smem, stream);
+  return launch_slot<8, false, EST, 0, false>(a, B, smem, stream);
 }
 
 }  // namespace b2c
@@ -487,7 +528,7 @@ extern "C" int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, co
               "b2c_slot_pipeline: estimation outputs requested without a pattern pool");
   B2C_REQUIRE(!inj || !(est || rx || tx) || (inj->sym_turns && inj->noise), B2C_E_ARG,
               "b2c_slot_pipeline: inject struct needs sym_turns and noise");
-  B2C_REQUIRE(!est || pat->np_max <= 65535, B2C_E_UNSUPPORTED, "b2c_slot_pipeline: more than 65535 pilots");
+  B2C_REQUIRE(!est || pat->np_max <= 65534, B2C_E_UNSUPPORTED, "b2c_slot_pipeline: more than 65534 pilots");
   if (B == 0) return B2C_OK;
   SlotArgs a = {};
   a.g = *g;

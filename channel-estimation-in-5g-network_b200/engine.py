@@ -39,13 +39,13 @@ class PatternPool:
         self.npilots_host = np.array([len(p) for p in self.pilot_indices], dtype=np.int32)
         self.np_max = int(self.npilots_host.max())
         pre = np.zeros((n, self.np_max), dtype=np.int32)
-        plans = np.zeros((n, nsym * nsc), dtype=_tables.PLAN_DTYPE)
+        plans = np.zeros((n + 1, nsym * nsc + 1), dtype=_tables.PLAN_DTYPE)   # +1 pattern of padding: kernels prefetch one symbol ahead
         for i, p in enumerate(self.pilot_indices):
             pre[i, :len(p)] = p
-            plans[i] = _tables.cached_plan(p, nsym, nsc, method)
+            plans[i] = _tables.finalize_plan(_tables.cached_plan(p, nsym, nsc, method), self.np_max)
         self.npilots = torch.from_numpy(self.npilots_host).to(self.device)
         self.pilot_re = torch.from_numpy(pre).to(self.device)
-        self.plan = torch.from_numpy(plans.view(np.uint8).reshape(n, nsym * nsc * 16)).to(self.device)
+        self.plan = torch.from_numpy(plans.view(np.uint8).reshape(n + 1, (nsym * nsc + 1) * 16)).to(self.device)
         self.struct = Patterns(n, self.np_max, self.npilots.data_ptr(), self.pilot_re.data_ptr(), self.plan.data_ptr())
 
     def __len__(self):
@@ -136,7 +136,7 @@ class SlotEngine:
                   "tx": (B, self.nsym, self.ntx, self.nsc)}
         out = {k: torch.empty(shapes[k], dtype=torch.complex64, device=self.device) for k in want if k in shapes}
         if "stats" in want:
-            out["stats"] = torch.empty((B, self.nrx, self.ntx, _b2c.N_STAT), dtype=torch.float64, device=self.device)
+            out["stats"] = torch.empty((B, self.nrx, 2, _b2c.N_STAT), dtype=torch.float64, device=self.device)
         return out
 
     # ---- K1a + fused slot kernel -------------------------------------------------------------------
@@ -184,7 +184,7 @@ class SlotEngine:
         if "hp" in want:
             out["hp"] = torch.zeros((B, g.nrx, pool.np_max), dtype=torch.complex64, device=self.device)
         if "stats" in want:
-            out["stats"] = torch.empty((B, g.nrx, g.ntx, _b2c.N_STAT), dtype=torch.float64, device=self.device)
+            out["stats"] = torch.empty((B, g.nrx, 2, _b2c.N_STAT), dtype=torch.float64, device=self.device)
         stride = pilots.shape[1] if (pilots is not None and pilots.shape[0] > 1) else 0
         check(lib().b2c_ls_interp(ref(g), ref(pool.struct), dptr(pid, "i32"), dptr(snr, "f32", True), B,
                                   dptr(rx, "c64", True), dptr(pilots, "c64", True), stride, dptr(hp_in, "c64", True),

@@ -25,10 +25,11 @@
  *   Philox    -- Philox4x32-10 keyed by (seed, global slot index): results do not depend on
  *                batch size, launch geometry or the number of GPUs the slots are sharded over.
  *   Counter layout: key = (seed lo, seed hi); ctr = (index, stream, slot lo, slot hi)
- *     stream 0 SYMBOLS: index = (s>>2)*nsc + k, word s&3           -> phase of RE (s,k), in turns
+ *     (k is split as k = h*320 + l, h = k / B2C_RNG_LANES: the kernels' thread l owns bins l and l+320)
+ *     stream 0 SYMBOLS: index = (s>>1)*320 + l, word (s&1)*2 + h   -> phase of RE (s,k), in turns
  *     stream 1 JAKES  : index = ((p*ntx+tx)*nrx+rx)*10 + (n>>1), words (0,1) even n / (2,3) odd n
  *                                                                  -> (arrival angle, phase) of oscillator n
- *     stream 2 NOISE  : index = ((s>>1)*nrx+rx)*nsc + k, words (0,1) even s / (2,3) odd s
+ *     stream 2 NOISE  : index = (s*nrx+rx)*320 + l, words (2h, 2h+1)
  *                                                                  -> Box-Muller (u1,u2) of rx[s][rx][k]
  *     uniform u = ((word>>9)+0.5)*2^-23.   oracle/philox.py is the bit-exact CPU twin.
  */
@@ -45,8 +46,10 @@ extern "C" {
 #define B2C_MAX_TAPS 16     /* distinct sample delays per TDL profile (EPA 5, EVA 8, ETU 9)  */
 #define B2C_MAX_ANT 8       /* ntx, nrx <= 8                                                  */
 #define B2C_MAX_SYM 16      /* OFDM symbols per slot                                          */
+#define B2C_RNG_LANES 320   /* bins per Philox half-row (see "Random draws"); nsc <= 2*320    */
 #define B2C_N_OSC 20        /* Jakes oscillators, src/channel_simulator.py:100                */
-#define B2C_N_STAT 3        /* per antenna pair: sum|H-H_ls|^2, sum|H-H_mmse|^2, sum|H|^2     */
+#define B2C_N_STAT 3        /* sum|H-H_ls|^2, sum|H-H_mmse|^2, sum|H|^2 ...                    */
+#define B2C_N_STATGRP 2     /* ... per rx antenna for {antenna pair (rx,0), all tx of that rx} */
 
 enum {
   B2C_OK = 0,
@@ -84,15 +87,17 @@ typedef struct b2c_profiles {
  * (src/channel_simulator.py:209-236) + the Delaunay/barycentric (or nearest) structure that
  * scipy.interpolate.griddata builds inside LSEstimator.interpolate_channel
  * (src/baseline_estimators.py:65-79); built once per pattern on the host.
- * plan entry (16 bytes per resource element, row-major (sym, sc)):
- *   uint16 i0, i1, i2, flags(bit0 = inside hull); float w0, w1;   w2 = 1 - w0 - w1
- * value = inside ? w0*h[i0] + w1*h[i1] + w2*h[i2] : 0        (griddata fill_value=0.0)      */
+ * plan: nsym*nsc + 1 entries of 16 bytes per pattern, row-major (sym, sc):
+ *   uint16 i0, i1, i2, flags(bit0 = inside hull, informational); float w0, w1;   w2 = 1 - w0 - w1
+ *   value = w0*h[i0] + w1*h[i1] + w2*h[i2] over the pilot vector h extended by h[np_max] = 0.
+ *   Resource elements outside the pilots' convex hull carry i0 = i1 = i2 = np_max, w0 = 1, w1 = 0
+ *   (griddata fill_value=0.0, exactly); the extra last entry is such an "outside" row.         */
 typedef struct b2c_patterns {
   int32_t n_patterns;
   int32_t np_max;           /* row stride of pilot_re                                         */
   const int32_t *npilots;   /* [n_patterns]                                                   */
   const int32_t *pilot_re;  /* [n_patterns][np_max]  sorted flat RE index of pilot j          */
-  const void *plan;         /* [n_patterns][nsym*nsc] 16-byte plan entries                    */
+  const void *plan;         /* [n_patterns][nsym*nsc + 1] 16-byte plan entries                */
 } b2c_patterns;
 
 /* Per-slot parameters (device arrays of length B).  */
@@ -138,7 +143,7 @@ int b2c_tap_gains(const b2c_geom *g, const b2c_profiles *prof, const b2c_slots *
  * (:315-337).  Every output pointer is optional (NULL = not written); estimation is skipped
  * entirely when H_ls, H_mmse and stats are all NULL (then this is simulate_transmission alone).
  *   H_true [B][nsym][nrx][ntx][nsc], rx [B][nsym][nrx][nsc], tx [B][nsym][ntx][nsc] complex
- *   H_ls, H_mmse like H_true;  stats [B][nrx][ntx][B2C_N_STAT] double                          */
+ *   H_ls, H_mmse like H_true;  stats [B][nrx][B2C_N_STATGRP][B2C_N_STAT] double                          */
 int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat,
                       const b2c_slots *slots, const b2c_inject *inj, int64_t B,
                       const float *gains, const float *noise_std,
@@ -178,7 +183,7 @@ int b2c_mmse_dense(const float *W, int32_t np, const float *in, float *out, int6
 /* K5.  Fold per-slot statistics into per-bin float64 accumulators (deterministic order).
  * Replaces the per-sample evaluate_estimator / compute_nmse + list aggregation of
  * src/baseline_estimators.py:326-337 and run_phase8_pilot_optimization.py:32-37,186-206.
- *   stats [B][nrx][ntx][3] (from the kernels above), bin_id [B] in [0, nbins) or <0 to skip
+ *   stats [B][nrx][2][3] (from the kernels above), bin_id [B] in [0, nbins) or <0 to skip
  *   bins  [nbins][B2C_N_BINSTAT] double, ACCUMULATED INTO (zero it first):
  *     0 count  1 sum mse_ls  2 sum mse_mmse  3 sum nmse_ls  4 sum nmse_mmse  5 sum nmse_ls^2
  *     6 sum nmse_mmse^2  7 sum mean|H|^2  8 sum nmse00_ls  9 sum nmse00_ls^2  10 sum nmse00_mmse

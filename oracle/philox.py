@@ -13,11 +13,11 @@ RNG parity with it is by injection only.
 Counter layout (shared with include/b2c.h):
     key  = (seed & 0xffffffff, seed >> 32)
     ctr  = (index, stream, slot & 0xffffffff, slot >> 32)         slot = global sample index
-    stream 0 SYMBOLS: index = (s >> 2) * nsc + k ; word s & 3            -> phase of RE (s, k)
+    (bins are split as k = h*320 + l, h = k // RNG_LANES)
+    stream 0 SYMBOLS: index = (s >> 1) * 320 + l ; word (s & 1)*2 + h     -> phase of RE (s, k)
     stream 1 JAKES  : index = ((p*ntx + tx)*nrx + rx)*10 + (n >> 1)
                       words (0,1) for even n, (2,3) for odd n            -> (angle, phase) of oscillator n
-    stream 2 NOISE  : index = ((s >> 1)*nrx + rx)*nsc + k
-                      words (0,1) for even s, (2,3) for odd s            -> Box-Muller (u1, u2) of rx[s, rx, k]
+    stream 2 NOISE  : index = (s*nrx + rx)*320 + l ; words (2h, 2h+1)     -> Box-Muller (u1, u2) of rx[s, rx, k]
     stream 3 PARAMS : index = 0 ; words 0..3 -> model, doppler, snr, density choice: (word * n) >> 32
     uniform u = ((word >> 9) + 0.5) * 2**-23   (exact in fp32, never 0 or 1)
     noise   = sqrt(-2 ln u1) * (cos 2 pi u2 + j sin 2 pi u2)
@@ -31,6 +31,7 @@ M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = 0x9E3779B9, 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
 STREAM_SYMBOLS, STREAM_JAKES, STREAM_NOISE, STREAM_PARAMS = 0, 1, 2, 3
+RNG_LANES = 320
 
 
 def philox4x32_10(ctr, key):
@@ -64,8 +65,9 @@ def _block(seed, slot, stream, index):
 def symbol_u(seed, slot, nsym, nsc):
     """u[nsym, nsc]: phase (in turns) of every resource element."""
     s, k = np.meshgrid(np.arange(nsym), np.arange(nsc), indexing="ij")
-    w = _block(seed, slot, STREAM_SYMBOLS, (s >> 2) * nsc + k)
-    return u01(np.take_along_axis(w, (s & 3)[..., None], axis=-1)[..., 0])
+    h, l = k // RNG_LANES, k % RNG_LANES
+    w = _block(seed, slot, STREAM_SYMBOLS, (s >> 1) * RNG_LANES + l)
+    return u01(np.take_along_axis(w, ((s & 1) * 2 + h)[..., None], axis=-1)[..., 0])
 
 
 def jakes_u(seed, slot, npaths, ntx, nrx, nosc=20):
@@ -81,8 +83,9 @@ def jakes_u(seed, slot, npaths, ntx, nrx, nosc=20):
 def noise(seed, slot, nsym, nrx, nsc):
     """(re, im)[nsym, nrx, nsc] unit-variance-per-component Box-Muller normals."""
     s, r, k = np.meshgrid(np.arange(nsym), np.arange(nrx), np.arange(nsc), indexing="ij")
-    w = _block(seed, slot, STREAM_NOISE, ((s >> 1) * nrx + r) * nsc + k)
-    off = (s & 1) * 2
+    h, l = k // RNG_LANES, k % RNG_LANES
+    w = _block(seed, slot, STREAM_NOISE, (s * nrx + r) * RNG_LANES + l)
+    off = h * 2
     u1 = u01(np.take_along_axis(w, off[..., None], axis=-1)[..., 0])
     u2 = u01(np.take_along_axis(w, (off + 1)[..., None], axis=-1)[..., 0])
     rad = np.sqrt(-2.0 * np.log(u1))

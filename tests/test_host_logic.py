@@ -86,6 +86,17 @@ def test_plan_reproduces_reference_interpolation(name):
         assert np.array_equal(val == 0, g["H_ls_tx0"][:, r] == 0)
 
 
+def test_finalized_plan_device_format():
+    g = load_golden("slot_2x1_epa_1pct")
+    plan = _tables.cached_plan(g["pilot_indices"], 14, 599, "linear")
+    dev = _tables.finalize_plan(plan, 200)
+    assert dev.shape == (8387,) and dev.dtype.itemsize == 16
+    out = plan["flags"] == 0
+    assert out.sum() > 0 and (dev["i0"][:-1][out] == 200).all() and (dev["i2"][:-1][out] == 200).all()
+    assert (dev["w0"][:-1][out] == 1).all() and (dev["w1"][:-1][out] == 0).all() and dev["i1"][-1] == 200
+    assert np.array_equal(dev[:-1][~out], plan[~out])
+
+
 def test_nearest_plan_and_unknown_method():
     g = load_golden("slot_2x2_eva")
     plan = _tables.cached_plan(g["pilot_indices"], 14, 599, "nearest")
