@@ -45,7 +45,7 @@ class ChannelEstimationDataset:
     """Dataset generator with the reference's interface (src/dataset_generator.py:23-180)."""
 
     def __init__(self, config: Dict, rng: str = 'numpy', seed: int = 42, batch_size: int = 256,
-                 patterns_per_density: int = 1):
+                 patterns_per_density: int = 1, lists=None, out_dtype=np.complex128):
         self.config = config
         self.ofdm_config = config['ofdm']
         self.mimo_config = config['mimo']
@@ -55,19 +55,23 @@ class ChannelEstimationDataset:
             raise ValueError(f"Unknown rng mode: {rng}")
         self.rng, self.seed, self.batch_size = rng, seed, batch_size
         self.patterns_per_density = patterns_per_density
+        self._list_override = lists          # (models, dopplers, snrs, densities) of the script twins
+        self.out_dtype = out_dtype           # complex128 like src/dataset_generator.py; the twins use complex64
         self._engine: Optional[SlotEngine] = None
         self._pool = None
         self._next_slot = 0
 
     # ---- parameter lists (src/dataset_generator.py:105-108) -------------------------------------------
     def _lists(self):
+        if self._list_override is not None:
+            return tuple(list(v) for v in self._list_override)
         return (list(self.channel_config['models']), list(self.channel_config['doppler_hz']),
                 list(self.config['simulation']['snr_range']), list(self.config['pilots']['density']))
 
     @property
     def engine(self) -> SlotEngine:
         if self._engine is None:
-            self._engine = SlotEngine(self.config, models=tuple(m.upper() for m in self.channel_config.get('models', ('EPA', 'EVA', 'ETU'))))
+            self._engine = SlotEngine(self.config, models=tuple(str(m).upper() for m in self._lists()[0]))
         return self._engine
 
     # ---- one sample, reference draw order -----------------------------------------------------------------
@@ -89,7 +93,7 @@ class ChannelEstimationDataset:
             done += n
         return out
 
-    def _numpy_batch(self, params, draw_params, first_index=0):
+    def _numpy_batch(self, params, draw_params, first_index=0, want_stats=False):
         eng = self.engine
         nsym, nsc, ntx, nrx = eng.nsym, eng.nsc, eng.ntx, eng.nrx
         models, dopplers, snrs, dens = self._lists() if draw_params else (None, None, None, None)
@@ -133,8 +137,10 @@ class ChannelEstimationDataset:
                   "noise": torch.from_numpy(np.stack(noise)).to(dev, torch.complex64)}
         out = eng.run(B, [eng.models.index(str(m[0]).upper()) for m in meta], [float(m[1]) for m in meta],
                       [float(m[2]) for m in meta], np.arange(B), pool, inject=inject,
-                      want=("H_true", "rx", "tx", "H_ls"))
-        host = {k: out[k].cpu().numpy().astype(np.complex128) for k in ("H_true", "rx", "tx", "H_ls")}
+                      want=("stats",) if want_stats else ("H_true", "rx", "tx", "H_ls"))
+        if want_stats:
+            return out["stats"]
+        host = {k: out[k].cpu().numpy().astype(self.out_dtype) for k in ("H_true", "rx", "tx", "H_ls")}
         return [{'rx_symbols': host["rx"][i], 'tx_symbols': host["tx"][i], 'H_ls': host["H_ls"][i],
                  'H_true': host["H_true"][i], 'pilot_mask': meta[i][4], 'snr_db': meta[i][2],
                  'channel_type': meta[i][0], 'doppler_hz': meta[i][1], 'pilot_density': meta[i][3]}

@@ -206,3 +206,105 @@ def test_dataset_generator_philox_mode_and_sharding():
     assert torch.equal(a["H_ls"][3:6], b["H_ls"]) and np.array_equal(pa["snr"][3:6], pb["snr"])
     lst = ds.generate_dataset(6)
     assert len(lst) == 6 and lst[0]["H_true"].shape == (14, 2, 2, 599) and lst[0]["pilot_mask"].dtype == bool
+
+
+def _replay_sample(cfg, ch, fd, snr, dens, ntx=2, nrx=2):
+    """Oracle replay of one sample from the global numpy stream, reference draw order."""
+    perm = np.arange(8386)
+    np.random.shuffle(perm)
+    n_p = int(8386 * dens)
+    draws = {"perm": perm, "pilot_phase": np.random.uniform(0, 2 * np.pi, n_p),
+             "data_phase": np.random.uniform(0, 2 * np.pi, 8386 - n_p),
+             "jakes_u": np.random.rand(len(orc.TDL_NS[str(ch)]), ntx, nrx, 2, 20)}
+    z = np.random.randn(2, 14, nrx, 599)
+    draws["noise_re"], draws["noise_im"] = z[0], z[1]
+    ref = orc.simulate(OFDM_CFG, ntx, nrx, str(ch), float(fd), float(snr), float(dens), draws)
+    rx4d = np.repeat(ref["rx_symbols"][:, :, None, :], ntx, axis=2)
+    ref["H_ls"] = orc.ls_estimate(rx4d, ref["pilot_symbols"], ref["pilot_mask"], ref["pilot_positions"])
+    return ref
+
+
+def test_phase3_generator_twin_matches_reference_order_and_dtypes(tmp_path):
+    """run_phase3_dataset_generation.DatasetGenerator: set_seed, probe sample, 4 x choice + draws per
+    sample (reference :98-176); stacked complex64 / float32 / U3 arrays (:135-143)."""
+    import run_phase3_dataset_generation as p3
+    gen = p3.DatasetGenerator(batch_size=3)
+    data = gen.generate_dataset(4, split='val')
+    assert data["rx_symbols"].shape == (4, 14, 2, 599) and data["H_true"].shape == (4, 14, 2, 2, 599)
+    assert data["pilot_mask"].shape == (4, 14, 599)                      # verify_phase3_datasets.py:68-74
+    assert data["H_ls"].dtype == np.complex64 and data["pilot_mask"].dtype == np.float32
+    assert data["snr_db"].dtype == np.float32 and data["channel_type"].dtype == np.dtype('U3')
+    np.random.seed(123)                                                  # 'val' split seed (:98-101)
+    _replay_sample(None, 'EPA', 50.0, 10.0, 0.1)                         # the shape probe (:122)
+    for i in range(4):
+        ch = np.random.choice(p3.CHANNEL_TYPES)
+        fd = float(np.random.choice(p3.DOPPLER_VALUES))
+        snr = float(np.random.choice(p3.SNR_VALUES))
+        dens = float(np.random.choice(p3.PILOT_DENSITIES))
+        ref = _replay_sample(None, ch, fd, snr, dens)
+        assert data["channel_type"][i] == ch and data["snr_db"][i] == snr and data["doppler_hz"][i] == fd
+        assert np.array_equal(data["pilot_mask"][i] > 0, ref["pilot_mask"])
+        assert relerr(data["H_true"][i], ref["channel"]) < RTOL and relerr(data["H_ls"][i], ref["H_ls"]) < RTOL
+        assert relerr(data["rx_symbols"][i], ref["rx_symbols"]) < RTOL
+    f = tmp_path / "val.npz"
+    gen.save_dataset(data, str(f))
+    assert set(np.load(f).files) == set(data)
+
+
+def test_robust_generator_resume_is_exact_in_philox_mode(tmp_path):
+    """Chunk files + JSON checkpoint + resume (run_phase3_robust.py:95-301).  With Philox keyed by the
+    global sample index an interrupted-and-resumed run equals an uninterrupted one bit for bit."""
+    import run_phase3_robust as rb
+    a = rb.RobustDatasetGenerator(output_dir=str(tmp_path / "a"), rng='philox')
+    whole = a.generate_dataset_chunked(10, 'train', chunk_size=4)
+    assert whole["H_true"].shape == (10, 14, 2, 2, 599) and (tmp_path / "a" / "train.npz").exists()
+    assert not list((tmp_path / "a" / "checkpoints").glob("*"))            # chunks + checkpoint cleaned up
+    b = rb.RobustDatasetGenerator(output_dir=str(tmp_path / "b"), rng='philox')
+    assert b.generate_dataset_chunked(10, 'train', chunk_size=4, stop_after_chunks=1) == {}
+    ck = b.load_checkpoint('train')
+    assert ck["completed"] == 4 and ck["chunk_id"] == 1 and ck["total"] == 10
+    b2 = rb.RobustDatasetGenerator(output_dir=str(tmp_path / "b"), rng='philox')
+    resumed = b2.generate_dataset_chunked(10, 'train', chunk_size=4, resume=True)
+    for k in whole:
+        assert np.array_equal(whole[k], resumed[k]), k
+    # numpy mode keeps the reference's (non bit-reproducible) resume rule but the same file protocol
+    c = rb.RobustDatasetGenerator(output_dir=str(tmp_path / "c"), rng='numpy', batch_size=2)
+    out = c.generate_dataset_chunked(3, 'test', chunk_size=2)
+    assert out["rx_symbols"].shape == (3, 14, 2, 599) and out["channel_type"].dtype == np.dtype('U3')
+
+
+def test_pilot_density_sweep():
+    """run_phase8 PilotOptimizer.analyze_pilot_density: per-(density, SNR) pair-(0,0) NMSE mean/std/dB."""
+    import torch
+    import run_phase8_pilot_optimization as p8
+    opt = p8.PilotOptimizer(rng='philox', seed=7)
+    dens, snrs, n = [0.02, 0.10], [5, 15], 6
+    res = opt.analyze_pilot_density(dens, snrs, num_samples=n)
+    assert res["pilot_densities"] == dens and res["snr_values"] == snrs and set(res["methods"]) == {"LS", "MMSE"}
+    # recompute from the full arrays of the same (Philox-keyed) slots
+    from dataset_generator import ChannelEstimationDataset
+    ds = ChannelEstimationDataset(opt.config, rng='philox', seed=7, lists=(['EVA'], [50.0], snrs, dens))
+    eng, pool = ds.engine, ds.pattern_pool()
+    cell = np.arange(len(dens) * len(snrs) * n) // n
+    out = eng.run(len(cell), 0, 50.0, np.asarray(snrs, np.float32)[cell % 2], (cell // 2).astype(np.int32), pool, slot0=0, seed=7)
+    H, Hl = out["H_true"].cpu().numpy().astype(np.complex128), out["H_ls"].cpu().numpy().astype(np.complex128)
+    for di, d in enumerate(dens):
+        for si, s in enumerate(snrs):
+            vals = [orc.nmse_pair00(Hl[b], H[b]) for b in np.flatnonzero(cell == di * 2 + si)]
+            got = res["methods"]["LS"][s][d]
+            assert abs(got["nmse_mean"] / np.mean(vals) - 1) < 1e-4 and abs(got["nmse_std"] - np.std(vals)) < 1e-3 * np.mean(vals)
+            assert abs(got["nmse_db"] - 10 * np.log10(np.mean(vals) + 1e-12)) < 0.01
+    # denser pilots estimate better at high SNR
+    assert res["methods"]["LS"][15][0.10]["nmse_mean"] < res["methods"]["LS"][15][0.02]["nmse_mean"]
+    # numpy mode: reference loop order (density, snr, sample), one pattern per sample
+    np.random.seed(5)
+    r2 = p8.PilotOptimizer(rng='numpy').analyze_pilot_density([0.05], [10], num_samples=2)
+    np.random.seed(5)
+    vals = []
+    for _ in range(2):
+        ref = _replay_sample(None, 'EVA', 50.0, 10, 0.05)
+        vals.append(orc.nmse_pair00(ref["H_ls"], ref["channel"]))
+    assert abs(r2["methods"]["LS"][10][0.05]["nmse_mean"] / np.mean(vals) - 1) < 1e-4
+    s = p8.PilotOptimizer().generate_test_sample(0.1, snr_db=12.0)
+    assert set(s) == {"rx_symbols", "H_ls", "H_true", "pilot_mask", "snr_db"}
+    assert abs(p8.compute_nmse(s["H_ls"][:, 0, 0], s["H_true"][:, 0, 0]) / orc.nmse_pair00(s["H_ls"], s["H_true"]) - 1) < 1e-4
