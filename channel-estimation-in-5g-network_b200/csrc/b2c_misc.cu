@@ -1,7 +1,6 @@
 // Stand-alone public-API kernels that are not on the fused path:
 //   b2c_apply_channel -- MIMOChannel.apply_channel for arbitrary tx / H (src/channel_simulator.py:313-345)
 //   b2c_tdl_full      -- ChannelModel.generate_time_varying_channel (:84-127), every time sample
-//   b2c_mmse_dense    -- W @ h_ls for the known-covariance MMSE branch (src/baseline_estimators.py:181-190)
 #include "b2c_common.cuh"
 #include "b2c_rng.cuh"
 
@@ -119,64 +118,6 @@ __global__ void __launch_bounds__(256) tdl_full_kernel(TdlArgs a) {
   a.out[((n * a.nrx + rx) * a.ntx + tx) * (int64_t)a.L + a.tap_delay[t]] = make_float2(amp * ar, amp * ai);
 }
 
-// ---- dense Wiener apply: out[c][i] = sum_j W[i][j] in[c][j] -------------------------------------------
-// fp32 SIMT tiles: 64 (i) x 64 (c) outputs per CTA, 16-deep K steps, 4x4 complex per thread.
-constexpr int GM = 64, GN = 64, GK = 16;
-__global__ void __launch_bounds__(256) mmse_dense_kernel(const float2 *__restrict__ W, int np,
-                                                         const float2 *__restrict__ in, float2 *__restrict__ out,
-                                                         int64_t ncols, int64_t ld) {
-  __shared__ float2 sW[GK][GM + 1];   // [j][i]
-  __shared__ float2 sX[GK][GN + 1];   // [j][c]
-  const int i0 = blockIdx.x * GM;
-  const int64_t c0 = (int64_t)blockIdx.y * GN;
-  const int ti = threadIdx.x & 15, tc = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 outputs each
-  float2 acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = make_float2(0.f, 0.f);
-
-  for (int j0 = 0; j0 < np; j0 += GK) {
-    // W tile: rows i0.., cols j0..  (row-major, j contiguous)
-    for (int idx = threadIdx.x; idx < GM * GK; idx += 256) {
-      int jj = idx % GK, ii = idx / GK;
-      int i = i0 + ii, j = j0 + jj;
-      sW[jj][ii] = (i < np && j < np) ? __ldg(W + (int64_t)i * np + j) : make_float2(0.f, 0.f);
-    }
-    for (int idx = threadIdx.x; idx < GN * GK; idx += 256) {
-      int jj = idx % GK, cc = idx / GK;
-      int64_t c = c0 + cc;
-      int j = j0 + jj;
-      sX[jj][cc] = (c < ncols && j < np) ? __ldg(in + c * ld + j) : make_float2(0.f, 0.f);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int jj = 0; jj < GK; ++jj) {
-      float2 w[4], x[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) w[a] = sW[jj][ti + 16 * a];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) x[b] = sX[jj][tc + 16 * b];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          acc[a][b].x = fmaf(w[a].x, x[b].x, fmaf(-w[a].y, x[b].y, acc[a][b].x));
-          acc[a][b].y = fmaf(w[a].x, x[b].y, fmaf(w[a].y, x[b].x, acc[a][b].y));
-        }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      int i = i0 + ti + 16 * a;
-      int64_t c = c0 + tc + 16 * b;
-      if (i < np && c < ncols) out[c * ld + i] = acc[a][b];
-    }
-}
-
 }  // namespace b2c
 
 using namespace b2c;
@@ -239,22 +180,6 @@ extern "C" int b2c_tdl_full(const b2c_geom *g, const b2c_profiles *prof, int32_t
   B2C_CUDA(cudaMemsetAsync(out, 0, sizeof(float2) * (size_t)num_samples * g->nrx * g->ntx * L, st));
   dim3 grid((unsigned)((num_samples + 255) / 256), (unsigned)(ntaps * g->ntx * g->nrx));
   tdl_full_kernel<<<grid, 256, 0, st>>>(a);
-  B2C_CUDA(cudaGetLastError());
-  return B2C_OK;
-}
-
-extern "C" int b2c_mmse_dense(const float *W, int32_t np, const float *in, float *out, int64_t ncols, int64_t ld,
-                              void *stream) {
-  B2C_REQUIRE(W && in && out, B2C_E_ARG, "b2c_mmse_dense: null argument");
-  B2C_REQUIRE(np >= 1 && ld >= np && ncols >= 0, B2C_E_ARG, "b2c_mmse_dense: np=%d ld=%lld ncols=%lld", np, (long long)ld,
-              (long long)ncols);
-  B2C_REQUIRE(in != out, B2C_E_ARG, "b2c_mmse_dense: in-place not supported");
-  if (ncols == 0) return B2C_OK;
-  dim3 grid((unsigned)((np + GM - 1) / GM), (unsigned)((ncols + GN - 1) / GN));
-  B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_mmse_dense: ncols=%lld too large for one launch", (long long)ncols);
-  mmse_dense_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(W), np,
-                                                            reinterpret_cast<const float2 *>(in),
-                                                            reinterpret_cast<float2 *>(out), ncols, ld);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }

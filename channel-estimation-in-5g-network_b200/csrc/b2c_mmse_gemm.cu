@@ -1,0 +1,234 @@
+// K4: dense Wiener filter at the pilots on the 5th-generation tensor cores.
+//
+//   out[c][i] = sum_j W[i][j] * in[c][j]        complex64, W [np][np], c over (slot, rx) columns
+//
+// replaces `mmse_matrix @ h_ls` of MMSEEstimator.estimate_at_pilots' known-covariance branch
+// (src/baseline_estimators.py:181-190).  The complex product is run as ONE real GEMM on the
+// interleaved (re, im) views:   D[i'][c] = sum_j' A[i'][j'] * X[c][j'],  i' = 2i+q, j' = 2j+p,
+//   A[2i][2j] = Wr, A[2i][2j+1] = -Wi, A[2i+1][2j] = Wi, A[2i+1][2j+1] = Wr      (built on the fly)
+// so X is `in` and D is `out` exactly as they lie in memory (no de-interleave pass).
+//
+// Tensor-core path: tcgen05.mma.cta_group::1.kind::tf32, M = 128 (rows i'), N = 128 (columns c),
+// K = 8 per instruction, operands in shared memory in the canonical K-major no-swizzle layout
+// (8 x 16-byte core matrices), fp32 accumulator in TMEM (128 lanes x 128 columns), read back with
+// tcgen05.ld.  Plain TF32 (10-bit mantissa) cannot hold the 1e-4 parity bound, so each operand is
+// split  v = hi + lo  (hi = v with the low 13 mantissa bits cleared, lo = v - hi, both exact) and
+// three MMAs are issued per K step:  hi*hi + hi*lo + lo*hi   ("3xTF32", error ~2^-21).
+#include "b2c_common.cuh"
+
+namespace b2c {
+
+constexpr int TC_BM = 128;    // rows i' per CTA (TMEM lanes)
+constexpr int TC_BN = 128;    // columns c per CTA (TMEM columns)
+constexpr int TC_BK = 32;     // real k per stage = 8 x 16-byte chunks per row
+constexpr int TC_THREADS = 128;
+constexpr int TC_KCH = TC_BK / 4;                 // 16-byte chunks per row per stage
+constexpr int TC_LBO_A = TC_BM * 16;              // bytes between consecutive K chunks (A tile)
+constexpr int TC_LBO_B = TC_BN * 16;
+constexpr int TC_SBO = 128;                       // bytes between consecutive 8-row groups
+constexpr int TC_TILE_A = TC_BM * TC_BK * 4;      // bytes of one A tile (hi or lo)
+constexpr int TC_TILE_B = TC_BN * TC_BK * 4;
+constexpr int TC_SMEM = 2 * TC_TILE_A + 2 * TC_TILE_B + 1024;   // hi+lo for A and B, + alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) leading byte offset>>4, [32,46) stride byte offset>>4, [46,48) version = 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+// kind::tf32 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
+// both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  lo = v - hi;
+}
+
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok;
+}
+
+__global__ void __launch_bounds__(TC_THREADS) mmse_dense_tc_kernel(const float2 *__restrict__ W, int np,
+                                                                    const float2 *__restrict__ in,
+                                                                    float *__restrict__ out, int64_t ncols, int64_t ld) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ uint32_t tmem_base_sm;
+  __shared__ __align__(8) uint64_t mma_bar;
+
+  // 1024-byte aligned operand tiles: [A hi][A lo][B hi][B lo]
+  const uint32_t s0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char *sp = smem_dyn + (s0 - smem_u32(smem_dyn));
+  unsigned char *sAh = sp, *sAl = sp + TC_TILE_A, *sBh = sp + 2 * TC_TILE_A, *sBl = sp + 2 * TC_TILE_A + TC_TILE_B;
+  const uint32_t aAh = s0, aAl = s0 + TC_TILE_A, aBh = s0 + 2 * TC_TILE_A, aBl = s0 + 2 * TC_TILE_A + TC_TILE_B;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0c = blockIdx.x * (TC_BM / 2);          // first complex row of W in this tile
+  const int64_t c0 = (int64_t)blockIdx.y * TC_BN;    // first column
+  const int kreal = 2 * np;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "r"((uint32_t)TC_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mma_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_d = tmem_base_sm;
+
+  // ---- per-thread load assignments ----------------------------------------------------------
+  // A: 64 complex rows x 16 complex columns of W per stage = 1024 values, 8 per thread:
+  //    value v -> complex row il = v / 16, complex column jl = v % 16
+  // B: 128 rows (columns c) x 16 complex per stage = 2048 float2, 16 per thread:
+  //    value v -> row cl = v / 16, complex column jl = v % 16   (16 consecutive threads read 128 B)
+  float2 ra[8], rb[16];
+  auto load_stage = [&](int k0) {     // k0: real k offset of the stage (multiple of 32)
+    const int jc0 = k0 >> 1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int v = q * TC_THREADS + tid, il = v >> 4, jl = v & 15;
+      const int i = i0c + il, j = jc0 + jl;
+      ra[q] = (i < np && j < np) ? __ldg(W + (int64_t)i * np + j) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int v = q * TC_THREADS + tid, cl = v >> 4, jl = v & 15;
+      const int64_t c = c0 + cl;
+      const int j = jc0 + jl;
+      rb[q] = (c < ncols && j < np) ? __ldg(in + c * ld + j) : make_float2(0.f, 0.f);
+    }
+  };
+  auto store_stage = [&]() {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int v = q * TC_THREADS + tid, il = v >> 4, jl = v & 15;
+      // real rows 2il, 2il+1 ; real k = 2jl, 2jl+1 -> chunk jl>>1, element offset 2*(jl&1)
+      const int kc = jl >> 1, eo = (jl & 1) * 8;
+      float wr_h, wr_l, wi_h, wi_l;
+      split_tf32(ra[q].x, wr_h, wr_l);
+      split_tf32(ra[q].y, wi_h, wi_l);
+      const int r0 = 2 * il, r1 = 2 * il + 1;
+      const int o0 = kc * TC_LBO_A + (r0 >> 3) * TC_SBO + (r0 & 7) * 16 + eo;
+      const int o1 = kc * TC_LBO_A + (r1 >> 3) * TC_SBO + (r1 & 7) * 16 + eo;
+      *reinterpret_cast<float2 *>(sAh + o0) = make_float2(wr_h, -wi_h);   // row 2i  : ( Wr, -Wi)
+      *reinterpret_cast<float2 *>(sAl + o0) = make_float2(wr_l, -wi_l);
+      *reinterpret_cast<float2 *>(sAh + o1) = make_float2(wi_h, wr_h);    // row 2i+1: ( Wi,  Wr)
+      *reinterpret_cast<float2 *>(sAl + o1) = make_float2(wi_l, wr_l);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int v = q * TC_THREADS + tid, cl = v >> 4, jl = v & 15;
+      const int kc = jl >> 1, eo = (jl & 1) * 8;
+      float xr_h, xr_l, xi_h, xi_l;
+      split_tf32(rb[q].x, xr_h, xr_l);
+      split_tf32(rb[q].y, xi_h, xi_l);
+      const int o = kc * TC_LBO_B + (cl >> 3) * TC_SBO + (cl & 7) * 16 + eo;
+      *reinterpret_cast<float2 *>(sBh + o) = make_float2(xr_h, xi_h);
+      *reinterpret_cast<float2 *>(sBl + o) = make_float2(xr_l, xi_l);
+    }
+  };
+
+  const int nstages = (kreal + TC_BK - 1) / TC_BK;
+  uint32_t parity = 0;
+  load_stage(0);
+  for (int st = 0; st < nstages; ++st) {
+    store_stage();
+    // generic-proxy smem writes -> visible to the tensor core (async proxy), then CTA barrier
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+      for (int kk = 0; kk < TC_BK / 8; ++kk) {     // one instruction covers K = 8 = two 16-byte chunks
+        const uint64_t dAh = umma_desc(aAh + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+        const uint64_t dAl = umma_desc(aAl + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+        const uint64_t dBh = umma_desc(aBh + kk * 2 * TC_LBO_B, TC_LBO_B, TC_SBO);
+        const uint64_t dBl = umma_desc(aBl + kk * 2 * TC_LBO_B, TC_LBO_B, TC_SBO);
+        umma_tf32(tmem_d, dAh, dBh, (st | kk) != 0);
+        umma_tf32(tmem_d, dAh, dBl, 1u);
+        umma_tf32(tmem_d, dAl, dBh, 1u);
+      }
+      // arrives on the mbarrier once every MMA issued so far has finished reading smem / writing TMEM
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mma_bar))
+                   : "memory");
+    }
+    if (st + 1 < nstages) load_stage((st + 1) * TC_BK);   // global loads overlap the MMAs
+    while (!mbar_try_wait(smem_u32(&mma_bar), parity)) {
+    }
+    parity ^= 1u;
+  }
+
+  // ---- epilogue: TMEM -> registers -> global (row i' contiguous in memory) -----------------------
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const int ip = blockIdx.x * TC_BM + warp * 32 + lane;     // real output row of this thread (its TMEM lane)
+  const int64_t ld2 = 2 * ld;
+#pragma unroll 1
+  for (int cb = 0; cb < TC_BN; cb += 32) {
+    uint32_t r[32];
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    if (ip < kreal) {
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int64_t c = c0 + cb + q;
+        if (c < ncols) out[c * ld2 + ip] = __uint_as_float(r[q]);   // a warp writes 32 consecutive floats
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)TC_BN));
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_mmse_dense(const float *W, int32_t np, const float *in, float *out, int64_t ncols, int64_t ld,
+                              void *stream) {
+  B2C_REQUIRE(W && in && out, B2C_E_ARG, "b2c_mmse_dense: null argument");
+  B2C_REQUIRE(np >= 1 && ld >= np && ncols >= 0, B2C_E_ARG, "b2c_mmse_dense: np=%d ld=%lld ncols=%lld", np, (long long)ld,
+              (long long)ncols);
+  B2C_REQUIRE(in != out, B2C_E_ARG, "b2c_mmse_dense: in-place not supported");
+  if (ncols == 0) return B2C_OK;
+  dim3 grid((unsigned)((2 * np + TC_BM - 1) / TC_BM), (unsigned)((ncols + TC_BN - 1) / TC_BN));
+  B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_mmse_dense: ncols=%lld too large for one launch", (long long)ncols);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2C_CUDA(cudaFuncSetAttribute(mmse_dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    attr_set = true;
+  }
+  mmse_dense_tc_kernel<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2 *>(W), np, reinterpret_cast<const float2 *>(in), out, ncols, ld);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}

@@ -101,8 +101,8 @@ class SlotEngine:
     def _vec(self, v, B, dtype):
         if isinstance(v, torch.Tensor):
             return v.to(device=self.device, dtype=dtype).contiguous()
-        a = np.broadcast_to(np.asarray(v), (B,))
-        return torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dtype)
+        a = np.array(np.broadcast_to(np.asarray(v), (B,)))     # writable copy (torch.from_numpy needs one)
+        return torch.from_numpy(a).to(device=self.device, dtype=dtype)
 
     def _slots(self, B, model_id, doppler_hz, snr_db, pattern_id, slot0, seed):
         keep = (self._vec(model_id, B, torch.int32), self._vec(doppler_hz, B, torch.float32),

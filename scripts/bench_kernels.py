@@ -1,0 +1,84 @@
+"""Per-kernel micro-benchmarks on one B200 (CUDA events, 3 warm-ups, inputs >> L2 where it matters).
+Writes one JSON object; the numbers go to profiles/kernels_rNN.json.  bench.py remains the headline."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "channel-estimation-in-5g-network_b200")):
+    sys.path.insert(0, p)
+from engine import SlotEngine  # noqa: E402
+
+PEAK_HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n * 1e-3
+
+
+def cfg(ntx, nrx):
+    return {"ofdm": {"fft_size": 1024, "cp_length": 72, "num_symbols": 14, "useful_subcarriers": 600, "subcarrier_spacing": 15000},
+            "mimo": {"num_tx_antennas": ntx, "num_rx_antennas": nrx}}
+
+
+res = {"peak_hbm_gbs": PEAK_HBM}
+eng = SlotEngine(cfg(4, 4))
+dev = eng.device
+pool = eng.random_pool([0.10], seed=42)
+
+# K4 dense Wiener GEMM: W 838x838 complex, columns = slots x rx
+npil = 838
+W = (torch.randn(npil, npil, dtype=torch.complex64, device=dev) / np.sqrt(npil)).contiguous()
+for ncols in (4096, 16384):
+    h = torch.randn(ncols, npil, dtype=torch.complex64, device=dev)
+    t = timeit(lambda: eng.mmse_dense(W, h), n=5)
+    flops = 8.0 * npil * npil * ncols
+    ref = (h[:64].to(torch.complex128) @ W.to(torch.complex128).T)
+    err = ((eng.mmse_dense(W, h)[:64].to(torch.complex128) - ref).abs().max() / ref.abs().max()).item()
+    res[f"k4_mmse_dense_{ncols}cols"] = {"ms": t * 1e3, "useful_tflops": flops / t / 1e12, "issued_tf32_tflops": 3 * flops / t / 1e12,
+                                          "rel_err_vs_fp64": err}
+
+# K3 stand-alone LS + MMSE + stats on resident rx / H_true
+B = 2048
+out = eng.run(B, 2, 200.0, 10.0, 0, pool, slot0=0, seed=1)
+rx, Ht = out["rx"], out["H_true"]
+tx_p = out["tx"][:, :, 0].reshape(B, -1)[:, torch.from_numpy(pool.pilot_indices[0]).to(dev)].contiguous()
+t = timeit(lambda: eng.ls_interp(rx, tx_p, pool, snr_db=10.0, mmse=True, H_true=Ht, want=("H_ls", "H_mmse", "stats")), n=5)
+bytes_k3 = B * (rx[0].numel() * 8 + 3 * Ht[0].numel() * 8)      # read rx + H_true, write H_ls + H_mmse
+res["k3_ls_interp_mmse_stats"] = {"ms": t * 1e3, "gbs": bytes_k3 / t / 1e9, "frac_hbm": bytes_k3 / t / 1e9 / PEAK_HBM, "slots": B}
+del out, rx, Ht
+torch.cuda.empty_cache()
+
+# K2 OFDM modulate / demodulate
+e1 = SlotEngine(cfg(1, 1))
+rows = 14 * 4 * 16384
+x = torch.randn(rows, 599, dtype=torch.complex64, device=dev)
+t = timeit(lambda: e1.ofdm_modulate(x), n=5)
+bm = rows * (599 + 1096) * 8
+res["k2_ofdm_modulate"] = {"ms": t * 1e3, "gbs": bm / t / 1e9, "frac_hbm": bm / t / 1e9 / PEAK_HBM, "rows": rows}
+y = e1.ofdm_modulate(x)
+t = timeit(lambda: e1.ofdm_demodulate(y), n=5)
+res["k2_ofdm_demodulate"] = {"ms": t * 1e3, "gbs": bm / t / 1e9, "frac_hbm": bm / t / 1e9 / PEAK_HBM, "rows": rows}
+del x, y
+torch.cuda.empty_cache()
+
+# K1a tap gains alone, and simulate-only (no estimation outputs)
+B = 4096
+ws = eng.workspace(B)
+o = eng.alloc_outputs(B, ("H_true", "rx", "tx"))
+t = timeit(lambda: eng.run(B, 2, 200.0, 10.0, want=("H_true", "rx", "tx"), out=o, ws=ws), n=5)
+bs = B * (o["H_true"][0].numel() + o["rx"][0].numel() + o["tx"][0].numel()) * 8
+res["k1_simulate_only"] = {"ms": t * 1e3, "gbs": bs / t / 1e9, "frac_hbm": bs / t / 1e9 / PEAK_HBM, "slots_per_s": B / t}
+print(json.dumps(res))

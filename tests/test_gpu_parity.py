@@ -322,6 +322,14 @@ def test_dense_wiener_path(engines):
     X = rng.standard_normal((c, n)) + 1j * rng.standard_normal((c, n))
     Y = eng.mmse_dense(torch.from_numpy(A).to(dev, torch.complex64), torch.from_numpy(X).to(dev, torch.complex64))
     assert relerr(Y.cpu().numpy(), X @ A.T) < RTOL
+    # full-size Wiener matrix (838 pilots), ragged column count, padded leading dimension: the 3xTF32
+    # tensor-core path stays at fp32-level accuracy (plain TF32 would sit near 5e-4)
+    n, c, ld = 838, 300, 840
+    A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)
+    X = np.zeros((c, ld), complex)
+    X[:, :n] = rng.standard_normal((c, n)) + 1j * rng.standard_normal((c, n))
+    Y = eng.mmse_dense(torch.from_numpy(A).to(dev, torch.complex64), torch.from_numpy(X).to(dev, torch.complex64)).cpu().numpy()
+    assert relerr(Y[:, :n], X[:, :n] @ A.T) < 5e-6 and not Y[:, n:].any()
 
 
 def test_error_reporting(engines):
