@@ -235,8 +235,8 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
   const int64_t slot_h = (int64_t)nsym * nrx * ntx * nsc;
   const int nre = nsym * nsc;
   float2 *const Hb = (FAST || a.H_true) ? a.H_true + c.b * slot_h : nullptr;
-  float2 *const Lb = (FAST || (EST && a.H_ls)) ? a.H_ls + c.b * slot_h : nullptr;
-  float2 *const Mb = (FAST || (EST && a.H_mmse)) ? a.H_mmse + c.b * slot_h : nullptr;
+  float2 *const Lb = (EST && (FAST || a.H_ls)) ? a.H_ls + c.b * slot_h : nullptr;
+  float2 *const Mb = (EST && (FAST || a.H_mmse)) ? a.H_mmse + c.b * slot_h : nullptr;
   float2 *const Rb = (FAST || a.rx) ? a.rx + c.b * (int64_t)nsym * nrx * nsc : nullptr;
   float2 *const Tb = ((FAST || a.tx) && c.rx == 0) ? a.tx + c.b * (int64_t)nsym * ntx * nsc : nullptr;
   const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * (nre + 1) : nullptr;
@@ -469,18 +469,19 @@ static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t s
 }
 
 // Fast path: the throughput configuration -- default grid (599 used bins), power-of-two TX count,
-// even symbol count, Philox draws, every output requested.  Everything else (parity runs with
+// even symbol count, Philox draws, every output of the call's kind requested (simulate-only: H, rx, tx;
+// with estimation: all five arrays + stats).  Everything else (parity runs with
 // injected draws, partial outputs, other geometries) takes the generic instantiation.
 template <bool EST>
 static int launch_slot_ntx(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
   const int ntx = a.g.ntx;
-  const bool fast = EST && a.g.nsc == 599 && (a.g.nsym & 1) == 0 && !a.has_inj && a.H_true && a.rx && a.tx &&
-                    a.H_ls && a.H_mmse && a.stats;
+  const bool fast = a.g.nsc == 599 && (a.g.nsym & 1) == 0 && !a.has_inj && a.H_true && a.rx && a.tx &&
+                    (!EST || (a.H_ls && a.H_mmse && a.stats));
   if (fast) {
-    if (ntx == 1) return launch_slot<1, true, true, 599, true>(a, B, smem, stream);
-    if (ntx == 2) return launch_slot<2, true, true, 599, true>(a, B, smem, stream);
-    if (ntx == 4) return launch_slot<4, true, true, 599, true>(a, B, smem, stream);
-    if (ntx == 8) return launch_slot<8, true, true, 599, true>(a, B, smem, stream);
+    if (ntx == 1) return launch_slot<1, true, EST, 599, true>(a, B, smem, stream);
+    if (ntx == 2) return launch_slot<2, true, EST, 599, true>(a, B, smem, stream);
+    if (ntx == 4) return launch_slot<4, true, EST, 599, true>(a, B, smem, stream);
+    if (ntx == 8) return launch_slot<8, true, EST, 599, true>(a, B, smem, stream);
   }
   if (ntx <= 1) return launch_slot<1, false, EST, 0, false>(a, B, smem, stream);
   if (ntx <= 2) return launch_slot<2, false, EST, 0, false>(a, B, smem, stream);
