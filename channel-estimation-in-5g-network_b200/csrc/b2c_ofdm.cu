@@ -1,106 +1,136 @@
-// K2: OFDM modulate / demodulate.  1024-point radix-4 Stockham FFT in shared memory fused with the
-// subcarrier map, (i)fftshift, 1/sqrt(N) scaling and cyclic-prefix insert / strip.
-// Replaces OFDMSystem.modulate / demodulate (src/channel_simulator.py:150-203).
+// K2: OFDM modulate / demodulate.  Replaces OFDMSystem.modulate / demodulate
+// (src/channel_simulator.py:150-203): subcarrier map, (i)fftshift, 1024-point (I)FFT with the
+// sqrt(N) scaling, cyclic-prefix insert / strip -- fused into one pass over HBM.
+//
+// One WARP per OFDM symbol row, no block barriers: the 1024-point transform is factored 32 x 32.
+// Lane l loads x[32*n1 + l] (coalesced), runs a 32-point radix-2 FFT entirely in registers, applies
+// the inter-stage twiddles W_1024^(l*k1) from a CTA-shared table, transposes through a padded
+// per-warp shared-memory tile (the only shared-memory round trip), runs the second 32-point FFT in
+// registers and stores X[l + 32*k2] (coalesced).  The subcarrier map / shift is index arithmetic
+// on the loads (modulate) or stores (demodulate); the cyclic prefix is a second predicated store.
 #include "b2c_common.cuh"
 
 namespace b2c {
 
 constexpr int FFT_N = 1024;
-constexpr int FFT_THREADS = FFT_N / 4;
+constexpr int OFDM_WARPS = 8;
+constexpr int OFDM_THREADS = OFDM_WARPS * 32;
+constexpr int OFDM_SMEM = (1024 + OFDM_WARPS * 32 * 33) * (int)sizeof(float2);
 
-// Shifted-domain index of used bin k (src/channel_simulator.py:141-148): a contiguous block
-// centred on DC with DC itself removed.
-__device__ __forceinline__ int used_bin(int k, int nsc) {
-  int useful = nsc + 1;
-  return FFT_N / 2 - useful / 2 + k + (k >= useful / 2 ? 1 : 0);
+__device__ constexpr float C32[16] = {1.f, 0.98078528f, 0.923879533f, 0.831469612f, 0.707106781f, 0.555570233f,
+                                      0.382683432f, 0.195090322f, 0.f, -0.195090322f, -0.382683432f, -0.555570233f,
+                                      -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f};
+__device__ constexpr float S32[16] = {0.f, 0.195090322f, 0.382683432f, 0.555570233f, 0.707106781f, 0.831469612f,
+                                      0.923879533f, 0.98078528f, 1.f, 0.98078528f, 0.923879533f, 0.831469612f,
+                                      0.707106781f, 0.555570233f, 0.382683432f, 0.195090322f};
+
+__host__ __device__ constexpr int bitrev5(int i) {
+  return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
 }
 
-// One radix-4 Stockham pass.  tw[m] = exp(-j 2 pi m / N); INV conjugates.
+// 32-point radix-2 decimation-in-frequency FFT in registers (fully unrolled, compile-time twiddles).
+// Output is left in bit-reversed order: natural bin k is x[bitrev5(k)].
 template <bool INV>
-__device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, float2 *__restrict__ dst,
-                                              const float2 *__restrict__ tw, int Ns) {
-  const int j = threadIdx.x;
-  const int k = j & (Ns - 1);
-  const int step = FFT_N / (4 * Ns);
-  float2 v0 = src[j], v1 = src[j + FFT_N / 4], v2 = src[j + FFT_N / 2], v3 = src[j + 3 * FFT_N / 4];
-  float2 w1 = tw[(k * step) & (FFT_N - 1)], w2 = tw[(2 * k * step) & (FFT_N - 1)],
-         w3 = tw[(3 * k * step) & (FFT_N - 1)];
-  if (INV) {
-    w1.y = -w1.y;
-    w2.y = -w2.y;
-    w3.y = -w3.y;
-  }
-  v1 = cmul(v1, w1);
-  v2 = cmul(v2, w2);
-  v3 = cmul(v3, w3);
-  float2 a = cadd(v0, v2), b = make_float2(v0.x - v2.x, v0.y - v2.y);
-  float2 c = cadd(v1, v3), d = make_float2(v1.x - v3.x, v1.y - v3.y);
-  // forward: multiply d by -j ; inverse: by +j
-  float2 dj = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
-  const int j0 = ((j - k) << 2) + k;
-  dst[j0] = cadd(a, c);
-  dst[j0 + Ns] = cadd(b, dj);
-  dst[j0 + 2 * Ns] = make_float2(a.x - c.x, a.y - c.y);
-  dst[j0 + 3 * Ns] = make_float2(b.x - dj.x, b.y - dj.y);
-}
-
-template <bool INV>
-__device__ __forceinline__ float2 *fft1024(float2 *a, float2 *b, const float2 *tw) {
+__device__ __forceinline__ void fft32(float2 (&x)[32]) {
 #pragma unroll
-  for (int Ns = 1; Ns < FFT_N; Ns <<= 2) {
-    __syncthreads();
-    stockham_pass<INV>(a, b, tw, Ns);
-    float2 *t = a;
-    a = b;
-    b = t;
-  }
-  __syncthreads();
-  return a;   // buffer holding the result (5 passes: the second buffer)
-}
-
-__global__ void __launch_bounds__(FFT_THREADS) ofdm_modulate_kernel(b2c_geom g, const float2 *__restrict__ in,
-                                                                    float2 *__restrict__ out, int64_t rows) {
-  __shared__ float2 buf0[FFT_N], buf1[FFT_N], tw[FFT_N];
-  for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) {
-    float s, c;
-    sincospif(-2.0f * (float)i / (float)FFT_N, &s, &c);
-    tw[i] = make_float2(c, s);
-  }
-  const int nsc = g.nsc, cp = g.cp_length;
-  const float scale = rsqrtf((float)FFT_N);   // ifft (1/N) * sqrt(N)
-  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) buf0[i] = make_float2(0.f, 0.f);
-    __syncthreads();
-    // freq_domain[used] = symbols; ifftshift: natural bin = (shifted + N/2) mod N
-    for (int k = threadIdx.x; k < nsc; k += FFT_THREADS)
-      buf0[(used_bin(k, nsc) + FFT_N / 2) & (FFT_N - 1)] = __ldg(in + r * nsc + k);
-    float2 *t = fft1024<true>(buf0, buf1, tw);
-    float2 *o = out + r * (FFT_N + cp);
-    for (int i = threadIdx.x; i < FFT_N + cp; i += FFT_THREADS) {
-      int n = i < cp ? FFT_N - cp + i : i - cp;   // cyclic prefix = last cp samples
-      o[i] = cscale(scale, t[n]);
+  for (int h = 16; h >= 1; h >>= 1) {
+#pragma unroll
+    for (int blk = 0; blk < 32; blk += 2 * h) {
+#pragma unroll
+      for (int i = 0; i < h; ++i) {
+        const int tw = i * (16 / h);   // W_{2h}^i = W_32^tw
+        const float2 a = x[blk + i], b = x[blk + i + h];
+        x[blk + i] = make_float2(a.x + b.x, a.y + b.y);
+        const float dx = a.x - b.x, dy = a.y - b.y;
+        if (tw == 0) {
+          x[blk + i + h] = make_float2(dx, dy);
+        } else if (tw == 8) {   // multiply by -j (forward) / +j (inverse)
+          x[blk + i + h] = INV ? make_float2(-dy, dx) : make_float2(dy, -dx);
+        } else {
+          const float c = C32[tw], s = INV ? S32[tw] : -S32[tw];
+          x[blk + i + h] = make_float2(fmaf(dx, c, -dy * s), fmaf(dx, s, dy * c));
+        }
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(FFT_THREADS) ofdm_demodulate_kernel(b2c_geom g, const float2 *__restrict__ in,
-                                                                      float2 *__restrict__ out, int64_t rows) {
-  __shared__ float2 buf0[FFT_N], buf1[FFT_N], tw[FFT_N];
-  for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) {
-    float s, c;
-    sincospif(-2.0f * (float)i / (float)FFT_N, &s, &c);
-    tw[i] = make_float2(c, s);
+// 1024-point transform of the 32 values each lane holds (x[n1] = element 32*n1 + lane).  On return
+// lane k1 holds, in bit-reversed register order, X[k1 + 32*k2] = x[bitrev5(k2)].
+template <bool INV>
+__device__ __forceinline__ void fft1024_warp(float2 (&x)[32], float2 (*tile)[33], const float2 (*twid)[32], int lane) {
+  fft32<INV>(x);
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) {
+    float2 v = x[bitrev5(k1)];
+    if (k1 != 0) {
+      float2 w = twid[k1][lane];        // exp(-j 2 pi lane k1 / 1024); conjugate for the inverse
+      if (INV) w.y = -w.y;
+      v = cmul(v, w);
+    }
+    tile[k1][lane] = v;
   }
-  const int nsc = g.nsc, cp = g.cp_length;
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) x[n2] = tile[lane][n2];
+  __syncwarp();
+  fft32<INV>(x);
+}
+
+// used bin index k of natural FFT bin j (or -1): the occupied block is centred on DC with DC removed
+// (src/channel_simulator.py:141-148) and (i)fftshift moves shifted index i to natural bin (i + N/2) mod N.
+__device__ __forceinline__ int used_of_bin(int j, int half) {
+  if (j >= 1 && j < half) return j + half - 1;
+  if (j >= FFT_N - half) return j - (FFT_N - half);
+  return -1;
+}
+
+template <bool MOD>
+__global__ void __launch_bounds__(OFDM_THREADS, 2) ofdm_kernel(b2c_geom g, const float2 *__restrict__ in,
+                                                               float2 *__restrict__ out, int64_t rows) {
+  extern __shared__ __align__(16) float2 ofdm_smem[];
+  float2(*twid)[32] = reinterpret_cast<float2(*)[32]>(ofdm_smem);                    // [32][32]
+  float2(*tiles)[32][33] = reinterpret_cast<float2(*)[32][33]>(ofdm_smem + 1024);    // [warps][32][33]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 1024; i += OFDM_THREADS) {
+    float s, c;
+    sincospif(-2.0f * (float)((i >> 5) * (i & 31)) / (float)FFT_N, &s, &c);
+    twid[i >> 5][i & 31] = make_float2(c, s);
+  }
+  __syncthreads();
+  const int nsc = g.nsc, cp = g.cp_length, half = (g.nsc + 1) / 2;
   const float scale = rsqrtf((float)FFT_N);
-  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
-    __syncthreads();
-    const float2 *x = in + r * (FFT_N + cp) + cp;   // strip the prefix
-    for (int i = threadIdx.x; i < FFT_N; i += FFT_THREADS) buf0[i] = __ldg(x + i);
-    float2 *t = fft1024<false>(buf0, buf1, tw);
-    for (int k = threadIdx.x; k < nsc; k += FFT_THREADS)
-      out[r * nsc + k] = cscale(scale, t[(used_bin(k, nsc) + FFT_N / 2) & (FFT_N - 1)]);
+  const int64_t stride_t = FFT_N + cp;
+  for (int64_t r = (int64_t)blockIdx.x * OFDM_WARPS + warp; r < rows; r += (int64_t)gridDim.x * OFDM_WARPS) {
+    float2 x[32];
+    if (MOD) {
+      const float2 *src = in + r * nsc;
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) {
+        const int k = used_of_bin(32 * n1 + lane, half);
+        x[n1] = k >= 0 ? __ldg(src + k) : make_float2(0.f, 0.f);
+      }
+      fft1024_warp<true>(x, tiles[warp], twid, lane);
+      float2 *dst = out + r * stride_t;
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) {
+        const int n = lane + 32 * k2;
+        const float2 v = cscale(scale, x[bitrev5(k2)]);      // ifft * sqrt(N) = sum / sqrt(N)
+        st_stream(dst + cp + n, v);
+        if (n >= FFT_N - cp) st_stream(dst + n - (FFT_N - cp), v);   // cyclic prefix = last cp samples
+      }
+    } else {
+      const float2 *src = in + r * stride_t + cp;               // strip the prefix
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) x[n1] = __ldg(src + 32 * n1 + lane);
+      fft1024_warp<false>(x, tiles[warp], twid, lane);
+      float2 *dst = out + r * nsc;
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) {
+        const int k = used_of_bin(lane + 32 * k2, half);
+        if (k >= 0) st_stream(dst + k, cscale(scale, x[bitrev5(k2)]));
+      }
+    }
   }
 }
 
@@ -111,17 +141,22 @@ using namespace b2c;
 static int ofdm_check(const b2c_geom *g, const void *in, void *out, int64_t rows, const char *who) {
   B2C_REQUIRE(g && in && out, B2C_E_ARG, "%s: null argument", who);
   B2C_REQUIRE(g->fft_size == FFT_N, B2C_E_UNSUPPORTED, "%s: fft_size=%d (only 1024 is built)", who, g->fft_size);
-  B2C_REQUIRE(g->nsc >= 1 && g->nsc < FFT_N && g->cp_length >= 0 && g->cp_length <= FFT_N, B2C_E_ARG,
-              "%s: nsc=%d cp=%d", who, g->nsc, g->cp_length);
+  B2C_REQUIRE(g->nsc >= 1 && g->nsc < FFT_N && (g->nsc & 1) == 1 && g->cp_length >= 0 && g->cp_length <= FFT_N, B2C_E_ARG,
+              "%s: nsc=%d (odd, < 1024) cp=%d", who, g->nsc, g->cp_length);
   B2C_REQUIRE(rows >= 0, B2C_E_ARG, "%s: rows=%lld", who, (long long)rows);
   return B2C_OK;
+}
+
+static unsigned ofdm_grid(int64_t rows) {
+  int64_t ctas = (rows + OFDM_WARPS - 1) / OFDM_WARPS;
+  return (unsigned)(ctas < 148 * 2 ? ctas : 148 * 2);   // persistent: 2 CTAs per SM, grid-stride over rows
 }
 
 extern "C" int b2c_ofdm_modulate(const b2c_geom *g, const float *in, float *out, int64_t rows, void *stream) {
   if (int rc = ofdm_check(g, in, out, rows, "b2c_ofdm_modulate")) return rc;
   if (rows == 0) return B2C_OK;
-  unsigned grid = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
-  ofdm_modulate_kernel<<<grid, FFT_THREADS, 0, (cudaStream_t)stream>>>(
+  B2C_CUDA(cudaFuncSetAttribute(ofdm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OFDM_SMEM));
+  ofdm_kernel<true><<<ofdm_grid(rows), OFDM_THREADS, OFDM_SMEM, (cudaStream_t)stream>>>(
       *g, reinterpret_cast<const float2 *>(in), reinterpret_cast<float2 *>(out), rows);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
@@ -130,8 +165,8 @@ extern "C" int b2c_ofdm_modulate(const b2c_geom *g, const float *in, float *out,
 extern "C" int b2c_ofdm_demodulate(const b2c_geom *g, const float *in, float *out, int64_t rows, void *stream) {
   if (int rc = ofdm_check(g, in, out, rows, "b2c_ofdm_demodulate")) return rc;
   if (rows == 0) return B2C_OK;
-  unsigned grid = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
-  ofdm_demodulate_kernel<<<grid, FFT_THREADS, 0, (cudaStream_t)stream>>>(
+  B2C_CUDA(cudaFuncSetAttribute(ofdm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OFDM_SMEM));
+  ofdm_kernel<false><<<ofdm_grid(rows), OFDM_THREADS, OFDM_SMEM, (cudaStream_t)stream>>>(
       *g, reinterpret_cast<const float2 *>(in), reinterpret_cast<float2 *>(out), rows);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
