@@ -173,21 +173,28 @@ def equalize_channel(rx_symbols: np.ndarray, H_est: np.ndarray, method: str = 'z
 def evaluate_estimator(H_true: np.ndarray, H_est: np.ndarray) -> dict:
     """mse / nmse / nmse_db over the whole 4-D array (src/baseline_estimators.py:315-337), reduced on
     the GPU by the statistics kernels."""
-    eng = _engine()
-    H_true, H_est = np.asarray(H_true), np.asarray(H_est)
-    shape = H_true.shape
-    nsc = shape[-1]
-    rows = int(np.prod(shape[:-1]))
-    # one "slot" of `rows` single-symbol 1x1 grids: per-element squared errors summed by K3's stats path
-    g = Geom(1, nsc, 1, 1, 1024, 72, 0.0)
-    t = _c64(H_true.reshape(rows, 1, 1, 1, nsc), eng.device)
-    e = _c64(H_est.reshape(rows, 1, 1, nsc), eng.device)
-    stats = _sq_error_stats(eng, t, e, g)
-    tot = stats[:, :, 1].sum(dim=(0, 1)).cpu().numpy()
-    n = rows * nsc
-    mse = tot[0] / n
-    nmse = mse / (tot[2] / n + 1e-12)
+    H_true = np.asarray(H_true)
+    err, pw = squared_error_sums(H_true, H_est)
+    n = H_true.size
+    mse = err / n
+    nmse = mse / (pw / n + 1e-12)
     return {'mse': mse, 'nmse': nmse, 'nmse_db': 10 * np.log10(nmse + 1e-12)}
+
+
+def squared_error_sums(H_true, H_est, width: int = 599):
+    """(sum |H_true - H_est|^2, sum |H_true|^2) over arrays of any shape, reduced on the GPU: the data
+    are laid out as zero-padded rows of `width` and pushed through K3's statistics path."""
+    eng = _engine()
+    t = np.asarray(H_true, dtype=np.complex64).reshape(-1)
+    e = np.asarray(H_est, dtype=np.complex64).reshape(-1)
+    rows = max(1, -(-t.size // width))
+    tp, ep = np.zeros(rows * width, np.complex64), np.zeros(rows * width, np.complex64)
+    tp[:t.size], ep[:e.size] = t, e
+    g = Geom(1, width, 1, 1, 1024, 72, 0.0)
+    stats = _sq_error_stats(eng, _c64(tp.reshape(rows, 1, 1, 1, width), eng.device),
+                            _c64(ep.reshape(rows, 1, 1, width), eng.device), g)
+    tot = stats[:, :, 1].sum(dim=(0, 1)).cpu().numpy()
+    return float(tot[0]), float(tot[2])
 
 
 _IDENTITY_POOLS = {}

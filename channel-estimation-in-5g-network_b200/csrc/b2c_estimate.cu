@@ -21,14 +21,14 @@ struct LsArgs {
 // One CTA per (slot, rx antenna).  The reference's rx_4d is rx replicated over tx
 // (src/dataset_generator.py:63-64), so the LS/MMSE grids are computed once per (slot, rx) and
 // written ntx times.
-template <int NTX>
+template <int NTX, bool EXACT, int NSC>
 __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *hp = reinterpret_cast<float2 *>(smem_raw);
   __shared__ float red[33];
   __shared__ float ssm[EST_THREADS / 32][6];
 
-  const int nsc = a.g.nsc, nsym = a.g.nsym, ntx = a.g.ntx, nrx = a.g.nrx;
+  const int nsc = NSC ? NSC : a.g.nsc, nsym = a.g.nsym, ntx = EXACT ? NTX : a.g.ntx, nrx = a.g.nrx;
   const int64_t b = blockIdx.x / nrx;
   const int rx = blockIdx.x - (int)b * nrx;
   const int pid = a.pattern_id[b];
@@ -61,36 +61,65 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
 
   float st[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // [0] antenna pair (rx, 0), [1] all tx of this rx
 
-  const uint4 *plan = reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)pid * (nsym * nsc + 1);
-  for (int k = threadIdx.x; k < nsc; k += EST_THREADS) {
-    for (int s = 0; s < nsym; ++s) {
-      PlanTap p = plan_decode(__ldg(plan + s * nsc + k));
-      float2 l = plan_apply(p, hp);
-      float2 m = cscale(alpha, l);
-      const int64_t row = ((b * nsym + s) * nrx + rx) * (int64_t)ntx * nsc + k;
+  // Main pass.  Thread t owns bins t and t + EST_THREADS (the grid has at most 2 * EST_THREADS used
+  // bins); all loads of a symbol (2 plan entries, up to 2 * ntx true-channel values) are issued
+  // before anything is consumed.  Per-slot 64-bit bases + 32-bit element offsets; with NSC fixed the
+  // per-tx offsets are immediates.
+  const int nre = nsym * nsc;
+  const uint4 *plan = reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)pid * (nre + 1);
+  const int64_t slot_h = (int64_t)nsym * nrx * ntx * nsc;
+  float2 *const Lb = a.H_ls ? a.H_ls + b * slot_h : nullptr;
+  float2 *const Mb = a.H_mmse ? a.H_mmse + b * slot_h : nullptr;
+  const float2 *const Tb = (a.H_true && a.stats) ? a.H_true + b * slot_h : nullptr;
+  const int k0 = threadIdx.x;
+  const bool v0 = k0 < nsc, v1 = k0 + EST_THREADS < nsc;
+  int oP0 = v0 ? k0 : nre, oP1 = v1 ? k0 + EST_THREADS : nre;      // row nre = the all-outside entry
+  const int dP0 = v0 ? nsc : 0, dP1 = v1 ? nsc : 0;
+  int oH = rx * ntx * nsc + k0;
+  const int dH = nrx * ntx * nsc;
+  const float2 zero2 = make_float2(0.f, 0.f);
+#pragma unroll 2
+  for (int sy = 0; sy < nsym; ++sy) {
+    const uint4 e0 = __ldg(plan + oP0), e1 = __ldg(plan + oP1);
+    float2 h0[NTX], h1[NTX];
 #pragma unroll
-      for (int tx = 0; tx < NTX; ++tx) {
-        if (tx < ntx) {
-          const int64_t o = row + (int64_t)tx * nsc;
-          if (a.H_ls) st_stream(a.H_ls + o, l);
-          if (a.H_mmse) st_stream(a.H_mmse + o, m);
-          if (a.H_true && a.stats) {
-            float2 h = __ldg(a.H_true + o);
-            const float e_ls = cabs2(make_float2(h.x - l.x, h.y - l.y));
-            const float e_mm = cabs2(make_float2(h.x - m.x, h.y - m.y));
-            const float pw = cabs2(h);
-            st[1][0] += e_ls;
-            st[1][1] += e_mm;
-            st[1][2] += pw;
-            if (tx == 0) {
-              st[0][0] += e_ls;
-              st[0][1] += e_mm;
-              st[0][2] += pw;
-            }
+    for (int tx = 0; tx < NTX; ++tx) {
+      const bool on = (EXACT || tx < ntx) && Tb != nullptr;
+      h0[tx] = (on && v0) ? __ldg(Tb + oH + tx * nsc) : zero2;
+      h1[tx] = (on && v1) ? __ldg(Tb + oH + tx * nsc + EST_THREADS) : zero2;
+    }
+    const float2 l0 = plan_apply(plan_decode(e0), hp), l1 = plan_apply(plan_decode(e1), hp);
+    const float2 m0 = cscale(alpha, l0), m1 = cscale(alpha, l1);
+#pragma unroll
+    for (int tx = 0; tx < NTX; ++tx) {
+      if (EXACT || tx < ntx) {
+        const int o = oH + tx * nsc;
+        if (Lb) {
+          if (v0) st_stream(Lb + o, l0);
+          if (v1) st_stream(Lb + o + EST_THREADS, l1);
+        }
+        if (Mb) {
+          if (v0) st_stream(Mb + o, m0);
+          if (v1) st_stream(Mb + o + EST_THREADS, m1);
+        }
+        if (Tb) {   // idle lanes hold h = l = 0 and add nothing
+          const float e_ls = cabs2(make_float2(h0[tx].x - l0.x, h0[tx].y - l0.y)) + cabs2(make_float2(h1[tx].x - l1.x, h1[tx].y - l1.y));
+          const float e_mm = cabs2(make_float2(h0[tx].x - m0.x, h0[tx].y - m0.y)) + cabs2(make_float2(h1[tx].x - m1.x, h1[tx].y - m1.y));
+          const float pw = cabs2(h0[tx]) + cabs2(h1[tx]);
+          st[1][0] += e_ls;
+          st[1][1] += e_mm;
+          st[1][2] += pw;
+          if (tx == 0) {
+            st[0][0] += e_ls;
+            st[0][1] += e_mm;
+            st[0][2] += pw;
           }
         }
       }
     }
+    oP0 += dP0;
+    oP1 += dP1;
+    oH += dH;
   }
 
   if (a.stats) {
@@ -111,10 +140,10 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
   }
 }
 
-template <int NTX>
+template <int NTX, bool EXACT, int NSC>
 static int launch_ls(const LsArgs &a, int64_t B, cudaStream_t stream) {
   size_t smem = (size_t)(a.pat.np_max + 1) * sizeof(float2);
-  auto kern = ls_interp_kernel<NTX>;
+  auto kern = ls_interp_kernel<NTX, EXACT, NSC>;
   if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(B * a.g.nrx), EST_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
@@ -205,7 +234,7 @@ extern "C" int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const i
                              const float *H_true, float *H_ls, float *H_mmse, float *hp_out, double *stats,
                              void *stream) {
   B2C_REQUIRE(g && pat && pattern_id, B2C_E_ARG, "b2c_ls_interp: null argument");
-  B2C_REQUIRE(g->nsym >= 1 && g->nsc >= 1 && g->nsym * (int64_t)g->nsc <= (1 << 22) && g->ntx >= 1 &&
+  B2C_REQUIRE(g->nsym >= 1 && g->nsc >= 1 && g->nsc <= 2 * EST_THREADS && g->ntx >= 1 &&
                   g->ntx <= B2C_MAX_ANT && g->nrx >= 1 && g->nrx <= B2C_MAX_ANT * B2C_MAX_ANT,
               B2C_E_UNSUPPORTED, "b2c_ls_interp: geometry %dx%d grid, %dx%d antennas unsupported", g->nsym, g->nsc,
               g->ntx, g->nrx);
@@ -234,10 +263,16 @@ extern "C" int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const i
   a.hp_out = reinterpret_cast<float2 *>(hp_out);
   a.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g->ntx <= 1) return launch_ls<1>(a, B, st);
-  if (g->ntx <= 2) return launch_ls<2>(a, B, st);
-  if (g->ntx <= 4) return launch_ls<4>(a, B, st);
-  return launch_ls<8>(a, B, st);
+  if (g->nsc == 599) {   // default grid, power-of-two TX count: compile-time offsets
+    if (g->ntx == 1) return launch_ls<1, true, 599>(a, B, st);
+    if (g->ntx == 2) return launch_ls<2, true, 599>(a, B, st);
+    if (g->ntx == 4) return launch_ls<4, true, 599>(a, B, st);
+    if (g->ntx == 8) return launch_ls<8, true, 599>(a, B, st);
+  }
+  if (g->ntx <= 1) return launch_ls<1, false, 0>(a, B, st);
+  if (g->ntx <= 2) return launch_ls<2, false, 0>(a, B, st);
+  if (g->ntx <= 4) return launch_ls<4, false, 0>(a, B, st);
+  return launch_ls<8, false, 0>(a, B, st);
 }
 
 extern "C" int b2c_stats_bins(const b2c_geom *g, const double *stats, const int32_t *bin_id, int64_t B,

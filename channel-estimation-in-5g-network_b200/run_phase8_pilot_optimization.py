@@ -19,16 +19,10 @@ from utils import linear2db, load_config
 
 def compute_nmse(H_est: np.ndarray, H_true: np.ndarray) -> float:
     """mean|H_est - H_true|^2 / (mean|H_true|^2 + 1e-10) (run_phase8_pilot_optimization.py:32-37), on the GPU."""
-    from baseline_estimators import _c64, _engine, _sq_error_stats
-    from _b2c import Geom
-    eng = _engine()
-    H_est, H_true = np.asarray(H_est), np.asarray(H_true)
-    nsc = H_true.shape[-1]
-    rows = H_true.size // nsc
-    st = _sq_error_stats(eng, _c64(H_true.reshape(rows, 1, 1, 1, nsc), eng.device),
-                         _c64(H_est.reshape(rows, 1, 1, nsc), eng.device), Geom(1, nsc, 1, 1, 1024, 72, 0.0))
-    tot = st[:, :, 1].sum(dim=(0, 1)).cpu().numpy()
-    return float((tot[0] / H_true.size) / (tot[2] / H_true.size + 1e-10))
+    from baseline_estimators import squared_error_sums
+    n = np.asarray(H_true).size
+    err, pw = squared_error_sums(H_true, H_est)
+    return float((err / n) / (pw / n + 1e-10))
 
 
 class PilotOptimizer:
