@@ -398,3 +398,40 @@ def pool_inside(pool):
     import _tables
     plan = _tables.cached_plan(pool.pilot_indices[0], pool.nsym, pool.nsc, pool.method)
     return plan["flags"].astype(bool).reshape(pool.nsym, pool.nsc)
+
+
+@pytest.mark.parametrize("ntx,nrx,nsym,useful,model", [(3, 2, 7, 300, "EVA"), (1, 3, 5, 72, "EPA"), (8, 8, 14, 600, "ETU"),
+                                                       (2, 5, 16, 640, "ETU")])
+def test_other_geometries_generic_path(ntx, nrx, nsym, useful, model):
+    """Non-default grids (odd symbol counts, other subcarrier counts, non power-of-two antenna
+    counts, the 8x8 / 16-symbol / 639-bin limits) run the generic instantiations; same parity bar."""
+    from engine import SlotEngine
+    cfg = {"ofdm": {"fft_size": 1024, "cp_length": 72, "num_symbols": nsym, "useful_subcarriers": useful,
+                    "subcarrier_spacing": 15000}, "mimo": {"num_tx_antennas": ntx, "num_rx_antennas": nrx}}
+    eng = SlotEngine(cfg)
+    nsc = useful - 1
+    assert eng.nsc == nsc
+    dens = 0.08
+    pool = eng.random_pool([dens], seed=5)
+    B, seed, slot0, snr, fd = 2, 99, 7, 12.0, 70.0
+    out = eng.run(B, eng.models.index(model), fd, snr, 0, pool, slot0=slot0, seed=seed)
+    torch.cuda.synchronize()
+    mask = pool.mask(0)
+    for i in range(B):
+        d = opx.slot_draws(seed, slot0 + i, nsym, nsc, len(orc.TDL_NS[model]), ntx, nrx, mask)
+        d["perm"] = np.concatenate([pool.pilot_indices[0], np.setdiff1d(np.arange(nsym * nsc), pool.pilot_indices[0])])
+        ref = orc.slot_pipeline(cfg["ofdm"], ntx, nrx, model, fd, snr, dens, d)
+        assert np.array_equal(ref["pilot_mask"], mask)
+        for k, rk in (("H_true", "channel"), ("rx", "rx_symbols"), ("tx", "tx_symbols"), ("H_ls", "H_ls"), ("H_mmse", "H_mmse")):
+            assert relerr(out[k][i].cpu().numpy(), ref[rk]) < RTOL, (k, i)
+        st = out["stats"][i].cpu().numpy()
+        m_ls = orc.evaluate(ref["channel"], ref["H_ls"])
+        tot = st[:, 1].sum(axis=0) / ref["channel"].size
+        assert abs(db(tot[0] / (tot[2] + 1e-12)) - m_ls["nmse_db"]) < DB_TOL
+        assert abs(st[0, 0, 0] / (nsym * nsc) / (st[0, 0, 2] / (nsym * nsc) + 1e-10) / orc.nmse_pair00(ref["H_ls"], ref["channel"]) - 1) < 1e-4
+    # stand-alone K3 on the same grids
+    rx, Ht = out["rx"], out["H_true"]
+    xp = out["tx"][:, :, 0].reshape(B, -1)[:, torch.from_numpy(pool.pilot_indices[0]).to(eng.device)].contiguous()
+    k3 = eng.ls_interp(rx, xp, pool, snr_db=snr, mmse=True, H_true=Ht, want=("H_ls", "H_mmse", "stats"))
+    assert (k3["H_ls"] - out["H_ls"]).abs().max().item() < 2e-5 and (k3["H_mmse"] - out["H_mmse"]).abs().max().item() < 2e-5
+    assert torch.allclose(k3["stats"], out["stats"], rtol=1e-4)
