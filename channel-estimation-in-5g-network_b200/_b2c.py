@@ -63,7 +63,7 @@ def lib():
         P, I64, I32, F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
         sig = {
             "b2c_tap_gains": [P, P, P, P, I64, P, P, P],
-            "b2c_slot_pipeline": [P, P, P, P, P, I64, P, P, P, P, P, P, P, P, P],
+            "b2c_slot_pipeline": [P, P, P, P, P, I64, P, P, P, P, P, P, P, P, I32, P],
             "b2c_ls_interp": [P, P, P, P, I64, P, P, I64, P, I32, P, P, P, P, P, P],
             "b2c_pilot_vectors": [P, P, I64, I32, F, I32, P, P],
             "b2c_mmse_dense": [P, I32, P, P, I64, I64, P],

@@ -144,6 +144,7 @@ struct SlotArgs {
   const float *noise_std;
   float2 *H_true, *rx, *tx, *H_ls, *H_mmse;
   double *stats;
+  int compact;   // 1: tx-replicated outputs written once (H_ls/H_mmse [B][nsym][nrx][nsc], tx [B][nsym][nsc])
 };
 
 struct SlotCtx {
@@ -235,10 +236,12 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
   const int64_t slot_h = (int64_t)nsym * nrx * ntx * nsc;
   const int nre = nsym * nsc;
   float2 *const Hb = (FAST || a.H_true) ? a.H_true + c.b * slot_h : nullptr;
-  float2 *const Lb = (EST && (FAST || a.H_ls)) ? a.H_ls + c.b * slot_h : nullptr;
-  float2 *const Mb = (EST && (FAST || a.H_mmse)) ? a.H_mmse + c.b * slot_h : nullptr;
-  float2 *const Rb = (FAST || a.rx) ? a.rx + c.b * (int64_t)nsym * nrx * nsc : nullptr;
-  float2 *const Tb = ((FAST || a.tx) && c.rx == 0) ? a.tx + c.b * (int64_t)nsym * ntx * nsc : nullptr;
+  const bool compact = !FAST && a.compact;   // compact layout: generic instantiation only
+  const int64_t slot_r = (int64_t)nsym * nrx * nsc;
+  float2 *const Lb = (EST && (FAST || a.H_ls)) ? a.H_ls + c.b * (compact ? slot_r : slot_h) : nullptr;
+  float2 *const Mb = (EST && (FAST || a.H_mmse)) ? a.H_mmse + c.b * (compact ? slot_r : slot_h) : nullptr;
+  float2 *const Rb = (FAST || a.rx) ? a.rx + c.b * slot_r : nullptr;
+  float2 *const Tb = ((FAST || a.tx) && c.rx == 0) ? a.tx + c.b * (int64_t)nsym * (compact ? 1 : ntx) * nsc : nullptr;
   const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * (nre + 1) : nullptr;
   const bool inj = !FAST && a.has_inj;
   const float2 *inj_noise = inj ? reinterpret_cast<const float2 *>(a.inj.noise) + c.b * (int64_t)nsym * nrx * nsc : nullptr;
@@ -249,7 +252,7 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
   int oT = k0;                      //                   tx[s][0][k0]
   int oP0 = v0 ? k0 : nre, oP1 = v1 ? k0 + SLOT_THREADS : nre;   // plan rows; row nre = "outside" for idle lanes
   const int dP0 = v0 ? nsc : 0, dP1 = v1 ? nsc : 0;
-  const int dH = nrx * ntx * nsc, dR = nrx * nsc, dT = ntx * nsc;
+  const int dH = nrx * ntx * nsc, dR = nrx * nsc, dT = (compact ? 1 : ntx) * nsc;
   const float4 *gps = c.gsp;
   const bool need_draws = FAST || Rb != nullptr || a.tx != nullptr;   // H-only calls skip the draws
 
@@ -299,13 +302,14 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
               if (v1) st_stream(Hb + o + SLOT_THREADS, h1);
             }
             if (EST) {
-              if (FAST || Lb) {
-                if (v0) st_stream(Lb + o, l0);
-                if (v1) st_stream(Lb + o + SLOT_THREADS, l1);
+              const int oe = compact ? oR : o;          // compact: one copy per (s, rx), rx's offsets
+              if ((FAST || Lb) && (!compact || tx == 0)) {
+                if (v0) st_stream(Lb + oe, l0);
+                if (v1) st_stream(Lb + oe + SLOT_THREADS, l1);
               }
-              if (FAST || Mb) {
-                if (v0) st_stream(Mb + o, cscale(c.alpha, l0));
-                if (v1) st_stream(Mb + o + SLOT_THREADS, cscale(c.alpha, l1));
+              if ((FAST || Mb) && (!compact || tx == 0)) {
+                if (v0) st_stream(Mb + oe, cscale(c.alpha, l0));
+                if (v1) st_stream(Mb + oe + SLOT_THREADS, cscale(c.alpha, l1));
               }
               // squared errors: d = h - l and h - alpha*l as one packed FMA each; idle lanes add zeros.
               // Accumulated over all tx ([1]) and, for the pair-(0,0) NMSE of the pilot sweep, for tx 0 ([0]).
@@ -355,7 +359,7 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
         if (Tb) {   // the rx-0 CTA writes the (tx-replicated) grid
 #pragma unroll
           for (int tx = 0; tx < NTX; ++tx) {
-            if (EXACT || tx < ntx) {
+            if ((EXACT || tx < ntx) && (!compact || tx == 0)) {
               if (v0) st_stream(Tb + oT + tx * nsc, x0);
               if (v1) st_stream(Tb + oT + tx * nsc + SLOT_THREADS, x1);
             }
@@ -475,7 +479,7 @@ static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t s
 template <bool EST>
 static int launch_slot_ntx(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
   const int ntx = a.g.ntx;
-  const bool fast = a.g.nsc == 599 && (a.g.nsym & 1) == 0 && !a.has_inj && a.H_true && a.rx && a.tx &&
+  const bool fast = !a.compact && a.g.nsc == 599 && (a.g.nsym & 1) == 0 && !a.has_inj && a.H_true && a.rx && a.tx &&
                     (!EST || (a.H_ls && a.H_mmse && a.stats));
   if (fast) {
     if (ntx == 1) return launch_slot<1, true, EST, 599, true>(a, B, smem, stream);
@@ -519,7 +523,8 @@ extern "C" int b2c_tap_gains(const b2c_geom *g, const b2c_profiles *prof, const 
 extern "C" int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat,
                                  const b2c_slots *slots, const b2c_inject *inj, int64_t B,
                                  const float *gains, const float *noise_std, float *H_true, float *rx,
-                                 float *tx, float *H_ls, float *H_mmse, double *stats, void *stream) {
+                                 float *tx, float *H_ls, float *H_mmse, double *stats, int32_t compact,
+                                 void *stream) {
   B2C_REQUIRE(g && prof && slots && gains && noise_std, B2C_E_ARG, "b2c_slot_pipeline: null argument");
   if (int rc = check_geom(g)) return rc;
   B2C_REQUIRE(B >= 0 && B * g->nrx < (1ll << 31), B2C_E_ARG, "b2c_slot_pipeline: B=%lld out of range",
@@ -546,6 +551,7 @@ extern "C" int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, co
   a.H_ls = reinterpret_cast<float2 *>(H_ls);
   a.H_mmse = reinterpret_cast<float2 *>(H_mmse);
   a.stats = stats;
+  a.compact = compact != 0;
   size_t smem = slot_smem_bytes(g, est ? pat->np_max : 0);
   B2C_REQUIRE(smem <= 100 * 1024, B2C_E_UNSUPPORTED, "b2c_slot_pipeline: %zu B shared memory needed", smem);
   return est ? launch_slot_ntx<true>(a, B, smem, (cudaStream_t)stream)

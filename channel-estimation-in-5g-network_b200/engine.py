@@ -130,10 +130,12 @@ class SlotEngine:
         return {"gains": torch.empty((B, self.nrx, self.nsym, self.ntx, _b2c.MAX_TAPS), dtype=torch.complex64, device=self.device),
                 "noise_std": torch.empty((B,), dtype=torch.float32, device=self.device)}
 
-    def alloc_outputs(self, B, want):
-        shapes = {"H_true": (B, self.nsym, self.nrx, self.ntx, self.nsc), "H_ls": (B, self.nsym, self.nrx, self.ntx, self.nsc),
-                  "H_mmse": (B, self.nsym, self.nrx, self.ntx, self.nsc), "rx": (B, self.nsym, self.nrx, self.nsc),
-                  "tx": (B, self.nsym, self.ntx, self.nsc)}
+    def alloc_outputs(self, B, want, compact=False):
+        """Output buffers.  compact=True: the tx-replicated arrays (H_ls, H_mmse, tx) hold one copy."""
+        full = (B, self.nsym, self.nrx, self.ntx, self.nsc)
+        est = (B, self.nsym, self.nrx, self.nsc) if compact else full
+        shapes = {"H_true": full, "H_ls": est, "H_mmse": est, "rx": (B, self.nsym, self.nrx, self.nsc),
+                  "tx": (B, self.nsym, self.nsc) if compact else (B, self.nsym, self.ntx, self.nsc)}
         out = {k: torch.empty(shapes[k], dtype=torch.complex64, device=self.device) for k in want if k in shapes}
         if "stats" in want:
             out["stats"] = torch.empty((B, self.nrx, 2, _b2c.N_STAT), dtype=torch.float64, device=self.device)
@@ -141,11 +143,13 @@ class SlotEngine:
 
     # ---- K1a + fused slot kernel -------------------------------------------------------------------
     def run(self, B, model_id, doppler_hz, snr_db, pattern_id=0, pool=None, slot0=0, seed=42, inject=None,
-            want=("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), out=None, ws=None):
+            want=("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), out=None, ws=None, compact=False):
         """Simulate B slots and (if any of H_ls/H_mmse/stats is wanted) estimate them.
-        Per-slot parameters are scalars or length-B arrays/tensors.  Returns dict of CUDA tensors."""
+        Per-slot parameters are scalars or length-B arrays/tensors.  Returns dict of CUDA tensors.
+        compact=True writes the tx-replicated arrays once (see alloc_outputs); expand_compact() turns
+        them into full-shape stride-0 views."""
         if out is None:
-            out = self.alloc_outputs(B, want)
+            out = self.alloc_outputs(B, want, compact)
         if ws is None:
             ws = self.workspace(B)
         est = any(k in out for k in ("H_ls", "H_mmse", "stats"))
@@ -163,9 +167,23 @@ class SlotEngine:
                                   dptr(out.get("H_true"), "c64", True), dptr(out.get("rx"), "c64", True),
                                   dptr(out.get("tx"), "c64", True), dptr(out.get("H_ls"), "c64", True),
                                   dptr(out.get("H_mmse"), "c64", True), dptr(out.get("stats"), "f64", True),
-                                  stream_ptr()), "b2c_slot_pipeline")
+                                  1 if compact else 0, stream_ptr()), "b2c_slot_pipeline")
         out["_keepalive"] = (keep, keep_inj, ws)
         return out
+
+    def expand_compact(self, out):
+        """Full-shape (stride-0 over tx) views of compact outputs; works for torch tensors and numpy arrays."""
+        res = dict(out)
+        for k in ("H_ls", "H_mmse"):
+            if k in out and out[k].ndim == 4:
+                v = out[k][:, :, :, None, :]
+                shape = v.shape[:3] + (self.ntx,) + v.shape[4:]
+                res[k] = v.expand(*shape) if isinstance(v, torch.Tensor) else np.broadcast_to(v, shape)
+        if "tx" in out and out["tx"].ndim == 3:
+            v = out["tx"][:, :, None, :]
+            shape = v.shape[:2] + (self.ntx,) + v.shape[3:]
+            res["tx"] = v.expand(*shape) if isinstance(v, torch.Tensor) else np.broadcast_to(v, shape)
+        return res
 
     # ---- K3 ------------------------------------------------------------------------------------------
     def ls_interp(self, rx, pilots, pool, pattern_id=0, snr_db=None, mmse=False, H_true=None, hp_in=None,

@@ -15,9 +15,12 @@ ARRAYS = ("H_true", "rx", "tx", "H_ls", "H_mmse")
 
 
 class HostPipeline:
-    def __init__(self, engine, pool, chunk=512, want=ARRAYS + ("stats",)):
-        self.eng, self.pool, self.chunk, self.want = engine, pool, chunk, tuple(want)
-        self.dev = [engine.alloc_outputs(chunk, self.want) for _ in range(2)]
+    def __init__(self, engine, pool, chunk=512, want=ARRAYS + ("stats",), compact=False):
+        """compact=True moves the tx-replicated arrays (H_ls, H_mmse, tx) over PCIe once and hands the
+        consumer full-shape NumPy broadcast views (SlotEngine.expand_compact): same values, 48 % fewer
+        bytes for a 4x4 slot."""
+        self.eng, self.pool, self.chunk, self.want, self.compact = engine, pool, chunk, tuple(want), compact
+        self.dev = [engine.alloc_outputs(chunk, self.want, compact) for _ in range(2)]
         self.ws = [engine.workspace(chunk) for _ in range(2)]
         self.host = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in d.items()} for d in self.dev]
         self.par_host = [torch.empty((4, chunk), dtype=torch.float32, pin_memory=True) for _ in range(2)]
@@ -42,7 +45,7 @@ class HostPipeline:
             if pending[i] is not None:                 # buffer i still owned by an earlier chunk
                 self.ev_copied[i].synchronize()
                 if consume is not None:
-                    consume(*pending[i], self.host[i])
+                    consume(*pending[i], self.views(i))
             self.par_host[i][:, :n] = torch.from_numpy(par[:, start:start + n])
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(self.ev_copied[i])
@@ -51,7 +54,7 @@ class HostPipeline:
                 out = {k: v[:n] for k, v in self.dev[i].items()}
                 ws = {k: v[:n] for k, v in self.ws[i].items()}
                 self.eng.run(n, p[0, :n].to(torch.int32), p[1, :n], p[2, :n], p[3, :n].to(torch.int32), self.pool,
-                             slot0=slot0 + start, seed=seed, want=self.want, out=out, ws=ws)
+                             slot0=slot0 + start, seed=seed, want=self.want, out=out, ws=ws, compact=self.compact)
                 self.ev_done[i].record(self.compute)
             with torch.cuda.stream(self.copy):
                 self.copy.wait_event(self.ev_done[i])
@@ -63,5 +66,10 @@ class HostPipeline:
             if pending[i] is not None:
                 self.ev_copied[i].synchronize()
                 if consume is not None:
-                    consume(*pending[i], self.host[i])
+                    consume(*pending[i], self.views(i))
         return total
+
+    def views(self, i):
+        """NumPy views of host buffer i (zero-copy; full reference shapes, stride 0 over tx if compact)."""
+        arrs = {k: v.numpy() for k, v in self.host[i].items()}
+        return self.eng.expand_compact(arrs) if self.compact else arrs

@@ -143,12 +143,15 @@ int b2c_tap_gains(const b2c_geom *g, const b2c_profiles *prof, const b2c_slots *
  * (:315-337).  Every output pointer is optional (NULL = not written); estimation is skipped
  * entirely when H_ls, H_mmse and stats are all NULL (then this is simulate_transmission alone).
  *   H_true [B][nsym][nrx][ntx][nsc], rx [B][nsym][nrx][nsc], tx [B][nsym][ntx][nsc] complex
+ *   compact = 1: the tx-replicated outputs are written once -- H_ls, H_mmse [B][nsym][nrx][nsc] and
+ *   tx [B][nsym][nsc] (every TX antenna sends the same grid, :402-404, and LS/MMSE never see tx) --
+ *   for callers that expand them as stride-0 views (the host-buffer pipeline: half the PCIe bytes).
  *   H_ls, H_mmse like H_true;  stats [B][nrx][B2C_N_STATGRP][B2C_N_STAT] double                          */
 int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat,
                       const b2c_slots *slots, const b2c_inject *inj, int64_t B,
                       const float *gains, const float *noise_std,
                       float *H_true, float *rx, float *tx, float *H_ls, float *H_mmse,
-                      double *stats, void *stream);
+                      double *stats, int32_t compact, void *stream);
 
 /* K3.  LS pilot division + plan interpolation on caller-supplied received grids.
  * Replaces LSEstimator.estimate (src/baseline_estimators.py:83-117) and, with mmse_mode=1,

@@ -435,3 +435,36 @@ def test_other_geometries_generic_path(ntx, nrx, nsym, useful, model):
     k3 = eng.ls_interp(rx, xp, pool, snr_db=snr, mmse=True, H_true=Ht, want=("H_ls", "H_mmse", "stats"))
     assert (k3["H_ls"] - out["H_ls"]).abs().max().item() < 2e-5 and (k3["H_mmse"] - out["H_mmse"]).abs().max().item() < 2e-5
     assert torch.allclose(k3["stats"], out["stats"], rtol=1e-4)
+
+
+def test_compact_layout_and_host_pipeline(engines):
+    """compact=True writes the tx-replicated arrays once; expanded views equal the full layout.  The
+    host-buffer pipeline (pinned memory, double-buffered D2H) hands back the same arrays."""
+    from host_pipeline import HostPipeline
+    eng = engines(4, 4)
+    pool = eng.random_pool([0.10], seed=2)
+    n = 37                                                # ragged: 3 chunks of 16 -> 16, 16, 5
+    snr = np.array([-5, 0, 5, 10, 15, 20, 25, 30], np.float32)[np.arange(n) % 8]
+    args = dict(model_id=2, doppler_hz=200.0, snr_db=snr, pattern_id=0, pool=pool, slot0=500, seed=8)
+    full = eng.run(n, **args)
+    comp = eng.run(n, compact=True, **args)
+    assert comp["H_ls"].shape == (n, 14, 4, 599) and comp["tx"].shape == (n, 14, 599)
+    exp = eng.expand_compact(comp)
+    torch.cuda.synchronize()
+    for k in ("H_true", "rx", "tx", "H_ls", "H_mmse"):
+        assert exp[k].shape == full[k].shape and (exp[k] - full[k]).abs().max().item() < 2e-6, k
+    assert torch.allclose(comp["stats"], full["stats"], rtol=1e-5)
+    for compact in (False, True):
+        got = {}
+
+        def consume(first, cnt, host):
+            for k, v in host.items():
+                got.setdefault(k, {})[first] = np.array(v[:cnt])      # copy out: buffers are reused
+        hp = HostPipeline(eng, pool, chunk=16, compact=compact)
+        done = hp.run(np.full(n, 2), np.full(n, 200.0), snr, np.zeros(n), slot0=500, seed=8, consume=consume)
+        assert done == n and sorted(got["rx"]) == [500, 516, 532]
+        for k in ("H_true", "rx", "tx", "H_ls", "H_mmse"):
+            host = np.concatenate([got[k][f] for f in sorted(got[k])])
+            assert host.shape == tuple(full[k].shape)
+            assert np.abs(host - full[k].cpu().numpy()).max() < 2e-6, (k, compact)
+        assert hp.d2h_bytes_per_slot == (1945552 + 192 if compact else 3756928 + 192)
