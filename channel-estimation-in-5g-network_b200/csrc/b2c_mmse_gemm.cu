@@ -96,53 +96,62 @@ __global__ void __launch_bounds__(TC_THREADS) mmse_dense_tc_kernel(const float2 
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_d = tmem_base_sm;
 
-  // ---- per-thread load assignments ----------------------------------------------------------
-  // A: 64 complex rows x 16 complex columns of W per stage = 1024 values, 8 per thread:
-  //    value v -> complex row il = v / 16, complex column jl = v % 16
-  // B: 128 rows (columns c) x 16 complex per stage = 2048 float2, 16 per thread:
-  //    value v -> row cl = v / 16, complex column jl = v % 16   (16 consecutive threads read 128 B)
+  // ---- per-thread load / store assignments -----------------------------------------------------
+  // The canonical layout puts element (row r, chunk kc, byte e) at kc*LBO + (r>>3)*128 + (r&7)*16 + e,
+  // so the shared-memory bank is decided by (r & 7, e) alone.  The maps below make the 16 lanes of
+  // every half-warp store to 16 distinct 8-byte bank pairs (conflict-free) while the global loads
+  // still consume whole 32-byte sectors.
+  //   A (64 complex rows il x 16 complex cols jl of W per stage, 8 values per thread):
+  //     il = 8*q' .. : il[1:0] = lane[1:0], il[2] = warp[1], il[5:3] = q ; jl[2:0] = lane[4:2], jl[3] = warp[0]
+  //     each value feeds two real rows (2il, 2il+1); lane[3] picks which of them goes out first, so
+  //     one store instruction covers even and odd rows (all 16 bank pairs) instead of only even ones.
+  //   B (128 rows cl x 16 complex cols jl of `in` per stage, 16 values per thread):
+  //     cl[2:0] = lane[2:0], cl[6:3] = q ; jl[0] = lane[3], jl[1] = lane[4], jl[3:2] = warp
   float2 ra[8], rb[16];
+  const int a_il_lo = (lane & 3) | ((warp >> 1) << 2), a_jl = ((lane >> 2) & 7) | ((warp & 1) << 3);
+  const int b_cl_lo = lane & 7, b_jl = ((lane >> 3) & 3) | (warp << 2);
   auto load_stage = [&](int k0) {     // k0: real k offset of the stage (multiple of 32)
     const int jc0 = k0 >> 1;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int v = q * TC_THREADS + tid, il = v >> 4, jl = v & 15;
-      const int i = i0c + il, j = jc0 + jl;
+      const int i = i0c + (q << 3) + a_il_lo, j = jc0 + a_jl;
       ra[q] = (i < np && j < np) ? __ldg(W + (int64_t)i * np + j) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      const int v = q * TC_THREADS + tid, cl = v >> 4, jl = v & 15;
-      const int64_t c = c0 + cl;
-      const int j = jc0 + jl;
+      const int64_t c = c0 + (q << 3) + b_cl_lo;
+      const int j = jc0 + b_jl;
       rb[q] = (c < ncols && j < np) ? __ldg(in + c * ld + j) : make_float2(0.f, 0.f);
     }
   };
   auto store_stage = [&]() {
+    const int a_kc = a_jl >> 1, a_eo = (a_jl & 1) * 8;
+    const bool odd_first = (lane >> 3) & 1;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int v = q * TC_THREADS + tid, il = v >> 4, jl = v & 15;
-      // real rows 2il, 2il+1 ; real k = 2jl, 2jl+1 -> chunk jl>>1, element offset 2*(jl&1)
-      const int kc = jl >> 1, eo = (jl & 1) * 8;
+      const int il = (q << 3) + a_il_lo;
       float wr_h, wr_l, wi_h, wi_l;
       split_tf32(ra[q].x, wr_h, wr_l);
       split_tf32(ra[q].y, wi_h, wi_l);
       const int r0 = 2 * il, r1 = 2 * il + 1;
-      const int o0 = kc * TC_LBO_A + (r0 >> 3) * TC_SBO + (r0 & 7) * 16 + eo;
-      const int o1 = kc * TC_LBO_A + (r1 >> 3) * TC_SBO + (r1 & 7) * 16 + eo;
-      *reinterpret_cast<float2 *>(sAh + o0) = make_float2(wr_h, -wi_h);   // row 2i  : ( Wr, -Wi)
-      *reinterpret_cast<float2 *>(sAl + o0) = make_float2(wr_l, -wi_l);
-      *reinterpret_cast<float2 *>(sAh + o1) = make_float2(wi_h, wr_h);    // row 2i+1: ( Wi,  Wr)
-      *reinterpret_cast<float2 *>(sAl + o1) = make_float2(wi_l, wr_l);
+      const int o0 = a_kc * TC_LBO_A + (r0 >> 3) * TC_SBO + (r0 & 7) * 16 + a_eo;   // row 2i  : ( Wr, -Wi)
+      const int o1 = a_kc * TC_LBO_A + (r1 >> 3) * TC_SBO + (r1 & 7) * 16 + a_eo;   // row 2i+1: ( Wi,  Wr)
+      const float2 e_h = make_float2(wr_h, -wi_h), e_l = make_float2(wr_l, -wi_l);
+      const float2 d_h = make_float2(wi_h, wr_h), d_l = make_float2(wi_l, wr_l);
+      const int of = odd_first ? o1 : o0, os = odd_first ? o0 : o1;
+      *reinterpret_cast<float2 *>(sAh + of) = odd_first ? d_h : e_h;
+      *reinterpret_cast<float2 *>(sAl + of) = odd_first ? d_l : e_l;
+      *reinterpret_cast<float2 *>(sAh + os) = odd_first ? e_h : d_h;
+      *reinterpret_cast<float2 *>(sAl + os) = odd_first ? e_l : d_l;
     }
+    const int b_kc = b_jl >> 1, b_eo = (b_jl & 1) * 8;
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      const int v = q * TC_THREADS + tid, cl = v >> 4, jl = v & 15;
-      const int kc = jl >> 1, eo = (jl & 1) * 8;
+      const int cl = (q << 3) + b_cl_lo;
       float xr_h, xr_l, xi_h, xi_l;
       split_tf32(rb[q].x, xr_h, xr_l);
       split_tf32(rb[q].y, xi_h, xi_l);
-      const int o = kc * TC_LBO_B + (cl >> 3) * TC_SBO + (cl & 7) * 16 + eo;
+      const int o = b_kc * TC_LBO_B + (cl >> 3) * TC_SBO + (cl & 7) * 16 + b_eo;
       *reinterpret_cast<float2 *>(sBh + o) = make_float2(xr_h, xi_h);
       *reinterpret_cast<float2 *>(sBl + o) = make_float2(xr_l, xi_l);
     }
@@ -222,11 +231,7 @@ extern "C" int b2c_mmse_dense(const float *W, int32_t np, const float *in, float
   if (ncols == 0) return B2C_OK;
   dim3 grid((unsigned)((2 * np + TC_BM - 1) / TC_BM), (unsigned)((ncols + TC_BN - 1) / TC_BN));
   B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_mmse_dense: ncols=%lld too large for one launch", (long long)ncols);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2C_CUDA(cudaFuncSetAttribute(mmse_dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    attr_set = true;
-  }
+  B2C_CUDA(cudaFuncSetAttribute(mmse_dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   mmse_dense_tc_kernel<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(
       reinterpret_cast<const float2 *>(W), np, reinterpret_cast<const float2 *>(in), out, ncols, ld);
   B2C_CUDA(cudaGetLastError());
