@@ -19,7 +19,10 @@ int check_geom(const b2c_geom *g) {
               B2C_MAX_SYM);
   B2C_REQUIRE(g->ntx >= 1 && g->ntx <= B2C_MAX_ANT && g->nrx >= 1 && g->nrx <= B2C_MAX_ANT, B2C_E_UNSUPPORTED,
               "antenna counts %dx%d outside [1,%d]", g->ntx, g->nrx, B2C_MAX_ANT);
-  B2C_REQUIRE(g->nsc >= 1 && g->nsc <= 2 * 320, B2C_E_UNSUPPORTED, "nsc=%d outside [1,640]", g->nsc);
+  // used bins = a block centred on DC with DC removed (src/channel_simulator.py:141-148): always an
+  // odd count, symmetric in frequency; the slot kernel pairs bins -f / +f and draws them from one lane
+  B2C_REQUIRE(g->nsc >= 1 && g->nsc <= 2 * B2C_RNG_LANES - 1 && (g->nsc & 1) == 1, B2C_E_UNSUPPORTED,
+              "nsc=%d must be odd and <= %d", g->nsc, 2 * B2C_RNG_LANES - 1);
   B2C_REQUIRE(g->nsym * g->nsc <= 65535 * 4, B2C_E_UNSUPPORTED, "grid too large");
   return B2C_OK;
 }

@@ -53,10 +53,9 @@ __global__ void __launch_bounds__(256) apply_noise_kernel(b2c_geom g, b2c_slots 
   } else {
     int k = e % g.nsc, q = e / g.nsc;
     int r = q % g.nrx, s = q / g.nrx;
-    const int half = k >= B2C_RNG_LANES;
-    uint4 w = draw(make_key(slots.seed, slots.slot0 + b), STREAM_NOISE,
-                   (uint32_t)((s * g.nrx + r) * B2C_RNG_LANES + k - half * B2C_RNG_LANES));
-    n = half ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
+    const int half = (g.nsc + 1) >> 1, h = k >= half, l = h ? k - half : half - 1 - k;   // b2c.h: lane |f|-1, half f>0
+    uint4 w = draw(make_key(slots.seed, slots.slot0 + b), STREAM_NOISE, (uint32_t)((s * g.nrx + r) * B2C_RNG_LANES + l));
+    n = h ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
   }
   float2 y = rx[b * per + e];
   rx[b * per + e] = make_float2(fmaf(sigma, n.x, y.x), fmaf(sigma, n.y, y.y));

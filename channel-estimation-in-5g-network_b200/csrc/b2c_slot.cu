@@ -15,7 +15,7 @@ namespace b2c {
 constexpr int MAXT = B2C_MAX_TAPS;
 constexpr int NOSC = B2C_N_OSC;
 constexpr int GAIN_THREADS = 256;
-constexpr int SLOT_THREADS = 320;   // 2 bins per thread cover the 599 used bins in one pass
+constexpr int SLOT_THREADS = 320;   // thread t owns the mirror bins -(t+1), +(t+1): covers up to 639 used bins
 constexpr int RNG_LANES = B2C_RNG_LANES;
 
 // ------------------------------------------------------------------------------------------
@@ -157,21 +157,28 @@ struct SlotCtx {
 };
 
 // Symbol and noise draws for resource element (s, k) of this CTA's rx antenna (layout in b2c.h:
-// bins are drawn in two halves of B2C_RNG_LANES = 320, so that the thread owning bins k and k+320
-// gets both from one Philox call).
+// bin k belongs to Philox lane l = |f| - 1 and word half h = (f > 0), so that the thread owning the
+// mirror pair (-f, +f) gets both bins from one call).
+__device__ __forceinline__ void rng_lane(int k, int nsc, int &l, int &h) {
+  const int half = (nsc + 1) >> 1;
+  h = k >= half;
+  l = h ? k - half : half - 1 - k;
+}
 __device__ __forceinline__ float2 draw_symbol(const SlotArgs &a, const SlotCtx &c, int s, int k) {
   if (a.has_inj) return cis_turns(__ldg(a.inj.sym_turns + (c.b * a.g.nsym + s) * a.g.nsc + k));
-  const int half = k >= RNG_LANES;
-  uint4 w = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 1) * RNG_LANES + k - half * RNG_LANES));
-  return cis_turns(u01(pick(w, (s & 1) * 2 + half)));
+  int l, h;
+  rng_lane(k, a.g.nsc, l, h);
+  uint4 w = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 1) * RNG_LANES + l));
+  return cis_turns(u01(pick(w, (s & 1) * 2 + h)));
 }
 __device__ __forceinline__ float2 draw_noise(const SlotArgs &a, const SlotCtx &c, int s, int k) {
   if (a.has_inj)
     return __ldg(reinterpret_cast<const float2 *>(a.inj.noise) +
                  ((c.b * a.g.nsym + s) * a.g.nrx + c.rx) * a.g.nsc + k);
-  const int half = k >= RNG_LANES;
-  uint4 w = draw(c.key, STREAM_NOISE, (uint32_t)((s * a.g.nrx + c.rx) * RNG_LANES + k - half * RNG_LANES));
-  return half ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
+  int l, h;
+  rng_lane(k, a.g.nsc, l, h);
+  uint4 w = draw(c.key, STREAM_NOISE, (uint32_t)((s * a.g.nrx + c.rx) * RNG_LANES + l));
+  return h ? normal_pair(w.z, w.w) : normal_pair(w.x, w.y);
 }
 
 // LS at the pilots: h_p = y_p / (x_p + 1e-12) (src/baseline_estimators.py:109-110), with y_p evaluated
@@ -205,58 +212,75 @@ __device__ __forceinline__ void pilot_phase(const SlotArgs &a, SlotCtx &c, const
   c.alpha = P / (P + sig2);
 }
 
-// Main loop of the slot kernel.  Thread t owns used bins t and t + SLOT_THREADS for every symbol.
+// Main loop of the slot kernel.
+//
+// Bin ownership.  The used bins are symmetric about DC: k < half  <->  f = k - half  in [-half, -1],
+// k >= half  <->  f = k - half + 1  in [1, half-1]  (half = (nsc+1)/2).  Thread t owns the mirror pair
+//   k0 = half-1-t  (f = -(t+1))   and   k1 = half+t  (f = +(t+1)),
+// whose twiddles are complex conjugates: tw[tap][k0] = conj(tw[tap][k1]).  With
+//   A = sum_t Re(g_t) * tw_t ,  B = sum_t Im(g_t) * tw_t        (tw_t of the +f bin, packed FFMA2)
+// both bins come out of the SAME two complex sums:
+//   H(+f) = (A.x - B.y, A.y + B.x)        H(-f) = (A.x + B.y, B.x - A.y)
+// i.e. half the FMA work and half the twiddle registers of evaluating the two bins separately.
+// A warp still stores 32 consecutive bins per instruction (ascending for k1, descending for k0).
+//
 //   T      compile-time tap count (>= the profile's surviving taps; absent taps have zero gain)
 //   NTX    compile-time TX bound; EXACT = (ntx == NTX) removes the per-tx predicate
-//   NSC    used bins when known at compile time (599 for the default grid), 0 = read from b2c_geom:
-//          with NSC fixed every store offset inside a symbol is an immediate
-//   FAST   the throughput configuration: Philox draws, every output requested, even nsym -- all
-//          the optional-output / injected-draw tests fold away
+//   NSC    used bins when known at compile time (599 for the default grid), 0 = read from b2c_geom
+//   FAST   the throughput configuration: Philox draws, every output requested, even nsym
 // Output addressing: one 64-bit base per slot (uniform) + 32-bit per-thread element offsets.
 template <int T, int NTX, bool EXACT, bool EST, int NSC, bool FAST>
 __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, float (&st)[2][3]) {
   const int nsc = NSC ? NSC : a.g.nsc;
+  const int half = (nsc + 1) >> 1;
   const int nsym = a.g.nsym, nrx = a.g.nrx;
   const int ntx = EXACT ? NTX : a.g.ntx;
-  const int k0 = threadIdx.x;
-  const bool v0 = (NSC >= SLOT_THREADS) || k0 < nsc, v1 = k0 + SLOT_THREADS < nsc;
-  const int kk0 = v0 ? k0 : 0, kk1 = v1 ? k0 + SLOT_THREADS : 0;   // idle lanes read bin 0, store nothing
+  const int t_ = threadIdx.x;
+  const bool v0 = t_ < half, v1 = t_ < half - 1;          // lower-half bin k0, upper-half bin k1
+  const int k0 = v0 ? half - 1 - t_ : 0, k1 = v1 ? half + t_ : 0;   // idle lanes: clamped, store nothing
+  const float m1 = v1 ? 1.f : 0.f;
 
-  // Twiddles.  Idle lanes get zeros (and the plan's all-zero row below), so their H, LS/MMSE
-  // values and error terms are exactly zero and need no predication in the loop.
+  // Twiddles of the +f bin (conjugate of the -f bin's table row when only that one exists).  Idle
+  // lanes get zeros, so their H, LS/MMSE values and error terms are exactly zero.
   const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * nsc;
   const float2 zero2 = make_float2(0.f, 0.f), neg1 = make_float2(-1.f, -1.f), nalpha = make_float2(-c.alpha, -c.alpha);
-  float2 tw0[T], tw1[T];
+  float2 twp[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    tw0[t] = v0 ? __ldg(tw + t * nsc + kk0) : zero2;
-    tw1[t] = v1 ? __ldg(tw + t * nsc + kk1) : zero2;
+    float2 w = zero2;
+    if (v1) w = __ldg(tw + t * nsc + k1);
+    else if (v0) {
+      w = __ldg(tw + t * nsc + k0);
+      w.y = -w.y;
+    }
+    twp[t] = w;
   }
 
   const int64_t slot_h = (int64_t)nsym * nrx * ntx * nsc;
   const int nre = nsym * nsc;
-  float2 *const Hb = (FAST || a.H_true) ? a.H_true + c.b * slot_h : nullptr;
   const bool compact = !FAST && a.compact;   // compact layout: generic instantiation only
   const int64_t slot_r = (int64_t)nsym * nrx * nsc;
+  float2 *const Hb = (FAST || a.H_true) ? a.H_true + c.b * slot_h : nullptr;
   float2 *const Lb = (EST && (FAST || a.H_ls)) ? a.H_ls + c.b * (compact ? slot_r : slot_h) : nullptr;
   float2 *const Mb = (EST && (FAST || a.H_mmse)) ? a.H_mmse + c.b * (compact ? slot_r : slot_h) : nullptr;
   float2 *const Rb = (FAST || a.rx) ? a.rx + c.b * slot_r : nullptr;
   float2 *const Tb = ((FAST || a.tx) && c.rx == 0) ? a.tx + c.b * (int64_t)nsym * (compact ? 1 : ntx) * nsc : nullptr;
   const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * (nre + 1) : nullptr;
   const bool inj = !FAST && a.has_inj;
-  const float2 *inj_noise = inj ? reinterpret_cast<const float2 *>(a.inj.noise) + c.b * (int64_t)nsym * nrx * nsc : nullptr;
+  const float2 *inj_noise = inj ? reinterpret_cast<const float2 *>(a.inj.noise) + c.b * slot_r : nullptr;
   const float *inj_sym = inj ? a.inj.sym_turns + c.b * (int64_t)nsym * nsc : nullptr;
 
-  int oH = c.rx * ntx * nsc + k0;   // element offset of H[s][rx][0][k0] inside the slot
-  int oR = c.rx * nsc + k0;         //                   rx[s][rx][k0]
-  int oT = k0;                      //                   tx[s][0][k0]
-  int oP0 = v0 ? k0 : nre, oP1 = v1 ? k0 + SLOT_THREADS : nre;   // plan rows; row nre = "outside" for idle lanes
+  // per-thread element offsets of this symbol's row start; the bin (k0 / k1) is added at the store
+  int oH = c.rx * ntx * nsc;        // H[s][rx][0][.]
+  int oR = c.rx * nsc;              // rx[s][rx][.]
+  int oT = 0;                       // tx[s][0][.]
+  int oP0 = v0 ? k0 : nre, oP1 = v1 ? k1 : nre;   // plan rows; row nre = "outside" for idle lanes
   const int dP0 = v0 ? nsc : 0, dP1 = v1 ? nsc : 0;
   const int dH = nrx * ntx * nsc, dR = nrx * nsc, dT = (compact ? 1 : ntx) * nsc;
   const float4 *gps = c.gsp;
   const bool need_draws = FAST || Rb != nullptr || a.tx != nullptr;   // H-only calls skip the draws
 
-  static_assert(SLOT_THREADS == RNG_LANES, "thread t owns bins t and t + RNG_LANES");
+  static_assert(SLOT_THREADS == RNG_LANES, "thread t draws Philox lane t");
   uint4 ws = make_uint4(0, 0, 0, 0);
   for (int s2 = 0; s2 < nsym; s2 += 2) {
 #pragma unroll
@@ -276,52 +300,50 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
           prefetch_l1(plan + oP0);
           prefetch_l1(plan + oP1);
         }
-        // ---- CFR per tx: H[s, rx, tx, k] = sum_t g[s, tx, t] * tw[t, k] ---------------------------
+        // ---- CFR per tx: H[s, rx, tx, +-f] from A = sum_t Re(g) tw, B = sum_t Im(g) tw ---------------
         float2 hs0 = zero2, hs1 = zero2;
 #pragma unroll
         for (int tx = 0; tx < NTX; ++tx) {
           if (EXACT || tx < ntx) {
             const float4 *gp = gps + tx * MAXT;
-            float2 A0 = zero2, B0 = zero2, A1 = zero2, B1 = zero2;
+            float2 A = zero2, B = zero2;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
               const float4 gq = gp[t];
-              const float2 gr = make_float2(gq.x, gq.y), gi = make_float2(gq.z, gq.w);
-              A0 = __ffma2_rn(gr, tw0[t], A0);
-              B0 = __ffma2_rn(gi, tw0[t], B0);
-              A1 = __ffma2_rn(gr, tw1[t], A1);
-              B1 = __ffma2_rn(gi, tw1[t], B1);
+              A = __ffma2_rn(make_float2(gq.x, gq.y), twp[t], A);
+              B = __ffma2_rn(make_float2(gq.z, gq.w), twp[t], B);
             }
-            const float2 h0 = make_float2(A0.x - B0.y, A0.y + B0.x);
-            const float2 h1 = make_float2(A1.x - B1.y, A1.y + B1.x);
+            const float2 h1 = make_float2(A.x - B.y, A.y + B.x);   // +f : sum_t g_t tw_t
+            const float2 h0 = make_float2(A.x + B.y, B.x - A.y);   // -f : sum_t g_t conj(tw_t)
             hs0 = __fadd2_rn(hs0, h0);
             hs1 = __fadd2_rn(hs1, h1);
             const int o = oH + tx * nsc;
             if (FAST || Hb) {
-              if (v0) st_stream(Hb + o, h0);
-              if (v1) st_stream(Hb + o + SLOT_THREADS, h1);
+              if (v0) st_stream(Hb + o + k0, h0);
+              if (v1) st_stream(Hb + o + k1, h1);
             }
             if (EST) {
               const int oe = compact ? oR : o;          // compact: one copy per (s, rx), rx's offsets
               if ((FAST || Lb) && (!compact || tx == 0)) {
-                if (v0) st_stream(Lb + oe, l0);
-                if (v1) st_stream(Lb + oe + SLOT_THREADS, l1);
+                if (v0) st_stream(Lb + oe + k0, l0);
+                if (v1) st_stream(Lb + oe + k1, l1);
               }
               if ((FAST || Mb) && (!compact || tx == 0)) {
-                if (v0) st_stream(Mb + oe, cscale(c.alpha, l0));
-                if (v1) st_stream(Mb + oe + SLOT_THREADS, cscale(c.alpha, l1));
+                if (v0) st_stream(Mb + oe + k0, cscale(c.alpha, l0));
+                if (v1) st_stream(Mb + oe + k1, cscale(c.alpha, l1));
               }
               // squared errors: d = h - l and h - alpha*l as one packed FMA each; idle lanes add zeros.
               // Accumulated over all tx ([1]) and, for the pair-(0,0) NMSE of the pilot sweep, for tx 0 ([0]).
+              // (the lane that owns only the unpaired bin -half still computes a +f value: m1 masks it)
               float2 d = __ffma2_rn(l0, neg1, h0);
               float e_ls = cabs2(d);
               d = __ffma2_rn(l1, neg1, h1);
-              e_ls += cabs2(d);
+              e_ls = fmaf(m1, cabs2(d), e_ls);
               d = __ffma2_rn(l0, nalpha, h0);
               float e_mm = cabs2(d);
               d = __ffma2_rn(l1, nalpha, h1);
-              e_mm += cabs2(d);
-              const float pw = cabs2(h0) + cabs2(h1);
+              e_mm = fmaf(m1, cabs2(d), e_mm);
+              const float pw = fmaf(m1, cabs2(h1), cabs2(h0));
               st[1][0] += e_ls;
               st[1][1] += e_mm;
               st[1][2] += pw;
@@ -337,15 +359,15 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
         float2 x0 = zero2, x1 = zero2, n0 = zero2, n1 = zero2;
         if (need_draws) {
           if (inj) {
-            x0 = cis_turns(__ldg(inj_sym + s * nsc + kk0));
-            x1 = cis_turns(__ldg(inj_sym + s * nsc + kk1));
-            n0 = __ldg(inj_noise + (oR - k0) + kk0);
-            n1 = __ldg(inj_noise + (oR - k0) + kk1);
+            x0 = cis_turns(__ldg(inj_sym + s * nsc + k0));
+            x1 = cis_turns(__ldg(inj_sym + s * nsc + k1));
+            n0 = __ldg(inj_noise + oR + k0);
+            n1 = __ldg(inj_noise + oR + k1);
           } else {
-            if (j == 0) ws = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 1) * RNG_LANES + k0));
+            if (j == 0) ws = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 1) * RNG_LANES + t_));
             x0 = cis_turns(u01(j ? ws.z : ws.x));
             x1 = cis_turns(u01(j ? ws.w : ws.y));
-            const uint4 wn = draw(c.key, STREAM_NOISE, (uint32_t)((s * nrx + c.rx) * RNG_LANES + k0));
+            const uint4 wn = draw(c.key, STREAM_NOISE, (uint32_t)((s * nrx + c.rx) * RNG_LANES + t_));
             n0 = normal_pair(wn.x, wn.y);
             n1 = normal_pair(wn.z, wn.w);
           }
@@ -353,15 +375,15 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
         // ---- y = (sum_tx H) x + sigma n  (:330-343) ------------------------------------------------
         if (FAST || Rb) {
           const float2 y0 = cmul(hs0, x0), y1 = cmul(hs1, x1);
-          if (v0) st_stream(Rb + oR, make_float2(fmaf(c.sigma, n0.x, y0.x), fmaf(c.sigma, n0.y, y0.y)));
-          if (v1) st_stream(Rb + oR + SLOT_THREADS, make_float2(fmaf(c.sigma, n1.x, y1.x), fmaf(c.sigma, n1.y, y1.y)));
+          if (v0) st_stream(Rb + oR + k0, make_float2(fmaf(c.sigma, n0.x, y0.x), fmaf(c.sigma, n0.y, y0.y)));
+          if (v1) st_stream(Rb + oR + k1, make_float2(fmaf(c.sigma, n1.x, y1.x), fmaf(c.sigma, n1.y, y1.y)));
         }
         if (Tb) {   // the rx-0 CTA writes the (tx-replicated) grid
 #pragma unroll
           for (int tx = 0; tx < NTX; ++tx) {
             if ((EXACT || tx < ntx) && (!compact || tx == 0)) {
-              if (v0) st_stream(Tb + oT + tx * nsc, x0);
-              if (v1) st_stream(Tb + oT + tx * nsc + SLOT_THREADS, x1);
+              if (v0) st_stream(Tb + oT + tx * nsc + k0, x0);
+              if (v1) st_stream(Tb + oT + tx * nsc + k1, x1);
             }
           }
         }

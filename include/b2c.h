@@ -25,7 +25,9 @@
  *   Philox    -- Philox4x32-10 keyed by (seed, global slot index): results do not depend on
  *                batch size, launch geometry or the number of GPUs the slots are sharded over.
  *   Counter layout: key = (seed lo, seed hi); ctr = (index, stream, slot lo, slot hi)
- *     (k is split as k = h*320 + l, h = k / B2C_RNG_LANES: the kernels' thread l owns bins l and l+320)
+ *     (used bin k has frequency offset f = k - half for k < half, f = k - half + 1 otherwise, half = (nsc+1)/2;
+ *      it is drawn from Philox lane l = |f| - 1 and word half h = (f > 0): the kernels' thread l owns the
+ *      mirror pair -f / +f, whose channel twiddles are complex conjugates)
  *     stream 0 SYMBOLS: index = (s>>1)*320 + l, word (s&1)*2 + h   -> phase of RE (s,k), in turns
  *     stream 1 JAKES  : index = ((p*ntx+tx)*nrx+rx)*10 + (n>>1), words (0,1) even n / (2,3) odd n
  *                                                                  -> (arrival angle, phase) of oscillator n
@@ -46,7 +48,7 @@ extern "C" {
 #define B2C_MAX_TAPS 16     /* distinct sample delays per TDL profile (EPA 5, EVA 8, ETU 9)  */
 #define B2C_MAX_ANT 8       /* ntx, nrx <= 8                                                  */
 #define B2C_MAX_SYM 16      /* OFDM symbols per slot                                          */
-#define B2C_RNG_LANES 320   /* bins per Philox half-row (see "Random draws"); nsc <= 2*320    */
+#define B2C_RNG_LANES 320   /* Philox lanes per row (see "Random draws"); nsc <= 2*320 - 1, odd */
 #define B2C_N_OSC 20        /* Jakes oscillators, src/channel_simulator.py:100                */
 #define B2C_N_STAT 3        /* sum|H-H_ls|^2, sum|H-H_mmse|^2, sum|H|^2 ...                    */
 #define B2C_N_STATGRP 2     /* ... per rx antenna for {antenna pair (rx,0), all tx of that rx} */

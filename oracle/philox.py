@@ -13,7 +13,8 @@ RNG parity with it is by injection only.
 Counter layout (shared with include/b2c.h):
     key  = (seed & 0xffffffff, seed >> 32)
     ctr  = (index, stream, slot & 0xffffffff, slot >> 32)         slot = global sample index
-    (bins are split as k = h*320 + l, h = k // RNG_LANES)
+    (bin k has frequency offset f = k - half (k < half) or k - half + 1, half = (nsc+1)//2;
+     it uses lane l = |f| - 1 and word half h = (f > 0))
     stream 0 SYMBOLS: index = (s >> 1) * 320 + l ; word (s & 1)*2 + h     -> phase of RE (s, k)
     stream 1 JAKES  : index = ((p*ntx + tx)*nrx + rx)*10 + (n >> 1)
                       words (0,1) for even n, (2,3) for odd n            -> (angle, phase) of oscillator n
@@ -62,10 +63,17 @@ def _block(seed, slot, stream, index):
     return philox4x32_10(ctr, (int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF))
 
 
+def _lane(k, nsc):
+    """(lane, word half) of used bin k: mirror bins -f / +f share a Philox call."""
+    half = (nsc + 1) // 2
+    h = (k >= half).astype(np.int64)
+    return np.where(h == 1, k - half, half - 1 - k), h
+
+
 def symbol_u(seed, slot, nsym, nsc):
     """u[nsym, nsc]: phase (in turns) of every resource element."""
     s, k = np.meshgrid(np.arange(nsym), np.arange(nsc), indexing="ij")
-    h, l = k // RNG_LANES, k % RNG_LANES
+    l, h = _lane(k, nsc)
     w = _block(seed, slot, STREAM_SYMBOLS, (s >> 1) * RNG_LANES + l)
     return u01(np.take_along_axis(w, ((s & 1) * 2 + h)[..., None], axis=-1)[..., 0])
 
@@ -83,7 +91,7 @@ def jakes_u(seed, slot, npaths, ntx, nrx, nosc=20):
 def noise(seed, slot, nsym, nrx, nsc):
     """(re, im)[nsym, nrx, nsc] unit-variance-per-component Box-Muller normals."""
     s, r, k = np.meshgrid(np.arange(nsym), np.arange(nrx), np.arange(nsc), indexing="ij")
-    h, l = k // RNG_LANES, k % RNG_LANES
+    l, h = _lane(k, nsc)
     w = _block(seed, slot, STREAM_NOISE, (s * nrx + r) * RNG_LANES + l)
     off = h * 2
     u1 = u01(np.take_along_axis(w, off[..., None], axis=-1)[..., 0])
