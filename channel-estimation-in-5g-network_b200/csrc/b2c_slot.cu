@@ -270,10 +270,15 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
   const float2 *inj_noise = inj ? reinterpret_cast<const float2 *>(a.inj.noise) + c.b * slot_r : nullptr;
   const float *inj_sym = inj ? a.inj.sym_turns + c.b * (int64_t)nsym * nsc : nullptr;
 
-  // per-thread element offsets of this symbol's row start; the bin (k0 / k1) is added at the store
-  int oH = c.rx * ntx * nsc;        // H[s][rx][0][.]
-  int oR = c.rx * nsc;              // rx[s][rx][.]
-  int oT = 0;                       // tx[s][0][.]
+  // Running 64-bit store pointers per bin (advanced once per symbol; with NSC fixed the per-tx
+  // offsets are immediates).  H_ls / H_mmse share H_true's layout: their addresses are H_true's plus a
+  // uniform byte delta (compact layout: rx's).
+  float2 *pH0 = Hb + (c.rx * ntx * nsc + k0), *pH1 = Hb + (c.rx * ntx * nsc + k1);   // H[s][rx][0][k]
+  float2 *pR0 = Rb + (c.rx * nsc + k0), *pR1 = Rb + (c.rx * nsc + k1);               // rx[s][rx][k]
+  float2 *pT0 = Tb + k0, *pT1 = Tb + k1;                                             // tx[s][0][k]
+  const int64_t dL = (const char *)Lb - (const char *)(compact ? Rb : Hb);
+  const int64_t dM = (const char *)Mb - (const char *)(compact ? Rb : Hb);
+  int oI = c.rx * nsc;              // injected-noise row offset (generic path)
   int oP0 = v0 ? k0 : nre, oP1 = v1 ? k1 : nre;   // plan rows; row nre = "outside" for idle lanes
   const int dP0 = v0 ? nsc : 0, dP1 = v1 ? nsc : 0;
   const int dH = nrx * ntx * nsc, dR = nrx * nsc, dT = (compact ? 1 : ntx) * nsc;
@@ -317,20 +322,20 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
             const float2 h0 = make_float2(A.x + B.y, B.x - A.y);   // -f : sum_t g_t conj(tw_t)
             hs0 = __fadd2_rn(hs0, h0);
             hs1 = __fadd2_rn(hs1, h1);
-            const int o = oH + tx * nsc;
             if (FAST || Hb) {
-              if (v0) st_stream(Hb + o + k0, h0);
-              if (v1) st_stream(Hb + o + k1, h1);
+              if (v0) st_stream(pH0 + tx * nsc, h0);
+              if (v1) st_stream(pH1 + tx * nsc, h1);
             }
             if (EST) {
-              const int oe = compact ? oR : o;          // compact: one copy per (s, rx), rx's offsets
+              // compact: one copy per (s, rx), at rx's offsets
+              const float2 *q0 = compact ? pR0 : pH0 + tx * nsc, *q1 = compact ? pR1 : pH1 + tx * nsc;
               if ((FAST || Lb) && (!compact || tx == 0)) {
-                if (v0) st_stream(Lb + oe + k0, l0);
-                if (v1) st_stream(Lb + oe + k1, l1);
+                if (v0) st_stream((float2 *)((char *)q0 + dL), l0);
+                if (v1) st_stream((float2 *)((char *)q1 + dL), l1);
               }
               if ((FAST || Mb) && (!compact || tx == 0)) {
-                if (v0) st_stream(Mb + oe + k0, cscale(c.alpha, l0));
-                if (v1) st_stream(Mb + oe + k1, cscale(c.alpha, l1));
+                if (v0) st_stream((float2 *)((char *)q0 + dM), cscale(c.alpha, l0));
+                if (v1) st_stream((float2 *)((char *)q1 + dM), cscale(c.alpha, l1));
               }
               // squared errors: d = h - l and h - alpha*l as one packed FMA each; idle lanes add zeros.
               // Accumulated over all tx ([1]) and, for the pair-(0,0) NMSE of the pilot sweep, for tx 0 ([0]).
@@ -361,8 +366,8 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
           if (inj) {
             x0 = cis_turns(__ldg(inj_sym + s * nsc + k0));
             x1 = cis_turns(__ldg(inj_sym + s * nsc + k1));
-            n0 = __ldg(inj_noise + oR + k0);
-            n1 = __ldg(inj_noise + oR + k1);
+            n0 = __ldg(inj_noise + oI + k0);
+            n1 = __ldg(inj_noise + oI + k1);
           } else {
             if (j == 0) ws = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 1) * RNG_LANES + t_));
             x0 = cis_turns(u01(j ? ws.z : ws.x));
@@ -375,21 +380,25 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
         // ---- y = (sum_tx H) x + sigma n  (:330-343) ------------------------------------------------
         if (FAST || Rb) {
           const float2 y0 = cmul(hs0, x0), y1 = cmul(hs1, x1);
-          if (v0) st_stream(Rb + oR + k0, make_float2(fmaf(c.sigma, n0.x, y0.x), fmaf(c.sigma, n0.y, y0.y)));
-          if (v1) st_stream(Rb + oR + k1, make_float2(fmaf(c.sigma, n1.x, y1.x), fmaf(c.sigma, n1.y, y1.y)));
+          if (v0) st_stream(pR0, make_float2(fmaf(c.sigma, n0.x, y0.x), fmaf(c.sigma, n0.y, y0.y)));
+          if (v1) st_stream(pR1, make_float2(fmaf(c.sigma, n1.x, y1.x), fmaf(c.sigma, n1.y, y1.y)));
         }
         if (Tb) {   // the rx-0 CTA writes the (tx-replicated) grid
 #pragma unroll
           for (int tx = 0; tx < NTX; ++tx) {
             if ((EXACT || tx < ntx) && (!compact || tx == 0)) {
-              if (v0) st_stream(Tb + oT + tx * nsc + k0, x0);
-              if (v1) st_stream(Tb + oT + tx * nsc + k1, x1);
+              if (v0) st_stream(pT0 + tx * nsc, x0);
+              if (v1) st_stream(pT1 + tx * nsc, x1);
             }
           }
         }
-        oH += dH;
-        oR += dR;
-        oT += dT;
+        pH0 += dH;
+        pH1 += dH;
+        pR0 += dR;
+        pR1 += dR;
+        pT0 += dT;
+        pT1 += dT;
+        oI += dR;
         gps += ntx * MAXT;
       }
     }
