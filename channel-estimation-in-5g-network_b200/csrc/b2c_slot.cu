@@ -230,7 +230,7 @@ __device__ __forceinline__ void pilot_phase(const SlotArgs &a, SlotCtx &c, const
 //   FAST   the throughput configuration: Philox draws, every output requested, even nsym
 // Output addressing: one 64-bit base per slot (uniform) + 32-bit per-thread element offsets.
 template <int T, int NTX, bool EXACT, bool EST, int NSC, bool FAST>
-__device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, float (&st)[2][3]) {
+__device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, float2 (&st)[2][3]) {
   const int nsc = NSC ? NSC : a.g.nsc;
   const int half = (nsc + 1) >> 1;
   const int nsym = a.g.nsym, nrx = a.g.nrx;
@@ -305,6 +305,7 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
           prefetch_l1(plan + oP0);
           prefetch_l1(plan + oP1);
         }
+        const float2 mm0 = cscale(c.alpha, l0), mm1 = cscale(c.alpha, l1);
         // ---- CFR per tx: H[s, rx, tx, +-f] from A = sum_t Re(g) tw, B = sum_t Im(g) tw ---------------
         float2 hs0 = zero2, hs1 = zero2;
 #pragma unroll
@@ -334,29 +335,24 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
                 if (v1) st_stream((float2 *)((char *)q1 + dL), l1);
               }
               if ((FAST || Mb) && (!compact || tx == 0)) {
-                if (v0) st_stream((float2 *)((char *)q0 + dM), cscale(c.alpha, l0));
-                if (v1) st_stream((float2 *)((char *)q1 + dM), cscale(c.alpha, l1));
+                if (v0) st_stream((float2 *)((char *)q0 + dM), mm0);
+                if (v1) st_stream((float2 *)((char *)q1 + dM), mm1);
               }
-              // squared errors: d = h - l and h - alpha*l as one packed FMA each; idle lanes add zeros.
-              // Accumulated over all tx ([1]) and, for the pair-(0,0) NMSE of the pilot sweep, for tx 0 ([0]).
-              // (the lane that owns only the unpaired bin -half still computes a +f value: m1 masks it)
+              // squared errors, packed: d = h - l (one FFMA2), acc += d*d (one FFMA2) with the re^2 / im^2
+              // halves summed at the end; idle lanes hold h = l = 0.  tx 0 goes to st[0] (antenna pair
+              // (rx,0) for the pilot sweep), the other tx to st[1]; the flush adds st[0] into st[1].
+              const float2 h1m = cscale(m1, h1);   // lane that owns only the unpaired bin -half: drop its +f value
+              float2 (&acc)[3] = st[tx == 0 ? 0 : 1];
               float2 d = __ffma2_rn(l0, neg1, h0);
-              float e_ls = cabs2(d);
-              d = __ffma2_rn(l1, neg1, h1);
-              e_ls = fmaf(m1, cabs2(d), e_ls);
+              acc[0] = __ffma2_rn(d, d, acc[0]);
+              d = __ffma2_rn(l1, neg1, h1m);
+              acc[0] = __ffma2_rn(d, d, acc[0]);
               d = __ffma2_rn(l0, nalpha, h0);
-              float e_mm = cabs2(d);
-              d = __ffma2_rn(l1, nalpha, h1);
-              e_mm = fmaf(m1, cabs2(d), e_mm);
-              const float pw = fmaf(m1, cabs2(h1), cabs2(h0));
-              st[1][0] += e_ls;
-              st[1][1] += e_mm;
-              st[1][2] += pw;
-              if (tx == 0) {
-                st[0][0] += e_ls;
-                st[0][1] += e_mm;
-                st[0][2] += pw;
-              }
+              acc[1] = __ffma2_rn(d, d, acc[1]);
+              d = __ffma2_rn(l1, nalpha, h1m);
+              acc[1] = __ffma2_rn(d, d, acc[1]);
+              acc[2] = __ffma2_rn(h0, h0, acc[2]);
+              acc[2] = __ffma2_rn(h1m, h1m, acc[2]);
             }
           }
         }
@@ -452,7 +448,9 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
     c.pid = a.slots.pattern_id[c.b];
   }
 
-  float st[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // [0] antenna pair (rx, 0), [1] all tx of this rx
+  float2 st[2][3];   // packed (re^2, im^2) sums: [0] tx 0 (antenna pair (rx, 0)), [1] tx >= 1
+#pragma unroll
+  for (int q = 0; q < 2; ++q) st[q][0] = st[q][1] = st[q][2] = make_float2(0.f, 0.f);
 
   if (c.ntaps <= 5) {
     if (EST) pilot_phase<5, NSC>(a, c, gs, hp, red);
@@ -477,7 +475,10 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
     for (int q = 0; q < 2; ++q)
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        float v = warp_sum(st[q][j]);
+        // [0] = pair (rx, 0); [1] = all tx of this rx = tx 0 + the rest
+        float v = st[0][j].x + st[0][j].y;
+        if (q == 1) v += st[1][j].x + st[1][j].y;
+        v = warp_sum(v);
         if (lane == 0) ssm[warp][q * 3 + j] = v;
       }
     __syncthreads();
