@@ -152,7 +152,7 @@ struct SlotCtx {
   int rx, m, ntaps, pid;
   float sigma, alpha;
   PhiloxKey key;
-  const float4 *gsp;   // smem [nsym][ntx][MAXT] (gr, gr, gi, gi)
+  const float2 *gsp;   // smem [nsym][ntx][MAXT] tap gains of this rx
   const float2 *hp;    // smem [np] LS estimates at the pilots
 };
 
@@ -282,7 +282,7 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
   int oP0 = v0 ? k0 : nre, oP1 = v1 ? k1 : nre;   // plan rows; row nre = "outside" for idle lanes
   const int dP0 = v0 ? nsc : 0, dP1 = v1 ? nsc : 0;
   const int dH = nrx * ntx * nsc, dR = nrx * nsc, dT = (compact ? 1 : ntx) * nsc;
-  const float4 *gps = c.gsp;
+  const float2 *gps = c.gsp;
   const bool need_draws = FAST || Rb != nullptr || a.tx != nullptr;   // H-only calls skip the draws
 
   static_assert(SLOT_THREADS == RNG_LANES, "thread t draws Philox lane t");
@@ -311,13 +311,13 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
 #pragma unroll
         for (int tx = 0; tx < NTX; ++tx) {
           if (EXACT || tx < ntx) {
-            const float4 *gp = gps + tx * MAXT;
+            const float2 *gp = gps + tx * MAXT;
             float2 A = zero2, B = zero2;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-              const float4 gq = gp[t];
-              A = __ffma2_rn(make_float2(gq.x, gq.y), twp[t], A);
-              B = __ffma2_rn(make_float2(gq.z, gq.w), twp[t], B);
+              const float2 gq = gp[t];        // broadcast load; the (x,x) / (y,y) splats are register moves
+              A = __ffma2_rn(make_float2(gq.x, gq.x), twp[t], A);
+              B = __ffma2_rn(make_float2(gq.y, gq.y), twp[t], B);
             }
             const float2 h1 = make_float2(A.x - B.y, A.y + B.x);   // +f : sum_t g_t tw_t
             const float2 h0 = make_float2(A.x + B.y, B.x - A.y);   // -f : sum_t g_t conj(tw_t)
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nsc = NSC ? NSC : a.g.nsc;
   const int nsym = a.g.nsym, ntx = a.g.ntx, nrx = a.g.nrx;
-  float4 *gsp = reinterpret_cast<float4 *>(smem_raw);                 // [nsym][ntx][MAXT]
+  float2 *gsp = reinterpret_cast<float2 *>(smem_raw);                 // [nsym][ntx][MAXT]
   float2 *gs = reinterpret_cast<float2 *>(gsp + nsym * ntx * MAXT);   // [nsym][MAXT] sum over tx
   float2 *hp = gs + nsym * MAXT;                                      // [np_max + 1], last = 0
   __shared__ float red[33];
@@ -426,8 +426,7 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
 
   const float2 *gin = a.gains + (c.b * nrx + c.rx) * (int64_t)(nsym * ntx * MAXT);
   for (int i = threadIdx.x; i < nsym * ntx * MAXT; i += SLOT_THREADS) {
-    float2 v = __ldg(gin + i);
-    gsp[i] = make_float4(v.x, v.x, v.y, v.y);
+    gsp[i] = __ldg(gin + i);
   }
   __syncthreads();
 
@@ -438,9 +437,9 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
       int s = i / MAXT, t = i - s * MAXT;
       float sr = 0.f, si = 0.f;
       for (int tx = 0; tx < ntx; ++tx) {
-        float4 v = gsp[(s * ntx + tx) * MAXT + t];
+        float2 v = gsp[(s * ntx + tx) * MAXT + t];
         sr += v.x;
-        si += v.z;
+        si += v.y;
       }
       gs[i] = make_float2(sr, si);
     }
@@ -491,7 +490,7 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
 }
 
 static size_t slot_smem_bytes(const b2c_geom *g, int np_max) {
-  return (size_t)g->nsym * g->ntx * MAXT * sizeof(float4) + (size_t)g->nsym * MAXT * sizeof(float2) +
+  return (size_t)g->nsym * g->ntx * MAXT * sizeof(float2) + (size_t)g->nsym * MAXT * sizeof(float2) +
          (size_t)(np_max + 1) * sizeof(float2);
 }
 
