@@ -178,20 +178,43 @@ def run_b200(args, rank, world, local_rank):
     from _b2c import check, dptr, lib, ref, stream_ptr, Slots
     L = lib()
 
-    def step(i, ev=None):
-        """One pass: slots [slot0, slot0 + B) of this rank's range."""
+    # With --overlap, K1a (tap gains) of step i+1 runs on a second stream while the slot kernel of step i
+    # runs on the main stream (double-buffered gains workspace, CUDA-event hand-offs); by default both
+    # are enqueued on the main stream in order.
+    main = torch.cuda.current_stream()
+    aux = torch.cuda.Stream(device=dev) if args.overlap else main
+    wss = [ws, eng.workspace(B)] if args.overlap else [ws, ws]
+    ev_gains = [torch.cuda.Event() for _ in range(2)]
+    ev_slot = [torch.cuda.Event() for _ in range(2)]
+
+    def slots_of(i):
         slot0 = (rank * per_rank_steps + i) * B
-        slots = Slots(slot0, args.seed, model_id.data_ptr(), doppler.data_ptr(), snr.data_ptr(), pattern.data_ptr())
-        check(L.b2c_tap_gains(ref(eng.geom), ref(eng.prof), ref(slots), None, B, dptr(ws["gains"], "c64"),
-                              dptr(ws["noise_std"], "f32"), stream_ptr()))
+        return Slots(slot0, args.seed, model_id.data_ptr(), doppler.data_ptr(), snr.data_ptr(), pattern.data_ptr())
+
+    def gains(i):
+        """K1a of step i into workspace i & 1 (on the aux stream)."""
+        w = wss[i & 1]
+        with torch.cuda.stream(aux):
+            aux.wait_event(ev_slot[i & 1])          # the slot kernel that last read this workspace
+            check(L.b2c_tap_gains(ref(eng.geom), ref(eng.prof), ref(slots_of(i)), None, B, dptr(w["gains"], "c64"),
+                                  dptr(w["noise_std"], "f32"), stream_ptr()))
+            ev_gains[i & 1].record(aux)
+
+    def step(i, ev=None, last=False):
+        """One pass: slots [slot0, slot0 + B) of this rank's range."""
+        w = wss[i & 1]
+        main.wait_event(ev_gains[i & 1])
         if ev is not None:
             ev[0].record()
-        check(L.b2c_slot_pipeline(ref(eng.geom), ref(eng.prof), ref(pool.struct), ref(slots), None, B,
-                                  dptr(ws["gains"], "c64"), dptr(ws["noise_std"], "f32"), dptr(out["H_true"], "c64"),
+        check(L.b2c_slot_pipeline(ref(eng.geom), ref(eng.prof), ref(pool.struct), ref(slots_of(i)), None, B,
+                                  dptr(w["gains"], "c64"), dptr(w["noise_std"], "f32"), dptr(out["H_true"], "c64"),
                                   dptr(out["rx"], "c64"), dptr(out["tx"], "c64"), dptr(out["H_ls"], "c64"),
                                   dptr(out["H_mmse"], "c64"), dptr(out["stats"], "f64"), 0, stream_ptr()))
         if ev is not None:
             ev[1].record()
+        ev_slot[i & 1].record(main)
+        if not last:
+            gains(i + 1)                            # overlaps the slot kernel just enqueued
         check(L.b2c_stats_bins(ref(eng.geom), dptr(out["stats"], "f64"), dptr(snr_idx, "i32"), B, len(SNRS),
                                dptr(bins, "f64"), stream_ptr()))
 
@@ -200,6 +223,7 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    gains(0)
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -209,7 +233,7 @@ def run_b200(args, rank, world, local_rank):
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_beg.record()
     for i in range(args.steps):
-        step(args.warmup + i, kev[i])
+        step(args.warmup + i, kev[i], last=(i == args.steps - 1))
     if world > 1:
         dist.all_reduce(bins)            # the path's only collective: per-SNR statistics over NVLink
     t_end.record()
@@ -298,6 +322,9 @@ def main():
     ap.add_argument("--e2e-full", action="store_true", help="copy the tx-replicated arrays in full instead of once")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="run K1a of step i+1 on a second stream under the slot kernel of step i (measured: no gain, "
+                         "the slot kernel slows down by the same amount; default off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
