@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libb2c.so")
 
 MAX_TAPS, MAX_ANT, MAX_SYM, N_OSC, N_STAT, N_BINSTAT = 16, 8, 16, 20, 3, 12
 EXPORTS = ["b2c_last_error_string", "b2c_abi_version", "b2c_tap_gains", "b2c_slot_pipeline",
-           "b2c_ls_interp", "b2c_pilot_vectors", "b2c_mmse_dense", "b2c_stats_bins",
+           "b2c_ls_interp", "b2c_pilot_vectors", "b2c_mmse_dense", "b2c_dense_real_apply", "b2c_stats_bins",
            "b2c_ofdm_modulate", "b2c_ofdm_demodulate", "b2c_apply_channel", "b2c_tdl_full"]
 
 
@@ -67,6 +67,7 @@ def lib():
             "b2c_ls_interp": [P, P, P, P, I64, P, P, I64, P, I32, P, P, P, P, P, P],
             "b2c_pilot_vectors": [P, P, I64, I32, F, I32, P, P],
             "b2c_mmse_dense": [P, I32, P, P, I64, I64, P],
+            "b2c_dense_real_apply": [P, I32, I32, P, P, I64, I64, I64, P],
             "b2c_stats_bins": [P, P, P, I64, I32, P, P],
             "b2c_ofdm_modulate": [P, P, P, I64, P],
             "b2c_ofdm_demodulate": [P, P, P, I64, P],

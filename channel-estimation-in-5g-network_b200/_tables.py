@@ -118,9 +118,45 @@ def interpolation_plan(pilot_positions, nsym, nsc, method="linear"):
         plan["i0"] = plan["i1"] = plan["i2"] = i
         plan["w0"], plan["w1"], plan["flags"] = 1.0, 0.0, 1
     else:
-        raise NotImplementedError(
-            f"interpolation method {method!r}: only 'linear' and 'nearest' are built "
-            "(Clough-Tocher 'cubic' is not a fixed linear map of the pilot values; see DESIGN.md)")
+        raise ValueError(f"Unknown interpolation method {method!r} (griddata knows 'linear', 'nearest', 'cubic'; "
+                         "'cubic' is a dense map, see cubic_matrix)")
+    return plan
+
+
+_CUBIC_CACHE: "OrderedDict[tuple, np.ndarray]" = OrderedDict()
+
+
+def cubic_matrix(pilot_indices, nsym, nsc, cache_size=8):
+    """griddata(method='cubic') as a dense linear map W [nsym*nsc, Np] (float32), fill_value 0.
+
+    SciPy's CloughTocher2DInterpolator estimates vertex gradients with an iterative global solver and
+    then evaluates a piecewise-cubic Bezier patch: for a fixed triangulation both steps are linear in
+    the pilot values (the solver's stopping rule perturbs this by ~1e-6), so interpolating the identity
+    matrix yields the map.  The basis run uses a tight tolerance; measured agreement with the
+    reference's own two-griddata-call route is 2e-7 (tests/test_host_logic.py)."""
+    from scipy.interpolate import CloughTocher2DInterpolator
+    idx = np.ascontiguousarray(np.asarray(pilot_indices, dtype=np.int64))
+    key = (hashlib.sha1(idx.tobytes()).hexdigest(), nsym, nsc)
+    hit = _CUBIC_CACHE.get(key)
+    if hit is not None:
+        _CUBIC_CACHE.move_to_end(key)
+        return hit
+    pos = np.unravel_index(idx, (nsym, nsc))
+    pts = np.column_stack([pos[0], pos[1]]).astype(np.float64)
+    ct = CloughTocher2DInterpolator(pts, np.eye(len(idx)), fill_value=0.0, tol=1e-10, maxiter=2000)
+    W = np.ascontiguousarray(ct(_queries(nsym, nsc)), dtype=np.float32)
+    _CUBIC_CACHE[key] = W
+    while len(_CUBIC_CACHE) > cache_size:
+        _CUBIC_CACHE.popitem(last=False)
+    return W
+
+
+def identity_plan(n):
+    """Plan in which resource element e is its own 'pilot' e (used to broadcast / score a grid that
+    already holds per-RE values: the cubic path, evaluate_estimator)."""
+    plan = np.zeros(n, dtype=PLAN_DTYPE)
+    plan["i0"] = plan["i1"] = plan["i2"] = np.arange(n)
+    plan["w0"], plan["flags"] = 1.0, 1
     return plan
 
 

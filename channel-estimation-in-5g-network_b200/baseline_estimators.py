@@ -46,10 +46,14 @@ def _interp_pairs(h_pairs, pilot_positions, grid_shape, method):
     eng = _engine()
     idx = _pilot_index(pilot_positions, nsc)
     order = np.argsort(idx, kind="stable")      # plans are keyed on the sorted (row-major) pilot set
-    pool = PatternPool([idx[order]], nsym, nsc, method, eng.device)
     npair = h_pairs.shape[0]
     g = Geom(nsym, nsc, 1, npair, 1024, 72, 0.0)
     hp = _c64(np.asarray(h_pairs)[:, order][None], eng.device)
+    if method == 'cubic':
+        W = torch.from_numpy(_tables.cubic_matrix(idx[order], nsym, nsc)).to(eng.device)
+        grid = eng.dense_real_apply(W, hp[0].contiguous(), ld_out=nsym * nsc)
+        return grid.reshape(npair, nsym, nsc).cpu().numpy().astype(np.complex128)
+    pool = PatternPool([idx[order]], nsym, nsc, method, eng.device)
     out = eng.ls_interp(None, None, pool, hp_in=hp, want=("H_ls",), geom=g)
     return out["H_ls"][0, :, :, 0, :].permute(1, 0, 2).cpu().numpy().astype(np.complex128)
 
@@ -82,13 +86,16 @@ def _estimate_4d(rx_symbols, tx_pilots, pilot_mask, method, snr_db):
     nsym, nrx, ntx, nsc = rx_symbols.shape
     eng = _engine()
     idx = np.flatnonzero(np.asarray(pilot_mask).reshape(-1))           # row-major = grid[mask] order
-    pool = PatternPool([idx], nsym, nsc, method, eng.device)
+    pool = PatternPool([idx], nsym, nsc, method, eng.device) if method != 'cubic' else None
     # (rx, tx) pairs are independent "receive antennas" of a 1-TX problem
     g = Geom(nsym, nsc, 1, nrx * ntx, 1024, 72, 0.0)
     rx = _c64(rx_symbols.reshape(nsym, nrx * ntx, nsc)[None], eng.device)
     want = ("H_mmse",) if snr_db is not None else ("H_ls",)
-    out = eng.ls_interp(rx, _c64(np.asarray(tx_pilots).reshape(1, -1), eng.device), pool,
-                        snr_db=snr_db, mmse=snr_db is not None, want=want, geom=g)
+    if method == 'cubic':    # dense Clough-Tocher map on the tensor cores (LS only, as in the reference)
+        out = eng.ls_cubic(rx, _c64(np.asarray(tx_pilots).reshape(1, -1), eng.device), idx, want=want, geom=g)
+    else:
+        out = eng.ls_interp(rx, _c64(np.asarray(tx_pilots).reshape(1, -1), eng.device), pool,
+                            snr_db=snr_db, mmse=snr_db is not None, want=want, geom=g)
     H = out[want[0]][0, :, :, 0, :]
     return H.reshape(nsym, nrx, ntx, nsc).cpu().numpy().astype(np.complex128)
 

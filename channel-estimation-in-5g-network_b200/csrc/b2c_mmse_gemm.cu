@@ -65,9 +65,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 
-__global__ void __launch_bounds__(TC_THREADS) mmse_dense_tc_kernel(const float2 *__restrict__ W, int np,
-                                                                    const float2 *__restrict__ in,
-                                                                    float *__restrict__ out, int64_t ncols, int64_t ld) {
+// REALW = false: W complex [np][np] (m = k = np), the interleaved embedding described above.
+// REALW = true : W REAL [m][k] applied to the real and imaginary parts alike (the Clough-Tocher 'cubic'
+//                interpolation as a dense linear map, [nsym*nsc] x [npilots]): column c of `in` becomes two
+//                GEMM columns (re, im), so a CTA covers 64 complex columns and K runs over k, not 2k.
+template <bool REALW>
+__global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__restrict__ Wf, int m, int k,
+                                                              const float2 *__restrict__ in, float *__restrict__ out,
+                                                              int64_t ncols, int64_t ld_in, int64_t ld_out) {
+  const float2 *__restrict__ W = reinterpret_cast<const float2 *>(Wf);
+  const int np = k;              // complex path: square matrix
+  const int64_t ld = ld_in;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ uint32_t tmem_base_sm;
   __shared__ __align__(8) uint64_t mma_bar;
@@ -79,9 +87,10 @@ __global__ void __launch_bounds__(TC_THREADS) mmse_dense_tc_kernel(const float2 
   const uint32_t aAh = s0, aAl = s0 + TC_TILE_A, aBh = s0 + 2 * TC_TILE_A, aBl = s0 + 2 * TC_TILE_A + TC_TILE_B;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int i0c = blockIdx.x * (TC_BM / 2);          // first complex row of W in this tile
-  const int64_t c0 = (int64_t)blockIdx.y * TC_BN;    // first column
-  const int kreal = 2 * np;
+  const int i0c = blockIdx.x * (TC_BM / 2);          // complex path: first complex row of W in this tile
+  const int e0 = blockIdx.x * TC_BM;                 // real path: first row of W in this tile
+  const int64_t c0 = (int64_t)blockIdx.y * (REALW ? TC_BN / 2 : TC_BN);    // first (complex) column
+  const int kreal = REALW ? k : 2 * np;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "r"((uint32_t)TC_BN));
@@ -107,10 +116,30 @@ __global__ void __launch_bounds__(TC_THREADS) mmse_dense_tc_kernel(const float2 
   //     one store instruction covers even and odd rows (all 16 bank pairs) instead of only even ones.
   //   B (128 rows cl x 16 complex cols jl of `in` per stage, 16 values per thread):
   //     cl[2:0] = lane[2:0], cl[6:3] = q ; jl[0] = lane[3], jl[1] = lane[4], jl[3:2] = warp
-  float2 ra[8], rb[16];
+  float2 ra[8], rb[16], ra_w[REALW ? 16 : 1];
   const int a_il_lo = (lane & 3) | ((warp >> 1) << 2), a_jl = ((lane >> 2) & 7) | ((warp & 1) << 3);
   const int b_cl_lo = lane & 7, b_jl = ((lane >> 3) & 3) | (warp << 2);
+  // real-W maps (16 values per thread for A and for B):
+  //   A (128 rows r x 16 float pairs jl): r[2:0] = lane[2:0], r[6:3] = q ; jl as for the complex B tile
+  //   B (64 complex columns cc x 32 k): cc[1:0] = lane[1:0], cc[5:2] = q ; kk[2:0] = lane[4:2], kk[4:3] = warp;
+  //     value (re, im) goes to rows 2cc / 2cc+1 as two 4-byte stores, lane[4] picks which first
+  const int rb_cc_lo = lane & 3, rb_kk = ((lane >> 2) & 7) | (warp << 3);
   auto load_stage = [&](int k0) {     // k0: real k offset of the stage (multiple of 32)
+    if (REALW) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int r = e0 + (q << 3) + b_cl_lo, j = k0 + 2 * b_jl;
+        const float *src = Wf + (int64_t)r * k + j;
+        ra_w[q] = make_float2((r < m && j < k) ? __ldg(src) : 0.f, (r < m && j + 1 < k) ? __ldg(src + 1) : 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int64_t c = c0 + (q << 2) + rb_cc_lo;
+        const int j = k0 + rb_kk;
+        rb[q] = (c < ncols && j < k) ? __ldg(in + c * ld_in + j) : make_float2(0.f, 0.f);
+      }
+      return;
+    }
     const int jc0 = k0 >> 1;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -125,6 +154,37 @@ __global__ void __launch_bounds__(TC_THREADS) mmse_dense_tc_kernel(const float2 
     }
   };
   auto store_stage = [&]() {
+    if (REALW) {
+      const int kc = b_jl >> 1, eo = (b_jl & 1) * 8;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int r = (q << 3) + b_cl_lo;
+        float x_h, x_l, y_h, y_l;
+        split_tf32(ra_w[q].x, x_h, x_l);
+        split_tf32(ra_w[q].y, y_h, y_l);
+        const int o = kc * TC_LBO_A + (r >> 3) * TC_SBO + (r & 7) * 16 + eo;
+        *reinterpret_cast<float2 *>(sAh + o) = make_float2(x_h, y_h);
+        *reinterpret_cast<float2 *>(sAl + o) = make_float2(x_l, y_l);
+      }
+      const int kc2 = rb_kk >> 2, eo2 = (rb_kk & 3) * 4;
+      const bool im_first = (lane >> 4) & 1;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int cc = (q << 2) + rb_cc_lo;
+        float xr_h, xr_l, xi_h, xi_l;
+        split_tf32(rb[q].x, xr_h, xr_l);
+        split_tf32(rb[q].y, xi_h, xi_l);
+        const int r0 = 2 * cc, r1 = 2 * cc + 1;
+        const int o0 = kc2 * TC_LBO_B + (r0 >> 3) * TC_SBO + (r0 & 7) * 16 + eo2;   // row 2c  : real part
+        const int o1 = kc2 * TC_LBO_B + (r1 >> 3) * TC_SBO + (r1 & 7) * 16 + eo2;   // row 2c+1: imaginary part
+        const int of = im_first ? o1 : o0, os = im_first ? o0 : o1;
+        *reinterpret_cast<float *>(sBh + of) = im_first ? xi_h : xr_h;
+        *reinterpret_cast<float *>(sBl + of) = im_first ? xi_l : xr_l;
+        *reinterpret_cast<float *>(sBh + os) = im_first ? xr_h : xi_h;
+        *reinterpret_cast<float *>(sBl + os) = im_first ? xr_l : xi_l;
+      }
+      return;
+    }
     const int a_kc = a_jl >> 1, a_eo = (a_jl & 1) * 8;
     const bool odd_first = (lane >> 3) & 1;
 #pragma unroll
@@ -190,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS) mmse_dense_tc_kernel(const float2 
   // ---- epilogue: TMEM -> registers -> global (row i' contiguous in memory) -----------------------
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const int ip = blockIdx.x * TC_BM + warp * 32 + lane;     // real output row of this thread (its TMEM lane)
-  const int64_t ld2 = 2 * ld;
+  const int64_t ld2 = 2 * ld_out;
 #pragma unroll 1
   for (int cb = 0; cb < TC_BN; cb += 32) {
     uint32_t r[32];
@@ -205,7 +265,16 @@ __global__ void __launch_bounds__(TC_THREADS) mmse_dense_tc_kernel(const float2 
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-    if (ip < kreal) {
+    if (REALW) {
+      if (ip < m) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {      // TMEM columns (2q, 2q+1) = (re, im) of complex column c
+          const int64_t c = c0 + (cb >> 1) + q;
+          if (c < ncols)
+            *reinterpret_cast<float2 *>(out + c * ld2 + 2 * ip) = make_float2(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
+        }
+      }
+    } else if (ip < kreal) {
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
         const int64_t c = c0 + cb + q;
@@ -231,9 +300,26 @@ extern "C" int b2c_mmse_dense(const float *W, int32_t np, const float *in, float
   if (ncols == 0) return B2C_OK;
   dim3 grid((unsigned)((2 * np + TC_BM - 1) / TC_BM), (unsigned)((ncols + TC_BN - 1) / TC_BN));
   B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_mmse_dense: ncols=%lld too large for one launch", (long long)ncols);
-  B2C_CUDA(cudaFuncSetAttribute(mmse_dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  mmse_dense_tc_kernel<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float2 *>(W), np, reinterpret_cast<const float2 *>(in), out, ncols, ld);
+  B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  dense_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(W, np, np, reinterpret_cast<const float2 *>(in),
+                                                                               out, ncols, ld, ld);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_dense_real_apply(const float *W, int32_t m, int32_t k, const float *in, float *out, int64_t ncols,
+                                    int64_t ld_in, int64_t ld_out, void *stream) {
+  B2C_REQUIRE(W && in && out, B2C_E_ARG, "b2c_dense_real_apply: null argument");
+  B2C_REQUIRE(m >= 1 && k >= 1 && ld_in >= k && ld_out >= m && ncols >= 0, B2C_E_ARG,
+              "b2c_dense_real_apply: m=%d k=%d ld_in=%lld ld_out=%lld ncols=%lld", m, k, (long long)ld_in, (long long)ld_out,
+              (long long)ncols);
+  B2C_REQUIRE(in != out, B2C_E_ARG, "b2c_dense_real_apply: in-place not supported");
+  if (ncols == 0) return B2C_OK;
+  dim3 grid((unsigned)((m + TC_BM - 1) / TC_BM), (unsigned)((ncols + TC_BN / 2 - 1) / (TC_BN / 2)));
+  B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_real_apply: ncols=%lld too large for one launch", (long long)ncols);
+  B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  dense_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(W, m, k, reinterpret_cast<const float2 *>(in), out,
+                                                                              ncols, ld_in, ld_out);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }

@@ -79,6 +79,7 @@ class SlotEngine:
                              self._dev["tap_path"].data_ptr(), self._dev["tap_amp"].data_ptr(),
                              self._dev["tap_tw"].data_ptr(), self._dev["tap_corr"].data_ptr())
         self.p_max = int(t["npaths"].max())
+        self._cubic, self._ident = {}, {}
 
     # ---- pools -------------------------------------------------------------------------------
     def pool(self, pilot_index_list, method="linear"):
@@ -217,6 +218,50 @@ class SlotEngine:
         check(lib().b2c_pilot_vectors(dptr(y, "c64"), dptr(x, "c64"), y.shape[0], y.shape[1], float(snr_db),
                                       1 if mmse else 0, dptr(out, "c64"), stream_ptr()), "b2c_pilot_vectors")
         return out
+
+    def dense_real_apply(self, W, h, ld_out=None):
+        """W [m,k] float32, h [ncols, ld_in>=k] c64 -> out [ncols, ld_out>=m] with out[c,:m] = W @ h[c,:k]."""
+        m, k = W.shape
+        ld_out = m if ld_out is None else ld_out
+        out = torch.zeros((h.shape[0], ld_out), dtype=torch.complex64, device=self.device)
+        check(lib().b2c_dense_real_apply(dptr(W, "f32"), m, k, dptr(h, "c64"), dptr(out, "c64"), h.shape[0], h.shape[1],
+                                         ld_out, stream_ptr()), "b2c_dense_real_apply")
+        return out
+
+    def ls_cubic(self, rx, pilots, pilot_indices, H_true=None, want=("H_ls",), geom=None):
+        """LS estimate with griddata's 'cubic' interpolation: LS at the pilots (K3), the dense
+        Clough-Tocher map on the tensor cores (K4b), then K3 again with an identity plan to lay the
+        grid out per (rx, tx) and score it.  rx [B,nsym,nrx,nsc], pilots [B or 1, Np].  (The reference's
+        MMSE estimator always interpolates linearly, src/baseline_estimators.py:200, so there is no
+        cubic MMSE.)"""
+        g = geom if geom is not None else self.geom
+        idx = np.asarray(pilot_indices, dtype=np.int64)
+        nre = g.nsym * g.nsc
+        pool = PatternPool([idx], g.nsym, g.nsc, "nearest", self.device)          # only its pilot list is used here
+        B = rx.shape[0]
+        hp = self.ls_interp(rx, pilots, pool, want=("hp",), geom=g)["hp"].reshape(B * g.nrx, -1)
+        key = (idx.tobytes(), g.nsym, g.nsc)
+        if key not in self._cubic:
+            self._cubic = {key: torch.from_numpy(_tables.cubic_matrix(idx, g.nsym, g.nsc)).to(self.device)}
+        grid = self.dense_real_apply(self._cubic[key], hp, ld_out=nre)             # [B*nrx, nre]
+        return self.ls_interp(None, None, self._identity_pool(g.nsym, g.nsc), hp_in=grid.reshape(B, g.nrx, nre),
+                              H_true=H_true, want=tuple(w for w in want if w in ("H_ls", "stats")), geom=g)
+
+    def _identity_pool(self, nsym, nsc):
+        nre = nsym * nsc
+        if nre not in self._ident:
+            pool = PatternPool.__new__(PatternPool)
+            pool.device, pool.nsym, pool.nsc, pool.method = self.device, nsym, nsc, "identity"
+            pool.pilot_indices, pool.np_max = [np.arange(nre)], nre
+            pool.npilots_host = np.array([nre], np.int32)
+            plan = np.zeros((2, nre + 1), dtype=_tables.PLAN_DTYPE)
+            plan[0] = _tables.finalize_plan(_tables.identity_plan(nre), nre)
+            pool.npilots = torch.tensor([nre], dtype=torch.int32, device=self.device)
+            pool.pilot_re = torch.arange(nre, dtype=torch.int32, device=self.device).reshape(1, nre)
+            pool.plan = torch.from_numpy(plan.view(np.uint8).reshape(2, (nre + 1) * 16)).to(self.device)
+            pool.struct = Patterns(1, nre, pool.npilots.data_ptr(), pool.pilot_re.data_ptr(), pool.plan.data_ptr())
+            self._ident[nre] = pool
+        return self._ident[nre]
 
     def mmse_dense(self, W, h):
         """W [np,np] c64, h [ncols, ld>=np] c64 -> W @ h[c, :np] per column set."""

@@ -185,6 +185,14 @@ int b2c_pilot_vectors(const float *y, const float *x, int64_t nvec, int32_t n, f
 int b2c_mmse_dense(const float *W, int32_t np, const float *in, float *out, int64_t ncols,
                    int64_t ld, void *stream);
 
+/* K4b.  Dense REAL linear map applied to complex columns on the tensor cores (same tcgen05 / 3xTF32
+ * machinery): out[c][e] = sum_j W[e][j] * in[c][j], W real [m][k] row-major, in [ncols][ld_in],
+ * out [ncols][ld_out] complex.  Used for LSEstimator(interpolation_method='cubic')
+ * (src/baseline_estimators.py:13-21, 65-79): SciPy's Clough-Tocher interpolant on a fixed pilot set is a
+ * linear map of the pilot values (to 1e-6), built once per pattern on the host as W [nsym*nsc][npilots]. */
+int b2c_dense_real_apply(const float *W, int32_t m, int32_t k, const float *in, float *out, int64_t ncols,
+                         int64_t ld_in, int64_t ld_out, void *stream);
+
 /* K5.  Fold per-slot statistics into per-bin float64 accumulators (deterministic order).
  * Replaces the per-sample evaluate_estimator / compute_nmse + list aggregation of
  * src/baseline_estimators.py:326-337 and run_phase8_pilot_optimization.py:32-37,186-206.

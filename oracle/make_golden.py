@@ -179,6 +179,22 @@ def tdl_case(name, seed):
     print(name)
 
 
+def cubic_case(name, sources=("slot_siso_epa", "slot_2x2_eva", "slot_2x1_epa_1pct")):
+    """LSEstimator('cubic') of the reference (Clough-Tocher griddata, test_phase2_ls.py:28) on the rx grids
+    already stored in the slot fixtures."""
+    import baseline_estimators as be
+    out = {}
+    for src in sources:
+        with np.load(os.path.join(OUT, src + ".npz")) as z:
+            rx, xp, mask, idx = z["rx_symbols"], z["pilot_symbols"], z["pilot_mask"], z["pilot_indices"]
+        pos = np.unravel_index(idx, mask.shape)
+        rx4d = rx.reshape(rx.shape[0], rx.shape[1], 1, rx.shape[2])
+        H = be.LSEstimator("cubic").estimate(rx4d, xp, mask, pos)
+        out[src] = H[:, :, 0]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit(f"reference not found at {REF}; fixtures can only be minted in the build container")
@@ -192,6 +208,7 @@ def main():
     dense_mmse_case("mmse_dense_2x2", 606)
     ofdm_case("ofdm_modem", 707)
     tdl_case("tdl_standalone", 808)
+    cubic_case("ls_cubic")
 
 
 if __name__ == "__main__":

@@ -64,8 +64,17 @@ def test_ls_and_mmse_estimators(name):
     rx_mod[:, 0, -1] *= 2.0
     H2 = be.LSEstimator().estimate(rx_mod, g["pilot_symbols"], g["pilot_mask"], pos)
     assert relerr(H2[:, 0, -1], 2.0 * g["H_ls_tx0"][:, 0]) < RTOL
-    with pytest.raises(NotImplementedError):
-        be.LSEstimator('cubic').estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos)
+    if name in load_golden("ls_cubic"):       # Clough-Tocher as a dense map on the tensor cores (test_phase2_ls.py:28)
+        H_c = be.LSEstimator('cubic').estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos)
+        cub = load_golden("ls_cubic")[name]
+        for t in range(ntx):
+            assert relerr(H_c[:, :, t], cub) < RTOL
+        assert np.array_equal(H_c[:, :, 0] == 0, cub == 0)
+        grid = be.LSEstimator('cubic').interpolate_channel(
+            orc.ls_at_pilots(g["rx_symbols"][:, 0], g["pilot_symbols"], g["pilot_mask"]), pos, (14, 599))
+        assert relerr(grid, cub[:, 0]) < RTOL
+    with pytest.raises(ValueError):
+        be.LSEstimator('quintic').estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos)
     with pytest.raises(ValueError):
         be.equalize_channel(g["rx_symbols"], H_ls, method='bogus')
 

@@ -468,3 +468,30 @@ def test_compact_layout_and_host_pipeline(engines):
             assert host.shape == tuple(full[k].shape)
             assert np.abs(host - full[k].cpu().numpy()).max() < 2e-6, (k, compact)
         assert hp.d2h_bytes_per_slot == (1945552 + 192 if compact else 3756928 + 192)
+
+
+def test_dense_real_map_and_cubic_ls(engines):
+    """K4b: real [m x k] map on complex columns (tcgen05, 3xTF32), and the cubic LS estimate built on it."""
+    eng = engines(2, 2)
+    dev = eng.device
+    rng = np.random.default_rng(4)
+    for m, k, c, ld_in in ((300, 167, 77, 170), (8386, 838, 70, 838), (129, 33, 3, 33)):
+        W = rng.standard_normal((m, k)) / np.sqrt(k)
+        X = np.zeros((c, ld_in), complex)
+        X[:, :k] = rng.standard_normal((c, k)) + 1j * rng.standard_normal((c, k))
+        Y = eng.dense_real_apply(torch.from_numpy(W).to(dev, torch.float32), torch.from_numpy(X).to(dev, torch.complex64),
+                                 ld_out=m + 5).cpu().numpy()
+        assert Y.shape == (c, m + 5) and not Y[:, m:].any()
+        assert relerr(Y[:, :m], X[:, :k] @ W.T) < 5e-5, (m, k, c)
+    g, cub = load_golden("slot_2x2_eva"), load_golden("ls_cubic")["slot_2x2_eva"]
+    rx = torch.from_numpy(g["rx_symbols"][None]).to(dev, torch.complex64)
+    xp = torch.from_numpy(g["pilot_symbols"][None]).to(dev, torch.complex64)
+    Ht = torch.from_numpy(g["channel"][None]).to(dev, torch.complex64)
+    out = eng.ls_cubic(rx, xp, g["pilot_indices"], H_true=Ht, want=("H_ls", "stats"))
+    H = out["H_ls"][0].cpu().numpy()
+    for t in range(2):
+        assert relerr(H[:, :, t], cub) < RTOL
+    assert np.array_equal(H[:, :, 0] == 0, cub == 0)
+    st = out["stats"][0].cpu().numpy()[:, 1].sum(axis=0) / g["channel"].size
+    want = orc.evaluate(g["channel"], np.repeat(cub[:, :, None, :], 2, axis=2))
+    assert abs(db(st[0] / (st[2] + 1e-12)) - want["nmse_db"]) < DB_TOL

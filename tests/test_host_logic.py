@@ -102,10 +102,27 @@ def test_nearest_plan_and_unknown_method():
     plan = _tables.cached_plan(g["pilot_indices"], 14, 599, "nearest")
     pos = np.unravel_index(g["pilot_indices"], (14, 599))
     assert np.array_equal(plan["i0"], orc.nearest_plan(pos, 14, 599))
-    with pytest.raises(NotImplementedError):
-        _tables.interpolation_plan(pos, 14, 599, "cubic")
+    with pytest.raises(ValueError):
+        _tables.interpolation_plan(pos, 14, 599, "quintic")
     with pytest.raises(KeyError):
         _tables.path_tables("XYZ", 15.36e6)
+
+
+@pytest.mark.parametrize("name", ["slot_siso_epa", "slot_2x1_epa_1pct"])
+def test_cubic_interpolation_is_a_linear_map(name):
+    """The dense matrix the GPU applies for interpolation_method='cubic' reproduces the reference's
+    Clough-Tocher griddata output (fixture minted from the reference) -- and so does the oracle."""
+    g, c = load_golden(name), load_golden("ls_cubic")
+    W = _tables.cubic_matrix(g["pilot_indices"], 14, 599)
+    assert W.shape == (14 * 599, len(g["pilot_indices"])) and W.dtype == np.float32
+    pos = np.unravel_index(g["pilot_indices"], (14, 599))
+    for r in range(int(g["nrx"])):
+        h_p = orc.ls_at_pilots(g["rx_symbols"][:, r], g["pilot_symbols"], g["pilot_mask"])
+        assert relerr((W.astype(np.float64) @ h_p).reshape(14, 599), c[name][:, r]) < 5e-6
+    rx4d = g["rx_symbols"][:, :, None, :]
+    H = orc.ls_estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos, method="cubic")
+    assert relerr(H[:, :, 0], c[name]) < 1e-12
+    assert np.array_equal(c[name] == 0, (W != 0).any(axis=1).reshape(14, 599)[None].repeat(int(g["nrx"]), 0).transpose(1, 0, 2) == 0)
 
 
 def test_shard_ranges_partition_the_samples():
