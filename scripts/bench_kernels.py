@@ -50,6 +50,14 @@ for ncols in (4096, 16384):
     res[f"k4_mmse_dense_{ncols}cols"] = {"ms": t * 1e3, "useful_tflops": flops / t / 1e12, "issued_tf32_tflops": 3 * flops / t / 1e12,
                                           "rel_err_vs_fp64": err}
 
+# K4b cubic interpolation map: real [8386 x 838] on (re, im) of 4096 pilot vectors (1024 4x4 slots)
+Wc = (torch.randn(8386, npil, device=dev) / np.sqrt(npil)).contiguous()
+h = torch.randn(4096, npil, dtype=torch.complex64, device=dev)
+t = timeit(lambda: eng.dense_real_apply(Wc, h), n=5)
+flops = 4.0 * 8386 * npil * 4096
+res["k4b_cubic_map_4096cols"] = {"ms": t * 1e3, "useful_tflops": flops / t / 1e12, "issued_tf32_tflops": 3 * flops / t / 1e12}
+del Wc, h
+
 # K3 stand-alone LS + MMSE + stats on resident rx / H_true
 B = 2048
 out = eng.run(B, 2, 200.0, 10.0, 0, pool, slot0=0, seed=1)
