@@ -14,7 +14,9 @@ LIB_PATH = os.path.join(HERE, "libb2c.so")
 MAX_TAPS, MAX_ANT, MAX_SYM, N_OSC, N_STAT, N_BINSTAT = 16, 8, 16, 20, 3, 12
 EXPORTS = ["b2c_last_error_string", "b2c_abi_version", "b2c_tap_gains", "b2c_slot_pipeline",
            "b2c_ls_interp", "b2c_pilot_vectors", "b2c_mmse_dense", "b2c_dense_real_apply", "b2c_stats_bins",
-           "b2c_ofdm_modulate", "b2c_ofdm_demodulate", "b2c_apply_channel", "b2c_tdl_full"]
+           "b2c_ofdm_modulate", "b2c_ofdm_demodulate", "b2c_apply_channel", "b2c_tdl_full", "b2c_equalize",
+           "b2c_qam_modulate", "b2c_qam_demodulate", "b2c_count_bit_errors", "b2c_pair00_moments", "b2c_pair00_errors",
+           "b2c_ml_features"]
 
 
 class B2CError(RuntimeError):
@@ -73,6 +75,13 @@ def lib():
             "b2c_ofdm_demodulate": [P, P, P, I64, P],
             "b2c_apply_channel": [P, P, P, I64, P, P, P, P, P],
             "b2c_tdl_full": [P, P, I32, F, F, I64, I32, P, P, C.c_uint64, I64, P, P],
+            "b2c_equalize": [P, I64, P, P, P, C.c_double, I32, P],
+            "b2c_qam_modulate": [P, I64, I32, P, P],
+            "b2c_qam_demodulate": [P, I64, I32, I32, P, P],
+            "b2c_count_bit_errors": [P, P, I64, P, P],
+            "b2c_pair00_moments": [P, I64, P, P, P, I64, P, P],
+            "b2c_pair00_errors": [P, I64, P, P, I64, P, P, P],
+            "b2c_ml_features": [P, P, P, I64, P, P, P, I64, I32, I32, P, P, P, P],
         }
         for name, argtypes in sig.items():
             fn = getattr(L, name)
@@ -89,7 +98,8 @@ def check(rc, what=""):
         raise B2CError(f"{what} failed ({rc}): {lib().b2c_last_error_string().decode()}")
 
 
-_DT = {"c64": torch.complex64, "f32": torch.float32, "f64": torch.float64, "i32": torch.int32, "u8": torch.uint8}
+_DT = {"c64": torch.complex64, "f32": torch.float32, "f64": torch.float64, "i32": torch.int32, "u8": torch.uint8,
+       "c128": torch.complex128, "i64": torch.int64}
 
 
 def dptr(t, kind, optional=False):

@@ -170,11 +170,15 @@ class MMSEEstimator:
 
 
 def equalize_channel(rx_symbols: np.ndarray, H_est: np.ndarray, method: str = 'zf') -> np.ndarray:
-    """Per-RE ZF / MMSE equaliser (src/baseline_estimators.py:273-312).  Outside this round's
-    hot-path scope (never called by the reference): not built on the GPU yet."""
+    """Per-RE ZF / MMSE equaliser (src/baseline_estimators.py:273-312):
+    x = (H^H H + lambda I)^-1 H^H y with lambda = 1e-8 ('zf') or 0.01 ('mmse'), solved in fp64 on the
+    GPU (b2c_equalize) on complex128 buffers, so the reference's dtype and conditioning are kept."""
     if method not in ('zf', 'mmse'):
         raise ValueError(f"Unknown equalization method: {method}")
-    raise NotImplementedError("equalize_channel is a 'next' row (SURVEY.md 8f); no GPU kernel yet and no CPU fallback")
+    eng = _engine()
+    H = torch.from_numpy(np.ascontiguousarray(np.asarray(H_est, dtype=np.complex128))[None]).to(eng.device)
+    y = torch.from_numpy(np.ascontiguousarray(np.asarray(rx_symbols, dtype=np.complex128))[None]).to(eng.device)
+    return eng.equalize(y, H, method)[0].cpu().numpy()
 
 
 def evaluate_estimator(H_true: np.ndarray, H_est: np.ndarray) -> dict:

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2c.so")
-SOURCES = ["b2c_api.cu", "b2c_slot.cu", "b2c_estimate.cu", "b2c_ofdm.cu", "b2c_misc.cu", "b2c_mmse_gemm.cu"]
+SOURCES = ["b2c_api.cu", "b2c_slot.cu", "b2c_estimate.cu", "b2c_ofdm.cu", "b2c_misc.cu", "b2c_mmse_gemm.cu", "b2c_link.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

@@ -165,6 +165,19 @@ class ChannelEstimationDataset:
                       pid.astype(np.int32), self.pattern_pool(), slot0=slot0, seed=self.seed, want=want, out=out, ws=ws)
         return res, {"model": mi, "doppler": di, "snr": si, "density": pi, "pattern": pid}
 
+    def generate_feature_batch(self, count: int, slot0: int = 0, layout: str = "last", normalize: bool = True,
+                               norm=None):
+        """Training features straight from GPU-resident slots, skipping disk:
+        `count` Philox slots -> (inputs, targets, params) with inputs = (rx re, rx im, H_ls re, H_ls im,
+        pilot mask) and targets = H_true (re, im) of antenna pair (0,0), float32 CUDA tensors.
+        layout='last' + normalize is prepare_ml_inputs per slot (src/dataset_generator.py:183-227);
+        layout='first' + norm (see SlotEngine.normalization_from_moments) is ChannelDataset.__getitem__
+        (src/train.py:62-94)."""
+        res, par = self.generate_batch(count, slot0, want=("H_true", "rx", "H_ls"))
+        x, y = self.engine.ml_features(res["rx"], res["H_ls"], res["H_true"], self.pattern_pool(),
+                                       par["pattern"].astype(np.int32), layout, normalize, norm)
+        return x, y, par
+
     def _philox_samples(self, n):
         models, dopplers, snrs, dens = self._lists()
         res, par = self.generate_batch(n, self._next_slot)
@@ -252,6 +265,41 @@ def summarize_bins(bins) -> List[Dict]:
         m["nmse00_ls_std"] = float(np.sqrt(max(r[9] / n - (r[8] / n) ** 2, 0.0)))
         rows.append(m)
     return rows
+
+
+_FEATURE_POOLS = {}
+
+
+def prepare_ml_inputs(sample: Dict, normalize: bool = True):
+    """(inputs [nsym, nsc, 5], targets [nsym, nsc, 2]) real-valued arrays from one dataset sample
+    (src/dataset_generator.py:183-227): first RX / TX antenna, channels (rx re, rx im, H_ls re, H_ls im,
+    pilot mask); with `normalize` the four signal channels are divided by their joint std + 1e-8 and the
+    targets by theirs.  Packed and reduced on the GPU (b2c_ml_features)."""
+    from engine import PatternPool
+    from _b2c import Geom
+    rx, H_ls, H_true = np.asarray(sample['rx_symbols']), np.asarray(sample['H_ls']), np.asarray(sample['H_true'])
+    nsym, nrx, nsc = rx.shape
+    ntx = H_ls.shape[2]
+    mask = np.asarray(sample['pilot_mask']).astype(bool)
+    idx = np.flatnonzero(mask.reshape(-1))
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    key = (dev, nsym, nsc)
+    if key not in _FEATURE_POOLS:
+        from baseline_estimators import _engine
+        _FEATURE_POOLS[key] = _engine()
+    eng = _FEATURE_POOLS[key]
+    # only the pilot positions of the pool are read by the feature kernel; the identity plan keeps this cheap
+    pool = PatternPool.__new__(PatternPool)
+    pool.device, pool.nsym, pool.nsc, pool.np_max = eng.device, nsym, nsc, max(1, idx.size)
+    pool.npilots = torch.tensor([idx.size], dtype=torch.int32, device=eng.device)
+    pool.pilot_re = torch.zeros((1, pool.np_max), dtype=torch.int32, device=eng.device)
+    pool.pilot_re[0, :idx.size] = torch.from_numpy(idx.astype(np.int32)).to(eng.device)
+    from _b2c import Patterns
+    pool.struct = Patterns(1, pool.np_max, pool.npilots.data_ptr(), pool.pilot_re.data_ptr(), None)
+    c64 = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.complex64))[None]).to(eng.device)
+    g = Geom(nsym, nsc, ntx, nrx, 1024, 72, 0.0)
+    x, y = eng.ml_features(c64(rx), c64(H_ls), c64(H_true), pool, 0, "last", normalize, None, geom=g)
+    return x[0].cpu().numpy().astype(np.float64), y[0].cpu().numpy().astype(np.float64)
 
 
 def main():

@@ -322,3 +322,112 @@ class SlotEngine:
                                  delays.ctypes.data_as(C.c_void_p), dptr(jakes_u, "f32", True), int(seed), int(slot),
                                  dptr(out, "c64"), stream_ptr()), "b2c_tdl_full")
         return out
+
+    # ---- next rows: equaliser, QAM, BER, ML features (b2c_link.cu) -------------------------------------
+    def equalize(self, rx, H, method="zf"):
+        """rx [B][nsym][nrx][nsc], H [B][nsym][nrx][ntx][nsc] (complex64 or complex128) -> [B][nsym][ntx][nsc]."""
+        if method not in ("zf", "mmse"):
+            raise ValueError(f"Unknown equalization method: {method}")
+        lam = 1e-8 if method == "zf" else 0.01      # src/baseline_estimators.py:297, 305
+        B, nsym, nrx, ntx, nsc = H.shape
+        kind = "c128" if H.dtype == torch.complex128 else "c64"
+        g = Geom(nsym, nsc, ntx, nrx, self.fft_size, self.cp, 0.0)
+        out = torch.empty((B, nsym, ntx, nsc), dtype=H.dtype, device=self.device)
+        check(lib().b2c_equalize(ref(g), B, dptr(rx, kind), dptr(H, kind), dptr(out, kind), lam, int(kind == "c128"),
+                                 stream_ptr()), "b2c_equalize")
+        return out
+
+    @staticmethod
+    def _qam_bits(M, what):
+        if M not in (4, 16):
+            raise NotImplementedError(f"{what} order {M} not implemented")
+        return 2 if M == 4 else 4
+
+    def qam_modulate(self, bits, M=4):
+        """bits uint8 [n * log2 M] (0/1, MSB first) -> complex64 [n]."""
+        bps = self._qam_bits(M, "Modulation")
+        n = bits.numel() // bps
+        out = torch.empty((n,), dtype=torch.complex64, device=self.device)
+        if n:
+            check(lib().b2c_qam_modulate(dptr(bits, "u8"), n, M, dptr(out, "c64"), stream_ptr()), "b2c_qam_modulate")
+        return out
+
+    def qam_demodulate(self, symbols, M=4):
+        bps = self._qam_bits(M, "Demodulation")
+        n = symbols.numel()
+        kind = "c128" if symbols.dtype == torch.complex128 else "c64"
+        bits = torch.empty((n * bps,), dtype=torch.uint8, device=self.device)
+        if n:
+            check(lib().b2c_qam_demodulate(dptr(symbols, kind), n, M, int(kind == "c128"), dptr(bits, "u8"), stream_ptr()),
+                  "b2c_qam_demodulate")
+        return bits
+
+    def count_bit_errors(self, a, b, count=None):
+        """Accumulates #{a != b} into the int64 device scalar `count` (created if None)."""
+        if a.numel() != b.numel():
+            raise ValueError("bit arrays differ in length")
+        if count is None:
+            count = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        if a.numel():
+            check(lib().b2c_count_bit_errors(dptr(a, "u8"), dptr(b, "u8"), a.numel(), dptr(count, "i64"), stream_ptr()),
+                  "b2c_count_bit_errors")
+        return count
+
+    def _ls_sym_stride(self, H_ls, g):
+        if H_ls.dim() == 5:
+            return g.nrx * g.ntx * g.nsc
+        return g.nrx * g.nsc          # compact [B][nsym][nrx][nsc]
+
+    def pair00_moments(self, rx, H_ls, H_true, moments=None, geom=None):
+        """moments[3][4] += (sum re, sum im, sum re^2, sum im^2) of the pair-(0,0) rows of rx, H_ls, H_true."""
+        g = geom if geom is not None else self.geom
+        if moments is None:
+            moments = torch.zeros((3, 4), dtype=torch.float64, device=self.device)
+        check(lib().b2c_pair00_moments(ref(g), rx.shape[0], dptr(rx, "c64"), dptr(H_ls, "c64"), dptr(H_true, "c64"),
+                                       self._ls_sym_stride(H_ls, g), dptr(moments, "f64"), stream_ptr()),
+              "b2c_pair00_moments")
+        return moments
+
+    def pair00_errors(self, H_ls, H_true, alpha=None, geom=None):
+        """[B][3] float64: sum |L-H|^2, sum |alpha L - H|^2, sum |H|^2 over the pair-(0,0) rows of each slot."""
+        g = geom if geom is not None else self.geom
+        B = H_true.shape[0]
+        out = torch.empty((B, 3), dtype=torch.float64, device=self.device)
+        a = None if alpha is None else self._vec(alpha, B, torch.float32)
+        check(lib().b2c_pair00_errors(ref(g), B, dptr(H_ls, "c64"), dptr(H_true, "c64"), self._ls_sym_stride(H_ls, g),
+                                      dptr(a, "f32", True), dptr(out, "f64"), stream_ptr()), "b2c_pair00_errors")
+        return out
+
+    @staticmethod
+    def normalization_from_moments(moments, count):
+        """{rx_mean, rx_scale, ls_mean, ls_scale, true_mean, true_scale} as ChannelDataset does it
+        (src/train.py:41-57, 80-83): mean of the re / im means, 1 / (mean of the re / im stds + 1e-8)."""
+        m = np.asarray(moments.cpu() if isinstance(moments, torch.Tensor) else moments, dtype=np.float64)
+        out = []
+        for q in range(3):
+            mu = m[q, :2] / count
+            sd = np.sqrt(np.maximum(m[q, 2:] / count - mu * mu, 0.0))
+            out += [mu.mean(), 1.0 / (sd.mean() + 1e-8)]
+        return np.array(out, dtype=np.float32)
+
+    def ml_features(self, rx, H_ls, H_true, pool, pattern_id=0, layout="last", normalize=True, norm=None, geom=None):
+        """5-channel inputs / 2-channel targets for the ML side from GPU-resident slots.
+        layout 'last' + normalize -> prepare_ml_inputs; layout 'first' + norm (6 floats) -> ChannelDataset items."""
+        g = geom if geom is not None else self.geom
+        B = rx.shape[0]
+        lay = {"last": 0, "first": 1}[layout]
+        pid = self._vec(pattern_id, B, torch.int32)
+        mode, nt = 0, None
+        if norm is not None:
+            mode, nt = 2, torch.as_tensor(np.asarray(norm, dtype=np.float32)).to(self.device)
+        elif normalize:
+            mode = 1
+        nre = g.nsym * g.nsc
+        shape_in = (B, g.nsym, g.nsc, 5) if lay == 0 else (B, 5, g.nsym, g.nsc)
+        shape_t = (B, g.nsym, g.nsc, 2) if lay == 0 else (B, 2, g.nsym, g.nsc)
+        inputs = torch.empty(shape_in, dtype=torch.float32, device=self.device)
+        targets = torch.empty(shape_t, dtype=torch.float32, device=self.device)
+        check(lib().b2c_ml_features(ref(g), ref(pool.struct), dptr(pid, "i32"), B, dptr(rx, "c64"), dptr(H_ls, "c64"),
+                                    dptr(H_true, "c64"), self._ls_sym_stride(H_ls, g), lay, mode, dptr(nt, "f32", True),
+                                    dptr(inputs, "f32"), dptr(targets, "f32"), stream_ptr()), "b2c_ml_features")
+        return inputs, targets

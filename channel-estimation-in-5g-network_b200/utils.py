@@ -1,6 +1,6 @@
 """Hot-path helpers of the reference's src/utils.py (seeding, config, dB conversion, channel metrics,
-complex<->real packing).  The QAM mod/demod, BER and torch-checkpoint helpers of that file belong to
-the ML side / 'next' rows and are not provided here."""
+complex<->real packing) plus its QAM mod/demod and BER helpers, all computed by
+libb2c.  The torch-checkpoint helpers of that file belong to the ML side and are not provided here."""
 
 from __future__ import annotations
 
@@ -58,6 +58,48 @@ def db2linear(db_value: float) -> float:
 def linear2db(linear_value: float) -> float:
     """10 log10(x + 1e-12) (src/utils.py:44-46)."""
     return 10 * np.log10(linear_value + 1e-12)
+
+
+def _bits_to_device(bits, eng):
+    import torch
+    b = np.ascontiguousarray((np.asarray(bits) != 0).astype(np.uint8).reshape(-1))
+    return torch.from_numpy(b).to(eng.device)
+
+
+def qam_modulation(bits: np.ndarray, M: int = 4) -> np.ndarray:
+    """QPSK / 16-QAM mapping (src/utils.py:71-108): MSB-first bit groups -> decimal -> gray[decimal] ->
+    constellation point; trailing bits that do not fill a symbol are dropped (:84).
+
+    The reference indexes the Python list `gray_map` with an ndarray (:106), which raises TypeError for
+    more than one symbol; this implements the evident intent, `constellation[np.asarray(gray_map)[decimal]]`
+    (pinned one symbol at a time against the reference in tests/golden/link_level.npz)."""
+    from baseline_estimators import _engine
+    eng = _engine()
+    bps = eng._qam_bits(M, "Modulation")
+    bits = np.asarray(bits).reshape(-1)
+    n = len(bits) // bps
+    return eng.qam_modulate(_bits_to_device(bits[:n * bps], eng), M).cpu().numpy().astype(np.complex128)
+
+
+def qam_demodulation(symbols: np.ndarray, M: int = 4) -> np.ndarray:
+    """Minimum-distance demapping to bits (src/utils.py:111-152), int array of 0/1, MSB first."""
+    import torch
+    from baseline_estimators import _engine
+    eng = _engine()
+    eng._qam_bits(M, "Demodulation")
+    sym = torch.from_numpy(np.ascontiguousarray(np.asarray(symbols, dtype=np.complex128).reshape(-1))).to(eng.device)
+    return eng.qam_demodulate(sym, M).cpu().numpy().astype(int)
+
+
+def calculate_ber(transmitted_bits: np.ndarray, received_bits: np.ndarray) -> float:
+    """Bit error rate (src/utils.py:155-157), mismatches counted on the GPU."""
+    from baseline_estimators import _engine
+    eng = _engine()
+    a, b = np.asarray(transmitted_bits).reshape(-1), np.asarray(received_bits).reshape(-1)
+    if a.shape != b.shape:
+        raise ValueError(f"operands could not be broadcast together with shapes {a.shape} {b.shape}")
+    count = eng.count_bit_errors(_bits_to_device(a, eng), _bits_to_device(b, eng))
+    return int(count.item()) / len(a)
 
 
 def calculate_mse(true_channel: np.ndarray, estimated_channel: np.ndarray) -> float:

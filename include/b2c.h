@@ -229,6 +229,46 @@ int b2c_tdl_full(const b2c_geom *g, const b2c_profiles *prof, int32_t model_id, 
                  float sample_period_s, int64_t num_samples, int32_t L, const int32_t *tap_delay_host,
                  const float *jakes_u, uint64_t seed, int64_t slot, float *out, void *stream);
 
+/* ---- "next" rows either side of the path ------------------------------- */
+
+/* equalize_channel (src/baseline_estimators.py:273-312): x = (H^H H + lambda I)^-1 H^H y per resource
+ * element; lambda = 1e-8 for 'zf' (:297), 0.01 for 'mmse' (:305-306).  Accumulated and solved in fp64.
+ *   rx [B][nsym][nrx][nsc], H [B][nsym][nrx][ntx][nsc], out [B][nsym][ntx][nsc]
+ *   fp64_io 0: complex64 buffers, 1: complex128 buffers (the drop-in keeps the reference's dtype)   */
+int b2c_equalize(const b2c_geom *g, int64_t B, const void *rx, const void *H, void *out, double lambda,
+                 int32_t fp64_io, void *stream);
+
+/* qam_modulation / qam_demodulation (src/utils.py:71-108, 111-152), M in {4, 16} (else
+ * B2C_E_UNSUPPORTED, the reference's NotImplementedError): bits are bytes 0/1, MSB first per symbol;
+ * demodulation is minimum distance, first minimum wins.  symbols complex64 (complex128 in if fp64_in). */
+int b2c_qam_modulate(const uint8_t *bits, int64_t nsymbols, int32_t M, float *symbols, void *stream);
+int b2c_qam_demodulate(const void *symbols, int64_t nsymbols, int32_t M, int32_t fp64_in, uint8_t *bits,
+                       void *stream);
+
+/* calculate_ber numerator (src/utils.py:155-157): *count += #{i : a[i] != b[i]}.                       */
+int b2c_count_bit_errors(const uint8_t *a, const uint8_t *b, int64_t n, uint64_t *count, void *stream);
+
+/* Feature packing for the ML side from GPU-resident slots, antenna pair (0,0).
+ *   rx [B][nsym][nrx][nsc]; H_true [B][nsym][nrx][ntx][nsc]; H_ls with ls_sym_stride complex elements
+ *   between consecutive symbols (nrx*ntx*nsc for the full layout, nrx*nsc for the compact one).
+ * b2c_pair00_moments: moments[3][4] += {sum re, sum im, sum re^2, sum im^2} of rx, H_ls, H_true rows
+ *   (ChannelDataset._compute_normalization_stats, src/train.py:41-57).
+ * b2c_ml_features: inputs (rx re, rx im, H_ls re, H_ls im, pilot mask), targets (H_true re, im), float32
+ *   layout 0: [B][nsym][nsc][5] / [B][nsym][nsc][2]   (prepare_ml_inputs, src/dataset_generator.py:183-227)
+ *   layout 1: [B][5][nsym][nsc] / [B][2][nsym][nsc]   (ChannelDataset.__getitem__, src/train.py:62-94)
+ *   norm_mode 0: none; 1: per-slot 1/(std+1e-8) of prepare_ml_inputs (:219-223);
+ *             2: (v - mean) * scale with norm = {rx_mean, rx_scale, ls_mean, ls_scale, true_mean, true_scale} */
+/* b2c_pair00_errors: out[b] = {sum |L-H|^2, sum |alpha_b L - H|^2, sum |H|^2} over the pair-(0,0) rows of
+ *   slot b (alpha NULL = 1): the per-sample LS / alpha-scaled NMSE of run_phase5_evaluation.py:283-296. */
+int b2c_pair00_errors(const b2c_geom *g, int64_t B, const float *H_ls, const float *H_true,
+                      int64_t ls_sym_stride, const float *alpha, double *out, void *stream);
+int b2c_pair00_moments(const b2c_geom *g, int64_t B, const float *rx, const float *H_ls, const float *H_true,
+                       int64_t ls_sym_stride, double *moments, void *stream);
+int b2c_ml_features(const b2c_geom *g, const b2c_patterns *pat, const int32_t *pattern_id, int64_t B,
+                    const float *rx, const float *H_ls, const float *H_true, int64_t ls_sym_stride,
+                    int32_t layout, int32_t norm_mode, const float *norm, float *inputs, float *targets,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

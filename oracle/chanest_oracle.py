@@ -416,3 +416,115 @@ def random_draws(rng, cfg, ntx, nrx, model, density):
         "noise_re": rng.standard_normal((nsym, nrx, nsc)),
         "noise_im": rng.standard_normal((nsym, nrx, nsc)),
     }
+
+
+# --------------------------------------------------------------------------
+# "next" rows either side of the path: equaliser,
+# QAM mapping, BER, ML feature packing.  Pinned by tests/golden/link_level.npz.
+# --------------------------------------------------------------------------
+def equalize(rx, H, method="zf"):
+    """src/baseline_estimators.py:273-312: x = inv(H^H H + lam I) H^H y per RE, lam = 1e-8 ('zf', :297)
+    or 0.01 ('mmse', :305-306).  rx [nsym,nrx,nsc], H [nsym,nrx,ntx,nsc] -> [nsym,ntx,nsc]."""
+    if method not in ("zf", "mmse"):
+        raise ValueError(f"Unknown equalization method: {method}")
+    lam = 1e-8 if method == "zf" else 0.01
+    Hm = np.moveaxis(np.asarray(H, dtype=complex), 3, 1)             # [nsym, nsc, nrx, ntx]
+    y = np.moveaxis(np.asarray(rx, dtype=complex), 2, 1)[..., None]  # [nsym, nsc, nrx, 1]
+    Hh = np.conj(np.swapaxes(Hm, -1, -2))
+    A = Hh @ Hm + lam * np.eye(Hm.shape[-1])
+    x = np.linalg.inv(A) @ Hh @ y
+    return np.moveaxis(x[..., 0], 1, 2)
+
+
+_QAM_LEVELS = np.array([-3.0, -1.0, 3.0, 1.0])
+
+
+def qam_tables(M):
+    """(constellation, gray_map) as listed at src/utils.py:91-103 / :126-138."""
+    if M == 4:
+        return np.array([1 + 1j, -1 + 1j, 1 - 1j, -1 - 1j]) / np.sqrt(2), np.array([0, 1, 3, 2])
+    if M == 16:
+        const = (_QAM_LEVELS[:, None] + 1j * _QAM_LEVELS[None, :]).reshape(-1) / np.sqrt(10)
+        return const, np.array([0, 1, 3, 2, 4, 5, 7, 6, 12, 13, 15, 14, 8, 9, 11, 10])
+    raise NotImplementedError(f"Modulation order {M} not implemented")
+
+
+def qam_modulate(bits, M=4):
+    """src/utils.py:71-108 as intended: the reference's `gray_map[decimal_values]` (:106) indexes a list
+    with an ndarray and raises TypeError under NumPy 2; the evident meaning is the array lookup below
+    (it is the inverse of qam_demodulation, which is how the golden file pins it)."""
+    const, gray = qam_tables(M)
+    bps = int(np.log2(M))
+    bits = np.asarray(bits).reshape(-1)
+    n = len(bits) // bps
+    dec = bits[:n * bps].reshape(-1, bps) @ (2 ** np.arange(bps)[::-1])
+    return const[gray[dec]]
+
+
+def qam_demodulate(symbols, M=4):
+    """src/utils.py:111-152: argmin |s - c| (first minimum), argsort(gray) back to decimal, MSB-first bits."""
+    const, gray = qam_tables(M)
+    bps = int(np.log2(M))
+    symbols = np.asarray(symbols).reshape(-1)
+    det = np.argmin(np.abs(symbols[:, None] - const[None, :]), axis=1)
+    dec = np.argsort(gray)[det]
+    return ((dec[:, None] >> np.arange(bps)[::-1]) & 1).reshape(-1)
+
+
+def bit_error_rate(a, b):
+    """src/utils.py:155-157."""
+    a, b = np.asarray(a), np.asarray(b)
+    return np.sum(a != b) / len(a)
+
+
+def ber_approximation(H_est, H_true, snr_db):
+    """run_phase5_evaluation.py:57-68: QPSK BER proxy from the estimation NMSE (power eps 1e-10, :40-42)."""
+    nmse = np.mean(np.abs(H_est - H_true) ** 2) / (np.mean(np.abs(H_true) ** 2) + 1e-10)
+    snr = 10 ** (snr_db / 10)
+    return float(np.clip(0.5 * np.exp(-(snr / (1 + snr * nmse)) / 2), 1e-10, 0.5))
+
+
+def ml_inputs(rx, H_ls, H_true, mask, normalize=True):
+    """prepare_ml_inputs, src/dataset_generator.py:183-227: pair (0,0), channel-last."""
+    c2r = lambda a: np.stack([a.real, a.imag], axis=-1)
+    x = np.concatenate([c2r(rx[:, 0, :]), c2r(H_ls[:, 0, 0, :]), mask.astype(float)[..., None]], axis=-1)
+    t = c2r(H_true[:, 0, 0, :])
+    if normalize:
+        x[..., :4] = x[..., :4] / (np.std(x[..., :4]) + 1e-8)
+        t = t / (np.std(t) + 1e-8)
+    return x, t
+
+
+def dataset_norm(rx, H_ls, H_true):
+    """ChannelDataset._compute_normalization_stats, src/train.py:41-57, on stacked arrays [N, ...]:
+    (mean, std) for rx, H_ls, H_true pair-(0,0) rows = mean of the re / im means and of the re / im stds."""
+    out = []
+    for a in (rx[:, :, 0, :], H_ls[:, :, 0, 0, :], H_true[:, :, 0, 0, :]):
+        out.append((np.mean([a.real.mean(), a.imag.mean()]), np.mean([a.real.std(), a.imag.std()])))
+    return out
+
+
+def dataset_item(rx, H_ls, H_true, mask, norm=None):
+    """ChannelDataset.__getitem__, src/train.py:62-94, for one sample: channel-first float32 (5, nsym, nsc) /
+    (2, nsym, nsc); norm = dataset_norm(...) or None."""
+    c2r = lambda a: np.stack([a.real, a.imag], axis=0)
+    parts = [c2r(rx[:, 0, :]), c2r(H_ls[:, 0, 0, :]), c2r(H_true[:, 0, 0, :])]
+    if norm is not None:
+        parts = [(p - m) / (s + 1e-8) for p, (m, s) in zip(parts, norm)]
+    x = np.concatenate([parts[0], parts[1], mask[None].astype(float)], axis=0)
+    return x.astype(np.float32), parts[2].astype(np.float32)
+
+
+def snr_sweep_baselines(H_true, H_ls, snr_db):
+    """run_phase5_evaluation.py:264-312 without a model: per-sample NMSE (eps 1e-10) of H_ls and of
+    alpha * H_ls, alpha = 1/(1 + 1/snr), pair (0,0); 10 log10(mean + 1e-12) per SNR value."""
+    nm = lambda e, t: np.mean(np.abs(e - t) ** 2) / (np.mean(np.abs(t) ** 2) + 1e-10)
+    values = sorted(set(float(s) for s in snr_db))
+    res = {s: ([], []) for s in values}
+    for i in range(len(snr_db)):
+        t, l = H_true[i, :, 0, 0, :], H_ls[i, :, 0, 0, :]
+        a = 1 / (1 + 1 / 10 ** (float(snr_db[i]) / 10))
+        res[float(snr_db[i])][0].append(nm(l, t))
+        res[float(snr_db[i])][1].append(nm(a * l, t))
+    db = lambda v: 10 * np.log10(np.mean(v) + 1e-12)
+    return values, [db(res[s][0]) for s in values], [db(res[s][1]) for s in values]

@@ -195,6 +195,83 @@ def cubic_case(name, sources=("slot_siso_epa", "slot_2x2_eva", "slot_2x1_epa_1pc
     print(name, {k: v.shape for k, v in out.items()})
 
 
+def link_case(name, seed):
+    """'next' rows: equalize_channel, qam_demodulation, calculate_ber,
+    compute_ber_approximation, prepare_ml_inputs, ChannelDataset items -- all from the reference.
+    qam_modulation cannot be run (src/utils.py:106 raises TypeError under NumPy 2), so the symbols fed to the
+    reference's demodulator come from the oracle's restatement; `qam*_bits_back == qam*_bits` pins it."""
+    import types
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))     # imported at module level, unused here
+    import baseline_estimators as be
+    import utils as ru
+    import dataset_generator as dg
+    import train as rt
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import chanest_oracle as orc
+    import tempfile
+
+    rng = np.random.RandomState(seed)
+    out = {}
+    c = lambda *sh: (rng.randn(*sh) + 1j * rng.randn(*sh)) / np.sqrt(2)
+    for tag, (ntx, nrx) in {"2x2": (2, 2), "4x4": (4, 4), "2x4": (2, 4), "3x3": (3, 3)}.items():
+        H = c(3, nrx, ntx, 37)
+        x = np.exp(1j * rng.uniform(0, 2 * np.pi, (3, ntx, 37)))
+        y = np.einsum("srtk,stk->srk", H, x) + 0.05 * c(3, nrx, 37)
+        out[f"eq_{tag}_H"], out[f"eq_{tag}_y"] = H, y
+        out[f"eq_{tag}_zf"], out[f"eq_{tag}_mmse"] = be.equalize_channel(y, H, "zf"), be.equalize_channel(y, H, "mmse")
+    # the reference's own estimates are tx-replicated, i.e. rank one
+    h = c(3, 4, 1, 37)
+    H = np.repeat(h, 4, axis=2)
+    y = np.einsum("srtk,stk->srk", H, np.exp(1j * rng.uniform(0, 2 * np.pi, (3, 4, 37)))) + 0.05 * c(3, 4, 37)
+    out["eq_rank1_H"], out["eq_rank1_y"] = H, y
+    out["eq_rank1_zf"], out["eq_rank1_mmse"] = be.equalize_channel(y, H, "zf"), be.equalize_channel(y, H, "mmse")
+
+    for M in (4, 16):
+        bps = int(np.log2(M))
+        bits = rng.randint(0, 2, 600 * bps)
+        sym = orc.qam_modulate(bits, M)
+        noisy = sym + 0.25 * c(sym.size)
+        out[f"qam{M}_bits"], out[f"qam{M}_symbols"] = bits, sym
+        out[f"qam{M}_bits_back"] = ru.qam_demodulation(sym, M)
+        out[f"qam{M}_noisy"], out[f"qam{M}_noisy_bits"] = noisy, ru.qam_demodulation(noisy, M)
+        out[f"qam{M}_ber"] = np.array(ru.calculate_ber(bits, out[f"qam{M}_noisy_bits"]))
+
+    # ML feature packing on three 2x2 samples cut down to a [14, 2, (2,) 96] grid
+    N, nsym, nsc = 3, 14, 96
+    rx, Hls, Htr = c(N, nsym, 2, nsc) * 1.3 + 0.1, c(N, nsym, 2, 2, nsc) * 0.8, c(N, nsym, 2, 2, nsc) * 0.7 - 0.05j
+    mask = rng.rand(N, nsym, nsc) < 0.1
+    out.update(ml_rx=rx, ml_H_ls=Hls, ml_H_true=Htr, ml_mask=mask)
+    for i in range(N):
+        smp = {"rx_symbols": rx[i], "H_ls": Hls[i], "H_true": Htr[i], "pilot_mask": mask[i]}
+        for nz in (True, False):
+            xi, ti = dg.prepare_ml_inputs(smp, normalize=nz)
+            out[f"ml_inputs_{i}_{int(nz)}"], out[f"ml_targets_{i}_{int(nz)}"] = xi, ti
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "tiny.npz")
+        np.savez(f, rx_symbols=rx.astype(np.complex64), H_ls=Hls.astype(np.complex64), H_true=Htr.astype(np.complex64),
+                 pilot_mask=mask.astype(np.float32), snr_db=np.zeros(N, np.float32))
+        for nz in (True, False):
+            ds = rt.ChannelDataset(f, normalize=nz)
+            if nz:
+                out["ds_norm"] = np.array([ds.rx_mean, ds.rx_std, ds.H_ls_mean, ds.H_ls_std, ds.H_true_mean, ds.H_true_std])
+            for i in range(N):
+                xi, ti, mi = ds[i]
+                out[f"ds_inputs_{i}_{int(nz)}"], out[f"ds_targets_{i}_{int(nz)}"] = xi.numpy(), ti.numpy()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("phase5", os.path.join(REF, "run_phase5_evaluation.py"))
+    try:
+        mod = importlib.util.module_from_spec(spec)
+        for missing in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+            sys.modules.setdefault(missing, types.ModuleType(missing))
+        spec.loader.exec_module(mod)
+        out["ber_approx"] = np.array([mod.compute_ber_approximation(Hls[0], Htr[0], s) for s in (-5.0, 10.0, 30.0)])
+        out["ber_approx_small_err"] = np.array([mod.compute_ber_approximation(Htr[0] * 1.01, Htr[0], s) for s in (-5.0, 10.0, 30.0)])
+    except Exception as e:       # plotting imports; the formula is three lines and is restated in the oracle
+        print("run_phase5_evaluation not importable here:", type(e).__name__, e)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, len(out), "arrays")
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit(f"reference not found at {REF}; fixtures can only be minted in the build container")
@@ -209,6 +286,7 @@ def main():
     ofdm_case("ofdm_modem", 707)
     tdl_case("tdl_standalone", 808)
     cubic_case("ls_cubic")
+    link_case("link_level", 909)
 
 
 if __name__ == "__main__":

@@ -317,3 +317,91 @@ def test_pilot_density_sweep():
     s = p8.PilotOptimizer().generate_test_sample(0.1, snr_db=12.0)
     assert set(s) == {"rx_symbols", "H_ls", "H_true", "pilot_mask", "snr_db"}
     assert abs(p8.compute_nmse(s["H_ls"][:, 0, 0], s["H_true"][:, 0, 0]) / orc.nmse_pair00(s["H_ls"], s["H_true"]) - 1) < 1e-4
+
+
+# ---- "next" rows -------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["2x2", "4x4", "2x4", "3x3", "rank1"])
+def test_equalize_channel_drop_in(tag):
+    """equalize_channel (src/baseline_estimators.py:273-312) against the reference's outputs."""
+    import baseline_estimators as be
+    g = load_golden("link_level")
+    for meth in ("zf", "mmse"):
+        x = be.equalize_channel(g[f"eq_{tag}_y"], g[f"eq_{tag}_H"], meth)
+        assert x.dtype == np.complex128 and x.shape == g[f"eq_{tag}_{meth}"].shape
+        assert relerr(x, g[f"eq_{tag}_{meth}"]) < (1e-5 if (tag == "rank1" and meth == "zf") else 1e-9)
+    with pytest.raises(ValueError):
+        be.equalize_channel(g["eq_2x2_y"], g["eq_2x2_H"], "mrc")
+
+
+@pytest.mark.parametrize("M", [4, 16])
+def test_qam_and_ber_drop_in(M):
+    import utils as u
+    g = load_golden("link_level")
+    bits = g[f"qam{M}_bits"]
+    sym = u.qam_modulation(bits, M)
+    assert sym.dtype == np.complex128 and relerr(sym, g[f"qam{M}_symbols"]) < 1e-6
+    assert np.array_equal(u.qam_demodulation(sym, M), bits)
+    back = u.qam_demodulation(g[f"qam{M}_noisy"], M)
+    assert np.array_equal(back, g[f"qam{M}_noisy_bits"])                      # bit-exact decisions
+    assert u.calculate_ber(bits, back) == float(g[f"qam{M}_ber"])
+    assert u.calculate_ber(bits, bits) == 0.0
+    assert u.qam_modulation(bits[:len(bits) - 1], M).size == (len(bits) - 1) // int(np.log2(M))   # ragged tail dropped
+    with pytest.raises(NotImplementedError):
+        u.qam_modulation(bits, 64)
+    with pytest.raises(NotImplementedError):
+        u.qam_demodulation(sym, 256)
+
+
+def test_prepare_ml_inputs_drop_in():
+    import dataset_generator as dg
+    g = load_golden("link_level")
+    for i in range(g["ml_rx"].shape[0]):
+        smp = {"rx_symbols": g["ml_rx"][i], "H_ls": g["ml_H_ls"][i], "H_true": g["ml_H_true"][i], "pilot_mask": g["ml_mask"][i]}
+        for nz in (0, 1):
+            x, t = dg.prepare_ml_inputs(smp, normalize=bool(nz))
+            assert x.shape == (14, 96, 5) and t.shape == (14, 96, 2)
+            assert np.array_equal(x[..., 4], g["ml_mask"][i].astype(float))           # mask channel bit-exact
+            assert relerr(x, g[f"ml_inputs_{i}_{nz}"]) < RTOL and relerr(t, g[f"ml_targets_{i}_{nz}"]) < RTOL
+
+
+def test_channel_dataset_features_and_phase5_baselines():
+    """ChannelDataset normalisation + items (src/train.py:41-94) and the per-SNR LS / MMSE aggregation of
+    run_phase5_evaluation.py:264-312 from device-resident arrays."""
+    import torch
+    import run_phase5_evaluation as p5
+    from baseline_estimators import _engine
+    from engine import PatternPool
+    from _b2c import Geom
+    g = load_golden("link_level")
+    eng = _engine()
+    rx, Hls, Htr, mask = g["ml_rx"], g["ml_H_ls"], g["ml_H_true"], g["ml_mask"]
+    N, nsym, nrx, ntx, nsc = Htr.shape
+    geom = Geom(nsym, nsc, ntx, nrx, 1024, 72, 0.0)
+    dev = lambda a: torch.from_numpy(a.astype(np.complex64)).to(eng.device)
+    mom = eng.pair00_moments(dev(rx), dev(Hls), dev(Htr), geom=geom)
+    norm = eng.normalization_from_moments(mom, N * nsym * nsc)
+    ref = g["ds_norm"]
+    want = np.array([ref[0], 1 / (ref[1] + 1e-8), ref[2], 1 / (ref[3] + 1e-8), ref[4], 1 / (ref[5] + 1e-8)])
+    # the means are ~1e-2 of the signal scale: compare them on that scale
+    assert np.max(np.abs(norm[0::2] - want[0::2])) < 1e-5 and relerr(norm[1::2], want[1::2]) < 1e-5
+    pool = PatternPool([np.flatnonzero(m.reshape(-1)) for m in mask], nsym, nsc, "nearest", eng.device)
+    pid = np.arange(N, dtype=np.int32)
+    for nz in (0, 1):
+        x, t = eng.ml_features(dev(rx), dev(Hls), dev(Htr), pool, pid, "first", False, norm if nz else None, geom=geom)
+        for i in range(N):
+            assert relerr(x[i].cpu().numpy(), g[f"ds_inputs_{i}_{nz}"]) < RTOL
+            assert relerr(t[i].cpu().numpy(), g[f"ds_targets_{i}_{nz}"]) < RTOL
+    # compact H_ls layout ([B][nsym][nrx][nsc], tx = 0 only) gives the same features
+    xc, _ = eng.ml_features(dev(rx), dev(Hls[:, :, :, 0]).contiguous(), dev(Htr), pool, pid, "first", False, norm, geom=geom)
+    assert torch.equal(xc, x)
+    # phase-5 metric helpers and the per-SNR sweep
+    if "ber_approx" in g:
+        for j, s in enumerate((-5.0, 10.0, 30.0)):
+            assert abs(p5.compute_ber_approximation(Hls[0], Htr[0], s) / g["ber_approx"][j] - 1) < 1e-4
+            assert abs(p5.compute_ber_approximation(Htr[0] * 1.01, Htr[0], s) / g["ber_approx_small_err"][j] - 1) < 1e-4
+    snr = np.array([0.0, 10.0, 0.0])
+    sweep = p5.snr_sweep_baselines({"H_true": Htr, "H_ls": Hls, "snr_db": snr})
+    vals, ls_db, mm_db = orc.snr_sweep_baselines(Htr, Hls, snr)
+    assert sweep["snr_db"] == vals
+    assert np.allclose(sweep["methods"]["LS"]["nmse_db"], ls_db, atol=1e-4)
+    assert np.allclose(sweep["methods"]["MMSE"]["nmse_db"], mm_db, atol=1e-4)

@@ -495,3 +495,40 @@ def test_dense_real_map_and_cubic_ls(engines):
     st = out["stats"][0].cpu().numpy()[:, 1].sum(axis=0) / g["channel"].size
     want = orc.evaluate(g["channel"], np.repeat(cub[:, :, None, :], 2, axis=2))
     assert abs(db(st[0] / (st[2] + 1e-12)) - want["nmse_db"]) < DB_TOL
+
+
+def test_link_level_chain_at_full_size(engines):
+    """Size-independent properties of the 'next' rows on 4x4 slots through the C ABI:
+    bits -> QAM -> H x (noise 60 dB down) -> ZF equaliser with the true channel -> demap recovers every bit;
+    the equaliser in complex64 I/O matches the fp64 oracle on one slot; the feature batch is consistent."""
+    eng = engines(4, 4)
+    B, nsym, nsc = 64, 14, 599
+    pool = eng.random_pool([0.10], 1)
+    out = eng.run(B, 0, 10.0, 20.0, 0, pool, slot0=11, seed=7, want=("H_true", "rx", "H_ls"))     # EPA: well conditioned mostly
+    H = out["H_true"]
+    rng = np.random.default_rng(5)
+    for M in (4, 16):
+        bps = 2 if M == 4 else 4
+        bits = torch.from_numpy(rng.integers(0, 2, B * nsym * 4 * nsc * bps, dtype=np.uint8)).to(eng.device)
+        x = eng.qam_modulate(bits, M).reshape(B, nsym, 4, nsc)
+        y = eng.apply_channel(x.contiguous(), H, 60.0, slot0=3, seed=9)
+        xh = eng.equalize(y, H, "zf")
+        back = eng.qam_demodulate(xh.reshape(-1), M)
+        nerr = int(eng.count_bit_errors(bits, back).item())
+        assert nerr <= bits.numel() * 2e-4, (M, nerr)        # only REs where the 4x4 channel is near-singular
+        if M == 4:
+            ref = orc.equalize(y[0].cpu().numpy(), H[0].cpu().numpy(), "mmse")
+            got = eng.equalize(y[:1], H[:1], "mmse")[0].cpu().numpy()
+            assert relerr(got, ref) < 1e-5
+    # feature batch: mask channel equals the pool mask, normalised signal channels have unit joint std
+    xin, tgt = eng.ml_features(out["rx"], out["H_ls"], H, pool, 0, "last", True)
+    assert xin.shape == (B, nsym, nsc, 5) and tgt.shape == (B, nsym, nsc, 2)
+    assert np.array_equal(xin[3, :, :, 4].cpu().numpy().astype(bool), pool.mask(0))
+    assert abs(float(xin[..., :4][5].double().std(unbiased=False)) - 1.0) < 1e-4
+    assert abs(float(tgt[5].double().std(unbiased=False)) - 1.0) < 1e-4
+    ref_x, ref_t = orc.ml_inputs(out["rx"][2].cpu().numpy(), out["H_ls"][2].cpu().numpy(), H[2].cpu().numpy(), pool.mask(0))
+    assert relerr(xin[2].cpu().numpy(), ref_x) < RTOL and relerr(tgt[2].cpu().numpy(), ref_t) < RTOL
+    err = eng.pair00_errors(out["H_ls"], H).cpu().numpy()
+    d = (out["H_ls"][:, :, 0, 0] - H[:, :, 0, 0]).cpu().numpy()
+    assert np.allclose(err[:, 0], (np.abs(d) ** 2).sum(axis=(1, 2)), rtol=1e-5)
+    assert np.allclose(err[:, 1], err[:, 0], rtol=1e-12)                       # alpha = 1

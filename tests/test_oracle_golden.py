@@ -115,3 +115,53 @@ def test_documented_integer_facts():
     assert [int(8386 * d) for d in (0.01, 0.02, 0.05, 0.10)] == [83, 167, 419, 838]
     with pytest.raises(KeyError):
         orc.tdl_profile("XYZ", 15.36e6)
+
+
+# ---- "next" rows: equaliser, QAM, BER, ML features ------------------------------
+EQ_CASES = ["2x2", "4x4", "2x4", "3x3", "rank1"]
+
+
+@pytest.mark.parametrize("tag", EQ_CASES)
+def test_equalizer_matches_reference(tag):
+    g = load_golden("link_level")
+    for meth in ("zf", "mmse"):
+        # rank-1 ZF has condition number ~1e9: inv() itself is only good to ~1e-6 there
+        tol = 1e-5 if (tag == "rank1" and meth == "zf") else 1e-9
+        assert relerr(orc.equalize(g[f"eq_{tag}_y"], g[f"eq_{tag}_H"], meth), g[f"eq_{tag}_{meth}"]) < tol
+    with pytest.raises(ValueError):
+        orc.equalize(g["eq_2x2_y"], g["eq_2x2_H"], "mrc")
+
+
+@pytest.mark.parametrize("M", [4, 16])
+def test_qam_and_ber_match_reference(M):
+    g = load_golden("link_level")
+    bits = g[f"qam{M}_bits"]
+    # the reference's demodulator inverts the restated modulator: pins constellation order and gray map
+    assert np.array_equal(g[f"qam{M}_bits_back"], bits)
+    assert relerr(orc.qam_modulate(bits, M), g[f"qam{M}_symbols"]) < TOL
+    assert np.array_equal(orc.qam_demodulate(g[f"qam{M}_noisy"], M), g[f"qam{M}_noisy_bits"])
+    assert orc.bit_error_rate(bits, g[f"qam{M}_noisy_bits"]) == float(g[f"qam{M}_ber"])
+    assert abs(np.mean(np.abs(g[f"qam{M}_symbols"]) ** 2) - 1.0) < 0.05       # unit average power
+    with pytest.raises(NotImplementedError):
+        orc.qam_modulate(bits, 64)
+
+
+def test_ml_feature_packing_matches_reference():
+    g = load_golden("link_level")
+    rx, Hls, Htr, mask = g["ml_rx"], g["ml_H_ls"], g["ml_H_true"], g["ml_mask"]
+    for i in range(rx.shape[0]):
+        for nz in (0, 1):
+            x, t = orc.ml_inputs(rx[i], Hls[i], Htr[i], mask[i], bool(nz))
+            assert relerr(x, g[f"ml_inputs_{i}_{nz}"]) < TOL and relerr(t, g[f"ml_targets_{i}_{nz}"]) < TOL
+    # ChannelDataset works on the complex64 copies it loads from disk
+    c = lambda a: a.astype(np.complex64)
+    norm = orc.dataset_norm(c(rx), c(Hls), c(Htr))
+    assert relerr(np.array(norm).reshape(-1), g["ds_norm"]) < 1e-6
+    for i in range(rx.shape[0]):
+        for nz in (0, 1):
+            x, t = orc.dataset_item(c(rx[i]), c(Hls[i]), c(Htr[i]), mask[i], norm if nz else None)
+            assert relerr(x, g[f"ds_inputs_{i}_{nz}"]) < 1e-6 and relerr(t, g[f"ds_targets_{i}_{nz}"]) < 1e-6
+    if "ber_approx" in g:
+        for j, s in enumerate((-5.0, 10.0, 30.0)):
+            assert abs(orc.ber_approximation(Hls[0], Htr[0], s) - g["ber_approx"][j]) < 1e-15
+            assert abs(orc.ber_approximation(Htr[0] * 1.01, Htr[0], s) - g["ber_approx_small_err"][j]) < 1e-15
