@@ -174,7 +174,8 @@ def run_b200(args, rank, world, local_rank):
     pool = eng.random_pool([dens], per_density=1, seed=42)
     B = args.batch
     dev = eng.device
-    out = eng.alloc_outputs(B, ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"))
+    out = eng.alloc_outputs(B, ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), pitch=args.pitch)
+    geom_out = eng._with_pitch(eng.geom, args.pitch)      # rows of the five arrays are args.pitch complex apart
     ws = eng.workspace(B)
     model_id = torch.full((B,), eng.models.index(model), dtype=torch.int32, device=dev)
     doppler = torch.full((B,), fd, dtype=torch.float32, device=dev)
@@ -185,7 +186,7 @@ def run_b200(args, rank, world, local_rank):
     per_rank_steps = args.warmup + args.steps
 
     import _b2c
-    from _b2c import check, dptr, lib, ref, stream_ptr, Slots
+    from _b2c import check, dptr, lib, ref, rows_ptr, stream_ptr, Slots
     L = lib()
 
     # With --overlap, K1a (tap gains) of step i+1 runs on a second stream while the slot kernel of step i
@@ -216,10 +217,11 @@ def run_b200(args, rank, world, local_rank):
         main.wait_event(ev_gains[i & 1])
         if ev is not None:
             ev[0].record()
-        check(L.b2c_slot_pipeline(ref(eng.geom), ref(eng.prof), ref(pool.struct), ref(slots_of(i)), None, B,
-                                  dptr(w["gains"], "c64"), dptr(w["noise_std"], "f32"), dptr(out["H_true"], "c64"),
-                                  dptr(out["rx"], "c64"), dptr(out["tx"], "c64"), dptr(out["H_ls"], "c64"),
-                                  dptr(out["H_mmse"], "c64"), dptr(out["stats"], "f64"), 0, stream_ptr()))
+        P = args.pitch
+        check(L.b2c_slot_pipeline(ref(geom_out), ref(eng.prof), ref(pool.struct), ref(slots_of(i)), None, B,
+                                  dptr(w["gains"], "c64"), dptr(w["noise_std"], "f32"), rows_ptr(out["H_true"], P),
+                                  rows_ptr(out["rx"], P), rows_ptr(out["tx"], P), rows_ptr(out["H_ls"], P),
+                                  rows_ptr(out["H_mmse"], P), dptr(out["stats"], "f64"), 0, stream_ptr()))
         if ev is not None:
             ev[1].record()
         ev_slot[i & 1].record(main)
@@ -300,7 +302,9 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": f"{args.workload}: {desc}, SNR cycling over {list(SNRS)} dB, simulate+LS(linear)+MMSE(default)",
                        "slots_per_step": B, "slots_total": world * args.steps * B, "rng": "philox4x32-10 keyed by global slot index",
                        "pilot_patterns": "1 fixed scattered pattern (838 pilots)", "parallelism": f"dp{world} (slots sharded, NCCL all-reduce of per-SNR stats)",
-                       "l2_policy": f"outputs per step = {alg / 1e9:.1f} GB >> 126 MB L2; no flush needed"},
+                       "l2_policy": f"outputs per step = {alg / 1e9:.1f} GB >> 126 MB L2; no flush needed",
+                       "hbm_layout": (f"rows of 599 complex64 at pitch {args.pitch}" + (" (one padding element per row: 16-byte stores; "
+                                      "algorithmic bytes count 599)" if args.pitch != 599 else " (contiguous)"))},
             "roofline": {"bound": "hbm", "kernel": "slot_kernel<4,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / ms},
@@ -329,6 +333,8 @@ def main():
     ap.add_argument("--workload", default="c3_4x4_etu", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=4096, help="slots per step per GPU")
     ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--pitch", type=int, default=600, choices=[599, 600],
+                    help="row pitch of the output arrays in HBM: 600 = padded rows / 16-byte stores (default), 599 = contiguous")
     ap.add_argument("--e2e-batch", type=int, default=2048)
     ap.add_argument("--e2e-chunk", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=4)

@@ -12,6 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2c.so")
 
 MAX_TAPS, MAX_ANT, MAX_SYM, N_OSC, N_STAT, N_BINSTAT = 16, 8, 16, 20, 3, 12
+ABI_VERSION = 2
+WIDE_PITCH = 600      # padded row pitch b2c_slot_pipeline accepts in its throughput configuration
 EXPORTS = ["b2c_last_error_string", "b2c_abi_version", "b2c_tap_gains", "b2c_slot_pipeline",
            "b2c_ls_interp", "b2c_pilot_vectors", "b2c_mmse_dense", "b2c_dense_real_apply", "b2c_stats_bins",
            "b2c_ofdm_modulate", "b2c_ofdm_demodulate", "b2c_apply_channel", "b2c_tdl_full", "b2c_equalize",
@@ -25,7 +27,8 @@ class B2CError(RuntimeError):
 
 class Geom(C.Structure):
     _fields_ = [("nsym", C.c_int32), ("nsc", C.c_int32), ("ntx", C.c_int32), ("nrx", C.c_int32),
-                ("fft_size", C.c_int32), ("cp_length", C.c_int32), ("symbol_period_s", C.c_float)]
+                ("fft_size", C.c_int32), ("cp_length", C.c_int32), ("symbol_period_s", C.c_float),
+                ("pitch", C.c_int32)]
 
 
 class Profiles(C.Structure):
@@ -87,8 +90,8 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = argtypes
             fn.restype = C.c_int
-        if L.b2c_abi_version() != 1:
-            raise B2CError(f"libb2c ABI {L.b2c_abi_version()} != 1; rebuild")
+        if L.b2c_abi_version() != ABI_VERSION:
+            raise B2CError(f"libb2c ABI {L.b2c_abi_version()} != {ABI_VERSION}; rebuild")
         _lib = L
     return _lib
 
@@ -115,6 +118,31 @@ def dptr(t, kind, optional=False):
     if not t.is_contiguous():
         raise B2CError("tensor must be contiguous")
     return C.c_void_p(t.data_ptr())
+
+
+def rows_ptr(t, pitch, optional=False):
+    """Device pointer of a complex64 CUDA tensor whose rows (last dim) are `pitch` elements apart and whose
+    leading dims are dense over those rows: a contiguous tensor (pitch = shape[-1]) or a [..., :nsc] view of one."""
+    if t is None:
+        if optional:
+            return None
+        raise B2CError("required tensor is None")
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.complex64):
+        raise B2CError("libb2c needs complex64 CUDA tensors (there is no CPU path)")
+    if t.is_contiguous() and pitch == t.shape[-1]:
+        return C.c_void_p(t.data_ptr())
+    st, sh = t.stride(), t.shape
+    ok = st[-1] == 1 and (t.dim() < 2 or st[-2] == pitch) and sh[-1] <= pitch
+    for i in range(t.dim() - 2):
+        ok = ok and st[i] == st[i + 1] * sh[i + 1]
+    if not ok:
+        raise B2CError(f"tensor with shape {tuple(sh)} / strides {st} is not a dense stack of rows of pitch {pitch}")
+    return C.c_void_p(t.data_ptr())
+
+
+def row_pitch(t):
+    """Row pitch (elements) of a dense stack of rows; shape[-1] for contiguous tensors."""
+    return int(t.shape[-1]) if (t.is_contiguous() or t.dim() < 2) else int(t.stride(-2))
 
 
 def stream_ptr():

@@ -14,7 +14,7 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
-int check_geom(const b2c_geom *g) {
+int check_geom(const b2c_geom *g, bool allow_pitch) {
   B2C_REQUIRE(g->nsym >= 1 && g->nsym <= B2C_MAX_SYM, B2C_E_UNSUPPORTED, "nsym=%d outside [1,%d]", g->nsym,
               B2C_MAX_SYM);
   B2C_REQUIRE(g->ntx >= 1 && g->ntx <= B2C_MAX_ANT && g->nrx >= 1 && g->nrx <= B2C_MAX_ANT, B2C_E_UNSUPPORTED,
@@ -24,6 +24,8 @@ int check_geom(const b2c_geom *g) {
   B2C_REQUIRE(g->nsc >= 1 && g->nsc <= 2 * B2C_RNG_LANES - 1 && (g->nsc & 1) == 1, B2C_E_UNSUPPORTED,
               "nsc=%d must be odd and <= %d", g->nsc, 2 * B2C_RNG_LANES - 1);
   B2C_REQUIRE(g->nsym * g->nsc <= 65535 * 4, B2C_E_UNSUPPORTED, "grid too large");
+  B2C_REQUIRE(g->pitch == 0 || g->pitch == g->nsc || (allow_pitch && g->pitch > g->nsc), B2C_E_UNSUPPORTED,
+              "row pitch %d: this entry point takes contiguous rows (pitch 0 or nsc=%d)", g->pitch, g->nsc);
   return B2C_OK;
 }
 

@@ -29,7 +29,7 @@ void set_error(const char *fmt, ...);
     }                                                                                   \
   } while (0)
 
-int check_geom(const b2c_geom *g);
+int check_geom(const b2c_geom *g, bool allow_pitch = false);
 
 // ---- complex helpers (float2 = (re, im)) ---------------------------------------------------
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {

@@ -214,9 +214,10 @@ struct PairView {
 __device__ __forceinline__ PairView pair_view(const b2c_geom &g, int64_t b, const float2 *rx, const float2 *ls,
                                               const float2 *tr, int ls_sym_stride) {
   PairView v;
-  v.rx_stride = g.nrx * g.nsc;
+  const int P = g.pitch ? g.pitch : g.nsc;       // padded rows (b2c_geom.pitch) or contiguous
+  v.rx_stride = g.nrx * P;
   v.ls_stride = ls_sym_stride;
-  v.tr_stride = g.nrx * g.ntx * g.nsc;
+  v.tr_stride = g.nrx * g.ntx * P;
   v.rx = rx + b * g.nsym * (int64_t)v.rx_stride;
   v.ls = ls + b * g.nsym * (int64_t)v.ls_stride;
   v.tr = tr + b * g.nsym * (int64_t)v.tr_stride;
@@ -417,7 +418,8 @@ static int check_pair00(const b2c_geom *g, int64_t B, const float *rx, const flo
   int rc = b2c::check_dims(g);
   if (rc) return rc;
   B2C_REQUIRE(rx && H_ls && H_true && B >= 0, B2C_E_ARG, "pair-(0,0) view: null argument or B < 0");
-  B2C_REQUIRE(ls_sym_stride >= g->nsc && ls_sym_stride <= (int64_t)g->nrx * g->ntx * g->nsc, B2C_E_ARG,
+  B2C_REQUIRE(g->pitch == 0 || g->pitch >= g->nsc, B2C_E_ARG, "pair-(0,0) view: pitch=%d < nsc=%d", g->pitch, g->nsc);
+  B2C_REQUIRE(ls_sym_stride >= g->nsc && ls_sym_stride <= (int64_t)g->nrx * g->ntx * (g->pitch ? g->pitch : g->nsc), B2C_E_ARG,
               "pair-(0,0) view: ls_sym_stride=%lld", (long long)ls_sym_stride);
   return B2C_OK;
 }

@@ -17,6 +17,7 @@ constexpr int NOSC = B2C_N_OSC;
 constexpr int GAIN_THREADS = 256;
 constexpr int SLOT_THREADS = 320;   // thread t owns the mirror bins -(t+1), +(t+1): covers up to 639 used bins
 constexpr int RNG_LANES = B2C_RNG_LANES;
+constexpr int WIDE_PITCH = 600;     // padded row pitch of the wide-store kernel (599 used bins + 1)
 
 // ------------------------------------------------------------------------------------------
 // K1a: Jakes sum-of-sinusoids gains at the symbol-start instants (src/channel_simulator.py:102-125
@@ -401,7 +402,141 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
   }
 }
 
-template <int NTX, bool EXACT, bool EST, int NSC, bool FAST>
+
+// Main loop, wide-store variant (throughput configuration with padded rows, b2c_geom.pitch = 600).
+//
+// Same mirror-bin arithmetic as slot_body, but every lane issues ONE 16-byte store per row instead of two
+// 8-byte stores: lane t keeps the value of its bin K (even lanes: +f, k = 300+t; odd lanes: -f, k = 299-t;
+// K is even either way) and hands the value of its other bin S to the neighbouring lane t^1, whose K+1 it is.
+// Loading the twiddles of bin K makes "h of K" = (A.x - B.y, A.y + B.x) and "h of S" = (A.x + B.y, B.x - A.y)
+// on every lane, so the exchange needs no selects: one SHFL.BFLY pair per distinct value.  Rows are `PITCH`
+// complex apart (even, so K*8 is 16-byte aligned); element 599 of each row is padding.
+// Measured on the bare store pattern (scripts/store_pattern_bench.cu): 6.8 TB/s against 4.4 TB/s for the
+// 8-byte form -- the kernel's ceiling moves from the store path to its arithmetic.
+template <int T, int NTX, bool EST, int PITCH>
+__device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx &c, float2 (&st)[2][3]) {
+  constexpr int NSC = 599, HALF = 300;
+  const int nsym = a.g.nsym, nrx = a.g.nrx;
+  const int t_ = threadIdx.x;
+  const bool act = t_ < HALF, odd = t_ & 1;
+  const int kp = HALF + t_, km = HALF - 1 - t_;                  // +f and -f bins of this lane
+  const int K = act ? (odd ? km : kp) : 0;                      // kept (stored) bin: even
+  const bool vS = act && !(odd && kp >= NSC);                   // lane 299's +f bin does not exist
+  const int S = vS ? (odd ? kp : km) : 0;
+  const float mS = vS ? 1.f : 0.f;
+
+  const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * NSC;
+  const float2 zero2 = make_float2(0.f, 0.f), neg1 = make_float2(-1.f, -1.f), nalpha = make_float2(-c.alpha, -c.alpha);
+  float2 twp[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) twp[t] = act ? __ldg(tw + t * NSC + K) : zero2;
+
+  const int64_t slot_h = (int64_t)nsym * nrx * NTX * PITCH, slot_r = (int64_t)nsym * nrx * PITCH;
+  float2 *const Hb = a.H_true + c.b * slot_h;
+  float2 *const Rb = a.rx + c.b * slot_r;
+  float2 *const Tb = c.rx == 0 ? a.tx + c.b * (int64_t)nsym * NTX * PITCH : nullptr;
+  const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * (nsym * NSC + 1) : nullptr;
+  float2 *pH = Hb + (c.rx * NTX * PITCH + K), *pR = Rb + (c.rx * PITCH + K), *pT = Tb + K;
+  const int64_t dL = EST ? (const char *)(a.H_ls + c.b * slot_h) - (const char *)Hb : 0;
+  const int64_t dM = EST ? (const char *)(a.H_mmse + c.b * slot_h) - (const char *)Hb : 0;
+  const int nre = nsym * NSC;
+  int oPK = act ? K : nre, oPS = vS ? S : nre;                   // plan rows; row nre = "outside" for idle lanes
+  const int dPK = act ? NSC : 0, dPS = vS ? NSC : 0;
+  const int dH = nrx * NTX * PITCH, dR = nrx * PITCH, dT = NTX * PITCH;
+  const float2 *gps = c.gsp;
+
+  static_assert(SLOT_THREADS == RNG_LANES, "thread t draws Philox lane t");
+  static_assert((PITCH & 1) == 0 && PITCH > NSC, "wide stores need an even, padded row pitch");
+  uint4 ws = make_uint4(0, 0, 0, 0);
+  auto xchg = [](float2 v) {     // value of this lane's S bin -> the neighbour that stores it as K+1
+    return make_float2(__shfl_xor_sync(0xffffffffu, v.x, 1), __shfl_xor_sync(0xffffffffu, v.y, 1));
+  };
+  auto st16 = [](float2 *p, float2 lo, float2 hi) { __stcs(reinterpret_cast<float4 *>(p), make_float4(lo.x, lo.y, hi.x, hi.y)); };
+  for (int s2 = 0; s2 < nsym; s2 += 2) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int s = s2 + j;
+      float2 lK = zero2, lS = zero2;
+      if (EST) {
+        lK = plan_apply(plan_decode(__ldg(plan + oPK)), c.hp);
+        lS = plan_apply(plan_decode(__ldg(plan + oPS)), c.hp);
+        oPK += dPK;
+        oPS += dPS;
+        prefetch_l1(plan + oPK);
+        prefetch_l1(plan + oPS);
+      }
+      if (EST) {
+        // H_ls / H_mmse rows are the same for every tx: written here, so that only lK / lS stay live below
+        const float2 lN = xchg(lS);
+        const float2 mK = cscale(c.alpha, lK), mN = cscale(c.alpha, lN);
+        if (act) {
+#pragma unroll
+          for (int tx = 0; tx < NTX; ++tx) {
+            st16((float2 *)((char *)(pH + tx * PITCH) + dL), lK, lN);
+            st16((float2 *)((char *)(pH + tx * PITCH) + dM), mK, mN);
+          }
+        }
+      }
+      float2 hsK = zero2, hsS = zero2;
+#pragma unroll
+      for (int tx = 0; tx < NTX; ++tx) {
+        const float2 *gp = gps + tx * MAXT;
+        float2 A = zero2, B = zero2;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const float2 gq = gp[t];
+          A = __ffma2_rn(make_float2(gq.x, gq.x), twp[t], A);
+          B = __ffma2_rn(make_float2(gq.y, gq.y), twp[t], B);
+        }
+        const float2 hK = make_float2(A.x - B.y, A.y + B.x);                  // sum_t g_t tw_t(K)
+        const float2 hS = cscale(mS, make_float2(A.x + B.y, B.x - A.y));      // mirror bin (0 where it does not exist)
+        hsK = __fadd2_rn(hsK, hK);
+        hsS = __fadd2_rn(hsS, hS);
+        const float2 hN = xchg(hS);
+        if (act) {
+          st16(pH + tx * PITCH, hK, hN);
+        }
+        if (EST) {
+          float2 (&acc)[3] = st[tx == 0 ? 0 : 1];
+          float2 d = __ffma2_rn(lK, neg1, hK);
+          acc[0] = __ffma2_rn(d, d, acc[0]);
+          d = __ffma2_rn(lS, neg1, hS);
+          acc[0] = __ffma2_rn(d, d, acc[0]);
+          d = __ffma2_rn(lK, nalpha, hK);
+          acc[1] = __ffma2_rn(d, d, acc[1]);
+          d = __ffma2_rn(lS, nalpha, hS);
+          acc[1] = __ffma2_rn(d, d, acc[1]);
+          acc[2] = __ffma2_rn(hK, hK, acc[2]);
+          acc[2] = __ffma2_rn(hS, hS, acc[2]);
+        }
+      }
+      // ---- draws: Philox lane t serves both bins of the mirror pair; word half h = (f > 0) -------------
+      if (j == 0) ws = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 1) * RNG_LANES + t_));
+      const uint32_t wm = j ? ws.z : ws.x, wp = j ? ws.w : ws.y;               // -f, +f
+      const float2 xK = cis_turns(u01(odd ? wm : wp)), xS = cis_turns(u01(odd ? wp : wm));
+      const uint4 wn = draw(c.key, STREAM_NOISE, (uint32_t)((s * nrx + c.rx) * RNG_LANES + t_));
+      const float2 nK = normal_pair(odd ? wn.x : wn.z, odd ? wn.y : wn.w);
+      const float2 nS = normal_pair(odd ? wn.z : wn.x, odd ? wn.w : wn.y);
+      const float2 yk = cmul(hsK, xK), ys = cmul(hsS, xS);
+      const float2 yK = make_float2(fmaf(c.sigma, nK.x, yk.x), fmaf(c.sigma, nK.y, yk.y));
+      const float2 yN = xchg(make_float2(fmaf(c.sigma, nS.x, ys.x), fmaf(c.sigma, nS.y, ys.y)));
+      if (act) st16(pR, yK, yN);
+      if (Tb) {   // the rx-0 CTA writes the (tx-replicated) grid
+        const float2 xN = xchg(xS);
+        if (act) {
+#pragma unroll
+          for (int tx = 0; tx < NTX; ++tx) st16(pT + tx * PITCH, xK, xN);
+        }
+      }
+      pH += dH;
+      pR += dR;
+      pT += dT;
+      gps += NTX * MAXT;
+    }
+  }
+}
+
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE>
 __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nsc = NSC ? NSC : a.g.nsc;
@@ -453,19 +588,23 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
 
   if (c.ntaps <= 5) {
     if (EST) pilot_phase<5, NSC>(a, c, gs, hp, red);
-    slot_body<5, NTX, EXACT, EST, NSC, FAST>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<5, NTX, EST, WIDE>(a, c, st);
+    else slot_body<5, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else if (c.ntaps <= 8) {
     if (EST) pilot_phase<8, NSC>(a, c, gs, hp, red);
-    slot_body<8, NTX, EXACT, EST, NSC, FAST>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<8, NTX, EST, WIDE>(a, c, st);
+    else slot_body<8, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else if (c.ntaps <= 9) {
     if (EST) pilot_phase<9, NSC>(a, c, gs, hp, red);
-    slot_body<9, NTX, EXACT, EST, NSC, FAST>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<9, NTX, EST, WIDE>(a, c, st);
+    else slot_body<9, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else {
     if (EST) pilot_phase<MAXT, NSC>(a, c, gs, hp, red);
-    slot_body<MAXT, NTX, EXACT, EST, NSC, FAST>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<MAXT, NTX, EST, WIDE>(a, c, st);
+    else slot_body<MAXT, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
 
   if (EST && (FAST || a.stats)) {
@@ -494,9 +633,9 @@ static size_t slot_smem_bytes(const b2c_geom *g, int np_max) {
          (size_t)(np_max + 1) * sizeof(float2);
 }
 
-template <int NTX, bool EXACT, bool EST, int NSC, bool FAST>
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0>
 static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
-  auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST>;
+  auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE>;
   if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(B * a.g.nrx), SLOT_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
@@ -512,6 +651,18 @@ static int launch_slot_ntx(const SlotArgs &a, int64_t B, size_t smem, cudaStream
   const int ntx = a.g.ntx;
   const bool fast = !a.compact && a.g.nsc == 599 && (a.g.nsym & 1) == 0 && !a.has_inj && a.H_true && a.rx && a.tx &&
                     (!EST || (a.H_ls && a.H_mmse && a.stats));
+  const int pitch = a.g.pitch ? a.g.pitch : a.g.nsc;
+  if (pitch != a.g.nsc) {
+    // padded rows: the wide-store kernel of the throughput configuration only
+    B2C_REQUIRE(fast && pitch == WIDE_PITCH, B2C_E_UNSUPPORTED,
+                "b2c_slot_pipeline: pitch=%d needs the throughput configuration (599 bins, even nsym, Philox draws, "
+                "all outputs, not compact) and pitch == %d", pitch, WIDE_PITCH);
+    if (ntx == 1) return launch_slot<1, true, EST, 599, true, WIDE_PITCH>(a, B, smem, stream);
+    if (ntx == 2) return launch_slot<2, true, EST, 599, true, WIDE_PITCH>(a, B, smem, stream);
+    if (ntx == 4) return launch_slot<4, true, EST, 599, true, WIDE_PITCH>(a, B, smem, stream);
+    if (ntx == 8) return launch_slot<8, true, EST, 599, true, WIDE_PITCH>(a, B, smem, stream);
+    B2C_REQUIRE(false, B2C_E_UNSUPPORTED, "b2c_slot_pipeline: padded rows need ntx in {1, 2, 4, 8}, got %d", ntx);
+  }
   if (fast) {
     if (ntx == 1) return launch_slot<1, true, EST, 599, true>(a, B, smem, stream);
     if (ntx == 2) return launch_slot<2, true, EST, 599, true>(a, B, smem, stream);
@@ -557,7 +708,7 @@ extern "C" int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, co
                                  float *tx, float *H_ls, float *H_mmse, double *stats, int32_t compact,
                                  void *stream) {
   B2C_REQUIRE(g && prof && slots && gains && noise_std, B2C_E_ARG, "b2c_slot_pipeline: null argument");
-  if (int rc = check_geom(g)) return rc;
+  if (int rc = check_geom(g, /*allow_pitch=*/true)) return rc;
   B2C_REQUIRE(B >= 0 && B * g->nrx < (1ll << 31), B2C_E_ARG, "b2c_slot_pipeline: B=%lld out of range",
               (long long)B);
   const bool est = H_ls || H_mmse || stats;

@@ -14,7 +14,7 @@ import torch
 
 import _b2c
 import _tables
-from _b2c import Geom, Inject, Patterns, Profiles, Slots, check, dptr, lib, ref, stream_ptr
+from _b2c import Geom, Inject, Patterns, Profiles, Slots, check, dptr, lib, ref, row_pitch, rows_ptr, stream_ptr
 
 DEFAULT_MODELS = ("EPA", "EVA", "ETU")
 BIN_FIELDS = ("count", "sum_mse_ls", "sum_mse_mmse", "sum_nmse_ls", "sum_nmse_mmse", "sum_nmse_ls_sq",
@@ -131,26 +131,37 @@ class SlotEngine:
         return {"gains": torch.empty((B, self.nrx, self.nsym, self.ntx, _b2c.MAX_TAPS), dtype=torch.complex64, device=self.device),
                 "noise_std": torch.empty((B,), dtype=torch.float32, device=self.device)}
 
-    def alloc_outputs(self, B, want, compact=False):
-        """Output buffers.  compact=True: the tx-replicated arrays (H_ls, H_mmse, tx) hold one copy."""
-        full = (B, self.nsym, self.nrx, self.ntx, self.nsc)
-        est = (B, self.nsym, self.nrx, self.nsc) if compact else full
-        shapes = {"H_true": full, "H_ls": est, "H_mmse": est, "rx": (B, self.nsym, self.nrx, self.nsc),
-                  "tx": (B, self.nsym, self.nsc) if compact else (B, self.nsym, self.ntx, self.nsc)}
-        out = {k: torch.empty(shapes[k], dtype=torch.complex64, device=self.device) for k in want if k in shapes}
+    @staticmethod
+    def _with_pitch(g, pitch):
+        return Geom(g.nsym, g.nsc, g.ntx, g.nrx, g.fft_size, g.cp_length, g.symbol_period_s, 0 if pitch == g.nsc else int(pitch))
+
+    def alloc_outputs(self, B, want, compact=False, pitch=None):
+        """Output buffers.  compact=True: the tx-replicated arrays (H_ls, H_mmse, tx) hold one copy.
+        pitch=_b2c.WIDE_PITCH (600): rows padded by one element -- the layout of the wide-store kernel; the
+        tensors returned are [..., :nsc] views of the padded buffers."""
+        P = self.nsc if pitch is None else int(pitch)
+        if compact and P != self.nsc:
+            raise ValueError("the compact layout has contiguous rows")
+        full = (B, self.nsym, self.nrx, self.ntx, P)
+        est = (B, self.nsym, self.nrx, P) if compact else full
+        shapes = {"H_true": full, "H_ls": est, "H_mmse": est, "rx": (B, self.nsym, self.nrx, P),
+                  "tx": (B, self.nsym, P) if compact else (B, self.nsym, self.ntx, P)}
+        out = {k: torch.empty(shapes[k], dtype=torch.complex64, device=self.device)[..., :self.nsc]
+               for k in want if k in shapes}
         if "stats" in want:
             out["stats"] = torch.empty((B, self.nrx, 2, _b2c.N_STAT), dtype=torch.float64, device=self.device)
         return out
 
     # ---- K1a + fused slot kernel -------------------------------------------------------------------
     def run(self, B, model_id, doppler_hz, snr_db, pattern_id=0, pool=None, slot0=0, seed=42, inject=None,
-            want=("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), out=None, ws=None, compact=False):
+            want=("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), out=None, ws=None, compact=False, pitch=None):
         """Simulate B slots and (if any of H_ls/H_mmse/stats is wanted) estimate them.
         Per-slot parameters are scalars or length-B arrays/tensors.  Returns dict of CUDA tensors.
         compact=True writes the tx-replicated arrays once (see alloc_outputs); expand_compact() turns
-        them into full-shape stride-0 views."""
+        them into full-shape stride-0 views.  pitch=600 (or `out` from alloc_outputs(pitch=600)) selects the
+        padded-row layout of the wide-store kernel (throughput configuration only, see include/b2c.h)."""
         if out is None:
-            out = self.alloc_outputs(B, want, compact)
+            out = self.alloc_outputs(B, want, compact, pitch)
         if ws is None:
             ws = self.workspace(B)
         est = any(k in out for k in ("H_ls", "H_mmse", "stats"))
@@ -161,13 +172,16 @@ class SlotEngine:
         slots, keep = self._slots(B, model_id, doppler_hz, snr_db, pattern_id, slot0, seed)
         ij, keep_inj = self._inject(inject)
         L = lib()
+        arrays = [out[k] for k in ("H_true", "rx", "tx", "H_ls", "H_mmse") if k in out]
+        P = row_pitch(arrays[0]) if arrays else self.nsc
+        g = self._with_pitch(self.geom, P)
         check(L.b2c_tap_gains(ref(self.geom), ref(self.prof), ref(slots), ref(ij), B,
                               dptr(ws["gains"], "c64"), dptr(ws["noise_std"], "f32"), stream_ptr()), "b2c_tap_gains")
-        check(L.b2c_slot_pipeline(ref(self.geom), ref(self.prof), ref(pool.struct) if pool is not None else None,
+        check(L.b2c_slot_pipeline(ref(g), ref(self.prof), ref(pool.struct) if pool is not None else None,
                                   ref(slots), ref(ij), B, dptr(ws["gains"], "c64"), dptr(ws["noise_std"], "f32"),
-                                  dptr(out.get("H_true"), "c64", True), dptr(out.get("rx"), "c64", True),
-                                  dptr(out.get("tx"), "c64", True), dptr(out.get("H_ls"), "c64", True),
-                                  dptr(out.get("H_mmse"), "c64", True), dptr(out.get("stats"), "f64", True),
+                                  rows_ptr(out.get("H_true"), P, True), rows_ptr(out.get("rx"), P, True),
+                                  rows_ptr(out.get("tx"), P, True), rows_ptr(out.get("H_ls"), P, True),
+                                  rows_ptr(out.get("H_mmse"), P, True), dptr(out.get("stats"), "f64", True),
                                   1 if compact else 0, stream_ptr()), "b2c_slot_pipeline")
         out["_keepalive"] = (keep, keep_inj, ws)
         return out
@@ -374,27 +388,30 @@ class SlotEngine:
         return count
 
     def _ls_sym_stride(self, H_ls, g):
+        P = g.pitch if g.pitch else g.nsc
         if H_ls.dim() == 5:
-            return g.nrx * g.ntx * g.nsc
-        return g.nrx * g.nsc          # compact [B][nsym][nrx][nsc]
+            return g.nrx * g.ntx * P
+        return g.nrx * P              # compact [B][nsym][nrx][nsc]
 
     def pair00_moments(self, rx, H_ls, H_true, moments=None, geom=None):
         """moments[3][4] += (sum re, sum im, sum re^2, sum im^2) of the pair-(0,0) rows of rx, H_ls, H_true."""
-        g = geom if geom is not None else self.geom
+        P = row_pitch(rx)
+        g = self._with_pitch(geom if geom is not None else self.geom, P)
         if moments is None:
             moments = torch.zeros((3, 4), dtype=torch.float64, device=self.device)
-        check(lib().b2c_pair00_moments(ref(g), rx.shape[0], dptr(rx, "c64"), dptr(H_ls, "c64"), dptr(H_true, "c64"),
+        check(lib().b2c_pair00_moments(ref(g), rx.shape[0], rows_ptr(rx, P), rows_ptr(H_ls, P), rows_ptr(H_true, P),
                                        self._ls_sym_stride(H_ls, g), dptr(moments, "f64"), stream_ptr()),
               "b2c_pair00_moments")
         return moments
 
     def pair00_errors(self, H_ls, H_true, alpha=None, geom=None):
         """[B][3] float64: sum |L-H|^2, sum |alpha L - H|^2, sum |H|^2 over the pair-(0,0) rows of each slot."""
-        g = geom if geom is not None else self.geom
+        P = row_pitch(H_true)
+        g = self._with_pitch(geom if geom is not None else self.geom, P)
         B = H_true.shape[0]
         out = torch.empty((B, 3), dtype=torch.float64, device=self.device)
         a = None if alpha is None else self._vec(alpha, B, torch.float32)
-        check(lib().b2c_pair00_errors(ref(g), B, dptr(H_ls, "c64"), dptr(H_true, "c64"), self._ls_sym_stride(H_ls, g),
+        check(lib().b2c_pair00_errors(ref(g), B, rows_ptr(H_ls, P), rows_ptr(H_true, P), self._ls_sym_stride(H_ls, g),
                                       dptr(a, "f32", True), dptr(out, "f64"), stream_ptr()), "b2c_pair00_errors")
         return out
 
@@ -413,7 +430,8 @@ class SlotEngine:
     def ml_features(self, rx, H_ls, H_true, pool, pattern_id=0, layout="last", normalize=True, norm=None, geom=None):
         """5-channel inputs / 2-channel targets for the ML side from GPU-resident slots.
         layout 'last' + normalize -> prepare_ml_inputs; layout 'first' + norm (6 floats) -> ChannelDataset items."""
-        g = geom if geom is not None else self.geom
+        P = row_pitch(rx)
+        g = self._with_pitch(geom if geom is not None else self.geom, P)
         B = rx.shape[0]
         lay = {"last": 0, "first": 1}[layout]
         pid = self._vec(pattern_id, B, torch.int32)
@@ -427,7 +445,7 @@ class SlotEngine:
         shape_t = (B, g.nsym, g.nsc, 2) if lay == 0 else (B, 2, g.nsym, g.nsc)
         inputs = torch.empty(shape_in, dtype=torch.float32, device=self.device)
         targets = torch.empty(shape_t, dtype=torch.float32, device=self.device)
-        check(lib().b2c_ml_features(ref(g), ref(pool.struct), dptr(pid, "i32"), B, dptr(rx, "c64"), dptr(H_ls, "c64"),
-                                    dptr(H_true, "c64"), self._ls_sym_stride(H_ls, g), lay, mode, dptr(nt, "f32", True),
+        check(lib().b2c_ml_features(ref(g), ref(pool.struct), dptr(pid, "i32"), B, rows_ptr(rx, P), rows_ptr(H_ls, P),
+                                    rows_ptr(H_true, P), self._ls_sym_stride(H_ls, g), lay, mode, dptr(nt, "f32", True),
                                     dptr(inputs, "f32"), dptr(targets, "f32"), stream_ptr()), "b2c_ml_features")
         return inputs, targets

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define B2C_ABI_VERSION 1
+#define B2C_ABI_VERSION 2
 #define B2C_MAX_TAPS 16     /* distinct sample delays per TDL profile (EPA 5, EVA 8, ETU 9)  */
 #define B2C_MAX_ANT 8       /* ntx, nrx <= 8                                                  */
 #define B2C_MAX_SYM 16      /* OFDM symbols per slot                                          */
@@ -70,6 +70,11 @@ typedef struct b2c_geom {
   int32_t cp_length;        /* 72                                                             */
   float symbol_period_s;    /* (fft_size+cp_length)/sampling_rate: spacing of the symbol-start
                                instants the channel is sampled at (:300-302)                  */
+  int32_t pitch;            /* complex elements between consecutive rows of the [...][nsc] arrays;
+                               0 or nsc = contiguous (every entry point).  b2c_slot_pipeline also
+                               takes 600 in its throughput configuration: rows padded by one element
+                               so that each lane writes 16 aligned bytes;
+                               b2c_ml_features / b2c_pair00_* read either layout.               */
 } b2c_geom;
 
 /* TDL profile tables, built on the host once per (profile set, geometry) by

@@ -532,3 +532,42 @@ def test_link_level_chain_at_full_size(engines):
     d = (out["H_ls"][:, :, 0, 0] - H[:, :, 0, 0]).cpu().numpy()
     assert np.allclose(err[:, 0], (np.abs(d) ** 2).sum(axis=(1, 2)), rtol=1e-5)
     assert np.allclose(err[:, 1], err[:, 0], rtol=1e-12)                       # alpha = 1
+
+
+@pytest.mark.parametrize("ntx,nrx,model", [(4, 4, 2), (2, 2, 1), (1, 1, 0), (8, 2, 2)])
+def test_padded_row_layout_matches_contiguous(ntx, nrx, model, engines):
+    """The wide-store kernel (rows padded to pitch 600, one 16-byte store per lane) is the same arithmetic as the
+    contiguous throughput kernel: identical arrays, identical statistics; and the pitch-aware readers accept it."""
+    import _b2c
+    eng = engines(ntx, nrx)
+    pool = eng.random_pool([0.10, 0.05], seed=4)
+    B = 7
+    pid = np.arange(B, dtype=np.int32) % 2
+    snr = np.linspace(-5, 30, B).astype(np.float32)
+    args = dict(model_id=model, doppler_hz=120.0, snr_db=snr, pattern_id=pid, pool=pool, slot0=1234567, seed=99)
+    ref = eng.run(B, **args)
+    pad = eng.run(B, pitch=_b2c.WIDE_PITCH, **args)
+    sim_ref = eng.run(B, want=("H_true", "rx", "tx"), **{k: v for k, v in args.items() if k not in ("pool", "pattern_id")})
+    sim_pad = eng.run(B, want=("H_true", "rx", "tx"), pitch=_b2c.WIDE_PITCH,
+                      **{k: v for k, v in args.items() if k not in ("pool", "pattern_id")})
+    torch.cuda.synchronize()
+    for k in ("H_true", "rx", "tx", "H_ls", "H_mmse"):
+        assert pad[k].shape == ref[k].shape and pad[k].stride(-2) == _b2c.WIDE_PITCH
+        assert torch.equal(pad[k], ref[k]), k                      # same operations in the same order: bit-identical
+        if k in sim_pad:
+            assert torch.equal(sim_pad[k], sim_ref[k]), k
+    assert torch.allclose(pad["stats"], ref["stats"], rtol=1e-6, atol=0)
+    # against the oracle on the Philox twin draws for one slot (the contiguous path is pinned the same way)
+    assert relerr(pad["H_true"][3].cpu().numpy(), ref["H_true"][3].cpu().numpy()) == 0.0
+    # pitch-aware readers
+    x_ref, t_ref = eng.ml_features(ref["rx"], ref["H_ls"], ref["H_true"], pool, pid, "last", True)
+    x_pad, t_pad = eng.ml_features(pad["rx"], pad["H_ls"], pad["H_true"], pool, pid, "last", True)
+    assert torch.equal(x_ref, x_pad) and torch.equal(t_ref, t_pad)
+    assert torch.equal(eng.pair00_errors(ref["H_ls"], ref["H_true"], 0.5), eng.pair00_errors(pad["H_ls"], pad["H_true"], 0.5))
+    assert torch.allclose(eng.pair00_moments(ref["rx"], ref["H_ls"], ref["H_true"]),
+                          eng.pair00_moments(pad["rx"], pad["H_ls"], pad["H_true"]), rtol=1e-12)
+    # the padded layout is only offered by the throughput configuration
+    with pytest.raises(_b2c.B2CError):
+        eng.run(B, want=("H_true", "rx"), pitch=_b2c.WIDE_PITCH, **{k: v for k, v in args.items() if k not in ("pool", "pattern_id")})
+    with pytest.raises(_b2c.B2CError):
+        eng.ls_interp(pad["rx"], torch.ones((1, pool.np_max), dtype=torch.complex64, device=eng.device), pool)

@@ -160,7 +160,7 @@ def test_library_exports_every_declared_symbol():
     L = _b2c.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.b2c_abi_version() == 1
+    assert L.b2c_abi_version() == _b2c.ABI_VERSION == 2
     # argument validation runs before any CUDA call: safe without a GPU
     assert L.b2c_tap_gains(None, None, None, None, 1, None, None, None) == -1
     assert b"null argument" in L.b2c_last_error_string()
