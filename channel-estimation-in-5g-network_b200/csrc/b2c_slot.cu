@@ -14,7 +14,7 @@ namespace b2c {
 
 constexpr int MAXT = B2C_MAX_TAPS;
 constexpr int NOSC = B2C_N_OSC;
-constexpr int GAIN_THREADS = 256;
+constexpr int GAIN_THREADS = 288;   // 4x4 ETU: 9 taps x 16 links x 2 half-sums = 288 work items
 constexpr int SLOT_THREADS = 320;   // thread t owns the mirror bins -(t+1), +(t+1): covers up to 639 used bins
 constexpr int RNG_LANES = B2C_RNG_LANES;
 constexpr int WIDE_PITCH = 600;     // padded row pitch of the wide-store kernel (599 used bins + 1)
@@ -72,36 +72,62 @@ tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj,
   const int nout = nrx * nsym * ntx * MAXT;
   for (int o = threadIdx.x; o < nout; o += blockDim.x)
     if ((o % MAXT) >= ntaps) gout[o] = make_float2(0.f, 0.f);
-  for (int i = threadIdx.x; i < nlinks * nsym; i += blockDim.x) {
-    int link = i / nsym, s = i - link * nsym;
-    int t = link / (ntx * nrx), rem = link - t * (ntx * nrx);
-    int tx = rem / nrx, rx = rem - tx * nrx;
-    const float2 *oc = osc + link * NOSC;
-    float fs = (float)s, ar = 0.f, ai = 0.f;
-#pragma unroll 4
-    for (int n = 0; n < NOSC; ++n) {
-      float2 pd = oc[n];
-      float2 z = cis_turns(fmaf(fs, pd.y, pd.x));
-      ar += z.x;
-      ai += z.y;
+  // Two threads per link, ten oscillators each.  exp(j 2 pi (phase + s step)) advances from symbol to symbol
+  // by one complex rotation, so an oscillator costs two sincos and nsym-1 complex multiplies instead of nsym
+  // sincos (rounding grows by <= ~1e-7 per step; the parity bound is 1e-4).
+  const int nwork = nlinks * 2;
+  for (int base = 0; base < nwork; base += blockDim.x) {       // warp-uniform trip count (shuffles below)
+    const int i = base + threadIdx.x;
+    const bool valid = i < nwork;
+    const int link = valid ? i >> 1 : 0, q = i & 1;
+    const float2 *oc = osc + link * NOSC + q * (NOSC / 2);
+    float2 acc[B2C_MAX_SYM];
+#pragma unroll
+    for (int s = 0; s < B2C_MAX_SYM; ++s) acc[s] = make_float2(0.f, 0.f);
+    if (valid) {
+#pragma unroll 2
+      for (int n = 0; n < NOSC / 2; ++n) {
+        const float2 pd = oc[n];
+        // the start phase takes the SFU sincos (its 4e-7 error enters once); the per-symbol rotation w is applied
+        // nsym times, so it gets the full-precision sincospi
+        float2 z = cis_turns(pd.x), w;
+        sincospif(2.0f * pd.y, &w.y, &w.x);
+        const float2 wj = make_float2(-w.y, w.x);          // j w:  z w = z.x * w + z.y * (j w), two packed FMAs
+#pragma unroll
+        for (int s = 0; s < B2C_MAX_SYM; ++s) {
+          if (s < nsym) {
+            acc[s] = __fadd2_rn(acc[s], z);
+            z = __ffma2_rn(make_float2(z.x, z.x), w, __fmul2_rn(make_float2(z.y, z.y), wj));
+          }
+        }
+      }
     }
-    float a = tap_amp[t];
-    gout[((rx * nsym + s) * ntx + tx) * MAXT + t] = make_float2(a * ar, a * ai);
+    const int t = link / (ntx * nrx), rem = link - t * (ntx * nrx);
+    const int tx = rem / nrx, rx = rem - tx * nrx;
+    const float a = tap_amp[t];
+#pragma unroll
+    for (int s = 0; s < B2C_MAX_SYM; ++s) {
+      if (s < nsym) {                                          // nsym is uniform: no divergence around the shuffles
+        const float ar = acc[s].x + __shfl_xor_sync(0xffffffffu, acc[s].x, 1);
+        const float ai = acc[s].y + __shfl_xor_sync(0xffffffffu, acc[s].y, 1);
+        if (valid && (s & 1) == q) gout[((rx * nsym + s) * ntx + tx) * MAXT + t] = make_float2(a * ar, a * ai);
+      }
+    }
   }
   __syncthreads();   // this CTA's global writes are visible to its own threads past the barrier
 
   // stage 3: mean |sum_tx H x|^2 over the slot as the quadratic form gs^H C gs (|x| = 1,
   // same grid on every TX, :402-404), then noise_std of :338-340.  Tiny, done in double.
   float2 *gs = osc;   // reuse: [rx*nsym + s][MAXT] sum over tx
-  for (int i = threadIdx.x; i < nrx * nsym * MAXT; i += blockDim.x) {
-    int t = i % MAXT, rs = i / MAXT;
+  for (int i = threadIdx.x; i < nrx * nsym * ntaps; i += blockDim.x) {    // surviving taps only
+    int t = i % ntaps, rs = i / ntaps;
     float sr = 0.f, si = 0.f;
     for (int tx = 0; tx < ntx; ++tx) {
       float2 v = gout[(rs * ntx + tx) * MAXT + t];
       sr += v.x;
       si += v.y;
     }
-    gs[i] = make_float2(sr, si);
+    gs[rs * MAXT + t] = make_float2(sr, si);
   }
   __syncthreads();
   const float2 *corr = reinterpret_cast<const float2 *>(prof.tap_corr) + m * MAXT * MAXT;
@@ -109,14 +135,14 @@ tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj,
   for (int i = threadIdx.x; i < nrx * nsym * ntaps; i += blockDim.x) {
     int p = i % ntaps, rs = i / ntaps;
     float2 a = gs[rs * MAXT + p];
-    double accr = 0.0;
+    float accr = 0.f;                 // <= 16 fp32 terms per row; the sum over rows is carried in double
     for (int q = 0; q < ntaps; ++q) {
       float2 c = gs[rs * MAXT + q], k = corr[p * MAXT + q];
       // Re( a * conj(c) * k )
-      double zr = (double)a.x * c.x + (double)a.y * c.y, zi = (double)a.y * c.x - (double)a.x * c.y;
-      accr += zr * k.x - zi * k.y;
+      float zr = fmaf(a.x, c.x, a.y * c.y), zi = fmaf(a.y, c.x, -a.x * c.y);
+      accr = fmaf(zr, k.x, fmaf(-zi, k.y, accr));
     }
-    part += accr;
+    part += (double)accr;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
