@@ -140,6 +140,128 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
   }
 }
 
+
+// Wide-store variant for padded rows (b2c_geom.pitch = 600 on the default 599-bin grid, the layout the slot
+// pipeline's throughput configuration produces): thread t < 300 owns the ADJACENT bins (2t, 2t+1), so every
+// row is read / written as one aligned 16-byte access per lane (see scripts/store_pattern_bench.cu: this
+// store form reaches 6.8 TB/s where the 8-byte form stops at ~4.4 TB/s).  rx, H_true, H_ls and H_mmse all
+// use the padded pitch; element 599 of each output row is padding.
+template <int NTX, int PITCH>
+__global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_wide_kernel(LsArgs a) {
+  constexpr int NSC = 599;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *hp = reinterpret_cast<float2 *>(smem_raw);
+  __shared__ float red[33];
+  __shared__ float ssm[EST_THREADS / 32][6];
+
+  const int nsym = a.g.nsym, nrx = a.g.nrx;
+  const int64_t b = blockIdx.x / nrx;
+  const int rx = blockIdx.x - (int)b * nrx;
+  const int pid = a.pattern_id[b];
+  const int np = a.pat.npilots[pid];
+  const int *pre = a.pat.pilot_re + (int64_t)pid * a.pat.np_max;
+
+  float psum = 0.f;
+  for (int j = threadIdx.x; j < np; j += EST_THREADS) {
+    float2 h;
+    if (a.hp_in) {
+      h = __ldg(a.hp_in + (b * nrx + rx) * (int64_t)a.pat.np_max + j);
+    } else {
+      int e = __ldg(pre + j);
+      int s = e / NSC, k = e - s * NSC;
+      float2 y = __ldg(a.rx + ((b * nsym + s) * nrx + rx) * (int64_t)PITCH + k);
+      h = ls_divide(y, __ldg(a.pilots + b * a.pilots_stride + j));
+    }
+    hp[j] = h;
+    if (j == 0) hp[a.pat.np_max] = make_float2(0.f, 0.f);
+    if (a.hp_out) a.hp_out[(b * nrx + rx) * (int64_t)a.pat.np_max + j] = h;
+    psum += cabs2(h);
+  }
+  float P = block_sum(psum, red) / (float)np;
+  float alpha = 0.f;
+  if (a.mmse_mode == 1) alpha = P / (P + exp10f(-0.1f * a.snr_db[b]));
+
+  float st[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  const int nre = nsym * NSC;
+  const uint4 *plan = reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)pid * (nre + 1);
+  const int64_t slot_h = (int64_t)nsym * nrx * NTX * PITCH;
+  float2 *const Lb = a.H_ls ? a.H_ls + b * slot_h : nullptr;
+  float2 *const Mb = a.H_mmse ? a.H_mmse + b * slot_h : nullptr;
+  const float2 *const Tb = (a.H_true && a.stats) ? a.H_true + b * slot_h : nullptr;
+  const int t = threadIdx.x;
+  const bool act = t < (NSC + 1) / 2, v1 = 2 * t + 1 < NSC;     // bin 599 (t = 299) is padding
+  const int k0 = act ? 2 * t : 0;
+  int oP0 = act ? k0 : nre, oP1 = (act && v1) ? k0 + 1 : nre;
+  const int dP0 = act ? NSC : 0, dP1 = (act && v1) ? NSC : 0;
+  int oH = rx * NTX * PITCH + k0;
+  const int dH = nrx * NTX * PITCH;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+  for (int sy = 0; sy < nsym; ++sy) {
+    const uint4 e0 = __ldg(plan + oP0), e1 = __ldg(plan + oP1);
+    float4 h[NTX];
+#pragma unroll
+    for (int tx = 0; tx < NTX; ++tx)
+      h[tx] = (Tb && act) ? __ldg(reinterpret_cast<const float4 *>(Tb + oH + tx * PITCH)) : zero4;
+    const float2 l0 = plan_apply(plan_decode(e0), hp), l1 = plan_apply(plan_decode(e1), hp);
+    const float4 l = make_float4(l0.x, l0.y, l1.x, l1.y);
+    const float4 m = make_float4(alpha * l0.x, alpha * l0.y, alpha * l1.x, alpha * l1.y);
+    const float w1 = v1 ? 1.f : 0.f;      // the padding element of H_true is not part of the statistics
+#pragma unroll
+    for (int tx = 0; tx < NTX; ++tx) {
+      const int o = oH + tx * PITCH;
+      if (act) {
+        if (Lb) __stcs(reinterpret_cast<float4 *>(Lb + o), l);
+        if (Mb) __stcs(reinterpret_cast<float4 *>(Mb + o), m);
+      }
+      if (Tb) {
+        const float4 q = make_float4(h[tx].x, h[tx].y, w1 * h[tx].z, w1 * h[tx].w);
+        const float e_ls = cabs2(make_float2(q.x - l.x, q.y - l.y)) + cabs2(make_float2(q.z - l.z, q.w - l.w));
+        const float e_mm = cabs2(make_float2(q.x - m.x, q.y - m.y)) + cabs2(make_float2(q.z - m.z, q.w - m.w));
+        const float pw = cabs2(make_float2(q.x, q.y)) + cabs2(make_float2(q.z, q.w));
+        st[1][0] += e_ls;
+        st[1][1] += e_mm;
+        st[1][2] += pw;
+        if (tx == 0) {
+          st[0][0] += e_ls;
+          st[0][1] += e_mm;
+          st[0][2] += pw;
+        }
+      }
+    }
+    oP0 += dP0;
+    oP1 += dP1;
+    oH += dH;
+  }
+
+  if (a.stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float v = warp_sum(st[q][j]);
+        if (lane == 0) ssm[warp][q * 3 + j] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      double acc = 0.0;
+      for (int w = 0; w < EST_THREADS / 32; ++w) acc += (double)ssm[w][threadIdx.x];
+      a.stats[(b * nrx + rx) * 6 + threadIdx.x] = acc;
+    }
+  }
+}
+
+template <int NTX>
+static int launch_ls_wide(const LsArgs &a, int64_t B, cudaStream_t stream) {
+  size_t smem = (size_t)(a.pat.np_max + 1) * sizeof(float2);
+  auto kern = ls_interp_wide_kernel<NTX, 600>;
+  if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(B * a.g.nrx), EST_THREADS, smem, stream>>>(a);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
 template <int NTX, bool EXACT, int NSC>
 static int launch_ls(const LsArgs &a, int64_t B, cudaStream_t stream) {
   size_t smem = (size_t)(a.pat.np_max + 1) * sizeof(float2);
@@ -263,6 +385,14 @@ extern "C" int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const i
   a.hp_out = reinterpret_cast<float2 *>(hp_out);
   a.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g->pitch != 0 && g->pitch != g->nsc) {   // padded rows (rx, H_true, H_ls, H_mmse alike): wide kernel
+    B2C_REQUIRE(g->nsc == 599 && g->pitch == 600 && (g->ntx == 1 || g->ntx == 2 || g->ntx == 4 || g->ntx == 8), B2C_E_UNSUPPORTED,
+                "b2c_ls_interp: pitch=%d needs the default grid (599 bins, pitch 600) and ntx in {1,2,4,8}", g->pitch);
+    if (g->ntx == 1) return launch_ls_wide<1>(a, B, st);
+    if (g->ntx == 2) return launch_ls_wide<2>(a, B, st);
+    if (g->ntx == 4) return launch_ls_wide<4>(a, B, st);
+    return launch_ls_wide<8>(a, B, st);
+  }
   if (g->nsc == 599) {   // default grid, power-of-two TX count: compile-time offsets
     if (g->ntx == 1) return launch_ls<1, true, 599>(a, B, st);
     if (g->ntx == 2) return launch_ls<2, true, 599>(a, B, st);

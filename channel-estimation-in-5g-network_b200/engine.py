@@ -203,26 +203,30 @@ class SlotEngine:
     # ---- K3 ------------------------------------------------------------------------------------------
     def ls_interp(self, rx, pilots, pool, pattern_id=0, snr_db=None, mmse=False, H_true=None, hp_in=None,
                   want=("H_ls",), geom=None):
-        """rx [B,nsym,nrx,nsc] c64, pilots [B or 1, np_max] c64.  want subset of H_ls, H_mmse, hp, stats."""
+        """rx [B,nsym,nrx,nsc] c64, pilots [B or 1, np_max] c64.  want subset of H_ls, H_mmse, hp, stats.
+        If rx (and H_true) are padded-row views (pitch 600, as run(pitch=600) returns them) the outputs are
+        padded the same way and the wide-access kernel runs."""
         g = geom if geom is not None else self.geom
         B = rx.shape[0] if rx is not None else hp_in.shape[0]
+        P = row_pitch(rx) if rx is not None else g.nsc
+        g = self._with_pitch(g, P)
         pid = self._vec(pattern_id, B, torch.int32)
         snr = self._vec(snr_db, B, torch.float32) if snr_db is not None else None
         out = {}
-        shape = (B, g.nsym, g.nrx, g.ntx, g.nsc)
+        shape = (B, g.nsym, g.nrx, g.ntx, P)
         if "H_ls" in want:
-            out["H_ls"] = torch.empty(shape, dtype=torch.complex64, device=self.device)
+            out["H_ls"] = torch.empty(shape, dtype=torch.complex64, device=self.device)[..., :g.nsc]
         if "H_mmse" in want:
-            out["H_mmse"] = torch.empty(shape, dtype=torch.complex64, device=self.device)
+            out["H_mmse"] = torch.empty(shape, dtype=torch.complex64, device=self.device)[..., :g.nsc]
         if "hp" in want:
             out["hp"] = torch.zeros((B, g.nrx, pool.np_max), dtype=torch.complex64, device=self.device)
         if "stats" in want:
             out["stats"] = torch.empty((B, g.nrx, 2, _b2c.N_STAT), dtype=torch.float64, device=self.device)
         stride = pilots.shape[1] if (pilots is not None and pilots.shape[0] > 1) else 0
         check(lib().b2c_ls_interp(ref(g), ref(pool.struct), dptr(pid, "i32"), dptr(snr, "f32", True), B,
-                                  dptr(rx, "c64", True), dptr(pilots, "c64", True), stride, dptr(hp_in, "c64", True),
-                                  1 if mmse else 0, dptr(H_true, "c64", True), dptr(out.get("H_ls"), "c64", True),
-                                  dptr(out.get("H_mmse"), "c64", True), dptr(out.get("hp"), "c64", True),
+                                  rows_ptr(rx, P, True), dptr(pilots, "c64", True), stride, dptr(hp_in, "c64", True),
+                                  1 if mmse else 0, rows_ptr(H_true, P, True), rows_ptr(out.get("H_ls"), P, True),
+                                  rows_ptr(out.get("H_mmse"), P, True), dptr(out.get("hp"), "c64", True),
                                   dptr(out.get("stats"), "f64", True), stream_ptr()), "b2c_ls_interp")
         return out
 

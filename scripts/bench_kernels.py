@@ -58,16 +58,18 @@ flops = 4.0 * 8386 * npil * 4096
 res["k4b_cubic_map_4096cols"] = {"ms": t * 1e3, "useful_tflops": flops / t / 1e12, "issued_tf32_tflops": 3 * flops / t / 1e12}
 del Wc, h
 
-# K3 stand-alone LS + MMSE + stats on resident rx / H_true
+# K3 stand-alone LS + MMSE + stats on resident rx / H_true, padded rows (wide accesses) and contiguous rows
 B = 2048
-out = eng.run(B, 2, 200.0, 10.0, 0, pool, slot0=0, seed=1)
-rx, Ht = out["rx"], out["H_true"]
-tx_p = out["tx"][:, :, 0].reshape(B, -1)[:, torch.from_numpy(pool.pilot_indices[0]).to(dev)].contiguous()
-t = timeit(lambda: eng.ls_interp(rx, tx_p, pool, snr_db=10.0, mmse=True, H_true=Ht, want=("H_ls", "H_mmse", "stats")), n=5)
-bytes_k3 = B * (rx[0].numel() * 8 + 3 * Ht[0].numel() * 8)      # read rx + H_true, write H_ls + H_mmse
-res["k3_ls_interp_mmse_stats"] = {"ms": t * 1e3, "gbs": bytes_k3 / t / 1e9, "frac_hbm": bytes_k3 / t / 1e9 / PEAK_HBM, "slots": B}
-del out, rx, Ht
-torch.cuda.empty_cache()
+for tag, pitch in (("k3_ls_interp_mmse_stats", 600), ("k3_ls_interp_mmse_stats_contiguous", None)):
+    out = eng.run(B, 2, 200.0, 10.0, 0, pool, slot0=0, seed=1, pitch=pitch)
+    rx, Ht = out["rx"], out["H_true"]
+    tx_p = out["tx"][:, :, 0].reshape(B, -1)[:, torch.from_numpy(pool.pilot_indices[0]).to(dev)].contiguous()
+    t = timeit(lambda: eng.ls_interp(rx, tx_p, pool, snr_db=10.0, mmse=True, H_true=Ht, want=("H_ls", "H_mmse", "stats")), n=5)
+    bytes_k3 = B * (rx[0].numel() * 8 + 3 * Ht[0].numel() * 8)      # read rx + H_true, write H_ls + H_mmse (599 per row)
+    res[tag] = {"ms": t * 1e3, "gbs": bytes_k3 / t / 1e9, "frac_hbm": bytes_k3 / t / 1e9 / PEAK_HBM, "slots": B,
+                "note": "includes the output allocation of engine.ls_interp; " + ("pitch 600" if pitch else "contiguous")}
+    del out, rx, Ht
+    torch.cuda.empty_cache()
 
 # K2 OFDM modulate / demodulate
 e1 = SlotEngine(cfg(1, 1))
@@ -85,8 +87,11 @@ torch.cuda.empty_cache()
 # K1a tap gains alone, and simulate-only (no estimation outputs)
 B = 4096
 ws = eng.workspace(B)
-o = eng.alloc_outputs(B, ("H_true", "rx", "tx"))
-t = timeit(lambda: eng.run(B, 2, 200.0, 10.0, want=("H_true", "rx", "tx"), out=o, ws=ws), n=5)
-bs = B * (o["H_true"][0].numel() + o["rx"][0].numel() + o["tx"][0].numel()) * 8
-res["k1_simulate_only"] = {"ms": t * 1e3, "gbs": bs / t / 1e9, "frac_hbm": bs / t / 1e9 / PEAK_HBM, "slots_per_s": B / t}
+for tag, pitch in (("k1_simulate_only", 600), ("k1_simulate_only_contiguous", None)):
+    o = eng.alloc_outputs(B, ("H_true", "rx", "tx"), pitch=pitch)
+    t = timeit(lambda: eng.run(B, 2, 200.0, 10.0, want=("H_true", "rx", "tx"), out=o, ws=ws), n=5)
+    bs = B * (o["H_true"][0].numel() + o["rx"][0].numel() + o["tx"][0].numel()) * 8     # 599 per row: algorithmic bytes
+    res[tag] = {"ms": t * 1e3, "gbs": bs / t / 1e9, "frac_hbm": bs / t / 1e9 / PEAK_HBM, "slots_per_s": B / t,
+                "note": "includes K1a tap gains; " + ("rows at pitch 600, 16-byte stores" if pitch else "contiguous rows, 8-byte stores")}
+    del o
 print(json.dumps(res))

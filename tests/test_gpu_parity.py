@@ -569,5 +569,19 @@ def test_padded_row_layout_matches_contiguous(ntx, nrx, model, engines):
     # the padded layout is only offered by the throughput configuration
     with pytest.raises(_b2c.B2CError):
         eng.run(B, want=("H_true", "rx"), pitch=_b2c.WIDE_PITCH, **{k: v for k, v in args.items() if k not in ("pool", "pattern_id")})
-    with pytest.raises(_b2c.B2CError):
-        eng.ls_interp(pad["rx"], torch.ones((1, pool.np_max), dtype=torch.complex64, device=eng.device), pool)
+    # stand-alone K3 on the padded arrays (wide-access kernel) == K3 on the contiguous ones == the fused estimates
+    pil = torch.zeros((B, pool.np_max), dtype=torch.complex64, device=eng.device)
+    for b in range(B):
+        idx = torch.from_numpy(pool.pilot_indices[pid[b]]).to(eng.device)
+        pil[b, :idx.numel()] = ref["tx"][b, :, 0, :].reshape(-1)[idx]
+    kw = dict(pattern_id=pid, snr_db=snr, mmse=True, want=("H_ls", "H_mmse", "stats"))
+    k3_ref = eng.ls_interp(ref["rx"], pil, pool, H_true=ref["H_true"], **kw)
+    k3_pad = eng.ls_interp(pad["rx"], pil, pool, H_true=pad["H_true"], **kw)
+    assert k3_pad["H_ls"].stride(-2) == _b2c.WIDE_PITCH
+    for k in ("H_ls", "H_mmse"):
+        assert torch.equal(k3_pad[k], k3_ref[k]), k
+        assert (k3_pad[k] - ref[k]).abs().max().item() < 2e-6, k
+    assert torch.allclose(k3_pad["stats"], k3_ref["stats"], rtol=1e-6, atol=0)
+    assert torch.allclose(k3_pad["stats"], ref["stats"], rtol=1e-4, atol=0)
+    with pytest.raises(_b2c.B2CError):          # mixed layouts are refused
+        eng.ls_interp(pad["rx"], pil, pool, H_true=ref["H_true"], **kw)
