@@ -165,7 +165,7 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     from engine import SlotEngine
-    from host_pipeline import HostPipeline
+    from host_pipeline import HostPipeline, bind_to_gpu_numa_node
 
     ntx, nrx, model, fd, dens, desc = WORKLOADS[args.workload]
     cfg = {"ofdm": {"fft_size": 1024, "cp_length": 72, "num_symbols": 14, "useful_subcarriers": 600,
@@ -264,6 +264,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- end-to-end through the host-buffer API: params from pinned memory, all arrays back to pinned memory
     e2e_B = min(args.e2e_batch, B)
+    numa = None if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)     # before the pinned buffers exist
     hp = HostPipeline(eng, pool, chunk=min(args.e2e_chunk, e2e_B), compact=not args.e2e_full)
     par = (np.full(e2e_B, eng.models.index(model)), np.full(e2e_B, fd), np.asarray(SNRS, np.float32)[np.arange(e2e_B) % 8],
            np.zeros(e2e_B))
@@ -311,6 +312,7 @@ def run_b200(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes_per_slot * e2e_B,
                     "d2h_bytes_per_step": hp.d2h_bytes_per_slot * e2e_B, "slots_per_step": e2e_B, "steps": e2e_steps,
+                    "numa_node_rank0": numa,
                     "note": ("HostPipeline: params from pinned host memory, all five arrays + stats back to pinned host memory (PCIe-bound); "
                              + ("full replicated arrays cross PCIe" if args.e2e_full else
                                 "tx-replicated arrays (H_ls, H_mmse, tx) cross PCIe once and are exposed as full-shape NumPy broadcast views"))},
@@ -339,6 +341,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-full", action="store_true", help="copy the tx-replicated arrays in full instead of once")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA node for the e2e leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap", action="store_true",

@@ -14,6 +14,46 @@ import torch
 ARRAYS = ("H_true", "rx", "tx", "H_ls", "H_mmse")
 
 
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restrict this process to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned buffers are
+    allocated (first touch then places them on that node).  With one rank per GPU all writing results to host
+    memory, buffers that all land on one socket cap the aggregate device->host rate well below the sum of the
+    PCIe links.  Returns the node, or None when the topology is not visible (containers, single-node hosts)."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        if all(hasattr(p, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(p.uuid)).encode() if not str(p.uuid).startswith("GPU-") else str(p.uuid).encode())
+            bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()[-12:]
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = _cpulist(fh.read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 class HostPipeline:
     def __init__(self, engine, pool, chunk=512, want=ARRAYS + ("stats",), compact=False):
         """compact=True moves the tx-replicated arrays (H_ls, H_mmse, tx) over PCIe once and hands the
