@@ -17,7 +17,7 @@ WIDE_PITCH = 600      # padded row pitch b2c_slot_pipeline accepts in its throug
 EXPORTS = ["b2c_last_error_string", "b2c_abi_version", "b2c_tap_gains", "b2c_slot_pipeline",
            "b2c_ls_interp", "b2c_pilot_vectors", "b2c_mmse_dense", "b2c_dense_real_apply", "b2c_stats_bins",
            "b2c_ofdm_modulate", "b2c_ofdm_demodulate", "b2c_apply_channel", "b2c_tdl_full", "b2c_equalize",
-           "b2c_qam_modulate", "b2c_qam_demodulate", "b2c_count_bit_errors", "b2c_pair00_moments", "b2c_pair00_errors",
+           "b2c_qam_modulate", "b2c_qam_demodulate", "b2c_count_bit_errors", "b2c_pair00_moments", "b2c_pair00_errors", "b2c_count_nonfinite",
            "b2c_ml_features"]
 
 
@@ -84,6 +84,7 @@ def lib():
             "b2c_count_bit_errors": [P, P, I64, P, P],
             "b2c_pair00_moments": [P, I64, P, P, P, I64, P, P],
             "b2c_pair00_errors": [P, I64, P, P, I64, P, P, P],
+            "b2c_count_nonfinite": [P, I64, I32, P, P],
             "b2c_ml_features": [P, P, P, I64, P, P, P, I64, I32, I32, P, P, P, P],
         }
         for name, argtypes in sig.items():

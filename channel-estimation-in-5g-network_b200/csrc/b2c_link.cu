@@ -206,6 +206,33 @@ __global__ void __launch_bounds__(256) bit_errors_kernel(const uint8_t *__restri
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
 
+// counts[0] += #NaN, counts[1] += #Inf among n elements (verify_phase3_datasets.py:98-111).  CPLX: elements are
+// complex64 and one counts as NaN / Inf when either part is, as numpy.isnan / numpy.isinf do.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) nonfinite_kernel(const float *__restrict__ x, int64_t n, unsigned long long *__restrict__ counts) {
+  unsigned long long nn = 0, ni = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (CPLX) {
+      const float2 v = __ldg(reinterpret_cast<const float2 *>(x) + i);
+      nn += (isnan(v.x) || isnan(v.y)) ? 1 : 0;
+      ni += (isinf(v.x) || isinf(v.y)) ? 1 : 0;
+    } else {
+      const float v = __ldg(x + i);
+      nn += isnan(v) ? 1 : 0;
+      ni += isinf(v) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    ni += __shfl_xor_sync(0xffffffffu, ni, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nn) atomicAdd(counts, nn);
+    if (ni) atomicAdd(counts + 1, ni);
+  }
+}
+
 // ---- ML feature packing -----------------------------------------------------------------------------
 struct PairView {
   const float2 *rx, *ls, *tr;          // antenna pair (0,0) rows of slot b: base + s * stride
@@ -409,6 +436,18 @@ extern "C" int b2c_count_bit_errors(const uint8_t *a, const uint8_t *b, int64_t 
   const int64_t want = (n + 256 * 64 - 1) / (256 * 64);
   const unsigned grid = (unsigned)(want < 1 ? 1 : want > 148 * 8 ? 148 * 8 : want);
   bit_errors_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, n, reinterpret_cast<unsigned long long *>(count));
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_count_nonfinite(const float *x, int64_t n, int32_t is_complex, uint64_t *counts, void *stream) {
+  B2C_REQUIRE(x && counts && n >= 0, B2C_E_ARG, "b2c_count_nonfinite: null argument");
+  if (n == 0) return B2C_OK;
+  const int64_t want = (n + 256 * 16 - 1) / (256 * 16);
+  const unsigned grid = (unsigned)(want < 1 ? 1 : want > 148 * 8 ? 148 * 8 : want);
+  unsigned long long *c = reinterpret_cast<unsigned long long *>(counts);
+  if (is_complex) nonfinite_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, c);
+  else nonfinite_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, c);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }

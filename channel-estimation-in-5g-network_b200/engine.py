@@ -391,6 +391,17 @@ class SlotEngine:
                   "b2c_count_bit_errors")
         return count
 
+    def count_nonfinite(self, x, counts=None):
+        """(#NaN, #Inf) elements of a float32 / complex64 CUDA tensor (numpy.isnan / isinf semantics), accumulated
+        into the int64 pair `counts`."""
+        if counts is None:
+            counts = torch.zeros((2,), dtype=torch.int64, device=self.device)
+        x = x.contiguous()
+        if x.numel():
+            check(lib().b2c_count_nonfinite(dptr(x, "c64" if x.is_complex() else "f32"), x.numel(), int(x.is_complex()),
+                                            dptr(counts, "i64"), stream_ptr()), "b2c_count_nonfinite")
+        return counts
+
     def _ls_sym_stride(self, H_ls, g):
         P = g.pitch if g.pitch else g.nsc
         if H_ls.dim() == 5:

@@ -253,6 +253,10 @@ int b2c_qam_demodulate(const void *symbols, int64_t nsymbols, int32_t M, int32_t
 /* calculate_ber numerator (src/utils.py:155-157): *count += #{i : a[i] != b[i]}.                       */
 int b2c_count_bit_errors(const uint8_t *a, const uint8_t *b, int64_t n, uint64_t *count, void *stream);
 
+/* Dataset integrity check (verify_phase3_datasets.py:98-111): counts[0] += #NaN, counts[1] += #Inf among n
+ * elements; is_complex: elements are complex64 and count when either part is NaN / Inf (numpy.isnan / isinf). */
+int b2c_count_nonfinite(const float *x, int64_t n, int32_t is_complex, uint64_t *counts, void *stream);
+
 /* Feature packing for the ML side from GPU-resident slots, antenna pair (0,0).
  *   rx [B][nsym][nrx][nsc]; H_true [B][nsym][nrx][ntx][nsc]; H_ls with ls_sym_stride complex elements
  *   between consecutive symbols (nrx*ntx*nsc for the full layout, nrx*nsc for the compact one).

@@ -257,6 +257,37 @@ def link_case(name, seed):
             for i in range(N):
                 xi, ti, mi = ds[i]
                 out[f"ds_inputs_{i}_{int(nz)}"], out[f"ds_targets_{i}_{int(nz)}"] = xi.numpy(), ti.numpy()
+    # verify_phase3_datasets.verify_dataset on a tiny stacked file built from the arrays above (grid 14 x 96, so the
+    # reference reports 'shape_mismatch' but still computes every statistic); then with a NaN planted
+    sys.path.insert(0, REF)
+    import contextlib
+    import io
+    import verify_phase3_datasets as rv
+    meta = dict(snr_db=np.array([0.0, 10.0, 0.0], np.float32), channel_type=np.array(["EPA", "EVA", "EPA"]),
+                doppler_hz=np.array([10.0, 50.0, 10.0], np.float32), pilot_density=np.array([0.1, 0.1, 0.05], np.float32))
+    stacked = dict(rx_symbols=rx.astype(np.complex64), tx_symbols=rx.astype(np.complex64), H_ls=Hls.astype(np.complex64),
+                   H_true=Htr.astype(np.complex64), pilot_mask=mask.astype(np.float32), **meta)
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "tiny.npz")
+        np.savez(f, **stacked)
+        np.random.seed(77)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r1 = rv.verify_dataset(f)
+        bad = dict(stacked)
+        bad["H_ls"] = stacked["H_ls"].copy()
+        bad["H_ls"][1, 2, 0, 1, 5] = np.nan
+        bad["rx_symbols"] = stacked["rx_symbols"].copy()
+        bad["rx_symbols"][0, 0, 0, 0] = np.inf
+        np.savez(f, **bad)
+        np.random.seed(77)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r2 = rv.verify_dataset(f)
+    out["verify_status"] = np.array([r1["status"], r2["status"]])
+    out["verify_ls_nmse_db"] = np.array([r1["avg_ls_nmse_db"]])
+    out["verify_pilot_density"] = np.array([r1["avg_pilot_density"]])
+    out["verify_ranges"] = np.array(r1["snr_range"] + r1["doppler_range"])
+    print("verify:", r1["status"], r1["avg_ls_nmse_db"], "| planted:", r2["status"], r2.get("nan_count"), r2.get("inf_count"))
+
     import importlib.util
     spec = importlib.util.spec_from_file_location("phase5", os.path.join(REF, "run_phase5_evaluation.py"))
     try:

@@ -405,3 +405,42 @@ def test_channel_dataset_features_and_phase5_baselines():
     assert sweep["snr_db"] == vals
     assert np.allclose(sweep["methods"]["LS"]["nmse_db"], ls_db, atol=1e-4)
     assert np.allclose(sweep["methods"]["MMSE"]["nmse_db"], mm_db, atol=1e-4)
+
+
+def test_verify_phase3_datasets_drop_in(tmp_path):
+    """verify_phase3_datasets.verify_dataset against the reference's own verdicts on the same tiny file
+    (tests/golden/link_level.npz: clean -> 'shape_mismatch' (grid 14 x 96), planted NaN + Inf -> 'data_errors')."""
+    import verify_phase3_datasets as v3
+    g = load_golden("link_level")
+    rx, Hls, Htr, mask = g["ml_rx"], g["ml_H_ls"], g["ml_H_true"], g["ml_mask"]
+    meta = dict(snr_db=np.array([0.0, 10.0, 0.0], np.float32), channel_type=np.array(["EPA", "EVA", "EPA"]),
+                doppler_hz=np.array([10.0, 50.0, 10.0], np.float32), pilot_density=np.array([0.1, 0.1, 0.05], np.float32))
+    stacked = dict(rx_symbols=rx.astype(np.complex64), tx_symbols=rx.astype(np.complex64), H_ls=Hls.astype(np.complex64),
+                   H_true=Htr.astype(np.complex64), pilot_mask=mask.astype(np.float32), **meta)
+    f = str(tmp_path / "tiny.npz")
+    np.savez(f, **stacked)
+    np.random.seed(77)
+    r = v3.verify_dataset(f, verbose=False)
+    assert r["status"] == str(g["verify_status"][0]) == "shape_mismatch" and r["num_samples"] == 3
+    assert abs(r["avg_ls_nmse_db"] - float(g["verify_ls_nmse_db"][0])) < 1e-3
+    assert abs(r["avg_pilot_density"] - float(g["verify_pilot_density"][0])) < 1e-12
+    assert r["snr_range"] + r["doppler_range"] == list(g["verify_ranges"])
+    assert r["channel_types"] == ["EPA", "EVA"]
+    bad = dict(stacked)
+    bad["H_ls"] = stacked["H_ls"].copy()
+    bad["H_ls"][1, 2, 0, 1, 5] = np.nan
+    bad["rx_symbols"] = stacked["rx_symbols"].copy()
+    bad["rx_symbols"][0, 0, 0, 0] = np.inf
+    np.savez(f, **bad)
+    r = v3.verify_dataset(f, verbose=False)
+    assert r["status"] == str(g["verify_status"][1]) == "data_errors" and r["nan_count"] == 1 and r["inf_count"] == 1
+    np.savez(f, **{k: v for k, v in stacked.items() if k != "H_true"})
+    assert v3.verify_dataset(f, verbose=False) == {"status": "incomplete", "filepath": f, "missing_keys": ["H_true"]}
+    assert v3.verify_dataset(str(tmp_path / "absent.npz"), verbose=False)["status"] == "failed"
+    # a file written by the phase-3 twin passes at the default 2x2 geometry
+    import run_phase3_dataset_generation as p3
+    gen = p3.DatasetGenerator(batch_size=2)
+    good = str(tmp_path / "val.npz")
+    gen.save_dataset(gen.generate_dataset(2, split='val'), good)
+    r = v3.verify_dataset(good, verbose=False)
+    assert r["status"] == "success" and r["num_samples"] == 2 and np.isfinite(r["avg_ls_nmse_db"])
