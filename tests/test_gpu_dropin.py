@@ -423,7 +423,7 @@ def test_verify_phase3_datasets_drop_in(tmp_path):
     r = v3.verify_dataset(f, verbose=False)
     assert r["status"] == str(g["verify_status"][0]) == "shape_mismatch" and r["num_samples"] == 3
     assert abs(r["avg_ls_nmse_db"] - float(g["verify_ls_nmse_db"][0])) < 1e-3
-    assert abs(r["avg_pilot_density"] - float(g["verify_pilot_density"][0])) < 1e-12
+    assert abs(r["avg_pilot_density"] - float(g["verify_pilot_density"][0])) < 1e-6      # the reference sums the float32 mask in float32
     assert r["snr_range"] + r["doppler_range"] == list(g["verify_ranges"])
     assert r["channel_types"] == ["EPA", "EVA"]
     bad = dict(stacked)
