@@ -206,7 +206,6 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_wide_kernel(LsArgs a
     const float2 l0 = plan_apply(plan_decode(e0), hp), l1 = plan_apply(plan_decode(e1), hp);
     const float4 l = make_float4(l0.x, l0.y, l1.x, l1.y);
     const float4 m = make_float4(alpha * l0.x, alpha * l0.y, alpha * l1.x, alpha * l1.y);
-    const float w1 = v1 ? 1.f : 0.f;      // the padding element of H_true is not part of the statistics
 #pragma unroll
     for (int tx = 0; tx < NTX; ++tx) {
       const int o = oH + tx * PITCH;
@@ -215,7 +214,8 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_wide_kernel(LsArgs a
         if (Mb) __stcs(reinterpret_cast<float4 *>(Mb + o), m);
       }
       if (Tb) {
-        const float4 q = make_float4(h[tx].x, h[tx].y, w1 * h[tx].z, w1 * h[tx].w);
+        // the padding element of H_true is not part of the statistics (selected away, not multiplied: it may hold anything)
+        const float4 q = make_float4(h[tx].x, h[tx].y, v1 ? h[tx].z : 0.f, v1 ? h[tx].w : 0.f);
         const float e_ls = cabs2(make_float2(q.x - l.x, q.y - l.y)) + cabs2(make_float2(q.z - l.z, q.w - l.w));
         const float e_mm = cabs2(make_float2(q.x - m.x, q.y - m.y)) + cabs2(make_float2(q.z - m.z, q.w - m.w));
         const float pw = cabs2(make_float2(q.x, q.y)) + cabs2(make_float2(q.z, q.w));
