@@ -585,3 +585,12 @@ def test_padded_row_layout_matches_contiguous(ntx, nrx, model, engines):
     assert torch.allclose(k3_pad["stats"], ref["stats"], rtol=1e-4, atol=0)
     with pytest.raises(_b2c.B2CError):          # mixed layouts are refused
         eng.ls_interp(pad["rx"], pil, pool, H_true=ref["H_true"], **kw)
+    # caller-made padded buffers whose padding element holds NaN: never read into a result
+    def nan_padded(t):
+        buf = torch.full(t.shape[:-1] + (_b2c.WIDE_PITCH,), float("nan"), dtype=torch.complex64, device=t.device)
+        buf[..., :599] = t
+        return buf[..., :599]
+    k3_nan = eng.ls_interp(nan_padded(ref["rx"]), pil, pool, H_true=nan_padded(ref["H_true"]), **kw)
+    assert torch.equal(k3_nan["stats"], k3_pad["stats"]) and torch.equal(k3_nan["H_ls"], k3_pad["H_ls"])
+    xn, tn = eng.ml_features(nan_padded(ref["rx"]), nan_padded(ref["H_ls"]), nan_padded(ref["H_true"]), pool, pid, "last", True)
+    assert torch.equal(xn, x_ref) and torch.equal(tn, t_ref)
