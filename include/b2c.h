@@ -153,7 +153,11 @@ int b2c_tap_gains(const b2c_geom *g, const b2c_profiles *prof, const b2c_slots *
  *   compact = 1: the tx-replicated outputs are written once -- H_ls, H_mmse [B][nsym][nrx][nsc] and
  *   tx [B][nsym][nsc] (every TX antenna sends the same grid, :402-404, and LS/MMSE never see tx) --
  *   for callers that expand them as stride-0 views (the host-buffer pipeline: half the PCIe bytes).
- *   H_ls, H_mmse like H_true;  stats [B][nrx][B2C_N_STATGRP][B2C_N_STAT] double                          */
+ *   H_ls, H_mmse like H_true;  stats [B][nrx][B2C_N_STATGRP][B2C_N_STAT] double
+ *   g->pitch = 600 (throughput configuration only: nsc = 599, even nsym, ntx in {1,2,4,8}, Philox draws, all
+ *   outputs of the call's kind, compact = 0; B2C_E_UNSUPPORTED otherwise): the last axis of the five arrays
+ *   is 600 elements apart in memory (element 599 is padding) and every lane writes 16 aligned bytes per row;
+ *   same values as the contiguous layout, bit for bit.                                                    */
 int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat,
                       const b2c_slots *slots, const b2c_inject *inj, int64_t B,
                       const float *gains, const float *noise_std,
@@ -168,7 +172,8 @@ int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_pat
  *   hp_in    optional [B][nrx][np_max] complex: use these pilot-position values instead of
  *            rx/pilots (the dense-Wiener path feeds W h_ls here)
  *   mmse_mode 0: H_mmse not produced; 1: alpha = P/(P+10^(-snr/10)), P = mean|h_ls|^2 (:174-180)
- *   H_true   optional, for stats.  hp_out optional [B][nrx][np_max]: h_ls at the pilots (:110). */
+ *   H_true   optional, for stats.  hp_out optional [B][nrx][np_max]: h_ls at the pilots (:110).
+ *   g->pitch = 600 (nsc = 599, ntx in {1,2,4,8}): rx, H_true, H_ls and H_mmse all have padded rows.       */
 int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const int32_t *pattern_id,
                   const float *snr_db, int64_t B, const float *rx, const float *pilots,
                   int64_t pilots_stride, const float *hp_in, int32_t mmse_mode,
