@@ -130,7 +130,8 @@ class MMSEEstimator:
                 W = R @ np.linalg.inv(Ry)
             except np.linalg.LinAlgError:
                 W = R @ np.linalg.inv(Ry + 1e-6 * np.eye(R.shape[0]))
-            self._w_cache = {key: _c64(W, device)}
+            # applied to every (rx, tx) pair of every call at this SNR: keep it as a prepared GEMM operand
+            self._w_cache = {key: _engine().prepare_dense(_c64(W, device))}
         return self._w_cache[key]
 
     def estimate_at_pilots(self, rx_symbols: np.ndarray, tx_pilots: np.ndarray, pilot_mask: np.ndarray,

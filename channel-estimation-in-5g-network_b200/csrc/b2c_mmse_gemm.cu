@@ -69,7 +69,40 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 // REALW = true : W REAL [m][k] applied to the real and imaginary parts alike (the Clough-Tocher 'cubic'
 //                interpolation as a dense linear map, [nsym*nsc] x [npilots]): column c of `in` becomes two
 //                GEMM columns (re, im), so a CTA covers 64 complex columns and K runs over k, not 2k.
+// Element (row r, real column kk) of an operand tile in the canonical K-major no-swizzle layout (bytes).
+__host__ __device__ __forceinline__ int tile_off(int r, int kk, int lbo) { return (kk >> 2) * lbo + (r >> 3) * TC_SBO + (r & 7) * 16 + (kk & 3) * 4; }
+
+// One-time operand preparation (per Wiener matrix / interpolation map): the A operand of every (row tile, K stage)
+// is written to global memory already split into its TF32 hi / lo parts and already in the shared-memory tile
+// layout, [hi 16 KB][lo 16 KB] per tile, so that the GEMM fetches a stage of A with ONE 32 KB bulk copy
+// (cp.async.bulk -> mbarrier) and spends no CUDA-core work on it.
 template <bool REALW>
+__global__ void __launch_bounds__(256) dense_prepare_kernel(const float *__restrict__ Wf, int m, int k, float *__restrict__ prep,
+                                                            int nstages) {
+  const int tm = blockIdx.x, st = blockIdx.y;
+  float *hi = prep + ((int64_t)tm * nstages + st) * (2 * TC_TILE_A / 4), *lo = hi + TC_TILE_A / 4;
+  for (int e = threadIdx.x; e < TC_BM * TC_BK; e += 256) {
+    const int r = e / TC_BK, kk = e - r * TC_BK;
+    const int row = tm * TC_BM + r, col = st * TC_BK + kk;
+    float v = 0.f;
+    if (REALW) {
+      if (row < m && col < k) v = __ldg(Wf + (int64_t)row * k + col);
+    } else {
+      const int i = row >> 1, j = col >> 1;
+      if (i < k && j < k) {
+        const float2 w = __ldg(reinterpret_cast<const float2 *>(Wf) + (int64_t)i * k + j);
+        v = (row & 1) ? ((col & 1) ? w.x : w.y) : ((col & 1) ? -w.y : w.x);
+      }
+    }
+    float h, l;
+    split_tf32(v, h, l);
+    const int o = tile_off(r, kk, TC_LBO_A) / 4;
+    hi[o] = h;
+    lo[o] = l;
+  }
+}
+
+template <bool REALW, bool PREP>
 __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__restrict__ Wf, int m, int k,
                                                               const float2 *__restrict__ in, float *__restrict__ out,
                                                               int64_t ncols, int64_t ld_in, int64_t ld_out) {
@@ -79,6 +112,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__
   extern __shared__ unsigned char smem_dyn[];
   __shared__ uint32_t tmem_base_sm;
   __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ __align__(8) uint64_t a_bar;          // PREP: completion of the bulk copy of this stage's A tiles
 
   // 1024-byte aligned operand tiles: [A hi][A lo][B hi][B lo]
   const uint32_t s0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -98,6 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__
   }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mma_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&a_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -126,11 +161,13 @@ __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__
   const int rb_cc_lo = lane & 3, rb_kk = ((lane >> 2) & 7) | (warp << 3);
   auto load_stage = [&](int k0) {     // k0: real k offset of the stage (multiple of 32)
     if (REALW) {
+      if (!PREP) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int r = e0 + (q << 3) + b_cl_lo, j = k0 + 2 * b_jl;
-        const float *src = Wf + (int64_t)r * k + j;
-        ra_w[q] = make_float2((r < m && j < k) ? __ldg(src) : 0.f, (r < m && j + 1 < k) ? __ldg(src + 1) : 0.f);
+        for (int q = 0; q < 16; ++q) {
+          const int r = e0 + (q << 3) + b_cl_lo, j = k0 + 2 * b_jl;
+          const float *src = Wf + (int64_t)r * k + j;
+          ra_w[q] = make_float2((r < m && j < k) ? __ldg(src) : 0.f, (r < m && j + 1 < k) ? __ldg(src + 1) : 0.f);
+        }
       }
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
@@ -141,10 +178,12 @@ __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__
       return;
     }
     const int jc0 = k0 >> 1;
+    if (!PREP) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int i = i0c + (q << 3) + a_il_lo, j = jc0 + a_jl;
-      ra[q] = (i < np && j < np) ? __ldg(W + (int64_t)i * np + j) : make_float2(0.f, 0.f);
+      for (int q = 0; q < 8; ++q) {
+        const int i = i0c + (q << 3) + a_il_lo, j = jc0 + a_jl;
+        ra[q] = (i < np && j < np) ? __ldg(W + (int64_t)i * np + j) : make_float2(0.f, 0.f);
+      }
     }
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -156,15 +195,17 @@ __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__
   auto store_stage = [&]() {
     if (REALW) {
       const int kc = b_jl >> 1, eo = (b_jl & 1) * 8;
+      if (!PREP) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int r = (q << 3) + b_cl_lo;
-        float x_h, x_l, y_h, y_l;
-        split_tf32(ra_w[q].x, x_h, x_l);
-        split_tf32(ra_w[q].y, y_h, y_l);
-        const int o = kc * TC_LBO_A + (r >> 3) * TC_SBO + (r & 7) * 16 + eo;
-        *reinterpret_cast<float2 *>(sAh + o) = make_float2(x_h, y_h);
-        *reinterpret_cast<float2 *>(sAl + o) = make_float2(x_l, y_l);
+        for (int q = 0; q < 16; ++q) {
+          const int r = (q << 3) + b_cl_lo;
+          float x_h, x_l, y_h, y_l;
+          split_tf32(ra_w[q].x, x_h, x_l);
+          split_tf32(ra_w[q].y, y_h, y_l);
+          const int o = kc * TC_LBO_A + (r >> 3) * TC_SBO + (r & 7) * 16 + eo;
+          *reinterpret_cast<float2 *>(sAh + o) = make_float2(x_h, y_h);
+          *reinterpret_cast<float2 *>(sAl + o) = make_float2(x_l, y_l);
+        }
       }
       const int kc2 = rb_kk >> 2, eo2 = (rb_kk & 3) * 4;
       const bool im_first = (lane >> 4) & 1;
@@ -188,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__
     const int a_kc = a_jl >> 1, a_eo = (a_jl & 1) * 8;
     const bool odd_first = (lane >> 3) & 1;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < (PREP ? 0 : 8); ++q) {
       const int il = (q << 3) + a_il_lo;
       float wr_h, wr_l, wi_h, wi_l;
       split_tf32(ra[q].x, wr_h, wr_l);
@@ -219,13 +260,26 @@ __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__
 
   const int nstages = (kreal + TC_BK - 1) / TC_BK;
   uint32_t parity = 0;
+  const unsigned char *prep = reinterpret_cast<const unsigned char *>(Wf) + (int64_t)blockIdx.x * nstages * (2 * TC_TILE_A);
   load_stage(0);
   for (int st = 0; st < nstages; ++st) {
+    if (PREP && tid == 0) {
+      // the MMAs of the previous stage have completed (waited below), so both A tiles are free: fetch this stage's
+      // pre-split hi / lo pair (contiguous 32 KB, already in tile layout) while the threads stage B
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&a_bar)), "r"(2u * TC_TILE_A) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(aAh),
+                   "l"(prep + (int64_t)st * (2 * TC_TILE_A)), "r"(2u * TC_TILE_A), "r"(smem_u32(&a_bar))
+                   : "memory");
+    }
     store_stage();
     // generic-proxy smem writes -> visible to the tensor core (async proxy), then CTA barrier
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
     if (tid == 0) {
+      if (PREP) {
+        while (!mbar_try_wait(smem_u32(&a_bar), parity)) {
+        }
+      }
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
       for (int kk = 0; kk < TC_BK / 8; ++kk) {     // one instruction covers K = 8 = two 16-byte chunks
@@ -300,9 +354,9 @@ extern "C" int b2c_mmse_dense(const float *W, int32_t np, const float *in, float
   if (ncols == 0) return B2C_OK;
   dim3 grid((unsigned)((2 * np + TC_BM - 1) / TC_BM), (unsigned)((ncols + TC_BN - 1) / TC_BN));
   B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_mmse_dense: ncols=%lld too large for one launch", (long long)ncols);
-  B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  dense_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(W, np, np, reinterpret_cast<const float2 *>(in),
-                                                                               out, ncols, ld, ld);
+  B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  dense_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(W, np, np, reinterpret_cast<const float2 *>(in),
+                                                                                      out, ncols, ld, ld);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }
@@ -317,9 +371,64 @@ extern "C" int b2c_dense_real_apply(const float *W, int32_t m, int32_t k, const 
   if (ncols == 0) return B2C_OK;
   dim3 grid((unsigned)((m + TC_BM - 1) / TC_BM), (unsigned)((ncols + TC_BN / 2 - 1) / (TC_BN / 2)));
   B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_real_apply: ncols=%lld too large for one launch", (long long)ncols);
-  B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  dense_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(W, m, k, reinterpret_cast<const float2 *>(in), out,
-                                                                              ncols, ld_in, ld_out);
+  B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  dense_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(W, m, k, reinterpret_cast<const float2 *>(in), out,
+                                                                                     ncols, ld_in, ld_out);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+// ---- prepared-operand variants -------------------------------------------------------------------------------
+static void prep_dims(int32_t m, int32_t k, int32_t is_complex, int &tiles_m, int &nstages) {
+  const int mr = is_complex ? 2 * k : m, kr = is_complex ? 2 * k : k;
+  tiles_m = (mr + TC_BM - 1) / TC_BM;
+  nstages = (kr + TC_BK - 1) / TC_BK;
+}
+
+extern "C" int64_t b2c_dense_prepared_bytes(int32_t m, int32_t k, int32_t is_complex) {
+  if (m < 1 || k < 1) return 0;
+  int tiles_m, nstages;
+  prep_dims(m, k, is_complex, tiles_m, nstages);
+  return (int64_t)tiles_m * nstages * 2 * TC_TILE_A;
+}
+
+extern "C" int b2c_dense_prepare(const float *W, int32_t m, int32_t k, int32_t is_complex, void *prepared, void *stream) {
+  B2C_REQUIRE(W && prepared && m >= 1 && k >= 1 && (!is_complex || m == k), B2C_E_ARG, "b2c_dense_prepare: m=%d k=%d", m, k);
+  B2C_REQUIRE(((uintptr_t)prepared & 15) == 0, B2C_E_ARG, "b2c_dense_prepare: workspace must be 16-byte aligned");
+  int tiles_m, nstages;
+  prep_dims(m, k, is_complex, tiles_m, nstages);
+  dim3 grid((unsigned)tiles_m, (unsigned)nstages);
+  if (is_complex) dense_prepare_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(W, m, k, static_cast<float *>(prepared), nstages);
+  else dense_prepare_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(W, m, k, static_cast<float *>(prepared), nstages);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t k, int32_t is_complex, const float *in,
+                                        float *out, int64_t ncols, int64_t ld_in, int64_t ld_out, void *stream) {
+  B2C_REQUIRE(prepared && in && out && m >= 1 && k >= 1 && (!is_complex || m == k), B2C_E_ARG,
+              "b2c_dense_apply_prepared: null argument or m=%d k=%d", m, k);
+  B2C_REQUIRE(ld_in >= k && ld_out >= m && ncols >= 0 && in != out, B2C_E_ARG,
+              "b2c_dense_apply_prepared: ld_in=%lld ld_out=%lld ncols=%lld", (long long)ld_in, (long long)ld_out, (long long)ncols);
+  B2C_REQUIRE(((uintptr_t)prepared & 15) == 0, B2C_E_ARG, "b2c_dense_apply_prepared: workspace must be 16-byte aligned");
+  if (ncols == 0) return B2C_OK;
+  int tiles_m, nstages;
+  prep_dims(m, k, is_complex, tiles_m, nstages);
+  const float *P = static_cast<const float *>(prepared);
+  if (is_complex) {
+    B2C_REQUIRE(ld_in == ld_out, B2C_E_ARG, "b2c_dense_apply_prepared: complex form takes one leading dimension");
+    dim3 grid((unsigned)tiles_m, (unsigned)((ncols + TC_BN - 1) / TC_BN));
+    B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
+    B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    dense_tc_kernel<false, true><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(P, k, k, reinterpret_cast<const float2 *>(in), out,
+                                                                                       ncols, ld_in, ld_out);
+  } else {
+    dim3 grid((unsigned)tiles_m, (unsigned)((ncols + TC_BN / 2 - 1) / (TC_BN / 2)));
+    B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
+    B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    dense_tc_kernel<true, true><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(P, m, k, reinterpret_cast<const float2 *>(in), out,
+                                                                                      ncols, ld_in, ld_out);
+  }
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }

@@ -57,6 +57,13 @@ class PatternPool:
         return m.reshape(self.nsym, self.nsc)
 
 
+class PreparedDense:
+    """A GEMM operand in b2c_dense_prepare's form (see SlotEngine.prepare_dense)."""
+
+    def __init__(self, buf, m, k, is_complex):
+        self.buf, self.m, self.k, self.is_complex = buf, int(m), int(k), bool(is_complex)
+
+
 class SlotEngine:
     """Geometry + TDL profile tables on one GPU, and launchers for every libb2c entry point."""
 
@@ -238,13 +245,32 @@ class SlotEngine:
         return out
 
     def dense_real_apply(self, W, h, ld_out=None):
-        """W [m,k] float32, h [ncols, ld_in>=k] c64 -> out [ncols, ld_out>=m] with out[c,:m] = W @ h[c,:k]."""
-        m, k = W.shape
+        """W [m,k] float32 (or a PreparedDense of one), h [ncols, ld_in>=k] c64 -> out [ncols, ld_out>=m] with
+        out[c,:m] = W @ h[c,:k]."""
+        m, k = (W.m, W.k) if isinstance(W, PreparedDense) else W.shape
         ld_out = m if ld_out is None else ld_out
         out = torch.zeros((h.shape[0], ld_out), dtype=torch.complex64, device=self.device)
+        if isinstance(W, PreparedDense):
+            if W.is_complex:
+                raise ValueError("prepared operand is a complex Wiener matrix, not a real map")
+            check(lib().b2c_dense_apply_prepared(dptr(W.buf, "u8"), m, k, 0, dptr(h, "c64"), dptr(out, "c64"), h.shape[0],
+                                                 h.shape[1], ld_out, stream_ptr()), "b2c_dense_apply_prepared")
+            return out
         check(lib().b2c_dense_real_apply(dptr(W, "f32"), m, k, dptr(h, "c64"), dptr(out, "c64"), h.shape[0], h.shape[1],
                                          ld_out, stream_ptr()), "b2c_dense_real_apply")
         return out
+
+    def prepare_dense(self, W):
+        """One-time preparation of a GEMM operand that is applied many times (a Wiener matrix W [np,np] complex64, or
+        a real interpolation map [m,k] float32): TF32 hi / lo split tiles in the kernel's shared-memory layout, so
+        that every K stage of it is one bulk copy (b2c_dense_prepare)."""
+        cplx = W.is_complex()
+        m, k = W.shape
+        nbytes = lib().b2c_dense_prepared_bytes(m, k, int(cplx))
+        buf = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        check(lib().b2c_dense_prepare(dptr(W, "c64" if cplx else "f32"), m, k, int(cplx), dptr(buf, "u8"), stream_ptr()),
+              "b2c_dense_prepare")
+        return PreparedDense(buf, m, k, cplx)
 
     def ls_cubic(self, rx, pilots, pilot_indices, H_true=None, want=("H_ls",), geom=None):
         """LS estimate with griddata's 'cubic' interpolation: LS at the pilots (K3), the dense
@@ -259,8 +285,8 @@ class SlotEngine:
         B = rx.shape[0]
         hp = self.ls_interp(rx, pilots, pool, want=("hp",), geom=g)["hp"].reshape(B * g.nrx, -1)
         key = (idx.tobytes(), g.nsym, g.nsc)
-        if key not in self._cubic:
-            self._cubic = {key: torch.from_numpy(_tables.cubic_matrix(idx, g.nsym, g.nsc)).to(self.device)}
+        if key not in self._cubic:     # the map is applied to every batch of this pattern: keep it in prepared form
+            self._cubic = {key: self.prepare_dense(torch.from_numpy(_tables.cubic_matrix(idx, g.nsym, g.nsc)).to(self.device))}
         grid = self.dense_real_apply(self._cubic[key], hp, ld_out=nre)             # [B*nrx, nre]
         return self.ls_interp(None, None, self._identity_pool(g.nsym, g.nsc), hp_in=grid.reshape(B, g.nrx, nre),
                               H_true=H_true, want=tuple(w for w in want if w in ("H_ls", "stats")), geom=g)
@@ -282,8 +308,14 @@ class SlotEngine:
         return self._ident[nre]
 
     def mmse_dense(self, W, h):
-        """W [np,np] c64, h [ncols, ld>=np] c64 -> W @ h[c, :np] per column set."""
+        """W [np,np] c64 (or a PreparedDense of one), h [ncols, ld>=np] c64 -> W @ h[c, :np] per column set."""
         out = torch.zeros_like(h)
+        if isinstance(W, PreparedDense):
+            if not W.is_complex:
+                raise ValueError("prepared operand is a real map, not a complex Wiener matrix")
+            check(lib().b2c_dense_apply_prepared(dptr(W.buf, "u8"), W.m, W.k, 1, dptr(h, "c64"), dptr(out, "c64"), h.shape[0],
+                                                 h.shape[1], h.shape[1], stream_ptr()), "b2c_dense_apply_prepared")
+            return out
         check(lib().b2c_mmse_dense(dptr(W, "c64"), W.shape[0], dptr(h, "c64"), dptr(out, "c64"), h.shape[0],
                                    h.shape[1], stream_ptr()), "b2c_mmse_dense")
         return out

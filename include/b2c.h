@@ -203,6 +203,17 @@ int b2c_mmse_dense(const float *W, int32_t np, const float *in, float *out, int6
 int b2c_dense_real_apply(const float *W, int32_t m, int32_t k, const float *in, float *out, int64_t ncols,
                          int64_t ld_in, int64_t ld_out, void *stream);
 
+/* K4 / K4b with a prepared operand.  b2c_dense_prepare writes the A operand (the complex W of b2c_mmse_dense with
+ * is_complex = 1, m = k = np; or the real W [m][k] of b2c_dense_real_apply) once, already split into TF32 hi / lo
+ * parts and already in the GEMM's shared-memory tile layout, into a caller-owned workspace of
+ * b2c_dense_prepared_bytes(m, k, is_complex) bytes (16-byte aligned); b2c_dense_apply_prepared then fetches each
+ * K stage of A with one 32 KB bulk copy (cp.async.bulk + mbarrier) instead of staging it through registers.
+ * Same results as the one-shot entry points, bit for bit.                                                     */
+int64_t b2c_dense_prepared_bytes(int32_t m, int32_t k, int32_t is_complex);
+int b2c_dense_prepare(const float *W, int32_t m, int32_t k, int32_t is_complex, void *prepared, void *stream);
+int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t k, int32_t is_complex, const float *in,
+                             float *out, int64_t ncols, int64_t ld_in, int64_t ld_out, void *stream);
+
 /* K5.  Fold per-slot statistics into per-bin float64 accumulators (deterministic order).
  * Replaces the per-sample evaluate_estimator / compute_nmse + list aggregation of
  * src/baseline_estimators.py:326-337 and run_phase8_pilot_optimization.py:32-37,186-206.

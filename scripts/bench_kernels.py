@@ -49,6 +49,11 @@ for ncols in (4096, 16384):
     err = ((eng.mmse_dense(W, h)[:64].to(torch.complex128) - ref).abs().max() / ref.abs().max()).item()
     res[f"k4_mmse_dense_{ncols}cols"] = {"ms": t * 1e3, "useful_tflops": flops / t / 1e12, "issued_tf32_tflops": 3 * flops / t / 1e12,
                                           "rel_err_vs_fp64": err}
+    Wp = eng.prepare_dense(W)
+    t = timeit(lambda: eng.mmse_dense(Wp, h), n=5)
+    res[f"k4_mmse_dense_prepared_{ncols}cols"] = {"ms": t * 1e3, "useful_tflops": flops / t / 1e12,
+                                                   "issued_tf32_tflops": 3 * flops / t / 1e12,
+                                                   "note": "W pre-split into hi/lo smem tiles once (b2c_dense_prepare), A stages by bulk copy"}
 
 # K4b cubic interpolation map: real [8386 x 838] on (re, im) of 4096 pilot vectors (1024 4x4 slots)
 Wc = (torch.randn(8386, npil, device=dev) / np.sqrt(npil)).contiguous()
@@ -56,7 +61,10 @@ h = torch.randn(4096, npil, dtype=torch.complex64, device=dev)
 t = timeit(lambda: eng.dense_real_apply(Wc, h), n=5)
 flops = 4.0 * 8386 * npil * 4096
 res["k4b_cubic_map_4096cols"] = {"ms": t * 1e3, "useful_tflops": flops / t / 1e12, "issued_tf32_tflops": 3 * flops / t / 1e12}
-del Wc, h
+Wcp = eng.prepare_dense(Wc)
+t = timeit(lambda: eng.dense_real_apply(Wcp, h), n=5)
+res["k4b_cubic_map_prepared_4096cols"] = {"ms": t * 1e3, "useful_tflops": flops / t / 1e12, "issued_tf32_tflops": 3 * flops / t / 1e12}
+del Wc, Wcp, h
 
 # K3 stand-alone LS + MMSE + stats on resident rx / H_true, padded rows (wide accesses) and contiguous rows
 B = 2048

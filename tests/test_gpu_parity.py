@@ -345,8 +345,16 @@ def test_dense_wiener_path(engines):
     A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)
     X = np.zeros((c, ld), complex)
     X[:, :n] = rng.standard_normal((c, n)) + 1j * rng.standard_normal((c, n))
-    Y = eng.mmse_dense(torch.from_numpy(A).to(dev, torch.complex64), torch.from_numpy(X).to(dev, torch.complex64)).cpu().numpy()
+    At, Xt = torch.from_numpy(A).to(dev, torch.complex64), torch.from_numpy(X).to(dev, torch.complex64)
+    Y = eng.mmse_dense(At, Xt).cpu().numpy()
     assert relerr(Y[:, :n], X[:, :n] @ A.T) < 5e-5 and not Y[:, n:].any()
+    # prepared operand (pre-split tiles fetched by bulk copy): same MMAs on the same bits
+    prep = eng.prepare_dense(At)
+    for _ in range(2):                      # second call: the prepared buffer is reusable
+        assert torch.equal(eng.mmse_dense(prep, Xt), torch.from_numpy(Y).to(dev))
+    small = torch.from_numpy(rng.standard_normal((167, 167)) + 1j * rng.standard_normal((167, 167))).to(dev, torch.complex64)
+    xs = torch.from_numpy(rng.standard_normal((77, 167)) + 1j * rng.standard_normal((77, 167))).to(dev, torch.complex64)
+    assert torch.equal(eng.mmse_dense(eng.prepare_dense(small), xs), eng.mmse_dense(small, xs))
 
 
 def test_error_reporting(engines):
@@ -483,6 +491,9 @@ def test_dense_real_map_and_cubic_ls(engines):
                                  ld_out=m + 5).cpu().numpy()
         assert Y.shape == (c, m + 5) and not Y[:, m:].any()
         assert relerr(Y[:, :m], X[:, :k] @ W.T) < 5e-5, (m, k, c)
+        Yp = eng.dense_real_apply(eng.prepare_dense(torch.from_numpy(W).to(dev, torch.float32)),
+                                  torch.from_numpy(X).to(dev, torch.complex64), ld_out=m + 5).cpu().numpy()
+        assert np.array_equal(Yp, Y), (m, k, c)             # prepared operand: bit-identical
     g, cub = load_golden("slot_2x2_eva"), load_golden("ls_cubic")["slot_2x2_eva"]
     rx = torch.from_numpy(g["rx_symbols"][None]).to(dev, torch.complex64)
     xp = torch.from_numpy(g["pilot_symbols"][None]).to(dev, torch.complex64)
