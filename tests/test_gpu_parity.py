@@ -271,6 +271,14 @@ def test_ofdm_modem(engines):
     assert relerr(eng.ofdm_demodulate(y).cpu().numpy(), x.cpu().numpy()) < RTOL
     assert relerr((eng.ofdm_modulate(2 * x[:64]) - 2 * y[:64]).abs().cpu().numpy() + 1, np.ones((64, 1096))) < 1e-5
     assert torch.equal(y[:, :72], y[:, 1024:])            # cyclic prefix
+    # another prefix length (odd: rows 8-byte aligned only); same transform
+    from engine import SlotEngine
+    cfg = full_config(1, 1)
+    cfg["ofdm"]["cp_length"] = 71
+    e71 = SlotEngine(cfg)
+    y71 = e71.ofdm_modulate(x[:300])
+    assert y71.shape == (300, 1095) and torch.equal(y71[:, 71:], y[:300, 72:]) and torch.equal(y71[:, :71], y71[:, 1024:])
+    assert relerr(e71.ofdm_demodulate(y71).cpu().numpy(), x[:300].cpu().numpy()) < RTOL
 
 
 @pytest.mark.parametrize("model", ["EPA", "EVA", "ETU"])
