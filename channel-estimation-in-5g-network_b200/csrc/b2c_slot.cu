@@ -439,7 +439,9 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
 // complex apart (even, so K*8 is 16-byte aligned); element 599 of each row is padding.
 // Measured on the bare store pattern (scripts/store_pattern_bench.cu): 6.8 TB/s against 4.4 TB/s for the
 // 8-byte form -- the kernel's ceiling moves from the store path to its arithmetic.
-template <int T, int NTX, bool EST, int PITCH>
+// STORE = false: statistics-only sweeps (pilot-density / SNR curves, sharded statistics): no array is written, so the
+// grid symbols, the noise and the lane exchanges that only feed stores are skipped altogether.
+template <int T, int NTX, bool EST, int PITCH, bool STORE>
 __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx &c, float2 (&st)[2][3]) {
   constexpr int NSC = 599, HALF = 300;
   const int nsym = a.g.nsym, nrx = a.g.nrx;
@@ -458,13 +460,13 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
   for (int t = 0; t < T; ++t) twp[t] = act ? __ldg(tw + t * NSC + K) : zero2;
 
   const int64_t slot_h = (int64_t)nsym * nrx * NTX * PITCH, slot_r = (int64_t)nsym * nrx * PITCH;
-  float2 *const Hb = a.H_true + c.b * slot_h;
-  float2 *const Rb = a.rx + c.b * slot_r;
-  float2 *const Tb = c.rx == 0 ? a.tx + c.b * (int64_t)nsym * NTX * PITCH : nullptr;
+  float2 *const Hb = STORE ? a.H_true + c.b * slot_h : nullptr;
+  float2 *const Rb = STORE ? a.rx + c.b * slot_r : nullptr;
+  float2 *const Tb = (STORE && c.rx == 0) ? a.tx + c.b * (int64_t)nsym * NTX * PITCH : nullptr;
   const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * (nsym * NSC + 1) : nullptr;
   float2 *pH = Hb + (c.rx * NTX * PITCH + K), *pR = Rb + (c.rx * PITCH + K), *pT = Tb + K;
-  const int64_t dL = EST ? (const char *)(a.H_ls + c.b * slot_h) - (const char *)Hb : 0;
-  const int64_t dM = EST ? (const char *)(a.H_mmse + c.b * slot_h) - (const char *)Hb : 0;
+  const int64_t dL = (EST && STORE) ? (const char *)(a.H_ls + c.b * slot_h) - (const char *)Hb : 0;
+  const int64_t dM = (EST && STORE) ? (const char *)(a.H_mmse + c.b * slot_h) - (const char *)Hb : 0;
   const int nre = nsym * NSC;
   int oPK = act ? K : nre, oPS = vS ? S : nre;                   // plan rows; row nre = "outside" for idle lanes
   const int dPK = act ? NSC : 0, dPS = vS ? NSC : 0;
@@ -491,7 +493,7 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
         prefetch_l1(plan + oPK);
         prefetch_l1(plan + oPS);
       }
-      if (EST) {
+      if (EST && STORE) {
         // H_ls / H_mmse rows are the same for every tx: written here, so that only lK / lS stay live below
         const float2 lN = xchg(lS);
         const float2 mK = cscale(c.alpha, lK), mN = cscale(c.alpha, lN);
@@ -518,9 +520,9 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
         const float2 hS = cscale(mS, make_float2(A.x + B.y, B.x - A.y));      // mirror bin (0 where it does not exist)
         hsK = __fadd2_rn(hsK, hK);
         hsS = __fadd2_rn(hsS, hS);
-        const float2 hN = xchg(hS);
-        if (act) {
-          st16(pH + tx * PITCH, hK, hN);
+        if (STORE) {
+          const float2 hN = xchg(hS);
+          if (act) st16(pH + tx * PITCH, hK, hN);
         }
         if (EST) {
           float2 (&acc)[3] = st[tx == 0 ? 0 : 1];
@@ -535,6 +537,10 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
           acc[2] = __ffma2_rn(hK, hK, acc[2]);
           acc[2] = __ffma2_rn(hS, hS, acc[2]);
         }
+      }
+      if (!STORE) {
+        gps += NTX * MAXT;
+        continue;
       }
       // ---- draws: Philox lane t serves both bins of the mirror pair; word half h = (f > 0) -------------
       if (j == 0) ws = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 1) * RNG_LANES + t_));
@@ -562,7 +568,7 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
   }
 }
 
-template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE>
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE, bool STORE = true>
 __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nsc = NSC ? NSC : a.g.nsc;
@@ -614,22 +620,22 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
 
   if (c.ntaps <= 5) {
     if (EST) pilot_phase<5, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<5, NTX, EST, WIDE>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<5, NTX, EST, WIDE, STORE>(a, c, st);
     else slot_body<5, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else if (c.ntaps <= 8) {
     if (EST) pilot_phase<8, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<8, NTX, EST, WIDE>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<8, NTX, EST, WIDE, STORE>(a, c, st);
     else slot_body<8, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else if (c.ntaps <= 9) {
     if (EST) pilot_phase<9, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<9, NTX, EST, WIDE>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<9, NTX, EST, WIDE, STORE>(a, c, st);
     else slot_body<9, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else {
     if (EST) pilot_phase<MAXT, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<MAXT, NTX, EST, WIDE>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<MAXT, NTX, EST, WIDE, STORE>(a, c, st);
     else slot_body<MAXT, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
 
@@ -659,9 +665,9 @@ static size_t slot_smem_bytes(const b2c_geom *g, int np_max) {
          (size_t)(np_max + 1) * sizeof(float2);
 }
 
-template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0>
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0, bool STORE = true>
 static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
-  auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE>;
+  auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE>;
   if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(B * a.g.nrx), SLOT_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
@@ -678,6 +684,17 @@ static int launch_slot_ntx(const SlotArgs &a, int64_t B, size_t smem, cudaStream
   const bool fast = !a.compact && a.g.nsc == 599 && (a.g.nsym & 1) == 0 && !a.has_inj && a.H_true && a.rx && a.tx &&
                     (!EST || (a.H_ls && a.H_mmse && a.stats));
   const int pitch = a.g.pitch ? a.g.pitch : a.g.nsc;
+  if constexpr (EST) {
+    // statistics only (no array requested) on the default grid: the store-free instantiation of the wide kernel
+    const bool stats_only = a.stats && !a.H_true && !a.rx && !a.tx && !a.H_ls && !a.H_mmse && !a.compact && a.g.nsc == 599 &&
+                            (a.g.nsym & 1) == 0 && !a.has_inj;
+    if (stats_only) {
+      if (ntx == 1) return launch_slot<1, true, true, 599, true, WIDE_PITCH, false>(a, B, smem, stream);
+      if (ntx == 2) return launch_slot<2, true, true, 599, true, WIDE_PITCH, false>(a, B, smem, stream);
+      if (ntx == 4) return launch_slot<4, true, true, 599, true, WIDE_PITCH, false>(a, B, smem, stream);
+      if (ntx == 8) return launch_slot<8, true, true, 599, true, WIDE_PITCH, false>(a, B, smem, stream);
+    }
+  }
   if (pitch != a.g.nsc) {
     // padded rows: the wide-store kernel of the throughput configuration only
     B2C_REQUIRE(fast && pitch == WIDE_PITCH, B2C_E_UNSUPPORTED,

@@ -226,7 +226,9 @@ def sharded_statistics(config: Dict, total_slots: int, rank: int = 0, world_size
     while pos < hi:
         n = min(batch, hi - pos)
         if out is None or n != batch:
-            out, ws = eng.alloc_outputs(n, want), eng.workspace(n)
+            # all five arrays requested: the row-padded throughput layout (wide-store kernel); callers see 599-wide views
+            full = all(k in want for k in ("H_true", "rx", "tx", "H_ls", "H_mmse"))
+            out, ws = eng.alloc_outputs(n, want, pitch=600 if (full and eng.nsc == 599 and eng.nsym % 2 == 0 and eng.ntx in (1, 2, 4, 8)) else None), eng.workspace(n)
         res, par = ds.generate_batch(n, pos, want=want, out=out, ws=ws)
         eng.stats_bins(res["stats"], par[bin_by].astype(np.int32), nbins, bins)
         if on_batch is not None:

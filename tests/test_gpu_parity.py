@@ -576,6 +576,10 @@ def test_padded_row_layout_matches_contiguous(ntx, nrx, model, engines):
         if k in sim_pad:
             assert torch.equal(sim_pad[k], sim_ref[k]), k
     assert torch.allclose(pad["stats"], ref["stats"], rtol=1e-6, atol=0)
+    # statistics-only call (pilot-density / SNR sweeps): the store-free instantiation gives the same sums
+    so = eng.run(B, want=("stats",), **args)
+    assert set(k for k in so if not k.startswith("_")) == {"stats"}
+    assert torch.allclose(so["stats"], ref["stats"], rtol=1e-6, atol=0)
     # against the oracle on the Philox twin draws for one slot (the contiguous path is pinned the same way)
     assert relerr(pad["H_true"][3].cpu().numpy(), ref["H_true"][3].cpu().numpy()) == 0.0
     # pitch-aware readers
