@@ -207,7 +207,7 @@ class ChannelEstimationDataset:
         print(f"Dataset saved to {filepath}")
 
 
-def sharded_statistics(config: Dict, total_slots: int, rank: int = 0, world_size: int = 1, batch: int = 2048,
+def sharded_statistics(config: Dict, total_slots: int, rank: int = 0, world_size: int = 1, batch: int = 8192,
                        seed: int = 42, bin_by: str = "snr", want_arrays=(), on_batch=None, dataset: Optional[ChannelEstimationDataset] = None):
     """Multi-GPU dataset statistics: rank r simulates + estimates global samples
     [r*N/R, (r+1)*N/R) in batches and folds MSE/NMSE into per-bin float64 accumulators on its
