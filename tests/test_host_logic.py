@@ -189,3 +189,21 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(PKG, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_row_pitch_and_numa_helpers():
+    """Host-side helpers of the padded-row layout and of the e2e leg (no GPU needed)."""
+    import torch
+    import _b2c
+    import host_pipeline as hp
+    buf = torch.zeros((3, 14, 4, 600), dtype=torch.complex64)
+    view = buf[..., :599]
+    assert _b2c.row_pitch(buf) == 600 and _b2c.row_pitch(view) == 600 and not view.is_contiguous()
+    assert _b2c.row_pitch(torch.zeros((3, 14, 4, 599), dtype=torch.complex64)) == 599
+    assert _b2c.row_pitch(torch.zeros((7,), dtype=torch.complex64)) == 7
+    with pytest.raises(_b2c.B2CError):            # the product path takes CUDA tensors only
+        _b2c.rows_ptr(view, 600)
+    assert _b2c.rows_ptr(None, 600, optional=True) is None
+    assert hp._cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and hp._cpulist("") == set()
+    if not torch.cuda.is_available():
+        assert hp.bind_to_gpu_numa_node(0) is None    # no device: nothing is bound, nothing raises
