@@ -130,13 +130,21 @@ def run_reference(args, rank, world):
     cores = host_cores()
     ntx, nrx, model, fd, dens, desc = WORKLOADS[args.workload]
     pool = cpu_bench.Pool(cores)
+    # One step = one slot per worker process (the smallest sample that keeps every host core busy), ~2-4 s each.
+    # A step count that would overrun the wall budget is cut short and the line reports the steps actually timed.
+    t_start = time.perf_counter()
     for w in range(args.warmup):
         pool.step(args.workload, 1, True, 10 + w)
     slots = secs = 0.0
+    done = 0
     for k in range(args.steps):
         s, t = pool.step(args.workload, 1, True, 1000 + k)
-        slots, secs = slots + s, secs + t
+        slots, secs, done = slots + s, secs + t, done + 1
+        if time.perf_counter() - t_start + 1.5 * t > args.reference_budget:
+            break
     pool.close()
+    truncated = done < args.steps
+    args.steps = done
     value = slots / secs
     sample = (f"each step = {cores} slots of {args.workload} (one per worker process), oracle port of "
               f"simulate_transmission + LSEstimator('linear') + MMSEEstimator() in its cost-faithful profile")
@@ -144,7 +152,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "slots_per_step": cores, "rng": "numpy Generator"},
+        "config": {"workload": f"{args.workload}: {desc}", "slots_per_step": cores, "rng": "numpy Generator",
+                   "note": (f"stopped after {done} timed steps: wall budget {args.reference_budget:.0f} s" if truncated else "all steps timed")},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -329,8 +338,10 @@ def run_b200(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=150)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 150; 6 for --impl reference)")
+    ap.add_argument("--warmup", type=int, default=None, help="warm-up steps (default 3; 1 for --impl reference)")
+    ap.add_argument("--reference-budget", type=float, default=240.0,
+                    help="--impl reference: wall-clock budget in seconds; the step loop stops early rather than overrun it")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_4x4_etu", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=4096, help="slots per step per GPU")
@@ -351,6 +362,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.steps is None:
+        args.steps = 150 if args.impl == "b200" else 6
+    if args.warmup is None:
+        args.warmup = 3 if args.impl == "b200" else 1
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3              # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
