@@ -4,6 +4,7 @@ library's exported symbols (no compute calls -- there is no GPU here)."""
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -207,3 +208,22 @@ def test_row_pitch_and_numa_helpers():
     assert hp._cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and hp._cpulist("") == set()
     if not torch.cuda.is_available():
         assert hp.bind_to_gpu_numa_node(0) is None    # no device: nothing is bound, nothing raises
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints one JSON line with the contract's keys,
+    honours its wall budget, and non-zero ranks stay silent."""
+    import json
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1_siso_epa",
+           "--steps", "50", "--warmup", "1", "--reference-budget", "6"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, check=True).stdout.strip().splitlines()
+    line = json.loads(out[-1])
+    assert line["impl"] == "reference" and line["unit"] == "slots/s" and line["higher_is_better"] is True
+    assert 1 <= line["steps"] < 50 and "wall budget" in line["config"]["note"]
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "slots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["vs_baseline"] is None
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    silent = subprocess.run(cmd, capture_output=True, text=True, timeout=120, check=True, env=env)
+    assert silent.stdout.strip() == ""
