@@ -376,14 +376,16 @@ def test_error_reporting(engines):
     assert out["H_true"].shape[0] == 0
 
 
-def test_full_size_properties(engines):
+@pytest.mark.parametrize("pitch", [600, None])
+def test_full_size_properties(pitch, engines):
     """BASELINE config 3 shape (4x4 ETU 200 Hz, 10 % pilots) at a batch too large for the oracle:
-    size-independent properties of the reference's algorithm."""
+    size-independent properties of the reference's algorithm, in the throughput layout bench.py measures
+    (rows at pitch 600, wide-store kernel) and in the contiguous one."""
     eng = engines(4, 4)
     pool = eng.random_pool([0.10], seed=42)
     B = 512
     snr = np.array([-5, 0, 5, 10, 15, 20, 25, 30], dtype=np.float32)[np.arange(B) % 8]
-    out = eng.run(B, eng.models.index("ETU"), 200.0, snr, 0, pool, slot0=0, seed=42)
+    out = eng.run(B, eng.models.index("ETU"), 200.0, snr, 0, pool, slot0=0, seed=42, pitch=pitch)
     torch.cuda.synchronize()
     H, rx, tx, Hl, Hm = (out[k] for k in ("H_true", "rx", "tx", "H_ls", "H_mmse"))
     for t in (H, rx, tx, Hl, Hm):
