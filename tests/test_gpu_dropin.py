@@ -215,6 +215,15 @@ def test_dataset_generator_philox_mode_and_sharding():
     assert torch.equal(a["H_ls"][3:6], b["H_ls"]) and np.array_equal(pa["snr"][3:6], pb["snr"])
     lst = ds.generate_dataset(6)
     assert len(lst) == 6 and lst[0]["H_true"].shape == (14, 2, 2, 599) and lst[0]["pilot_mask"].dtype == bool
+    # training features straight from the GPU-resident slots == prepare_ml_inputs on the same samples
+    x, y, par = ds.generate_feature_batch(4, slot0=10)
+    assert x.shape == (4, 14, 599, 5) and y.shape == (4, 14, 599, 2) and np.array_equal(par["snr"], pa["snr"][:4])
+    pool = ds.pattern_pool()
+    for i in range(4):
+        smp = {"rx_symbols": a["rx"][i].cpu().numpy(), "H_ls": a["H_ls"][i].cpu().numpy(), "H_true": a["H_true"][i].cpu().numpy(),
+               "pilot_mask": pool.mask(int(pa["pattern"][i]))}
+        rx_ref, t_ref = orc.ml_inputs(smp["rx_symbols"], smp["H_ls"], smp["H_true"], smp["pilot_mask"])
+        assert relerr(x[i].cpu().numpy(), rx_ref) < RTOL and relerr(y[i].cpu().numpy(), t_ref) < RTOL
 
 
 def _replay_sample(cfg, ch, fd, snr, dens, ntx=2, nrx=2):
