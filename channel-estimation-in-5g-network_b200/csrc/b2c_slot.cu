@@ -181,6 +181,7 @@ struct SlotCtx {
   PhiloxKey key;
   const float2 *gsp;   // smem [nsym][ntx][MAXT] tap gains of this rx
   const float2 *hp;    // smem [np] LS estimates at the pilots
+  uint4 *pstage;       // smem [2][2][SLOT_THREADS] plan-entry staging of the wide kernel (16-byte aligned)
 };
 
 // Symbol and noise draws for resource element (s, k) of this CTA's rx antenna (layout in b2c.h:
@@ -476,6 +477,19 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
   static_assert(SLOT_THREADS == RNG_LANES, "thread t draws Philox lane t");
   static_assert((PITCH & 1) == 0 && PITCH > NSC, "wide stores need an even, padded row pitch");
   uint4 ws = make_uint4(0, 0, 0, 0);
+  // Plan entries are staged one symbol ahead with cp.async into two per-thread shared-memory slots: their L2 latency
+  // (the kernel's top stall when they were plain loads behind an L1 prefetch) is spent under the previous symbol's work
+  // and costs no registers.  A thread reads back only what it copied itself, so cp.async.wait_group is all the
+  // synchronisation needed.  The last iteration stages the row after the pattern's plan: in bounds (padded pool).
+  uint4 *const ps = c.pstage + t_;
+  auto stage_plan = [&](int buf) {
+    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(ps + (buf * 2 + 0) * SLOT_THREADS);
+    const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(ps + (buf * 2 + 1) * SLOT_THREADS);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d0), "l"(plan + oPK) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d1), "l"(plan + oPS) : "memory");
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  if (EST) stage_plan(0);
   auto xchg = [](float2 v) {     // value of this lane's S bin -> the neighbour that stores it as K+1
     return make_float2(__shfl_xor_sync(0xffffffffu, v.x, 1), __shfl_xor_sync(0xffffffffu, v.y, 1));
   };
@@ -486,12 +500,12 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
       const int s = s2 + j;
       float2 lK = zero2, lS = zero2;
       if (EST) {
-        lK = plan_apply(plan_decode(__ldg(plan + oPK)), c.hp);
-        lS = plan_apply(plan_decode(__ldg(plan + oPS)), c.hp);
         oPK += dPK;
         oPS += dPS;
-        prefetch_l1(plan + oPK);
-        prefetch_l1(plan + oPS);
+        stage_plan(j ^ 1);                                   // next symbol's entries (s2 is even: buffer = s & 1 = j)
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        lK = plan_apply(plan_decode(ps[(j * 2 + 0) * SLOT_THREADS]), c.hp);
+        lS = plan_apply(plan_decode(ps[(j * 2 + 1) * SLOT_THREADS]), c.hp);
       }
       if (EST && STORE) {
         // H_ls / H_mmse rows are the same for every tx: written here, so that only lK / lS stay live below
@@ -588,6 +602,7 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   c.key = make_key(a.slots.seed, a.slots.slot0 + c.b);
   c.gsp = gsp;
   c.hp = hp;
+  c.pstage = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(hp + (EST ? a.pat.np_max + 1 : 0)) + 15) & ~(uintptr_t)15);
   c.alpha = 0.f;
   c.pid = 0;
 
@@ -668,6 +683,7 @@ static size_t slot_smem_bytes(const b2c_geom *g, int np_max) {
 template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0, bool STORE = true>
 static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
   auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE>;
+  if (WIDE && EST) smem += 16 + 4 * SLOT_THREADS * sizeof(uint4);      // plan-entry staging (+ alignment slack)
   if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(B * a.g.nrx), SLOT_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
