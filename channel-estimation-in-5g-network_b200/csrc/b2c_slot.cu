@@ -219,20 +219,39 @@ __device__ __forceinline__ void pilot_phase(const SlotArgs &a, SlotCtx &c, const
   const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * nsc;
   float psum = 0.f;
   if (threadIdx.x == 0) hp[a.pat.np_max] = make_float2(0.f, 0.f);   // the plan's "outside the hull" slot
-  for (int j = threadIdx.x; j < np; j += SLOT_THREADS) {
-    const int e = __ldg(pre + j);
-    const int s = e / nsc, k = e - s * nsc;
-    float2 twk[T];
+  // A pilot costs two dependent L2 round trips (its RE index, then its T twiddles).  Pilots are taken PB at a time per
+  // thread -- all PB indices first, then all PB * T twiddles, then the arithmetic -- so a CTA pays two round trips per
+  // PB * 320 pilots instead of two per 320 (838 pilots: 2 instead of 6).
+  constexpr int PB = T <= 9 ? 3 : 1;      // PB * T twiddles live at once: keep the 16-tap instantiation at one
+  for (int base = threadIdx.x; base < np; base += PB * SLOT_THREADS) {
+    int e[PB];
 #pragma unroll
-    for (int t = 0; t < T; ++t) twk[t] = __ldg(tw + t * nsc + k);   // issued together: one L2 round trip
-    float2 hsum = make_float2(0.f, 0.f);
+    for (int q = 0; q < PB; ++q) {
+      const int j = base + q * SLOT_THREADS;
+      e[q] = j < np ? __ldg(pre + j) : 0;
+    }
+    float2 twk[PB][T];
 #pragma unroll
-    for (int t = 0; t < T; ++t) hsum = cadd(hsum, cmul(gs[s * MAXT + t], twk[t]));
-    const float2 x = draw_symbol(a, c, s, k), n = draw_noise(a, c, s, k);
-    const float2 y = cmul(hsum, x);
-    const float2 h = ls_divide(make_float2(fmaf(c.sigma, n.x, y.x), fmaf(c.sigma, n.y, y.y)), x);
-    hp[j] = h;
-    psum += cabs2(h);
+    for (int q = 0; q < PB; ++q) {
+      const int k = e[q] % nsc;
+#pragma unroll
+      for (int t = 0; t < T; ++t) twk[q][t] = __ldg(tw + t * nsc + k);
+    }
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const int j = base + q * SLOT_THREADS;
+      if (j < np) {
+        const int s = e[q] / nsc, k = e[q] - s * nsc;
+        float2 hsum = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < T; ++t) hsum = cadd(hsum, cmul(gs[s * MAXT + t], twk[q][t]));
+        const float2 x = draw_symbol(a, c, s, k), n = draw_noise(a, c, s, k);
+        const float2 y = cmul(hsum, x);
+        const float2 h = ls_divide(make_float2(fmaf(c.sigma, n.x, y.x), fmaf(c.sigma, n.y, y.y)), x);
+        hp[j] = h;
+        psum += cabs2(h);
+      }
+    }
   }
   // default MMSE: R_h = P I  =>  W = P/(P + sigma^2) I  (src/baseline_estimators.py:174-190)
   const float P = block_sum(psum, red) / (float)np;
