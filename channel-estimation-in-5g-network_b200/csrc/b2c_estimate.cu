@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) pilot_vec_kernel(const float2 *__restrict
 }
 
 // ---- K5 ------------------------------------------------------------------------------------------
-constexpr int BIN_THREADS = 256;
+constexpr int BIN_THREADS = 1024;   // one CTA per bin scans every slot: latency-bound, so as many slots in flight as a CTA allows
 
 __global__ void __launch_bounds__(BIN_THREADS)
 stats_bins_kernel(b2c_geom g, const double *__restrict__ stats, const int32_t *__restrict__ bin_id,
