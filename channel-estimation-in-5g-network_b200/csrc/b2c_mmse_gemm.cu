@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__
                    : "memory");
     }
     store_stage();
+    if (st + 1 < nstages) load_stage((st + 1) * TC_BK);   // registers are free again: the next stage's global loads fly
+                                                          // under the barrier, the MMAs and the wait for them
     // generic-proxy smem writes -> visible to the tensor core (async proxy), then CTA barrier
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
@@ -295,7 +297,6 @@ __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mma_bar))
                    : "memory");
     }
-    if (st + 1 < nstages) load_stage((st + 1) * TC_BK);   // global loads overlap the MMAs
     while (!mbar_try_wait(smem_u32(&mma_bar), parity)) {
     }
     parity ^= 1u;
