@@ -356,6 +356,157 @@ __global__ void __launch_bounds__(TC_THREADS, 3) dense_tc_kernel(const float *__
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)TC_BN));
 }
 
+
+// ---- N = 256 form of the prepared complex product --------------------------------------------------------------
+// Same operands and arithmetic as dense_tc_kernel<false, true>, but one CTA (256 threads) owns a 128 x 256 tile: the
+// A tiles (the 32 KB bulk copy and the 3 x 4 KB the MMAs read per K step) are amortised over twice the columns, which
+// is what bounds the 128-column form (shared-memory bandwidth: operand reads + staging writes).  TMEM: 256 columns,
+// two CTAs per SM use all 512.  Warps 0-3 / 4-7 stage and read back the column halves 0-127 / 128-255.
+constexpr int T2_BN = 256;
+constexpr int T2_THREADS = 256;
+constexpr int T2_LBO_B = T2_BN * 16;
+constexpr int T2_TILE_B = T2_BN * TC_BK * 4;
+constexpr int T2_SMEM = 2 * TC_TILE_A + 2 * T2_TILE_B + 1024;
+constexpr uint32_t T2_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32_n256(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(T2_IDESC), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 2) dense_tc256_kernel(const float *__restrict__ prepared, int np,
+                                                                   const float2 *__restrict__ in, float *__restrict__ out,
+                                                                   int64_t ncols, int64_t ld) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ uint32_t tmem_base_sm;
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ __align__(8) uint64_t a_bar;
+  const uint32_t s0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char *sp = smem_dyn + (s0 - smem_u32(smem_dyn));
+  unsigned char *sBh = sp + 2 * TC_TILE_A, *sBl = sBh + T2_TILE_B;
+  const uint32_t aAh = s0, aAl = s0 + TC_TILE_A, aBh = s0 + 2 * TC_TILE_A, aBl = aBh + T2_TILE_B;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t c0 = (int64_t)blockIdx.y * T2_BN;
+  const int kreal = 2 * np;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "r"((uint32_t)T2_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mma_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&a_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_d = tmem_base_sm;
+
+  // B staging map (16 values per thread): column c = half * 128 + 8 q + lane[2:0], half = warp[2];
+  // complex j within the stage: jl[0] = lane[3], jl[1] = lane[4], jl[3:2] = warp[1:0]   (conflict-free, see above)
+  const int b_cl_lo = ((warp >> 2) << 7) | (lane & 7), b_jl = ((lane >> 3) & 3) | ((warp & 3) << 2);
+  const int b_kc = b_jl >> 1, b_eo = (b_jl & 1) * 8;
+  float2 rb0[16], rb1[16];
+  auto load_stage = [&](int k0, float2 (&rb)[16]) {
+    const int j = (k0 >> 1) + b_jl;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int64_t c = c0 + (q << 3) + b_cl_lo;
+      rb[q] = (c < ncols && j < np) ? __ldg(in + c * ld + j) : make_float2(0.f, 0.f);
+    }
+  };
+  auto store_stage = [&](float2 (&rb)[16]) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int cl = (q << 3) + b_cl_lo;
+      float xr_h, xr_l, xi_h, xi_l;
+      split_tf32(rb[q].x, xr_h, xr_l);
+      split_tf32(rb[q].y, xi_h, xi_l);
+      const int o = b_kc * T2_LBO_B + (cl >> 3) * TC_SBO + (cl & 7) * 16 + b_eo;
+      *reinterpret_cast<float2 *>(sBh + o) = make_float2(xr_h, xi_h);
+      *reinterpret_cast<float2 *>(sBl + o) = make_float2(xr_l, xi_l);
+    }
+  };
+
+  const int nstages = (kreal + TC_BK - 1) / TC_BK;
+  uint32_t parity = 0;
+  const unsigned char *prep = reinterpret_cast<const unsigned char *>(prepared) + (int64_t)blockIdx.x * nstages * (2 * TC_TILE_A);
+  auto do_stage = [&](int st, float2 (&rb)[16]) {
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&a_bar)), "r"(2u * TC_TILE_A) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(aAh),
+                   "l"(prep + (int64_t)st * (2 * TC_TILE_A)), "r"(2u * TC_TILE_A), "r"(smem_u32(&a_bar))
+                   : "memory");
+    }
+    store_stage(rb);
+    if (st + 2 < nstages) load_stage((st + 2) * TC_BK, rb);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      while (!mbar_try_wait(smem_u32(&a_bar), parity)) {
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+      for (int kk = 0; kk < TC_BK / 8; ++kk) {
+        const uint64_t dAh = umma_desc(aAh + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+        const uint64_t dAl = umma_desc(aAl + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+        const uint64_t dBh = umma_desc(aBh + kk * 2 * T2_LBO_B, T2_LBO_B, TC_SBO);
+        const uint64_t dBl = umma_desc(aBl + kk * 2 * T2_LBO_B, T2_LBO_B, TC_SBO);
+        umma_tf32_n256(tmem_d, dAh, dBh, (st | kk) != 0);
+        umma_tf32_n256(tmem_d, dAh, dBl, 1u);
+        umma_tf32_n256(tmem_d, dAl, dBh, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mma_bar))
+                   : "memory");
+    }
+    while (!mbar_try_wait(smem_u32(&mma_bar), parity)) {
+    }
+    parity ^= 1u;
+  };
+  load_stage(0, rb0);
+  if (nstages > 1) load_stage(TC_BK, rb1);
+  for (int st = 0; st < nstages; st += 2) {
+    do_stage(st, rb0);
+    if (st + 1 < nstages) do_stage(st + 1, rb1);
+  }
+
+  // epilogue: warp w reads TMEM lanes 32 (w & 3) .. + 31 (its hardware quarter), columns 128 (w >> 2) .. + 127
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const int ip = blockIdx.x * TC_BM + (warp & 3) * 32 + lane;
+  const int chalf = (warp >> 2) * 128;
+  const int64_t ld2 = 2 * ld;
+#pragma unroll 1
+  for (int cb = 0; cb < 128; cb += 32) {
+    uint32_t r[32];
+    const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf + cb);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    if (ip < kreal) {
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int64_t c = c0 + chalf + cb + q;
+        if (c < ncols) out[c * ld2 + ip] = __uint_as_float(r[q]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)T2_BN));
+}
+
 }  // namespace b2c
 
 using namespace b2c;
@@ -432,6 +583,27 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
   const float *P = static_cast<const float *>(prepared);
   if (is_complex) {
     B2C_REQUIRE(ld_in == ld_out, B2C_E_ARG, "b2c_dense_apply_prepared: complex form takes one leading dimension");
+    // Two tile shapes, equal per-SM throughput: 128 x 128 (3 CTAs/SM) and 128 x 256 (2 CTAs/SM).  What differs is the
+    // wave quantisation at this column count, so take the shape whose last wave is fuller.
+    static int sm_count = 0;
+    if (!sm_count) {
+      int dev = 0;
+      B2C_CUDA(cudaGetDevice(&dev));
+      B2C_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    auto wave_eff = [&](int64_t tiles, int per_sm) {
+      const int64_t slots = (int64_t)sm_count * per_sm;
+      return (double)tiles / (double)(((tiles + slots - 1) / slots) * slots);
+    };
+    const int64_t t128 = (int64_t)tiles_m * ((ncols + TC_BN - 1) / TC_BN), t256 = (int64_t)tiles_m * ((ncols + T2_BN - 1) / T2_BN);
+    if (ncols >= T2_BN && wave_eff(t256, 2) > wave_eff(t128, 3) + 0.02) {
+      dim3 grid2((unsigned)tiles_m, (unsigned)((ncols + T2_BN - 1) / T2_BN));
+      B2C_REQUIRE(grid2.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
+      B2C_CUDA(cudaFuncSetAttribute(dense_tc256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+      dense_tc256_kernel<<<grid2, T2_THREADS, T2_SMEM, (cudaStream_t)stream>>>(P, k, reinterpret_cast<const float2 *>(in), out, ncols, ld_in);
+      B2C_CUDA(cudaGetLastError());
+      return B2C_OK;
+    }
     dim3 grid((unsigned)tiles_m, (unsigned)((ncols + TC_BN - 1) / TC_BN));
     B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
     B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));

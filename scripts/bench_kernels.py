@@ -41,7 +41,7 @@ pool = eng.random_pool([0.10], seed=42)
 # K4 dense Wiener GEMM: W 838x838 complex, columns = slots x rx
 npil = 838
 W = (torch.randn(npil, npil, dtype=torch.complex64, device=dev) / np.sqrt(npil)).contiguous()
-for ncols in (4096, 16384):
+for ncols in (4096, 16384, 65536):
     h = torch.randn(ncols, npil, dtype=torch.complex64, device=dev)
     t = timeit(lambda: eng.mmse_dense(W, h), n=5)
     flops = 8.0 * npil * npil * ncols

@@ -360,6 +360,13 @@ def test_dense_wiener_path(engines):
     prep = eng.prepare_dense(At)
     for _ in range(2):                      # second call: the prepared buffer is reusable
         assert torch.equal(eng.mmse_dense(prep, Xt), torch.from_numpy(Y).to(dev))
+    # 4000 columns: the 128 x 256 tile form is chosen (fuller last wave), ragged last tile, padded leading dimension
+    Xw = np.zeros((4000, ld), complex)
+    Xw[:, :n] = rng.standard_normal((4000, n)) + 1j * rng.standard_normal((4000, n))
+    Xwt = torch.from_numpy(Xw).to(dev, torch.complex64)
+    Yw = eng.mmse_dense(prep, Xwt)
+    assert relerr(Yw.cpu().numpy()[:, :n], Xw[:, :n] @ A.T) < 5e-5 and not Yw[:, n:].abs().max().item()
+    assert torch.equal(Yw, eng.mmse_dense(At, Xwt))             # same products accumulated in the same order
     small = torch.from_numpy(rng.standard_normal((167, 167)) + 1j * rng.standard_normal((167, 167))).to(dev, torch.complex64)
     xs = torch.from_numpy(rng.standard_normal((77, 167)) + 1j * rng.standard_normal((77, 167))).to(dev, torch.complex64)
     assert torch.equal(eng.mmse_dense(eng.prepare_dense(small), xs), eng.mmse_dense(small, xs))
