@@ -14,6 +14,8 @@
 // tcgen05.ld.  Plain TF32 (10-bit mantissa) cannot hold the 1e-4 parity bound, so each operand is
 // split  v = hi + lo  (hi = v with the low 13 mantissa bits cleared, lo = v - hi, both exact) and
 // three MMAs are issued per K step:  hi*hi + hi*lo + lo*hi   ("3xTF32", error ~2^-21).
+#include <stdlib.h>
+
 #include "b2c_common.cuh"
 
 namespace b2c {
@@ -507,6 +509,214 @@ __global__ void __launch_bounds__(T2_THREADS, 2) dense_tc256_kernel(const float 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)T2_BN));
 }
 
+
+// ---- warp-specialised form of the prepared complex product ------------------------------------------------------
+// One CTA per SM, 128 x 256 tile, two-stage shared-memory ring (stage = A hi/lo 32 KB + B hi 32 KB + B lo 32 KB).
+//   warp 0, lane 0 : MMA issuer -- waits full barriers only, so the 12 MMAs of consecutive stages queue back to back
+//   warp 1, lane 0 : A producer -- one 32 KB bulk copy of the pre-split tiles per stage
+//   warps 2..9     : B producers -- global loads two stages ahead in registers, TF32 split, staging stores
+//   then warps 2..9 read the accumulator back (TMEM -> global)
+// Barriers per ring slot: fullA (transaction bytes), fullB (one arrival per producer warp), empty (tcgen05.commit).
+constexpr int WS_THREADS = 320;
+constexpr int WS_STAGE = 2 * TC_TILE_A + 2 * T2_TILE_B;      // 96 KB
+constexpr int WS_SMEM = 2 * WS_STAGE + 1024;
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// REALW = false: complex W [np][np] embedded as a real 2np x 2np operand (m = k = np), a tile covers 256 columns.
+// REALW = true : real W [m][k] applied to re / im alike, a tile covers 128 complex columns (= 256 GEMM columns).
+template <bool REALW>
+__global__ void __launch_bounds__(WS_THREADS, 1) dense_tc_ws_kernel(const float *__restrict__ prepared, int m, int k,
+                                                                   const float2 *__restrict__ in, float *__restrict__ out,
+                                                                   int64_t ncols, int64_t ld_in, int64_t ld_out) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ uint32_t tmem_base_sm;
+  __shared__ __align__(8) uint64_t full_a[2], full_b[2], empty[2], acc_bar;
+  const uint32_t s0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char *sp = smem_dyn + (s0 - smem_u32(smem_dyn));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t c0 = (int64_t)blockIdx.y * (REALW ? T2_BN / 2 : T2_BN);     // first (complex) column of the tile
+  const int np = k, kreal = REALW ? k : 2 * k;
+  const int mreal = REALW ? m : 2 * k;
+  const int64_t ld = ld_in;
+  const int nstages = (kreal + TC_BK - 1) / TC_BK;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "r"((uint32_t)T2_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&full_a[b])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;\n" ::"r"(smem_u32(&full_b[b])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&empty[b])));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&acc_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_d = tmem_base_sm;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int st = 0; st < nstages; ++st) {
+        const int b = st & 1;
+        const uint32_t ph = (uint32_t)(st >> 1) & 1u;
+        const uint32_t aAh = s0 + b * WS_STAGE, aAl = aAh + TC_TILE_A, aBh = aAh + 2 * TC_TILE_A, aBl = aBh + T2_TILE_B;
+        mbar_wait(smem_u32(&full_a[b]), ph);
+        mbar_wait(smem_u32(&full_b[b]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+          const uint64_t dAh = umma_desc(aAh + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+          const uint64_t dAl = umma_desc(aAl + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+          const uint64_t dBh = umma_desc(aBh + kk * 2 * T2_LBO_B, T2_LBO_B, TC_SBO);
+          const uint64_t dBl = umma_desc(aBl + kk * 2 * T2_LBO_B, T2_LBO_B, TC_SBO);
+          umma_tf32_n256(tmem_d, dAh, dBh, (st | kk) != 0);
+          umma_tf32_n256(tmem_d, dAh, dBl, 1u);
+          umma_tf32_n256(tmem_d, dAl, dBh, 1u);
+        }
+        // ring slot b is free once these MMAs have read it
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&empty[b])) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&acc_bar)) : "memory");
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const unsigned char *prep = reinterpret_cast<const unsigned char *>(prepared) + (int64_t)blockIdx.x * nstages * (2 * TC_TILE_A);
+      for (int st = 0; st < nstages; ++st) {
+        const int b = st & 1;
+        if (st >= 2) mbar_wait(smem_u32(&empty[b]), (uint32_t)((st >> 1) - 1) & 1u);
+        const uint32_t bar = smem_u32(&full_a[b]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2u * TC_TILE_A) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                         s0 + b * WS_STAGE),
+                     "l"(prep + (int64_t)st * (2 * TC_TILE_A)), "r"(2u * TC_TILE_A), "r"(bar)
+                     : "memory");
+      }
+    }
+  } else {
+    // B producers: the staging maps of dense_tc_kernel / dense_tc256_kernel with producer warp pw = warp - 2 in 0..7
+    // (pw >> 2 picks the tile half: rows 0-127 / 128-255 of the B tile)
+    const int pw = warp - 2;
+    const int b_cl_lo = ((pw >> 2) << 7) | (lane & 7), b_jl = ((lane >> 3) & 3) | ((pw & 3) << 2);
+    const int b_kc = b_jl >> 1, b_eo = (b_jl & 1) * 8;
+    // real-W map: complex column cc = 64 (pw >> 2) + 4 q + lane[1:0], k within the stage kk = lane[4:2] | (pw & 3) << 3
+    const int rb_cc_lo = ((pw >> 2) << 6) | (lane & 3), rb_kk = ((lane >> 2) & 7) | ((pw & 3) << 3);
+    float2 rb0[16], rb1[16];
+    auto load_stage = [&](int st, float2 (&rb)[16]) {
+      if (REALW) {
+        const int j = st * TC_BK + rb_kk;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int64_t c = c0 + (q << 2) + rb_cc_lo;
+          rb[q] = (c < ncols && j < k) ? __ldg(in + c * ld + j) : make_float2(0.f, 0.f);
+        }
+        return;
+      }
+      const int j = st * (TC_BK / 2) + b_jl;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int64_t c = c0 + (q << 3) + b_cl_lo;
+        rb[q] = (c < ncols && j < np) ? __ldg(in + c * ld + j) : make_float2(0.f, 0.f);
+      }
+    };
+    auto produce = [&](int st, float2 (&rb)[16]) {
+      const int b = st & 1;
+      if (st >= 2) mbar_wait(smem_u32(&empty[b]), (uint32_t)((st >> 1) - 1) & 1u);
+      unsigned char *sBh = sp + b * WS_STAGE + 2 * TC_TILE_A, *sBl = sBh + T2_TILE_B;
+      if (REALW) {
+        const int kc2 = rb_kk >> 2, eo2 = (rb_kk & 3) * 4;
+        const bool im_first = (lane >> 4) & 1;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int cc = (q << 2) + rb_cc_lo;
+          float xr_h, xr_l, xi_h, xi_l;
+          split_tf32(rb[q].x, xr_h, xr_l);
+          split_tf32(rb[q].y, xi_h, xi_l);
+          const int r0 = 2 * cc, r1 = 2 * cc + 1;
+          const int o0 = kc2 * T2_LBO_B + (r0 >> 3) * TC_SBO + (r0 & 7) * 16 + eo2;   // row 2c  : real part
+          const int o1 = kc2 * T2_LBO_B + (r1 >> 3) * TC_SBO + (r1 & 7) * 16 + eo2;   // row 2c+1: imaginary part
+          const int of = im_first ? o1 : o0, os = im_first ? o0 : o1;
+          *reinterpret_cast<float *>(sBh + of) = im_first ? xi_h : xr_h;
+          *reinterpret_cast<float *>(sBl + of) = im_first ? xi_l : xr_l;
+          *reinterpret_cast<float *>(sBh + os) = im_first ? xr_h : xi_h;
+          *reinterpret_cast<float *>(sBl + os) = im_first ? xr_l : xi_l;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int cl = (q << 3) + b_cl_lo;
+          float xr_h, xr_l, xi_h, xi_l;
+          split_tf32(rb[q].x, xr_h, xr_l);
+          split_tf32(rb[q].y, xi_h, xi_l);
+          const int o = b_kc * T2_LBO_B + (cl >> 3) * TC_SBO + (cl & 7) * 16 + b_eo;
+          *reinterpret_cast<float2 *>(sBh + o) = make_float2(xr_h, xi_h);
+          *reinterpret_cast<float2 *>(sBl + o) = make_float2(xr_l, xi_l);
+        }
+      }
+      if (st + 2 < nstages) load_stage(st + 2, rb);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // this thread's stores -> async proxy
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_b[b])) : "memory");
+    };
+    load_stage(0, rb0);
+    if (nstages > 1) load_stage(1, rb1);
+    for (int st = 0; st < nstages; st += 2) {
+      produce(st, rb0);
+      if (st + 1 < nstages) produce(st + 1, rb1);
+    }
+
+    // epilogue: TMEM lanes 32 (warp & 3) .. + 31 (this warp's hardware quarter), columns 128 (pw >> 2) .. + 127
+    mbar_wait(smem_u32(&acc_bar), 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int ip = blockIdx.x * TC_BM + (warp & 3) * 32 + lane;
+    const int chalf = (pw >> 2) * 128;
+    const int64_t ld2 = 2 * ld_out;
+#pragma unroll 1
+    for (int cb = 0; cb < 128; cb += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf + cb);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      if (REALW) {
+        if (ip < mreal) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {      // TMEM columns (2q, 2q+1) = (re, im) of complex column c
+            const int64_t c = c0 + ((chalf + cb) >> 1) + q;
+            if (c < ncols)
+              *reinterpret_cast<float2 *>(out + c * ld2 + 2 * ip) = make_float2(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
+          }
+        }
+      } else if (ip < mreal) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int64_t c = c0 + chalf + cb + q;
+          if (c < ncols) out[c * ld2 + ip] = __uint_as_float(r[q]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)T2_BN));
+}
+
 }  // namespace b2c
 
 using namespace b2c;
@@ -596,6 +806,18 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
       return (double)tiles / (double)(((tiles + slots - 1) / slots) * slots);
     };
     const int64_t t128 = (int64_t)tiles_m * ((ncols + TC_BN - 1) / TC_BN), t256 = (int64_t)tiles_m * ((ncols + T2_BN - 1) / T2_BN);
+    // Warp-specialised form (one CTA per SM, two-stage ring) whenever its waves are not much emptier than the best
+    // of the two single-stage shapes; it is ~20 % faster per SM.
+    const double eff_ws = wave_eff(t256, 1), eff_best = wave_eff(t256, 2) > wave_eff(t128, 3) ? wave_eff(t256, 2) : wave_eff(t128, 3);
+    if (ncols >= T2_BN && 1.2 * eff_ws >= eff_best) {
+      dim3 grid2((unsigned)tiles_m, (unsigned)((ncols + T2_BN - 1) / T2_BN));
+      B2C_REQUIRE(grid2.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
+      B2C_CUDA(cudaFuncSetAttribute(dense_tc_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+      dense_tc_ws_kernel<false><<<grid2, WS_THREADS, WS_SMEM, (cudaStream_t)stream>>>(P, k, k, reinterpret_cast<const float2 *>(in), out,
+                                                                                      ncols, ld_in, ld_out);
+      B2C_CUDA(cudaGetLastError());
+      return B2C_OK;
+    }
     if (ncols >= T2_BN && wave_eff(t256, 2) > wave_eff(t128, 3) + 0.02) {
       dim3 grid2((unsigned)tiles_m, (unsigned)((ncols + T2_BN - 1) / T2_BN));
       B2C_REQUIRE(grid2.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
@@ -610,6 +832,15 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
     dense_tc_kernel<false, true><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(P, k, k, reinterpret_cast<const float2 *>(in), out,
                                                                                        ncols, ld_in, ld_out);
   } else {
+    if (ncols >= T2_BN / 2) {     // warp-specialised form: a tile covers 128 complex columns
+      dim3 grid2((unsigned)tiles_m, (unsigned)((ncols + T2_BN / 2 - 1) / (T2_BN / 2)));
+      B2C_REQUIRE(grid2.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
+      B2C_CUDA(cudaFuncSetAttribute(dense_tc_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+      dense_tc_ws_kernel<true><<<grid2, WS_THREADS, WS_SMEM, (cudaStream_t)stream>>>(P, m, k, reinterpret_cast<const float2 *>(in), out, ncols,
+                                                                                     ld_in, ld_out);
+      B2C_CUDA(cudaGetLastError());
+      return B2C_OK;
+    }
     dim3 grid((unsigned)tiles_m, (unsigned)((ncols + TC_BN / 2 - 1) / (TC_BN / 2)));
     B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
     B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
