@@ -233,6 +233,37 @@ __global__ void __launch_bounds__(256) nonfinite_kernel(const float *__restrict_
   }
 }
 
+__device__ __forceinline__ double block_sum_d(double v, double *scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < nwarp ? scratch[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+// sum[0] += sum_i |a_i - b_i| over n complex64 elements (compute_mae, run_phase5_evaluation.py:51-54)
+__global__ void __launch_bounds__(256) abs_diff_kernel(const float2 *__restrict__ a, const float2 *__restrict__ b, int64_t n,
+                                                       double *__restrict__ sum) {
+  __shared__ double red[33];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 x = __ldg(a + i), y = __ldg(b + i);
+    const float dx = x.x - y.x, dy = x.y - y.y;
+    acc += (double)sqrtf(fmaf(dx, dx, dy * dy));
+  }
+  const double tot = block_sum_d(acc, red);
+  if (threadIdx.x == 0) atomicAdd(sum, tot);
+}
+
 // ---- ML feature packing -----------------------------------------------------------------------------
 struct PairView {
   const float2 *rx, *ls, *tr;          // antenna pair (0,0) rows of slot b: base + s * stride
@@ -251,22 +282,6 @@ __device__ __forceinline__ PairView pair_view(const b2c_geom &g, int64_t b, cons
   return v;
 }
 
-__device__ __forceinline__ double block_sum_d(double v, double *scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    double t = lane < nwarp ? scratch[lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) scratch[32] = t;
-  }
-  __syncthreads();
-  return scratch[32];
-}
 
 // Sum re, sum im, sum re^2, sum im^2 of the pair-(0,0) rows of rx, H_ls, H_true, accumulated into mom[3][4].
 __global__ void __launch_bounds__(256) pair00_moments_kernel(b2c_geom g, const float2 *__restrict__ rx,
@@ -448,6 +463,16 @@ extern "C" int b2c_count_nonfinite(const float *x, int64_t n, int32_t is_complex
   unsigned long long *c = reinterpret_cast<unsigned long long *>(counts);
   if (is_complex) nonfinite_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, c);
   else nonfinite_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, c);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_abs_diff_sum(const float *a, const float *b, int64_t n, double *sum, void *stream) {
+  B2C_REQUIRE(a && b && sum && n >= 0, B2C_E_ARG, "b2c_abs_diff_sum: null argument");
+  if (n == 0) return B2C_OK;
+  const int64_t want = (n + 256 * 8 - 1) / (256 * 8);
+  const unsigned grid = (unsigned)(want < 1 ? 1 : want > 148 * 8 ? 148 * 8 : want);
+  abs_diff_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(a), reinterpret_cast<const float2 *>(b), n, sum);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }

@@ -434,6 +434,16 @@ class SlotEngine:
                                             dptr(counts, "i64"), stream_ptr()), "b2c_count_nonfinite")
         return counts
 
+    def abs_diff_sum(self, a, b):
+        """sum |a - b| over two complex64 CUDA tensors of equal size (float64 device scalar)."""
+        if a.numel() != b.numel():
+            raise ValueError("arrays differ in size")
+        out = torch.zeros((1,), dtype=torch.float64, device=self.device)
+        if a.numel():
+            check(lib().b2c_abs_diff_sum(dptr(a.contiguous(), "c64"), dptr(b.contiguous(), "c64"), a.numel(), dptr(out, "f64"),
+                                         stream_ptr()), "b2c_abs_diff_sum")
+        return out
+
     def _ls_sym_stride(self, H_ls, g):
         P = g.pitch if g.pitch else g.nsc
         if H_ls.dim() == 5:

@@ -28,6 +28,14 @@ def compute_mse(H_est: np.ndarray, H_true: np.ndarray) -> float:
     return float(squared_error_sums(H_true, H_est)[0] / np.asarray(H_true).size)
 
 
+def compute_mae(H_est: np.ndarray, H_true: np.ndarray) -> float:
+    """mean|H_est - H_true| (run_phase5_evaluation.py:51-54), reduced on the GPU."""
+    from baseline_estimators import _c64, _engine
+    eng = _engine()
+    n = np.asarray(H_true).size
+    return float(eng.abs_diff_sum(_c64(np.asarray(H_est).reshape(-1), eng.device), _c64(np.asarray(H_true).reshape(-1), eng.device)).item() / n)
+
+
 def compute_ber_approximation(H_est: np.ndarray, H_true: np.ndarray, snr_db: float) -> float:
     """QPSK BER proxy from the estimation NMSE (run_phase5_evaluation.py:57-68)."""
     nmse = compute_nmse(H_est, H_true)

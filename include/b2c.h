@@ -273,6 +273,9 @@ int b2c_count_bit_errors(const uint8_t *a, const uint8_t *b, int64_t n, uint64_t
  * elements; is_complex: elements are complex64 and count when either part is NaN / Inf (numpy.isnan / isinf). */
 int b2c_count_nonfinite(const float *x, int64_t n, int32_t is_complex, uint64_t *counts, void *stream);
 
+/* compute_mae numerator (run_phase5_evaluation.py:51-54): *sum += sum_i |a_i - b_i| over n complex64 elements.  */
+int b2c_abs_diff_sum(const float *a, const float *b, int64_t n, double *sum, void *stream);
+
 /* Feature packing for the ML side from GPU-resident slots, antenna pair (0,0).
  *   rx [B][nsym][nrx][nsc]; H_true [B][nsym][nrx][ntx][nsc]; H_ls with ls_sym_stride complex elements
  *   between consecutive symbols (nrx*ntx*nsc for the full layout, nrx*nsc for the compact one).

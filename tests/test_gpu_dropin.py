@@ -408,6 +408,8 @@ def test_channel_dataset_features_and_phase5_baselines():
         for j, s in enumerate((-5.0, 10.0, 30.0)):
             assert abs(p5.compute_ber_approximation(Hls[0], Htr[0], s) / g["ber_approx"][j] - 1) < 1e-4
             assert abs(p5.compute_ber_approximation(Htr[0] * 1.01, Htr[0], s) / g["ber_approx_small_err"][j] - 1) < 1e-4
+    assert abs(p5.compute_mae(Hls[0], Htr[0]) / np.mean(np.abs(Hls[0] - Htr[0])) - 1) < 1e-5
+    assert abs(p5.compute_mse(Hls[1], Htr[1]) / np.mean(np.abs(Hls[1] - Htr[1]) ** 2) - 1) < 1e-5
     snr = np.array([0.0, 10.0, 0.0])
     sweep = p5.snr_sweep_baselines({"H_true": Htr, "H_ls": Hls, "snr_db": snr})
     vals, ls_db, mm_db = orc.snr_sweep_baselines(Htr, Hls, snr)
