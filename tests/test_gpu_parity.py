@@ -626,3 +626,35 @@ def test_padded_row_layout_matches_contiguous(ntx, nrx, model, engines):
     assert torch.equal(k3_nan["stats"], k3_pad["stats"]) and torch.equal(k3_nan["H_ls"], k3_pad["H_ls"])
     xn, tn = eng.ml_features(nan_padded(ref["rx"]), nan_padded(ref["H_ls"]), nan_padded(ref["H_true"]), pool, pid, "last", True)
     assert torch.equal(xn, x_ref) and torch.equal(tn, t_ref)
+
+
+@pytest.mark.parametrize("pitch", [600, None])
+def test_slot_pipeline_writes_stay_inside_their_arrays(pitch, engines):
+    """No out-of-bounds store (compute-sanitizer is not available on this pool): every output array sits between two
+    guard regions filled with a sentinel; after the run the guards are intact, every payload element was written and
+    the padding element of each row (pitch 600) holds a finite value."""
+    eng = engines(4, 4)
+    pool = eng.random_pool([0.10], seed=6)
+    B, nsym, nsc, P = 5, 14, 599, (pitch or 599)
+    guard = 4096                                    # complex elements on each side
+    sentinel = torch.tensor(complex(-7.25e33, 3.5e-33), dtype=torch.complex64, device=eng.device)
+    shapes = {"H_true": (B, nsym, 4, 4, P), "H_ls": (B, nsym, 4, 4, P), "H_mmse": (B, nsym, 4, 4, P), "rx": (B, nsym, 4, P),
+              "tx": (B, nsym, 4, P)}
+    bufs, out = {}, {}
+    for k, shp in shapes.items():
+        n = int(np.prod(shp))
+        bufs[k] = torch.full((n + 2 * guard,), sentinel.item(), dtype=torch.complex64, device=eng.device)
+        out[k] = bufs[k][guard:guard + n].view(shp)[..., :nsc]
+    out["stats"] = torch.zeros((B, 4, 2, 3), dtype=torch.float64, device=eng.device)
+    eng.run(B, 2, 200.0, 10.0, 0, pool, slot0=77, seed=5, out=out)
+    torch.cuda.synchronize()
+    for k, shp in shapes.items():
+        n = int(np.prod(shp))
+        assert (bufs[k][:guard] == sentinel).all() and (bufs[k][guard + n:] == sentinel).all(), k
+        assert not (out[k] == sentinel).any(), k                       # every payload element was written
+        if pitch:
+            pad = bufs[k][guard:guard + n].view(shp)[..., nsc:]
+            assert torch.isfinite(torch.view_as_real(pad)).all(), k
+    ref = eng.run(B, 2, 200.0, 10.0, 0, pool, slot0=77, seed=5, pitch=pitch)
+    for k in shapes:
+        assert torch.equal(out[k], ref[k]), k
