@@ -244,12 +244,13 @@ class SlotEngine:
                                       1 if mmse else 0, dptr(out, "c64"), stream_ptr()), "b2c_pilot_vectors")
         return out
 
-    def dense_real_apply(self, W, h, ld_out=None):
+    def dense_real_apply(self, W, h, ld_out=None, out=None):
         """W [m,k] float32 (or a PreparedDense of one), h [ncols, ld_in>=k] c64 -> out [ncols, ld_out>=m] with
-        out[c,:m] = W @ h[c,:k]."""
+        out[c,:m] = W @ h[c,:k] (columns m.. of a caller-supplied `out` are left as they are)."""
         m, k = (W.m, W.k) if isinstance(W, PreparedDense) else W.shape
-        ld_out = m if ld_out is None else ld_out
-        out = torch.zeros((h.shape[0], ld_out), dtype=torch.complex64, device=self.device)
+        ld_out = (m if ld_out is None else ld_out) if out is None else out.shape[1]
+        if out is None:
+            out = torch.zeros((h.shape[0], ld_out), dtype=torch.complex64, device=self.device)
         if isinstance(W, PreparedDense):
             if W.is_complex:
                 raise ValueError("prepared operand is a complex Wiener matrix, not a real map")
@@ -307,9 +308,10 @@ class SlotEngine:
             self._ident[nre] = pool
         return self._ident[nre]
 
-    def mmse_dense(self, W, h):
+    def mmse_dense(self, W, h, out=None):
         """W [np,np] c64 (or a PreparedDense of one), h [ncols, ld>=np] c64 -> W @ h[c, :np] per column set."""
-        out = torch.zeros_like(h)
+        if out is None:
+            out = torch.zeros_like(h)
         if isinstance(W, PreparedDense):
             if not W.is_complex:
                 raise ValueError("prepared operand is a real map, not a complex Wiener matrix")

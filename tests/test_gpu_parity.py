@@ -658,3 +658,45 @@ def test_slot_pipeline_writes_stay_inside_their_arrays(pitch, engines):
     ref = eng.run(B, 2, 200.0, 10.0, 0, pool, slot0=77, seed=5, pitch=pitch)
     for k in shapes:
         assert torch.equal(out[k], ref[k]), k
+
+
+def test_dense_products_write_only_their_outputs(engines):
+    """Guard regions around the outputs of the tensor-core products (one-shot, prepared 128-/256-column and
+    warp-specialised forms, ragged sizes): nothing outside [ncols x m] is touched."""
+    eng = engines(2, 2)
+    dev = eng.device
+    rng = np.random.default_rng(11)
+    sentinel = complex(-7.25e33, 3.5e-33)
+    guard = 2048
+
+    def guarded(rows, ld):
+        buf = torch.full((rows * ld + 2 * guard,), sentinel, dtype=torch.complex64, device=dev)
+        return buf, buf[guard:guard + rows * ld].view(rows, ld)
+
+    def intact(buf, rows, ld, m):
+        body = buf[guard:guard + rows * ld].view(rows, ld)
+        return bool((buf[:guard] == sentinel).all() and (buf[guard + rows * ld:] == sentinel).all()
+                    and (body[:, m:] == sentinel).all() and not (body[:, :m] == sentinel).any())
+
+    for n, c in ((167, 77), (838, 300), (838, 1000), (838, 4000)):       # 4000 / 1000 columns: 256-column tiles
+        ld = n + 3
+        A = torch.from_numpy((rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)).to(dev, torch.complex64)
+        X = torch.zeros((c, ld), dtype=torch.complex64, device=dev)
+        X[:, :n] = torch.from_numpy(rng.standard_normal((c, n)) + 1j * rng.standard_normal((c, n))).to(dev, torch.complex64)
+        want = eng.mmse_dense(A, X)
+        for W in (A, eng.prepare_dense(A)):
+            buf, out = guarded(c, ld)
+            eng.mmse_dense(W, X, out=out)
+            torch.cuda.synchronize()
+            assert intact(buf, c, ld, n), (n, c, type(W).__name__)
+            assert torch.equal(out[:, :n], want[:, :n])
+    for m, k, c in ((300, 167, 77), (8386, 838, 70), (8386, 838, 500), (129, 33, 3)):
+        Wr = torch.from_numpy(rng.standard_normal((m, k)) / np.sqrt(k)).to(dev, torch.float32)
+        X = torch.from_numpy(rng.standard_normal((c, k)) + 1j * rng.standard_normal((c, k))).to(dev, torch.complex64)
+        want = eng.dense_real_apply(Wr, X)
+        for W in (Wr, eng.prepare_dense(Wr)):
+            buf, out = guarded(c, m + 5)
+            eng.dense_real_apply(W, X, out=out)
+            torch.cuda.synchronize()
+            assert intact(buf, c, m + 5, m), (m, k, c, type(W).__name__)
+            assert torch.equal(out[:, :m], want)
