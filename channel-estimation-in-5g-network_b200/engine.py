@@ -209,7 +209,7 @@ class SlotEngine:
 
     # ---- K3 ------------------------------------------------------------------------------------------
     def ls_interp(self, rx, pilots, pool, pattern_id=0, snr_db=None, mmse=False, H_true=None, hp_in=None,
-                  want=("H_ls",), geom=None):
+                  want=("H_ls",), geom=None, out=None):
         """rx [B,nsym,nrx,nsc] c64, pilots [B or 1, np_max] c64.  want subset of H_ls, H_mmse, hp, stats.
         If rx (and H_true) are padded-row views (pitch 600, as run(pitch=600) returns them) the outputs are
         padded the same way and the wide-access kernel runs."""
@@ -219,11 +219,11 @@ class SlotEngine:
         g = self._with_pitch(g, P)
         pid = self._vec(pattern_id, B, torch.int32)
         snr = self._vec(snr_db, B, torch.float32) if snr_db is not None else None
-        out = {}
+        out = dict(out) if out is not None else {}          # caller-supplied H_ls / H_mmse buffers (same row pitch as rx)
         shape = (B, g.nsym, g.nrx, g.ntx, P)
-        if "H_ls" in want:
+        if "H_ls" in want and "H_ls" not in out:
             out["H_ls"] = torch.empty(shape, dtype=torch.complex64, device=self.device)[..., :g.nsc]
-        if "H_mmse" in want:
+        if "H_mmse" in want and "H_mmse" not in out:
             out["H_mmse"] = torch.empty(shape, dtype=torch.complex64, device=self.device)[..., :g.nsc]
         if "hp" in want:
             out["hp"] = torch.zeros((B, g.nrx, pool.np_max), dtype=torch.complex64, device=self.device)

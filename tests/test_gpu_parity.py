@@ -700,3 +700,25 @@ def test_dense_products_write_only_their_outputs(engines):
             torch.cuda.synchronize()
             assert intact(buf, c, m + 5, m), (m, k, c, type(W).__name__)
             assert torch.equal(out[:, :m], want)
+
+
+@pytest.mark.parametrize("pitch", [600, None])
+def test_ls_interp_writes_stay_inside_their_arrays(pitch, engines):
+    """Guard regions around the stand-alone K3 outputs (contiguous and padded-row kernels)."""
+    eng = engines(4, 4)
+    pool = eng.random_pool([0.10], seed=6)
+    B, nsym, nsc, P = 3, 14, 599, (pitch or 599)
+    src = eng.run(B, 1, 50.0, 12.0, 0, pool, slot0=5, seed=8, pitch=pitch)
+    idx = torch.from_numpy(pool.pilot_indices[0]).to(eng.device)
+    pil = src["tx"][:, :, 0, :].reshape(B, -1)[:, idx].contiguous()
+    guard = 4096
+    sentinel = complex(-7.25e33, 3.5e-33)
+    n = B * nsym * 4 * 4 * P
+    bufs = {k: torch.full((n + 2 * guard,), sentinel, dtype=torch.complex64, device=eng.device) for k in ("H_ls", "H_mmse")}
+    out = {k: v[guard:guard + n].view(B, nsym, 4, 4, P)[..., :nsc] for k, v in bufs.items()}
+    res = eng.ls_interp(src["rx"], pil, pool, snr_db=12.0, mmse=True, H_true=src["H_true"], want=("H_ls", "H_mmse", "stats"), out=out)
+    torch.cuda.synchronize()
+    for k, v in bufs.items():
+        assert (v[:guard] == sentinel).all() and (v[guard + n:] == sentinel).all(), k
+        assert not (res[k] == sentinel).any(), k
+        assert (res[k] - src[k]).abs().max().item() < 2e-6, k
