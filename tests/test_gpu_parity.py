@@ -678,7 +678,8 @@ def test_dense_products_write_only_their_outputs(engines):
         return bool((buf[:guard] == sentinel).all() and (buf[guard + rows * ld:] == sentinel).all()
                     and (body[:, m:] == sentinel).all() and not (body[:, :m] == sentinel).any())
 
-    for n, c in ((167, 77), (838, 300), (838, 1000), (838, 4000)):       # 4000 / 1000 columns: 256-column tiles
+    # 4000 / 1000 columns: 256-column tiles, warp-specialised ring; np = 12 / 40: one- and three-stage rings
+    for n, c in ((167, 77), (838, 300), (838, 1000), (838, 4000), (12, 600), (40, 777)):
         ld = n + 3
         A = torch.from_numpy((rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)).to(dev, torch.complex64)
         X = torch.zeros((c, ld), dtype=torch.complex64, device=dev)
@@ -690,7 +691,7 @@ def test_dense_products_write_only_their_outputs(engines):
             torch.cuda.synchronize()
             assert intact(buf, c, ld, n), (n, c, type(W).__name__)
             assert torch.equal(out[:, :n], want[:, :n])
-    for m, k, c in ((300, 167, 77), (8386, 838, 70), (8386, 838, 500), (129, 33, 3)):
+    for m, k, c in ((300, 167, 77), (8386, 838, 70), (8386, 838, 500), (129, 33, 3), (200, 20, 300), (130, 65, 129)):
         Wr = torch.from_numpy(rng.standard_normal((m, k)) / np.sqrt(k)).to(dev, torch.float32)
         X = torch.from_numpy(rng.standard_normal((c, k)) + 1j * rng.standard_normal((c, k))).to(dev, torch.complex64)
         want = eng.dense_real_apply(Wr, X)
