@@ -62,8 +62,9 @@ tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj,
       up1 = u01(w.w);
     }
     // doppler_shift = fd * cos(theta), theta = 2 pi u  (:109, :119)
-    osc[link * NOSC + 2 * pr] = make_float2(up0, fdT * cospif(2.0f * ua0));
-    osc[link * NOSC + 2 * pr + 1] = make_float2(up1, fdT * cospif(2.0f * ua1));
+    // SFU cosine: its 4e-7 absolute error is scaled by fdT (~1e-2 turns per symbol) before it reaches a phase
+    osc[link * NOSC + 2 * pr] = make_float2(up0, fdT * cis_turns(ua0).x);
+    osc[link * NOSC + 2 * pr + 1] = make_float2(up1, fdT * cis_turns(ua1).x);
   }
   __syncthreads();
 
@@ -76,6 +77,7 @@ tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj,
   // by one complex rotation, so an oscillator costs two sincos and nsym-1 complex multiplies instead of nsym
   // sincos (rounding grows by <= ~1e-7 per step; the parity bound is 1e-4).
   const int nwork = nlinks * 2;
+  const bool small_step = fabsf(fdT) <= 0.1f;                   // per-symbol Doppler rotation below 0.1 turn (fd <= 1.4 kHz)
   for (int base = 0; base < nwork; base += blockDim.x) {       // warp-uniform trip count (shuffles below)
     const int i = base + threadIdx.x;
     const bool valid = i < nwork;
@@ -91,7 +93,14 @@ tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj,
         // the start phase takes the SFU sincos (its 4e-7 error enters once); the per-symbol rotation w is applied
         // nsym times, so it gets the full-precision sincospi
         float2 z = cis_turns(pd.x), w;
-        sincospif(2.0f * pd.y, &w.y, &w.x);
+        if (small_step) {
+          // |x| = 2 pi |step| <= 0.63 rad: Taylor to x^9 / x^8 (truncation < 2e-9), cheaper than the general routine
+          const float x = 6.283185307179586f * pd.y, x2 = x * x;
+          w.y = x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.0f);
+          w.x = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
+        } else {
+          sincospif(2.0f * pd.y, &w.y, &w.x);
+        }
         const float2 wj = make_float2(-w.y, w.x);          // j w:  z w = z.x * w + z.y * (j w), two packed FMAs
 #pragma unroll
         for (int s = 0; s < B2C_MAX_SYM; ++s) {
