@@ -495,7 +495,8 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
   const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * (nsym * NSC + 1) : nullptr;
   float2 *pH = Hb + (c.rx * NTX * PITCH + K), *pR = Rb + (c.rx * PITCH + K), *pT = Tb + K;
   const int64_t dL = (EST && STORE) ? (const char *)(a.H_ls + c.b * slot_h) - (const char *)Hb : 0;
-  const int64_t dM = (EST && STORE) ? (const char *)(a.H_mmse + c.b * slot_h) - (const char *)Hb : 0;
+  const bool mstore = EST && STORE && a.H_mmse != nullptr;     // dataset mode (H_true, rx, tx, H_ls) leaves H_mmse out
+  const int64_t dM = mstore ? (const char *)(a.H_mmse + c.b * slot_h) - (const char *)Hb : 0;
   const int nre = nsym * NSC;
   int oPK = act ? K : nre, oPS = vS ? S : nre;                   // plan rows; row nre = "outside" for idle lanes
   const int dPK = act ? NSC : 0, dPS = vS ? NSC : 0;
@@ -543,7 +544,7 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
 #pragma unroll
           for (int tx = 0; tx < NTX; ++tx) {
             st16((float2 *)((char *)(pH + tx * PITCH) + dL), lK, lN);
-            st16((float2 *)((char *)(pH + tx * PITCH) + dM), mK, mN);
+            if (mstore) st16((float2 *)((char *)(pH + tx * PITCH) + dM), mK, mN);
           }
         }
       }
@@ -682,7 +683,7 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
     else slot_body<MAXT, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
 
-  if (EST && (FAST || a.stats)) {
+  if (EST && a.stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int q = 0; q < 2; ++q)
@@ -740,10 +741,13 @@ static int launch_slot_ntx(const SlotArgs &a, int64_t B, size_t smem, cudaStream
     }
   }
   if (pitch != a.g.nsc) {
-    // padded rows: the wide-store kernel of the throughput configuration only
-    B2C_REQUIRE(fast && pitch == WIDE_PITCH, B2C_E_UNSUPPORTED,
+    // padded rows: the wide-store kernel of the throughput configuration only (H_mmse and stats are optional there:
+    // H_true + rx + tx + H_ls is what the reference's generate_sample returns)
+    const bool wide_ok = !a.compact && a.g.nsc == 599 && (a.g.nsym & 1) == 0 && !a.has_inj && a.H_true && a.rx && a.tx &&
+                         (!EST || a.H_ls);
+    B2C_REQUIRE(wide_ok && pitch == WIDE_PITCH, B2C_E_UNSUPPORTED,
                 "b2c_slot_pipeline: pitch=%d needs the throughput configuration (599 bins, even nsym, Philox draws, "
-                "all outputs, not compact) and pitch == %d", pitch, WIDE_PITCH);
+                "H_true + rx + tx (+ H_ls when estimating) requested, not compact) and pitch == %d", pitch, WIDE_PITCH);
     if (ntx == 1) return launch_slot<1, true, EST, 599, true, WIDE_PITCH>(a, B, smem, stream);
     if (ntx == 2) return launch_slot<2, true, EST, 599, true, WIDE_PITCH>(a, B, smem, stream);
     if (ntx == 4) return launch_slot<4, true, EST, 599, true, WIDE_PITCH>(a, B, smem, stream);

@@ -152,9 +152,10 @@ class ChannelEstimationDataset:
             self._pool = self.engine.random_pool(self._lists()[3], self.patterns_per_density, seed=self.seed)
         return self._pool
 
-    def generate_batch(self, count: int, slot0: int = 0, want=("H_true", "rx", "tx", "H_ls"), out=None, ws=None):
+    def generate_batch(self, count: int, slot0: int = 0, want=("H_true", "rx", "tx", "H_ls"), out=None, ws=None, pitch=None):
         """`count` slots starting at global sample index slot0, Philox mode, all on the device.
-        Returns (dict of CUDA tensors, dict of per-slot parameter index arrays)."""
+        Returns (dict of CUDA tensors, dict of per-slot parameter index arrays).  pitch=600: row-padded
+        throughput layout (tensors are 599-wide views), see SlotEngine.run."""
         eng = self.engine
         models, dopplers, snrs, dens = self._lists()
         mi, di, si, pi = philox_param_choice(self.seed, slot0, count, (len(models), len(dopplers), len(snrs), len(dens)))
@@ -162,7 +163,7 @@ class ChannelEstimationDataset:
         pid = pi * self.patterns_per_density + (np.arange(slot0, slot0 + count) % self.patterns_per_density)
         model_id = np.array([eng.models.index(str(m).upper()) for m in models], dtype=np.int32)[mi]
         res = eng.run(count, model_id, np.asarray(dopplers, dtype=np.float32)[di], np.asarray(snrs, dtype=np.float32)[si],
-                      pid.astype(np.int32), self.pattern_pool(), slot0=slot0, seed=self.seed, want=want, out=out, ws=ws)
+                      pid.astype(np.int32), self.pattern_pool(), slot0=slot0, seed=self.seed, want=want, out=out, ws=ws, pitch=pitch)
         return res, {"model": mi, "doppler": di, "snr": si, "density": pi, "pattern": pid}
 
     def generate_feature_batch(self, count: int, slot0: int = 0, layout: str = "last", normalize: bool = True,
@@ -173,7 +174,8 @@ class ChannelEstimationDataset:
         layout='last' + normalize is prepare_ml_inputs per slot (src/dataset_generator.py:183-227);
         layout='first' + norm (see SlotEngine.normalization_from_moments) is ChannelDataset.__getitem__
         (src/train.py:62-94)."""
-        res, par = self.generate_batch(count, slot0, want=("H_true", "rx", "H_ls"))
+        wide = self.engine.nsc == 599 and self.engine.nsym % 2 == 0 and self.engine.ntx in (1, 2, 4, 8)
+        res, par = self.generate_batch(count, slot0, want=("H_true", "rx", "tx", "H_ls"), pitch=600 if wide else None)
         x, y = self.engine.ml_features(res["rx"], res["H_ls"], res["H_true"], self.pattern_pool(),
                                        par["pattern"].astype(np.int32), layout, normalize, norm)
         return x, y, par

@@ -92,6 +92,16 @@ res["k2_ofdm_demodulate"] = {"ms": t * 1e3, "gbs": bm / t / 1e9, "frac_hbm": bm 
 del x, y
 torch.cuda.empty_cache()
 
+# dataset mode: H_true + rx + tx + H_ls (what generate_sample returns), padded rows
+B = 4096
+o = eng.alloc_outputs(B, ("H_true", "rx", "tx", "H_ls"), pitch=600)
+ws = eng.workspace(B)
+t = timeit(lambda: eng.run(B, 2, 200.0, 10.0, 0, pool, want=("H_true", "rx", "tx", "H_ls"), out=o, ws=ws), n=5)
+bs = B * sum(o[k][0].numel() for k in ("H_true", "rx", "tx", "H_ls")) * 8
+res["k1_dataset_mode"] = {"ms": t * 1e3, "gbs": bs / t / 1e9, "frac_hbm": bs / t / 1e9 / PEAK_HBM, "slots_per_s": B / t,
+                          "note": "simulate + LS, no H_mmse / statistics written; includes K1a; pitch 600"}
+del o
+
 # K1a tap gains alone, and simulate-only (no estimation outputs)
 B = 4096
 ws = eng.workspace(B)

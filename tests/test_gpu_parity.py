@@ -585,6 +585,11 @@ def test_padded_row_layout_matches_contiguous(ntx, nrx, model, engines):
         if k in sim_pad:
             assert torch.equal(sim_pad[k], sim_ref[k]), k
     assert torch.allclose(pad["stats"], ref["stats"], rtol=1e-6, atol=0)
+    # dataset mode: what the reference's generate_sample returns (no H_mmse, no statistics), same wide-store kernel
+    dm = eng.run(B, want=("H_true", "rx", "tx", "H_ls"), pitch=_b2c.WIDE_PITCH, **args)
+    assert set(k for k in dm if not k.startswith("_")) == {"H_true", "rx", "tx", "H_ls"}
+    for k in ("H_true", "rx", "tx", "H_ls"):
+        assert dm[k].stride(-2) == _b2c.WIDE_PITCH and torch.equal(dm[k], ref[k]), k
     # statistics-only call (pilot-density / SNR sweeps): the store-free instantiation gives the same sums
     so = eng.run(B, want=("stats",), **args)
     assert set(k for k in so if not k.startswith("_")) == {"stats"}
