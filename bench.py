@@ -315,7 +315,7 @@ def run_b200(args, rank, world, local_rank):
                        "l2_policy": f"outputs per step = {alg / 1e9:.1f} GB >> 126 MB L2; no flush needed",
                        "hbm_layout": (f"rows of 599 complex64 at pitch {args.pitch}" + (" (one padding element per row: 16-byte stores; "
                                       "algorithmic bytes count 599)" if args.pitch != 599 else " (contiguous)"))},
-            "roofline": {"bound": "hbm", "kernel": "slot_kernel<4,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": (f"slot_kernel<{ntx}, ..., 599, FAST, pitch {args.pitch}> (16-byte stores)" if args.pitch != 599 else f"slot_kernel<{ntx}, ..., 599, FAST> (8-byte stores)"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / ms},
             "cpu_baseline": cpu,
