@@ -215,6 +215,14 @@ def test_dataset_generator_philox_mode_and_sharding():
     assert torch.equal(a["H_ls"][3:6], b["H_ls"]) and np.array_equal(pa["snr"][3:6], pb["snr"])
     lst = ds.generate_dataset(6)
     assert len(lst) == 6 and lst[0]["H_true"].shape == (14, 2, 2, 599) and lst[0]["pilot_mask"].dtype == bool
+    # arrays handed to on_batch by the sharded loop (row-padded layout inside) are the per-sample arrays
+    seen = {}
+    with_arrays = dg.sharded_statistics(cfg, 16, batch=8, seed=42, want_arrays=("H_true", "rx", "tx", "H_ls", "H_mmse"),
+                                        on_batch=lambda pos, res, par: seen.update({pos: (res["H_ls"].clone(), res["rx"].clone())}))
+    full, _ = ds.generate_batch(16, slot0=0, want=("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"))
+    assert sorted(seen) == [0, 8] and with_arrays[:, 0].sum().item() == 16
+    for pos, (hl, rx) in seen.items():
+        assert torch.equal(hl, full["H_ls"][pos:pos + 8]) and torch.equal(rx, full["rx"][pos:pos + 8])
     # training features straight from the GPU-resident slots == prepare_ml_inputs on the same samples
     x, y, par = ds.generate_feature_batch(4, slot0=10)
     assert x.shape == (4, 14, 599, 5) and y.shape == (4, 14, 599, 2) and np.array_equal(par["snr"], pa["snr"][:4])
