@@ -65,21 +65,21 @@ class Recorder:
             setattr(np.random, name, fn)
 
 
-def base_config(ntx, nrx):
+def base_config(ntx, nrx, nsym=14, useful=600):
     return {
-        "ofdm": {"fft_size": 1024, "cp_length": 72, "num_symbols": 14,
-                 "useful_subcarriers": 600, "subcarrier_spacing": 15000},
+        "ofdm": {"fft_size": 1024, "cp_length": 72, "num_symbols": nsym,
+                 "useful_subcarriers": useful, "subcarrier_spacing": 15000},
         "mimo": {"num_tx_antennas": ntx, "num_rx_antennas": nrx},
         "channel": {"carrier_freq": 2.0e9},
     }
 
 
-def slot_case(name, seed, ntx, nrx, model, doppler, snr, density, extra_methods=()):
+def slot_case(name, seed, ntx, nrx, model, doppler, snr, density, extra_methods=(), nsym=14, useful=600):
     import channel_simulator as cs
     import baseline_estimators as be
 
     np.random.seed(seed)
-    cfg = base_config(ntx, nrx)
+    cfg = base_config(ntx, nrx, nsym, useful)
     with Recorder() as rec:
         sim = cs.simulate_transmission(cfg, channel_type=model, doppler_hz=doppler,
                                        snr_db=snr, pilot_density=density)
@@ -104,6 +104,7 @@ def slot_case(name, seed, ntx, nrx, model, doppler, snr, density, extra_methods=
     m_ls, m_mm = be.evaluate_estimator(H, H_ls), be.evaluate_estimator(H, H_mm)
     out = dict(
         ntx=ntx, nrx=nrx, model=model, doppler_hz=float(doppler), snr_db=float(snr), density=float(density),
+        nsym=nsym, useful=useful,
         perm=perm.astype(np.int32), pilot_phase=pilot_phase, data_phase=data_phase, jakes_u=jakes_u,
         noise_re=noise_re, noise_im=noise_im,
         pilot_indices=pp.pilot_indices.astype(np.int64), pilot_mask=pp.pilot_mask,
@@ -313,6 +314,8 @@ def main():
     slot_case("slot_4x4_etu", 303, 4, 4, "ETU", 200, 10, 0.10)
     slot_case("slot_2x2_etu_5pct", 404, 2, 2, "ETU", 100, 10, 0.05)
     slot_case("slot_2x1_epa_1pct", 505, 2, 1, "EPA", 10, 0, 0.01)
+    # another grid: 7 symbols x 299 used bins, 3 TX x 2 RX (the generic kernels, odd symbol count, ntx not a power of two)
+    slot_case("slot_3x2_eva_7x299", 606, 3, 2, "EVA", 70, 8, 0.08, extra_methods=("nearest",), nsym=7, useful=300)
     dense_mmse_case("mmse_dense_2x2", 606)
     ofdm_case("ofdm_modem", 707)
     tdl_case("tdl_standalone", 808)

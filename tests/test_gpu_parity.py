@@ -728,3 +728,46 @@ def test_ls_interp_writes_stay_inside_their_arrays(pitch, engines):
         assert (v[:guard] == sentinel).all() and (v[guard + n:] == sentinel).all(), k
         assert not (res[k] == sentinel).any(), k
         assert (res[k] - src[k]).abs().max().item() < 2e-6, k
+
+
+def test_other_grid_on_reference_draws():
+    """The reference's own arrays on a 7 x 299 grid with 3 TX x 2 RX (generic instantiations: odd symbol count, ntx not a
+    power of two), injected with its recorded draws; plus the seeded drop-in call."""
+    from engine import SlotEngine
+    g = load_golden("slot_3x2_eva_7x299")
+    nsym, useful, ntx, nrx = int(g["nsym"]), int(g["useful"]), int(g["ntx"]), int(g["nrx"])
+    cfg = full_config(ntx, nrx)
+    cfg["ofdm"].update(num_symbols=nsym, useful_subcarriers=useful)
+    eng = SlotEngine(cfg)
+    nsc = useful - 1
+    mask = g["pilot_mask"]
+    turns = np.empty((nsym, nsc))
+    turns[mask] = g["pilot_phase"] / (2 * np.pi)
+    turns[~mask] = g["data_phase"] / (2 * np.pi)
+    ju = np.zeros((eng.p_max,) + g["jakes_u"].shape[1:])
+    ju[:g["jakes_u"].shape[0]] = g["jakes_u"]
+    inj = {"jakes_u": torch.from_numpy(ju[None]).to(eng.device, torch.float32),
+           "sym_turns": torch.from_numpy(turns[None]).to(eng.device, torch.float32),
+           "noise": torch.from_numpy((g["noise_re"] + 1j * g["noise_im"])[None]).to(eng.device, torch.complex64)}
+    out = eng.run(1, eng.models.index("EVA"), float(g["doppler_hz"]), float(g["snr_db"]), 0, eng.pool([g["pilot_indices"]]), inject=inj)
+    torch.cuda.synchronize()
+    assert relerr(out["H_true"][0].cpu().numpy(), g["channel"]) < RTOL and relerr(out["rx"][0].cpu().numpy(), g["rx_symbols"]) < RTOL
+    for t in range(ntx):
+        assert relerr(out["tx"][0, :, t].cpu().numpy(), g["tx_grid"]) < RTOL
+        assert relerr(out["H_ls"][0, :, :, t].cpu().numpy(), g["H_ls_tx0"]) < RTOL
+        assert relerr(out["H_mmse"][0, :, :, t].cpu().numpy(), g["H_mmse_tx0"]) < RTOL
+    st = out["stats"][0].cpu().numpy()[:, 1].sum(axis=0) / g["channel"].size
+    assert abs(db(st[0] / (st[2] + 1e-12)) - g["metrics_ls"][2]) < DB_TOL and abs(db(st[1] / (st[2] + 1e-12)) - g["metrics_mmse"][2]) < DB_TOL
+    # drop-in: np.random.seed(606); simulate_transmission(...) on this config, then the two estimators
+    import baseline_estimators as be
+    import channel_simulator as cs
+    np.random.seed(606)
+    sim = cs.simulate_transmission(cfg, channel_type="EVA", doppler_hz=70, snr_db=8, pilot_density=0.08)
+    assert np.array_equal(sim["pilot_pattern"].pilot_indices, g["pilot_indices"])
+    assert relerr(sim["channel"], g["channel"]) < RTOL and relerr(sim["rx_symbols"], g["rx_symbols"]) < RTOL
+    pp = sim["pilot_pattern"]
+    rx4d = np.repeat(sim["rx_symbols"].reshape(nsym, nrx, 1, nsc), ntx, axis=2)
+    H_n = be.LSEstimator('nearest').estimate(rx4d[:, :, :1], sim["pilot_symbols"], pp.pilot_mask, pp.pilot_positions)
+    assert relerr(H_n[:, :, 0], g["H_ls_nearest_tx0"]) < RTOL
+    H_m = be.MMSEEstimator().estimate(rx4d, sim["pilot_symbols"], pp.pilot_mask, pp.pilot_positions, snr_db=8)
+    assert relerr(H_m[:, :, 2], g["H_mmse_tx0"]) < RTOL

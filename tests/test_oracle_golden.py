@@ -165,3 +165,19 @@ def test_ml_feature_packing_matches_reference():
         for j, s in enumerate((-5.0, 10.0, 30.0)):
             assert abs(orc.ber_approximation(Hls[0], Htr[0], s) - g["ber_approx"][j]) < 1e-15
             assert abs(orc.ber_approximation(Htr[0] * 1.01, Htr[0], s) - g["ber_approx_small_err"][j]) < 1e-15
+
+
+def test_other_grid_matches_reference():
+    """7 symbols x 299 used bins, 3 TX x 2 RX, EVA: the oracle on a grid other than the default one."""
+    g = load_golden("slot_3x2_eva_7x299")
+    cfg = dict(OFDM_CFG, num_symbols=int(g["nsym"]), useful_subcarriers=int(g["useful"]))
+    ntx, nrx = int(g["ntx"]), int(g["nrx"])
+    sim = orc.simulate(cfg, ntx, nrx, str(g["model"]), float(g["doppler_hz"]), float(g["snr_db"]), float(g["density"]), golden_draws(g))
+    assert np.array_equal(sim["pilot_indices"], g["pilot_indices"]) and np.array_equal(sim["pilot_mask"], g["pilot_mask"])
+    assert sim["channel"].shape == (7, 2, 3, 299)
+    assert relerr(sim["channel"], g["channel"]) < TOL and relerr(sim["rx_symbols"], g["rx_symbols"]) < TOL
+    rx4d = np.repeat(g["rx_symbols"][:, :, None, :], ntx, axis=2)
+    pos = np.unravel_index(g["pilot_indices"], g["pilot_mask"].shape)
+    assert relerr(orc.ls_estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos)[:, :, 0], g["H_ls_tx0"]) < TOL
+    assert relerr(orc.ls_estimate(rx4d[:, :, :1], g["pilot_symbols"], g["pilot_mask"], pos, "nearest")[:, :, 0], g["H_ls_nearest_tx0"]) < TOL
+    assert relerr(orc.mmse_estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos, float(g["snr_db"]))[:, :, 0], g["H_mmse_tx0"]) < TOL
