@@ -155,7 +155,8 @@ int b2c_tap_gains(const b2c_geom *g, const b2c_profiles *prof, const b2c_slots *
  *   for callers that expand them as stride-0 views (the host-buffer pipeline: half the PCIe bytes).
  *   H_ls, H_mmse like H_true;  stats [B][nrx][B2C_N_STATGRP][B2C_N_STAT] double
  *   g->pitch = 600 (throughput configuration only: nsc = 599, even nsym, ntx in {1,2,4,8}, Philox draws, H_true + rx +
- *   tx requested and H_ls when estimating -- H_mmse and stats stay optional --, compact = 0; B2C_E_UNSUPPORTED otherwise): the last axis of the five arrays
+ *   tx requested and H_ls when estimating -- H_mmse and stats stay optional --, compact = 0; B2C_E_UNSUPPORTED
+ *   otherwise): the last axis of the five arrays
  *   is 600 elements apart in memory (element 599 is padding) and every lane writes 16 aligned bytes per row;
  *   same values as the contiguous layout, bit for bit.                                                    */
 int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat,

@@ -771,3 +771,45 @@ def test_other_grid_on_reference_draws():
     assert relerr(H_n[:, :, 0], g["H_ls_nearest_tx0"]) < RTOL
     H_m = be.MMSEEstimator().estimate(rx4d, sim["pilot_symbols"], pp.pilot_mask, pp.pilot_positions, snr_db=8)
     assert relerr(H_m[:, :, 2], g["H_mmse_tx0"]) < RTOL
+
+
+def test_c_abi_status_codes_and_empty_inputs(engines):
+    """The C ABI never throws: bad arguments give negative status codes and a message, empty inputs are no-ops."""
+    import ctypes as C
+    import _b2c
+    from _b2c import Geom, ref
+    L = _b2c.lib()
+    eng = engines(2, 2)
+    dev = eng.device
+    z = torch.zeros((8, 599), dtype=torch.complex64, device=dev)
+    bits = torch.zeros((64,), dtype=torch.uint8, device=dev)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    msg = lambda: L.b2c_last_error_string().decode()
+    E_ARG, E_UNSUPPORTED = -1, -3
+    # unsupported modulation order (the reference raises NotImplementedError for anything but 4 / 16)
+    assert L.b2c_qam_modulate(P(bits), 8, 64, P(z), None) == E_UNSUPPORTED and "64" in msg()
+    assert L.b2c_qam_demodulate(P(z), 8, 8, 0, P(bits), None) == E_UNSUPPORTED
+    # null pointers
+    g = Geom(14, 599, 2, 2, 1024, 72, 7.1e-5)
+    assert L.b2c_equalize(ref(g), 1, None, P(z), P(z), 1e-8, 0, None) == E_ARG and "null" in msg()
+    assert L.b2c_mmse_dense(None, 4, P(z), P(z), 1, 4, None) == E_ARG
+    assert L.b2c_count_bit_errors(P(bits), None, 8, P(bits), None) == E_ARG
+    # geometry outside the compiled limits: even bin count, too many symbols, too many antennas
+    for bad in (Geom(14, 600, 2, 2, 1024, 72, 7.1e-5), Geom(17, 599, 2, 2, 1024, 72, 7.1e-5), Geom(14, 599, 9, 2, 1024, 72, 7.1e-5)):
+        assert L.b2c_tap_gains(ref(bad), ref(eng.prof), ref(eng._slots(1, 0, 10.0, 10.0, 0, 0, 1)[0]), None, 1, P(z), P(z), None) == E_UNSUPPORTED
+        assert msg()
+    bad_fft = Geom(14, 599, 1, 1, 2048, 72, 7.1e-5)
+    assert L.b2c_ofdm_modulate(ref(bad_fft), P(z), P(z), 1, None) == E_UNSUPPORTED and "1024" in msg()
+    # row pitch on an entry point that takes contiguous rows only
+    pitched = Geom(14, 599, 2, 2, 1024, 72, 7.1e-5, 600)
+    assert L.b2c_tap_gains(ref(pitched), ref(eng.prof), ref(eng._slots(1, 0, 10.0, 10.0, 0, 0, 1)[0]), None, 1, P(z), P(z), None) == E_UNSUPPORTED
+    # empty inputs: status 0, nothing launched
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert L.b2c_equalize(ref(g), 0, P(z), P(z), P(z), 1e-8, 0, s) == 0
+    assert L.b2c_ofdm_modulate(ref(Geom(14, 599, 1, 1, 1024, 72, 7.1e-5)), P(z), P(z), 0, s) == 0
+    assert L.b2c_mmse_dense(P(z), 4, P(z), P(bits), 0, 4, s) == 0
+    assert L.b2c_count_bit_errors(P(bits), P(bits), 0, P(bits), s) == 0
+    assert L.b2c_qam_modulate(P(bits), 0, 4, P(z), s) == 0
+    torch.cuda.synchronize()
+    assert eng.qam_modulate(torch.zeros((0,), dtype=torch.uint8, device=dev)).numel() == 0
+    assert eng.count_bit_errors(bits[:0], bits[:0]).item() == 0
