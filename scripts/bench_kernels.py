@@ -92,6 +92,11 @@ res["k2_ofdm_demodulate"] = {"ms": t * 1e3, "gbs": bm / t / 1e9, "frac_hbm": bm 
 del x, y
 torch.cuda.empty_cache()
 
+# stand-alone TDL (ChannelModel.generate_time_varying_channel): 15344 samples of a 4x4 ETU realisation, L = 78 taps
+t = timeit(lambda: eng.tdl_full("ETU", 200.0, 15344, 4, 4), n=5)
+res["tdl_full_4x4_etu_15344_samples"] = {"ms": t * 1e3, "out_MB": 15344 * 16 * 78 * 8 / 1e6,
+                                           "note": "the reference spends ~1.5 s here per 4x4 ETU slot (SURVEY 8a3)"}
+
 # dataset mode: H_true + rx + tx + H_ls (what generate_sample returns), padded rows
 B = 4096
 o = eng.alloc_outputs(B, ("H_true", "rx", "tx", "H_ls"), pitch=600)
