@@ -37,9 +37,11 @@ WORKLOADS = {   # name: (ntx, nrx, model, doppler_hz, density, description)
 SNRS = (-5, 0, 5, 10, 15, 20, 25, 30)
 
 
-def slot_bytes(ntx, nrx, nsym=14, nsc=599):
+def slot_bytes(ntx, nrx, nsym=14, nsc=599, compact=False):
     """Algorithmic bytes one slot of the fused pipeline writes: H_true + H_ls +
-    H_mmse + rx + tx, complex64."""
+    H_mmse + rx + tx, complex64.  compact: the tx-replicated arrays (H_ls, H_mmse, tx) counted once."""
+    if compact:
+        return 8 * (nsym * nrx * ntx * nsc + 3 * nsym * nrx * nsc + nsym * nsc)
     return 8 * (3 * nsym * nrx * ntx * nsc + nsym * nrx * nsc + nsym * ntx * nsc)
 
 
@@ -183,7 +185,8 @@ def run_b200(args, rank, world, local_rank):
     pool = eng.random_pool([dens], per_density=1, seed=42)
     B = args.batch
     dev = eng.device
-    out = eng.alloc_outputs(B, ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), pitch=args.pitch)
+    compact = args.layout == "compact"
+    out = eng.alloc_outputs(B, ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), compact=compact, pitch=args.pitch)
     geom_out = eng._with_pitch(eng.geom, args.pitch)      # rows of the five arrays are args.pitch complex apart
     ws = eng.workspace(B)
     model_id = torch.full((B,), eng.models.index(model), dtype=torch.int32, device=dev)
@@ -230,7 +233,7 @@ def run_b200(args, rank, world, local_rank):
         check(L.b2c_slot_pipeline(ref(geom_out), ref(eng.prof), ref(pool.struct), ref(slots_of(i)), None, B,
                                   dptr(w["gains"], "c64"), dptr(w["noise_std"], "f32"), rows_ptr(out["H_true"], P),
                                   rows_ptr(out["rx"], P), rows_ptr(out["tx"], P), rows_ptr(out["H_ls"], P),
-                                  rows_ptr(out["H_mmse"], P), dptr(out["stats"], "f64"), 0, stream_ptr()))
+                                  rows_ptr(out["H_mmse"], P), dptr(out["stats"], "f64"), int(compact), stream_ptr()))
         if ev is not None:
             ev[1].record()
         ev_slot[i & 1].record(main)
@@ -295,7 +298,7 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         peak, peak_kind = measured_peaks()
         k_ms = statistics.mean(kern_ms)
-        alg = slot_bytes(ntx, nrx) * B
+        alg = slot_bytes(ntx, nrx, compact=compact) * B
         achieved = alg / (k_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -313,6 +316,7 @@ def run_b200(args, rank, world, local_rank):
                        "slots_per_step": B, "slots_total": world * args.steps * B, "rng": "philox4x32-10 keyed by global slot index",
                        "pilot_patterns": "1 fixed scattered pattern (838 pilots)", "parallelism": f"dp{world} (slots sharded, NCCL all-reduce of per-SNR stats)",
                        "l2_policy": f"outputs per step = {alg / 1e9:.1f} GB >> 126 MB L2; no flush needed",
+                       "layout": args.layout + (" (H_ls, H_mmse, tx written once; stride-0 views over tx)" if compact else " (reference shapes, tx-replicated arrays written ntx times)"),
                        "hbm_layout": (f"rows of 599 complex64 at pitch {args.pitch}" + (" (one padding element per row: 16-byte stores; "
                                       "algorithmic bytes count 599)" if args.pitch != 599 else " (contiguous)"))},
             "roofline": {"bound": "hbm", "kernel": (f"slot_kernel<{ntx}, ..., 599, FAST, pitch {args.pitch}> (16-byte stores)" if args.pitch != 599 else f"slot_kernel<{ntx}, ..., 599, FAST> (8-byte stores)"), "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -348,6 +352,8 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--pitch", type=int, default=600, choices=[599, 600],
                     help="row pitch of the output arrays in HBM: 600 = padded rows / 16-byte stores (default), 599 = contiguous")
+    ap.add_argument("--layout", default="full", choices=["full", "compact"],
+                    help="full: the five arrays in the reference's shapes; compact: each unique value written once")
     ap.add_argument("--e2e-batch", type=int, default=2048)
     ap.add_argument("--e2e-chunk", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=4)

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2c.so")
 
 MAX_TAPS, MAX_ANT, MAX_SYM, N_OSC, N_STAT, N_BINSTAT = 16, 8, 16, 20, 3, 12
-ABI_VERSION = 2
+ABI_VERSION = 3
 WIDE_PITCH = 600      # padded row pitch b2c_slot_pipeline accepts in its throughput configuration
 EXPORTS = ["b2c_last_error_string", "b2c_abi_version", "b2c_tap_gains", "b2c_slot_pipeline",
            "b2c_ls_interp", "b2c_pilot_vectors", "b2c_mmse_dense", "b2c_dense_real_apply", "b2c_stats_bins",
@@ -78,7 +78,7 @@ def lib():
             "b2c_ofdm_modulate": [P, P, P, I64, P],
             "b2c_ofdm_demodulate": [P, P, P, I64, P],
             "b2c_apply_channel": [P, P, P, I64, P, P, P, P, P],
-            "b2c_tdl_full": [P, P, I32, F, F, I64, I32, P, P, C.c_uint64, I64, P, P],
+            "b2c_tdl_full": [P, P, I32, F, F, I64, I32, P, I32, P, C.c_uint64, I64, P, P],
             "b2c_equalize": [P, I64, P, P, P, C.c_double, I32, P],
             "b2c_qam_modulate": [P, I64, I32, P, P],
             "b2c_qam_demodulate": [P, I64, I32, I32, P, P],

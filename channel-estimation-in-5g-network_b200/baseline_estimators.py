@@ -9,6 +9,7 @@ pilot pattern, cached) and a GPU blend per resource element; see _tables.py.
 
 from __future__ import annotations
 
+import hashlib
 from typing import Optional, Tuple
 
 import numpy as np
@@ -122,9 +123,10 @@ class MMSEEstimator:
 
     def _wiener(self, device):
         """W = R (R + sigma^2 I)^-1 in float64 on the host, cached per noise variance (:182-194)."""
-        key = (id(self.channel_covariance), float(self.noise_variance))
+        # keyed on the covariance's CONTENT: a matrix mutated in place, or a new one at a recycled id(), is a new W
+        R = np.asarray(self.channel_covariance)
+        key = (hashlib.sha1(np.ascontiguousarray(R).view(np.uint8)).hexdigest(), R.shape, str(R.dtype), float(self.noise_variance))
         if key not in self._w_cache:
-            R = np.asarray(self.channel_covariance)
             Ry = R + self.noise_variance * np.eye(R.shape[0])
             try:
                 W = R @ np.linalg.inv(Ry)

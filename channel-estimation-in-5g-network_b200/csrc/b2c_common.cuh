@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "b2c.h"
 
 namespace b2c {
@@ -30,6 +32,39 @@ void set_error(const char *fmt, ...);
   } while (0)
 
 int check_geom(const b2c_geom *g, bool allow_pitch = false);
+
+// Opt-in to > 48 KB of dynamic shared memory ONCE per (kernel instantiation, device) instead of on every launch.
+// `Kern` is the kernel itself (a non-type template argument), so every instantiation keeps its own per-device record.
+constexpr int MAX_DEVICES = 64;
+template <auto Kern>
+inline cudaError_t set_max_smem(size_t bytes) {
+  static std::atomic<int> granted[MAX_DEVICES];     // zero-initialised; bytes already granted on each device
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < MAX_DEVICES;
+  if (tracked && granted[dev].load(std::memory_order_acquire) >= (int)bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && tracked) granted[dev].store((int)bytes, std::memory_order_release);
+  return e;
+}
+
+// SM count of the current device (cached per device ordinal).
+inline int sm_count_current(int *out) {
+  static std::atomic<int> cached[MAX_DEVICES];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  const bool tracked = dev >= 0 && dev < MAX_DEVICES;
+  int n = tracked ? cached[dev].load(std::memory_order_acquire) : 0;
+  if (!n) {
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    if (tracked) cached[dev].store(n, std::memory_order_release);
+  }
+  *out = n;
+  return 0;
+}
 
 // ---- complex helpers (float2 = (re, im)) ---------------------------------------------------
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {

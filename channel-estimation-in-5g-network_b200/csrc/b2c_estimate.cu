@@ -256,7 +256,7 @@ template <int NTX>
 static int launch_ls_wide(const LsArgs &a, int64_t B, cudaStream_t stream) {
   size_t smem = (size_t)(a.pat.np_max + 1) * sizeof(float2);
   auto kern = ls_interp_wide_kernel<NTX, 600>;
-  if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) B2C_CUDA((set_max_smem<ls_interp_wide_kernel<NTX, 600>>(smem)));
   kern<<<(unsigned)(B * a.g.nrx), EST_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
@@ -266,7 +266,7 @@ template <int NTX, bool EXACT, int NSC>
 static int launch_ls(const LsArgs &a, int64_t B, cudaStream_t stream) {
   size_t smem = (size_t)(a.pat.np_max + 1) * sizeof(float2);
   auto kern = ls_interp_kernel<NTX, EXACT, NSC>;
-  if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) B2C_CUDA((set_max_smem<ls_interp_kernel<NTX, EXACT, NSC>>(smem)));
   kern<<<(unsigned)(B * a.g.nrx), EST_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;

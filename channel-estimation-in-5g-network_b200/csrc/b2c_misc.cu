@@ -146,7 +146,7 @@ extern "C" int b2c_apply_channel(const b2c_geom *g, const b2c_slots *slots, cons
 
 extern "C" int b2c_tdl_full(const b2c_geom *g, const b2c_profiles *prof, int32_t model_id, float doppler_hz,
                             float sample_period_s, int64_t num_samples, int32_t L, const int32_t *tap_delay_host,
-                            const float *jakes_u, uint64_t seed, int64_t slot, float *out, void *stream) {
+                            int32_t ntaps, const float *jakes_u, uint64_t seed, int64_t slot, float *out, void *stream) {
   B2C_REQUIRE(g && prof && tap_delay_host && out, B2C_E_ARG, "b2c_tdl_full: null argument");
   B2C_REQUIRE(g->ntx >= 1 && g->ntx <= B2C_MAX_ANT && g->nrx >= 1 && g->nrx <= B2C_MAX_ANT, B2C_E_UNSUPPORTED,
               "b2c_tdl_full: antenna counts %dx%d", g->ntx, g->nrx);
@@ -154,9 +154,7 @@ extern "C" int b2c_tdl_full(const b2c_geom *g, const b2c_profiles *prof, int32_t
   B2C_REQUIRE(num_samples >= 0 && L >= 1, B2C_E_ARG, "b2c_tdl_full: num_samples=%lld L=%d", (long long)num_samples, L);
   if (num_samples == 0) return B2C_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int ntaps = 0;
-  B2C_CUDA(cudaMemcpyAsync(&ntaps, prof->ntaps + model_id, sizeof(int), cudaMemcpyDeviceToHost, st));
-  B2C_CUDA(cudaStreamSynchronize(st));
+  // ntaps comes from the host tables (it is prof->ntaps[model_id]): no device read-back, nothing synchronises
   B2C_REQUIRE(ntaps >= 1 && ntaps <= MAXT, B2C_E_ARG, "b2c_tdl_full: ntaps=%d", ntaps);
   TdlArgs a = {};
   a.ntaps = ntaps;

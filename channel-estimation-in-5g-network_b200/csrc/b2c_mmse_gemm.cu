@@ -730,7 +730,7 @@ extern "C" int b2c_mmse_dense(const float *W, int32_t np, const float *in, float
   if (ncols == 0) return B2C_OK;
   dim3 grid((unsigned)((2 * np + TC_BM - 1) / TC_BM), (unsigned)((ncols + TC_BN - 1) / TC_BN));
   B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_mmse_dense: ncols=%lld too large for one launch", (long long)ncols);
-  B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  B2C_CUDA((set_max_smem<dense_tc_kernel<false, false>>(TC_SMEM)));
   dense_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(W, np, np, reinterpret_cast<const float2 *>(in),
                                                                                       out, ncols, ld, ld);
   B2C_CUDA(cudaGetLastError());
@@ -747,7 +747,7 @@ extern "C" int b2c_dense_real_apply(const float *W, int32_t m, int32_t k, const 
   if (ncols == 0) return B2C_OK;
   dim3 grid((unsigned)((m + TC_BM - 1) / TC_BM), (unsigned)((ncols + TC_BN / 2 - 1) / (TC_BN / 2)));
   B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_real_apply: ncols=%lld too large for one launch", (long long)ncols);
-  B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  B2C_CUDA((set_max_smem<dense_tc_kernel<true, false>>(TC_SMEM)));
   dense_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(W, m, k, reinterpret_cast<const float2 *>(in), out,
                                                                                      ncols, ld_in, ld_out);
   B2C_CUDA(cudaGetLastError());
@@ -795,12 +795,8 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
     B2C_REQUIRE(ld_in == ld_out, B2C_E_ARG, "b2c_dense_apply_prepared: complex form takes one leading dimension");
     // Two tile shapes, equal per-SM throughput: 128 x 128 (3 CTAs/SM) and 128 x 256 (2 CTAs/SM).  What differs is the
     // wave quantisation at this column count, so take the shape whose last wave is fuller.
-    static int sm_count = 0;
-    if (!sm_count) {
-      int dev = 0;
-      B2C_CUDA(cudaGetDevice(&dev));
-      B2C_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int sm_count = 0;
+    B2C_CUDA((cudaError_t)sm_count_current(&sm_count));
     auto wave_eff = [&](int64_t tiles, int per_sm) {
       const int64_t slots = (int64_t)sm_count * per_sm;
       return (double)tiles / (double)(((tiles + slots - 1) / slots) * slots);
@@ -812,7 +808,7 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
     if (ncols >= T2_BN && 1.2 * eff_ws >= eff_best) {
       dim3 grid2((unsigned)tiles_m, (unsigned)((ncols + T2_BN - 1) / T2_BN));
       B2C_REQUIRE(grid2.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
-      B2C_CUDA(cudaFuncSetAttribute(dense_tc_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+      B2C_CUDA((set_max_smem<dense_tc_ws_kernel<false>>(WS_SMEM)));
       dense_tc_ws_kernel<false><<<grid2, WS_THREADS, WS_SMEM, (cudaStream_t)stream>>>(P, k, k, reinterpret_cast<const float2 *>(in), out,
                                                                                       ncols, ld_in, ld_out);
       B2C_CUDA(cudaGetLastError());
@@ -821,21 +817,21 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
     if (ncols >= T2_BN && wave_eff(t256, 2) > wave_eff(t128, 3) + 0.02) {
       dim3 grid2((unsigned)tiles_m, (unsigned)((ncols + T2_BN - 1) / T2_BN));
       B2C_REQUIRE(grid2.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
-      B2C_CUDA(cudaFuncSetAttribute(dense_tc256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+      B2C_CUDA((set_max_smem<dense_tc256_kernel>(T2_SMEM)));
       dense_tc256_kernel<<<grid2, T2_THREADS, T2_SMEM, (cudaStream_t)stream>>>(P, k, reinterpret_cast<const float2 *>(in), out, ncols, ld_in);
       B2C_CUDA(cudaGetLastError());
       return B2C_OK;
     }
     dim3 grid((unsigned)tiles_m, (unsigned)((ncols + TC_BN - 1) / TC_BN));
     B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
-    B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    B2C_CUDA((set_max_smem<dense_tc_kernel<false, true>>(TC_SMEM)));
     dense_tc_kernel<false, true><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(P, k, k, reinterpret_cast<const float2 *>(in), out,
                                                                                        ncols, ld_in, ld_out);
   } else {
     if (ncols >= T2_BN / 2) {     // warp-specialised form: a tile covers 128 complex columns
       dim3 grid2((unsigned)tiles_m, (unsigned)((ncols + T2_BN / 2 - 1) / (T2_BN / 2)));
       B2C_REQUIRE(grid2.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
-      B2C_CUDA(cudaFuncSetAttribute(dense_tc_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+      B2C_CUDA((set_max_smem<dense_tc_ws_kernel<true>>(WS_SMEM)));
       dense_tc_ws_kernel<true><<<grid2, WS_THREADS, WS_SMEM, (cudaStream_t)stream>>>(P, m, k, reinterpret_cast<const float2 *>(in), out, ncols,
                                                                                      ld_in, ld_out);
       B2C_CUDA(cudaGetLastError());
@@ -843,7 +839,7 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
     }
     dim3 grid((unsigned)tiles_m, (unsigned)((ncols + TC_BN / 2 - 1) / (TC_BN / 2)));
     B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
-    B2C_CUDA(cudaFuncSetAttribute(dense_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    B2C_CUDA((set_max_smem<dense_tc_kernel<true, true>>(TC_SMEM)));
     dense_tc_kernel<true, true><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(P, m, k, reinterpret_cast<const float2 *>(in), out,
                                                                                       ncols, ld_in, ld_out);
   }

@@ -155,7 +155,7 @@ static unsigned ofdm_grid(int64_t rows) {
 extern "C" int b2c_ofdm_modulate(const b2c_geom *g, const float *in, float *out, int64_t rows, void *stream) {
   if (int rc = ofdm_check(g, in, out, rows, "b2c_ofdm_modulate")) return rc;
   if (rows == 0) return B2C_OK;
-  B2C_CUDA(cudaFuncSetAttribute(ofdm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OFDM_SMEM));
+  B2C_CUDA((set_max_smem<ofdm_kernel<true>>(OFDM_SMEM)));
   ofdm_kernel<true><<<ofdm_grid(rows), OFDM_THREADS, OFDM_SMEM, (cudaStream_t)stream>>>(
       *g, reinterpret_cast<const float2 *>(in), reinterpret_cast<float2 *>(out), rows);
   B2C_CUDA(cudaGetLastError());
@@ -165,7 +165,7 @@ extern "C" int b2c_ofdm_modulate(const b2c_geom *g, const float *in, float *out,
 extern "C" int b2c_ofdm_demodulate(const b2c_geom *g, const float *in, float *out, int64_t rows, void *stream) {
   if (int rc = ofdm_check(g, in, out, rows, "b2c_ofdm_demodulate")) return rc;
   if (rows == 0) return B2C_OK;
-  B2C_CUDA(cudaFuncSetAttribute(ofdm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OFDM_SMEM));
+  B2C_CUDA((set_max_smem<ofdm_kernel<false>>(OFDM_SMEM)));
   ofdm_kernel<false><<<ofdm_grid(rows), OFDM_THREADS, OFDM_SMEM, (cudaStream_t)stream>>>(
       *g, reinterpret_cast<const float2 *>(in), reinterpret_cast<float2 *>(out), rows);
   B2C_CUDA(cudaGetLastError());

@@ -470,7 +470,9 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
 // 8-byte form -- the kernel's ceiling moves from the store path to its arithmetic.
 // STORE = false: statistics-only sweeps (pilot-density / SNR curves, sharded statistics): no array is written, so the
 // grid symbols, the noise and the lane exchanges that only feed stores are skipped altogether.
-template <int T, int NTX, bool EST, int PITCH, bool STORE>
+// COMPACT: the tx-replicated outputs are written once, in rx's row layout: H_ls / H_mmse [B][nsym][nrx][PITCH] and
+// tx [B][nsym][PITCH] (1 945 552 unique bytes per 4x4 slot instead of 3 756 928).
+template <int T, int NTX, bool EST, int PITCH, bool STORE, bool COMPACT>
 __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx &c, float2 (&st)[2][3]) {
   constexpr int NSC = 599, HALF = 300;
   const int nsym = a.g.nsym, nrx = a.g.nrx;
@@ -491,16 +493,20 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
   const int64_t slot_h = (int64_t)nsym * nrx * NTX * PITCH, slot_r = (int64_t)nsym * nrx * PITCH;
   float2 *const Hb = STORE ? a.H_true + c.b * slot_h : nullptr;
   float2 *const Rb = STORE ? a.rx + c.b * slot_r : nullptr;
-  float2 *const Tb = (STORE && c.rx == 0) ? a.tx + c.b * (int64_t)nsym * NTX * PITCH : nullptr;
+  constexpr int TXC = COMPACT ? 1 : NTX;                        // copies of the grid / of the estimates per (s, rx)
+  float2 *const Tb = (STORE && c.rx == 0) ? a.tx + c.b * (int64_t)nsym * TXC * PITCH : nullptr;
   const uint4 *plan = EST ? reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * (nsym * NSC + 1) : nullptr;
   float2 *pH = Hb + (c.rx * NTX * PITCH + K), *pR = Rb + (c.rx * PITCH + K), *pT = Tb + K;
-  const int64_t dL = (EST && STORE) ? (const char *)(a.H_ls + c.b * slot_h) - (const char *)Hb : 0;
+  // H_ls / H_mmse addresses are H_true's (compact: rx's) plus a uniform byte delta
+  const char *const eb = COMPACT ? (const char *)Rb : (const char *)Hb;
+  const int64_t slot_e = COMPACT ? slot_r : slot_h;
+  const int64_t dL = (EST && STORE) ? (const char *)(a.H_ls + c.b * slot_e) - eb : 0;
   const bool mstore = EST && STORE && a.H_mmse != nullptr;     // dataset mode (H_true, rx, tx, H_ls) leaves H_mmse out
-  const int64_t dM = mstore ? (const char *)(a.H_mmse + c.b * slot_h) - (const char *)Hb : 0;
+  const int64_t dM = mstore ? (const char *)(a.H_mmse + c.b * slot_e) - eb : 0;
   const int nre = nsym * NSC;
   int oPK = act ? K : nre, oPS = vS ? S : nre;                   // plan rows; row nre = "outside" for idle lanes
   const int dPK = act ? NSC : 0, dPS = vS ? NSC : 0;
-  const int dH = nrx * NTX * PITCH, dR = nrx * PITCH, dT = NTX * PITCH;
+  const int dH = nrx * NTX * PITCH, dR = nrx * PITCH, dT = TXC * PITCH;
   const float2 *gps = c.gsp;
 
   static_assert(SLOT_THREADS == RNG_LANES, "thread t draws Philox lane t");
@@ -541,10 +547,11 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
         const float2 lN = xchg(lS);
         const float2 mK = cscale(c.alpha, lK), mN = cscale(c.alpha, lN);
         if (act) {
+          float2 *const pE = COMPACT ? pR : pH;
 #pragma unroll
-          for (int tx = 0; tx < NTX; ++tx) {
-            st16((float2 *)((char *)(pH + tx * PITCH) + dL), lK, lN);
-            if (mstore) st16((float2 *)((char *)(pH + tx * PITCH) + dM), mK, mN);
+          for (int tx = 0; tx < TXC; ++tx) {
+            st16((float2 *)((char *)(pE + tx * PITCH) + dL), lK, lN);
+            if (mstore) st16((float2 *)((char *)(pE + tx * PITCH) + dM), mK, mN);
           }
         }
       }
@@ -600,7 +607,7 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
         const float2 xN = xchg(xS);
         if (act) {
 #pragma unroll
-          for (int tx = 0; tx < NTX; ++tx) st16(pT + tx * PITCH, xK, xN);
+          for (int tx = 0; tx < TXC; ++tx) st16(pT + tx * PITCH, xK, xN);
         }
       }
       pH += dH;
@@ -611,7 +618,7 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
   }
 }
 
-template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE, bool STORE = true>
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE, bool STORE = true, bool COMPACT = false>
 __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nsc = NSC ? NSC : a.g.nsc;
@@ -664,22 +671,22 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
 
   if (c.ntaps <= 5) {
     if (EST) pilot_phase<5, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<5, NTX, EST, WIDE, STORE>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<5, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
     else slot_body<5, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else if (c.ntaps <= 8) {
     if (EST) pilot_phase<8, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<8, NTX, EST, WIDE, STORE>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<8, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
     else slot_body<8, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else if (c.ntaps <= 9) {
     if (EST) pilot_phase<9, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<9, NTX, EST, WIDE, STORE>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<9, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
     else slot_body<9, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else {
     if (EST) pilot_phase<MAXT, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<MAXT, NTX, EST, WIDE, STORE>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<MAXT, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
     else slot_body<MAXT, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
 
@@ -709,11 +716,11 @@ static size_t slot_smem_bytes(const b2c_geom *g, int np_max) {
          (size_t)(np_max + 1) * sizeof(float2);
 }
 
-template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0, bool STORE = true>
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0, bool STORE = true, bool COMPACT = false>
 static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
-  auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE>;
+  auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT>;
   if (WIDE && EST) smem += 16 + 4 * SLOT_THREADS * sizeof(uint4);      // plan-entry staging (+ alignment slack)
-  if (smem > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) B2C_CUDA((set_max_smem<slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT>>(smem)));
   kern<<<(unsigned)(B * a.g.nrx), SLOT_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
@@ -743,11 +750,17 @@ static int launch_slot_ntx(const SlotArgs &a, int64_t B, size_t smem, cudaStream
   if (pitch != a.g.nsc) {
     // padded rows: the wide-store kernel of the throughput configuration only (H_mmse and stats are optional there:
     // H_true + rx + tx + H_ls is what the reference's generate_sample returns)
-    const bool wide_ok = !a.compact && a.g.nsc == 599 && (a.g.nsym & 1) == 0 && !a.has_inj && a.H_true && a.rx && a.tx &&
+    const bool wide_ok = a.g.nsc == 599 && (a.g.nsym & 1) == 0 && !a.has_inj && a.H_true && a.rx && a.tx &&
                          (!EST || a.H_ls);
     B2C_REQUIRE(wide_ok && pitch == WIDE_PITCH, B2C_E_UNSUPPORTED,
                 "b2c_slot_pipeline: pitch=%d needs the throughput configuration (599 bins, even nsym, Philox draws, "
-                "H_true + rx + tx (+ H_ls when estimating) requested, not compact) and pitch == %d", pitch, WIDE_PITCH);
+                "H_true + rx + tx (+ H_ls when estimating) requested) and pitch == %d", pitch, WIDE_PITCH);
+    if (a.compact) {
+      if (ntx == 1) return launch_slot<1, true, EST, 599, true, WIDE_PITCH, true, true>(a, B, smem, stream);
+      if (ntx == 2) return launch_slot<2, true, EST, 599, true, WIDE_PITCH, true, true>(a, B, smem, stream);
+      if (ntx == 4) return launch_slot<4, true, EST, 599, true, WIDE_PITCH, true, true>(a, B, smem, stream);
+      if (ntx == 8) return launch_slot<8, true, EST, 599, true, WIDE_PITCH, true, true>(a, B, smem, stream);
+    }
     if (ntx == 1) return launch_slot<1, true, EST, 599, true, WIDE_PITCH>(a, B, smem, stream);
     if (ntx == 2) return launch_slot<2, true, EST, 599, true, WIDE_PITCH>(a, B, smem, stream);
     if (ntx == 4) return launch_slot<4, true, EST, 599, true, WIDE_PITCH>(a, B, smem, stream);
@@ -785,8 +798,7 @@ extern "C" int b2c_tap_gains(const b2c_geom *g, const b2c_profiles *prof, const 
   size_t gsb = (size_t)g->nrx * g->nsym * MAXT * sizeof(float2);
   size_t smem = osc > gsb ? osc : gsb;
   B2C_REQUIRE(smem <= 200 * 1024, B2C_E_UNSUPPORTED, "b2c_tap_gains: %zu B shared memory needed", smem);
-  if (smem > 48 * 1024)
-    B2C_CUDA(cudaFuncSetAttribute(tap_gains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) B2C_CUDA(set_max_smem<tap_gains_kernel>(smem));
   tap_gains_kernel<<<(unsigned)B, GAIN_THREADS, smem, (cudaStream_t)stream>>>(
       *g, *prof, *slots, ij, inj != nullptr, reinterpret_cast<float2 *>(gains), noise_std);
   B2C_CUDA(cudaGetLastError());

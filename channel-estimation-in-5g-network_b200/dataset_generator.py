@@ -61,6 +61,19 @@ class ChannelEstimationDataset:
         self._pool = None
         self._next_slot = 0
 
+    # The Philox pattern pool is a function of the seed: re-seeding (the script twins do it per split) drops the pool,
+    # so a split's pilot patterns never depend on which split this object generated before it -- a 'val' split resumed
+    # in a fresh process gets the patterns of the uninterrupted train + val run.
+    @property
+    def seed(self):
+        return self._seed
+
+    @seed.setter
+    def seed(self, value):
+        if getattr(self, "_seed", None) != value:
+            self._pool = None
+        self._seed = value
+
     # ---- parameter lists (src/dataset_generator.py:105-108) -------------------------------------------
     def _lists(self):
         if self._list_override is not None:

@@ -147,8 +147,6 @@ class SlotEngine:
         pitch=_b2c.WIDE_PITCH (600): rows padded by one element -- the layout of the wide-store kernel; the
         tensors returned are [..., :nsc] views of the padded buffers."""
         P = self.nsc if pitch is None else int(pitch)
-        if compact and P != self.nsc:
-            raise ValueError("the compact layout has contiguous rows")
         full = (B, self.nsym, self.nrx, self.ntx, P)
         est = (B, self.nsym, self.nrx, P) if compact else full
         shapes = {"H_true": full, "H_ls": est, "H_mmse": est, "rx": (B, self.nsym, self.nrx, P),
@@ -371,7 +369,7 @@ class SlotEngine:
         g = Geom(self.nsym, self.nsc, ntx, nrx, self.fft_size, self.cp, self.geom.symbol_period_s)
         out = torch.empty((num_samples, nrx, ntx, L), dtype=torch.complex64, device=self.device)
         check(lib().b2c_tdl_full(ref(g), ref(self.prof), m, float(doppler_hz), 1.0 / self.sampling_rate, num_samples, L,
-                                 delays.ctypes.data_as(C.c_void_p), dptr(jakes_u, "f32", True), int(seed), int(slot),
+                                 delays.ctypes.data_as(C.c_void_p), nt, dptr(jakes_u, "f32", True), int(seed), int(slot),
                                  dptr(out, "c64"), stream_ptr()), "b2c_tdl_full")
         return out
 

@@ -1,9 +1,9 @@
 """Host-buffer front end of the slot pipeline: per-slot parameters come from pinned host memory,
 results land in pinned host buffers (what the reference's NumPy API hands its caller).
 
-Chunks are double-buffered over two CUDA streams so the device->host copy of chunk i overlaps the
+Chunks are multi-buffered over two CUDA streams so the device->host copy of chunk i overlaps the
 kernels of chunk i+1.  This is the end-to-end (`e2e`) path bench.py times; it is PCIe-bound:
-a 4x4 slot is 3.76 MB of results.
+a 4x4 slot is 3.76 MB of results (1.95 MB with the tx-replicated arrays sent once).
 """
 
 from __future__ import annotations
@@ -55,61 +55,106 @@ def bind_to_gpu_numa_node(device_index):
 
 
 class HostPipeline:
-    def __init__(self, engine, pool, chunk=512, want=ARRAYS + ("stats",), compact=False):
-        """compact=True moves the tx-replicated arrays (H_ls, H_mmse, tx) over PCIe once and hands the
-        consumer full-shape NumPy broadcast views (SlotEngine.expand_compact): same values, 48 % fewer
-        bytes for a 4x4 slot."""
-        self.eng, self.pool, self.chunk, self.want, self.compact = engine, pool, chunk, tuple(want), compact
-        self.dev = [engine.alloc_outputs(chunk, self.want, compact) for _ in range(2)]
-        self.ws = [engine.workspace(chunk) for _ in range(2)]
-        self.host = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in d.items()} for d in self.dev]
-        self.par_host = [torch.empty((4, chunk), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-        self.par_dev = [torch.empty((4, chunk), dtype=torch.float32, device=engine.device) for _ in range(2)]
-        self.compute = torch.cuda.Stream(device=engine.device)
-        self.copy = torch.cuda.Stream(device=engine.device)
-        self.ev_done = [torch.cuda.Event() for _ in range(2)]
-        self.ev_copied = [torch.cuda.Event() for _ in range(2)]
-        self.d2h_bytes_per_slot = sum(v[0].numel() * v.element_size() for v in self.dev[0].values())
+    """Slots in, NumPy arrays out: per-slot parameters from pinned host memory, results in pinned host memory.
+
+    Each in-flight chunk owns ONE device slab and ONE pinned host slab with identical layouts
+    ([array][slot]..., arrays 256-byte aligned), so a full chunk leaves the device as a single cudaMemcpyAsync;
+    `depth` chunks are in flight (kernels of chunk i+1 overlap the copy of chunk i).  On the default grid the slot
+    kernel runs in its wide-store form (rows padded to pitch 600: one 16-byte store per lane); the host arrays are
+    the [..., :599] views of those rows.  compact=True keeps one copy of the tx-replicated arrays (H_ls, H_mmse, tx)
+    on the device AND on the link and hands the consumer full-shape broadcast views: 48 % fewer bytes for 4x4."""
+
+    def __init__(self, engine, pool, chunk=512, want=ARRAYS + ("stats",), compact=False, pitch=None, depth=2):
+        self.eng, self.pool, self.chunk, self.want, self.compact = engine, pool, int(chunk), tuple(want), bool(compact)
+        e = engine
+        est = any(k in self.want for k in ("H_ls", "H_mmse", "stats"))
+        wide_ok = (e.nsc == 599 and e.nsym % 2 == 0 and e.ntx in (1, 2, 4, 8) and all(k in self.want for k in ("H_true", "rx", "tx"))
+                   and (not est or "H_ls" in self.want))
+        self.pitch = int(pitch) if pitch is not None else (600 if wide_ok else e.nsc)
+        P, c = self.pitch, self.chunk
+        full = (c, e.nsym, e.nrx, e.ntx, P)
+        rep = (c, e.nsym, e.nrx, P) if compact else full
+        shapes = {"H_true": full, "H_ls": rep, "H_mmse": rep, "rx": (c, e.nsym, e.nrx, P),
+                  "tx": (c, e.nsym, P) if compact else (c, e.nsym, e.ntx, P)}
+        self.layout, off = {}, 0                        # name -> (byte offset, shape, torch dtype)
+        for k in ARRAYS:
+            if k in self.want:
+                self.layout[k] = (off, shapes[k], torch.complex64)
+                off += -(-int(np.prod(shapes[k])) * 8 // 256) * 256
+        if "stats" in self.want:
+            self.layout["stats"] = (off, (c, e.nrx, 2, 3), torch.float64)
+            off += -(-c * e.nrx * 48 // 256) * 256
+        self.slab_bytes = off
+        self.depth = max(2, int(depth))
+        self.dev_slab = [torch.empty((off,), dtype=torch.uint8, device=e.device) for _ in range(self.depth)]
+        self.host_slab = [torch.empty((off,), dtype=torch.uint8, pin_memory=True) for _ in range(self.depth)]
+        self.dev = [self._carve(sl) for sl in self.dev_slab]           # padded tensors (rows of `pitch`)
+        self.host = [self._carve(sl) for sl in self.host_slab]
+        self.ws = [e.workspace(c) for _ in range(self.depth)]
+        self.par_host = [torch.empty((4, c), dtype=torch.float32, pin_memory=True) for _ in range(self.depth)]
+        self.par_dev = [torch.empty((4, c), dtype=torch.float32, device=e.device) for _ in range(self.depth)]
+        self.compute = torch.cuda.Stream(device=e.device)
+        self.copy = torch.cuda.Stream(device=e.device)
+        self.ev_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.ev_copied = [torch.cuda.Event() for _ in range(self.depth)]
+        self.d2h_bytes_per_slot = self.slab_bytes / c                # what crosses the link (padding included)
         self.h2d_bytes_per_slot = 16
+
+    def _carve(self, slab):
+        out = {}
+        for k, (off, shape, dt) in self.layout.items():
+            n = int(np.prod(shape)) * (8 if dt == torch.complex64 else 8)
+            out[k] = slab[off:off + n].view(dt).view(shape)
+        return out
+
+    def _payload(self, arrs, n):
+        """[:n] slots, rows cut to the nsc payload elements."""
+        return {k: (v[:n] if k == "stats" else v[:n][..., :self.eng.nsc]) for k, v in arrs.items()}
 
     def run(self, model_id, doppler_hz, snr_db, pattern_id, slot0=0, seed=42, consume=None):
         """Process len(model_id) slots; `consume(first_slot, n, host_buffers)` is called once each
-        chunk's arrays are complete in pinned memory (buffers are reused two chunks later)."""
+        chunk's arrays are complete in pinned memory (buffers are reused `depth` chunks later)."""
         total = len(model_id)
-        pending = [None, None]
+        D = self.depth
+        pending = [None] * D
         par = np.stack([np.asarray(model_id, np.float32), np.asarray(doppler_hz, np.float32),
                         np.asarray(snr_db, np.float32), np.asarray(pattern_id, np.float32)])
+
+        def retire(i):
+            self.ev_copied[i].synchronize()
+            if consume is not None:
+                consume(*pending[i], self.views(i, pending[i][1]))
+            pending[i] = None
+
         for c, start in enumerate(range(0, total, self.chunk)):
-            i = c & 1
+            i = c % D
             n = min(self.chunk, total - start)
             if pending[i] is not None:                 # buffer i still owned by an earlier chunk
-                self.ev_copied[i].synchronize()
-                if consume is not None:
-                    consume(*pending[i], self.views(i))
+                retire(i)
             self.par_host[i][:, :n] = torch.from_numpy(par[:, start:start + n])
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(self.ev_copied[i])
                 self.par_dev[i].copy_(self.par_host[i], non_blocking=True)
                 p = self.par_dev[i]
-                out = {k: v[:n] for k, v in self.dev[i].items()}
                 ws = {k: v[:n] for k, v in self.ws[i].items()}
                 self.eng.run(n, p[0, :n].to(torch.int32), p[1, :n], p[2, :n], p[3, :n].to(torch.int32), self.pool,
-                             slot0=slot0 + start, seed=seed, want=self.want, out=out, ws=ws, compact=self.compact)
+                             slot0=slot0 + start, seed=seed, want=self.want, out=self._payload(self.dev[i], n), ws=ws,
+                             compact=self.compact)
                 self.ev_done[i].record(self.compute)
             with torch.cuda.stream(self.copy):
                 self.copy.wait_event(self.ev_done[i])
-                for k, v in self.dev[i].items():
-                    self.host[i][k][:n].copy_(v[:n], non_blocking=True)
+                if n == self.chunk:
+                    self.host_slab[i].copy_(self.dev_slab[i], non_blocking=True)       # one cudaMemcpyAsync per chunk
+                else:                                                                  # ragged tail: one per array
+                    for k, v in self.dev[i].items():
+                        self.host[i][k][:n].copy_(v[:n], non_blocking=True)
                 self.ev_copied[i].record(self.copy)
             pending[i] = (slot0 + start, n)
-        for i in sorted(range(2), key=lambda j: pending[j][0] if pending[j] is not None else -1):
-            if pending[i] is not None:
-                self.ev_copied[i].synchronize()
-                if consume is not None:
-                    consume(*pending[i], self.views(i))
+        for i in sorted((j for j in range(D) if pending[j] is not None), key=lambda j: pending[j][0]):
+            retire(i)
         return total
 
-    def views(self, i):
+    def views(self, i, n=None):
         """NumPy views of host buffer i (zero-copy; full reference shapes, stride 0 over tx if compact)."""
-        arrs = {k: v.numpy() for k, v in self.host[i].items()}
+        arrs = {k: v.numpy() for k, v in self._payload(self.host[i], self.chunk if n is None else n).items()}
         return self.eng.expand_compact(arrs) if self.compact else arrs

@@ -25,10 +25,13 @@ def set_seed(seed: int = 42):
 
 
 def load_config(config_path: str = 'configs/experiment_config.yaml') -> Dict[str, Any]:
-    """YAML -> dict (src/utils.py:25-29).  Falls back to the copy shipped with this package when the
-    relative default path does not exist in the working directory."""
+    """YAML -> dict (src/utils.py:25-29).  Only the literal default path falls back to the copy shipped with this
+    package (the reference is run from its own root, where that relative path exists); any other missing path
+    raises FileNotFoundError like the reference's open()."""
     import yaml
-    path = config_path if os.path.exists(config_path) else _DEFAULT_CONFIG
+    path = config_path
+    if not os.path.exists(path) and str(config_path) == 'configs/experiment_config.yaml':
+        path = _DEFAULT_CONFIG
     with open(path, 'r') as fh:
         return yaml.safe_load(fh)
 

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define B2C_ABI_VERSION 2
+#define B2C_ABI_VERSION 3
 #define B2C_MAX_TAPS 16     /* distinct sample delays per TDL profile (EPA 5, EVA 8, ETU 9)  */
 #define B2C_MAX_ANT 8       /* ntx, nrx <= 8                                                  */
 #define B2C_MAX_SYM 16      /* OFDM symbols per slot                                          */
@@ -155,10 +155,11 @@ int b2c_tap_gains(const b2c_geom *g, const b2c_profiles *prof, const b2c_slots *
  *   for callers that expand them as stride-0 views (the host-buffer pipeline: half the PCIe bytes).
  *   H_ls, H_mmse like H_true;  stats [B][nrx][B2C_N_STATGRP][B2C_N_STAT] double
  *   g->pitch = 600 (throughput configuration only: nsc = 599, even nsym, ntx in {1,2,4,8}, Philox draws, H_true + rx +
- *   tx requested and H_ls when estimating -- H_mmse and stats stay optional --, compact = 0; B2C_E_UNSUPPORTED
+ *   tx requested and H_ls when estimating -- H_mmse and stats stay optional --; B2C_E_UNSUPPORTED
  *   otherwise): the last axis of the five arrays
  *   is 600 elements apart in memory (element 599 is padding) and every lane writes 16 aligned bytes per row;
- *   same values as the contiguous layout, bit for bit.                                                    */
+ *   same values as the contiguous layout, bit for bit.  compact = 1 combines with it: each unique value is written
+ *   once (1 945 552 B per 4x4 slot instead of 3 756 928), in padded rows.                                  */
 int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat,
                       const b2c_slots *slots, const b2c_inject *inj, int64_t B,
                       const float *gains, const float *noise_std,
@@ -246,10 +247,12 @@ int b2c_apply_channel(const b2c_geom *g, const b2c_slots *slots, const b2c_injec
 /* a3 standalone.  ChannelModel.generate_time_varying_channel (src/channel_simulator.py:84-127):
  * the full (num_samples, nrx, ntx, max_delay+1) CIR of ONE realisation, sample n at t = n/fs.
  *   jakes_u [npaths][ntx][nrx][2][20] injected, or NULL for Philox (slot = slots->slot0)
+ *   tap_delay_host [ntaps] HOST array of the surviving taps' sample delays, ntaps = prof->ntaps[model_id] as the host
+ *   tables hold it (passed in so that the call reads nothing back from the device and never synchronises)
  *   out [num_samples][nrx][ntx][L] complex, L = max delay + 1 (written in full, zeros included) */
 int b2c_tdl_full(const b2c_geom *g, const b2c_profiles *prof, int32_t model_id, float doppler_hz,
                  float sample_period_s, int64_t num_samples, int32_t L, const int32_t *tap_delay_host,
-                 const float *jakes_u, uint64_t seed, int64_t slot, float *out, void *stream);
+                 int32_t ntaps, const float *jakes_u, uint64_t seed, int64_t slot, float *out, void *stream);
 
 /* ---- "next" rows either side of the path ------------------------------- */
 

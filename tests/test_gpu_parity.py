@@ -492,7 +492,54 @@ def test_compact_layout_and_host_pipeline(engines):
             host = np.concatenate([got[k][f] for f in sorted(got[k])])
             assert host.shape == tuple(full[k].shape)
             assert np.abs(host - full[k].cpu().numpy()).max() < 2e-6, (k, compact)
-        assert hp.d2h_bytes_per_slot == (1945552 + 192 if compact else 3756928 + 192)
+        # what crosses the link: the unique bytes in padded rows (600 / 599) + statistics + 256-byte array alignment
+        unique = (1945552 if compact else 3756928) * 600 / 599 + 192
+        assert unique <= hp.d2h_bytes_per_slot <= unique + 6 * 256 / 16
+        assert hp.pitch == 600
+
+
+@pytest.mark.parametrize("ntx,nrx,model", [(4, 4, 2), (2, 2, 1), (1, 1, 0), (8, 2, 2)])
+def test_compact_padded_layout_matches_full(ntx, nrx, model, engines):
+    """compact = 1 with pitch 600 (the throughput form of the unique-bytes layout: H_ls / H_mmse [B,14,nrx,600],
+    tx [B,14,600], one 16-byte store per lane) holds exactly the values of the full padded layout, inside guards."""
+    import _b2c
+    eng = engines(ntx, nrx)
+    pool = eng.random_pool([0.10, 0.05], seed=4)
+    B = 6
+    pid = np.arange(B, dtype=np.int32) % 2
+    snr = np.linspace(-5, 30, B).astype(np.float32)
+    args = dict(model_id=model, doppler_hz=120.0, snr_db=snr, pattern_id=pid, pool=pool, slot0=7654321, seed=17)
+    full = eng.run(B, pitch=_b2c.WIDE_PITCH, **args)
+    # guarded buffers: [guard | payload | guard] per array, sentinel must survive
+    P, nsym = _b2c.WIDE_PITCH, 14
+    shapes = {"H_true": (B, nsym, nrx, ntx, P), "H_ls": (B, nsym, nrx, P), "H_mmse": (B, nsym, nrx, P),
+              "rx": (B, nsym, nrx, P), "tx": (B, nsym, P)}
+    G, bufs, out = 4096, {}, {}
+    for k, sh in shapes.items():
+        n = int(np.prod(sh))
+        bufs[k] = torch.full((n + 2 * G,), 7.5 + 7.5j, dtype=torch.complex64, device=eng.device)
+        out[k] = bufs[k][G:G + n].view(sh)[..., :599]
+    out["stats"] = torch.empty((B, nrx, 2, 3), dtype=torch.float64, device=eng.device)
+    comp = eng.run(B, out=out, compact=True, **args)
+    torch.cuda.synchronize()
+    for k, sh in shapes.items():
+        assert torch.all(bufs[k][:G] == 7.5 + 7.5j) and torch.all(bufs[k][-G:] == 7.5 + 7.5j), k
+        assert comp[k].stride(-2) == P
+    exp = eng.expand_compact(comp)
+    for k in ("H_true", "rx", "tx", "H_ls", "H_mmse"):
+        assert exp[k].shape == full[k].shape and torch.equal(exp[k], full[k]), k
+    assert torch.equal(comp["stats"], full["stats"])
+    # simulate-only and dataset-mode (no H_mmse, no stats) calls of the same form
+    sim = eng.run(B, want=("H_true", "rx", "tx"), compact=True, pitch=P, **{k: v for k, v in args.items() if k not in ("pool", "pattern_id")})
+    dm = eng.run(B, want=("H_true", "rx", "tx", "H_ls"), compact=True, pitch=P, **args)
+    torch.cuda.synchronize()
+    assert sim["tx"].shape == (B, nsym, 599) and torch.equal(eng.expand_compact(sim)["tx"], full["tx"])
+    assert torch.equal(sim["H_true"], full["H_true"]) and torch.equal(sim["rx"], full["rx"])
+    assert torch.equal(eng.expand_compact(dm)["H_ls"], full["H_ls"]) and torch.equal(dm["rx"], full["rx"])
+    # compact-layout readers (ls_sym_stride = nrx * pitch)
+    x_f, t_f = eng.ml_features(full["rx"], full["H_ls"], full["H_true"], pool, pid, "last", True)
+    x_c, t_c = eng.ml_features(comp["rx"], comp["H_ls"], comp["H_true"], pool, pid, "last", True)
+    assert torch.equal(x_f, x_c) and torch.equal(t_f, t_c)
 
 
 def test_dense_real_map_and_cubic_ls(engines):
