@@ -1,19 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: OFDM slots/s simulated + LS-estimated + MMSE-estimated.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3_4x4_etu]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME] [--layout full|compact]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step is one pass of the hot path (K1a tap gains -> fused slot kernel -> K5 statistics fold)
-over one batch of synthetic slots.  Default workload = BASELINE.json configs[2]: 4x4 ETU, 200 Hz
-Doppler, FFT 1024 / CP 72, 14 symbols, 599 used bins, 10 % pilots, SNR cycling over
-{-5,...,30} dB.  Prints ONE JSON line (see the module docstring of the task contract).
+A step is `launches_per_step` passes of the hot path (K1a tap gains -> fused slot kernel [-> dense Wiener GEMM -> K3]
+-> K5 statistics fold), each over one batch of synthetic slots, into rotating output buffers; launches_per_step is
+sized in the warm-up so that the timed region lasts >= --min-seconds whatever --steps is (a 50 ms burst never
+reaches the board's power-capped steady state).  Default workload = BASELINE.json configs[2]: 4x4 ETU, 200 Hz
+Doppler, FFT 1024 / CP 72, 14 symbols, 599 used bins, 10 % pilots, SNR cycling over {-5,...,30} dB.
+Prints ONE JSON line.
+
+Workloads (BASELINE.json `configs`):
+  c1_siso_epa        config 1   SISO EPA 10 Hz
+  c2_2x2_eva         config 2   2x2 EVA 50 Hz, default (alpha) MMSE
+  c2_2x2_eva_dense   config 2   2x2 EVA 50 Hz, LS + dense Wiener MMSE on the tensor cores (one 838 x 838 W per SNR)
+  c3_4x4_etu         config 3   4x4 ETU 200 Hz (default)
+  c4_sweep           config 4   4x4 EVA 50 Hz, pilot density 1..10 % x 8 SNRs, MSE / NMSE / BER-proxy curves (statistics only)
+  c5_mixed           config 5   4x4 mixed EPA/EVA/ETU x 4 Dopplers x 8 SNRs x 2 densities, dataset arrays + statistics
 """
 
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -29,28 +41,48 @@ for p in (ROOT, PKG):
 
 METRIC = "OFDM slots/sec simulated+LS/MMSE-estimated"
 UNIT = "slots/s"
-WORKLOADS = {   # name: (ntx, nrx, model, doppler_hz, density, description)
-    "c1_siso_epa": (1, 1, "EPA", 10.0, 0.10, "SISO EPA 10 Hz, FFT 1024/CP 72, 10% pilots"),
-    "c2_2x2_eva": (2, 2, "EVA", 50.0, 0.10, "2x2 EVA 50 Hz, FFT 1024/CP 72, 10% pilots"),
-    "c3_4x4_etu": (4, 4, "ETU", 200.0, 0.10, "4x4 ETU 200 Hz, FFT 1024/CP 72, 10% pilots"),
-}
 SNRS = (-5, 0, 5, 10, 15, 20, 25, 30)
+ALL = ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats")
+_SNR_TXT = "SNR cycling over [-5, 0, 5, 10, 15, 20, 25, 30] dB"
+WORKLOADS = {
+    "c1_siso_epa": dict(ntx=1, nrx=1, models=["EPA"], dopplers=[10.0], densities=[0.10], mmse="default", want=ALL,
+                        desc=f"SISO EPA 10 Hz, FFT 1024/CP 72, 10% pilots, {_SNR_TXT}, simulate+LS(linear)+MMSE(default)"),
+    "c2_2x2_eva": dict(ntx=2, nrx=2, models=["EVA"], dopplers=[50.0], densities=[0.10], mmse="default", want=ALL,
+                       desc=f"2x2 EVA 50 Hz, FFT 1024/CP 72, 10% pilots, {_SNR_TXT}, simulate+LS(linear)+MMSE(default)"),
+    "c2_2x2_eva_dense": dict(ntx=2, nrx=2, models=["EVA"], dopplers=[50.0], densities=[0.10], mmse="dense", want=ALL,
+                             desc=f"2x2 EVA 50 Hz, FFT 1024/CP 72, 10% pilots, {_SNR_TXT}, simulate+LS(linear)+MMSE(known-covariance "
+                                  "Wiener filter W = R (R + s2 I)^-1, one 838 x 838 W per SNR)"),
+    "c3_4x4_etu": dict(ntx=4, nrx=4, models=["ETU"], dopplers=[200.0], densities=[0.10], mmse="default", want=ALL,
+                       desc=f"4x4 ETU 200 Hz, FFT 1024/CP 72, 10% pilots, {_SNR_TXT}, simulate+LS(linear)+MMSE(default)"),
+    "c4_sweep": dict(ntx=4, nrx=4, models=["EVA"], dopplers=[50.0], densities=[0.01 * d for d in range(1, 11)], mmse="default",
+                     want=("stats",),
+                     desc="4x4 EVA 50 Hz, pilot density 1..10 % x SNR [-5, 0, 5, 10, 15, 20, 25, 30] dB, simulate+LS(linear)+MMSE(default), "
+                          "per-cell MSE / NMSE / BER-proxy curves (statistics only, no array leaves the SM)"),
+    "c5_mixed": dict(ntx=4, nrx=4, models=["EPA", "EVA", "ETU"], dopplers=[10.0, 50.0, 100.0, 200.0], densities=[0.05, 0.10],
+                     mmse="default", want=("H_true", "rx", "tx", "H_ls", "stats"),
+                     desc="4x4 mixed EPA/EVA/ETU x Doppler [10, 50, 100, 200] Hz x SNR [-5..30] dB x pilot density [5, 10] %, every "
+                          "parameter drawn per slot (Philox stream 3), dataset arrays of generate_sample (H_true, rx, tx, H_ls) + statistics"),
+}
+CPU_WORKLOAD = {"c2_2x2_eva_dense": "c2_2x2_eva", "c4_sweep": "c3_4x4_etu", "c5_mixed": "c3_4x4_etu"}   # cost-equivalent CPU samples
 
 
-def slot_bytes(ntx, nrx, nsym=14, nsc=599, compact=False):
-    """Algorithmic bytes one slot of the fused pipeline writes: H_true + H_ls +
-    H_mmse + rx + tx, complex64.  compact: the tx-replicated arrays (H_ls, H_mmse, tx) counted once."""
-    if compact:
-        return 8 * (nsym * nrx * ntx * nsc + 3 * nsym * nrx * nsc + nsym * nsc)
-    return 8 * (3 * nsym * nrx * ntx * nsc + nsym * nrx * nsc + nsym * ntx * nsc)
+def slot_bytes(ntx, nrx, nsym=14, nsc=599, compact=False, want=ALL):
+    """Algorithmic bytes one slot of the pipeline writes: the requested arrays among H_true, H_ls,
+    H_mmse, rx, tx, complex64.  compact: the tx-replicated arrays (H_ls, H_mmse, tx) counted once."""
+    full, row = nsym * nrx * ntx * nsc, nsym * nrx * nsc
+    rep = row if compact else full
+    n = {"H_true": full, "H_ls": rep, "H_mmse": rep, "rx": row, "tx": nsym * nsc * (1 if compact else ntx)}
+    return 8 * sum(v for k, v in n.items() if k in want)
 
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+            j = json.load(fh)
+        return {"hbm_gbs": float(j["hbm_gbs"]), "bf16_tflops": float(j.get("bf16_tflops", 0) or 0),
+                "bf16_tflops_sustained": float(j.get("bf16_tflops_sustained", 0) or 0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1600.0, "bf16_tflops_sustained": 1350.0, "source": "fallback"}
 
 
 class ClockSampler:
@@ -59,7 +91,7 @@ class ClockSampler:
     fall between mark_begin() (start of warm-up) and stop() (end of the timed region) are kept."""
 
     Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.t0 = index, [], None, None
@@ -94,12 +126,17 @@ class ClockSampler:
         rows = [r for t, r in self.rows if len(r) >= 7 and (self.t0 is None or self.t0 <= t <= t1 + 0.05)]
         if not rows:                        # region shorter than one sampling period: nearest samples
             rows = [r for _, r in self.rows[-3:] if len(r) >= 7]
-        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+
+        def num(s):
+            return s.replace(".", "", 1).isdigit()
+        sm = [float(r[1]) for r in rows if num(r[1])]
+        mx = [float(r[2]) for r in rows if num(r[2])]
+        pw = [float(r[7]) for r in rows if len(r) > 7 and num(r[7])]
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         reasons = [n for j, n in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "window": "warm-up + timed steps"}
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "window": "warm-up + timed steps"}
 
 
 def host_cores():
@@ -109,38 +146,60 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(workload, cores, budget_s=20.0):
-    """Oracle port (cost-faithful profile) on the host cores, bounded sample."""
+def cpu_kind():
     from oracle import cpu_bench
-    # one slot per core per round; rounds sized to the time budget from a 1-round probe
-    slots, secs = cpu_bench.run_sample(workload, cores, 1, faithful=True, seed0=7)
+    return "reference" if cpu_bench.reference_available() else "port"
+
+
+def cpu_sample_text(kind, workload):
+    if kind == "reference":
+        return (f"slots of {workload} through the UNMODIFIED reference staged in oracle/_ref (src/channel_simulator.py "
+                "simulate_transmission + src/baseline_estimators.py LSEstimator('linear').estimate + MMSEEstimator().estimate + "
+                "evaluate_estimator)")
+    return (f"slots of {workload} through the oracle port (oracle/chanest_oracle.py, cost-faithful profile: simulate + LS + MMSE; "
+            "oracle/_ref is not staged on this box)")
+
+
+def cpu_baseline(workload, cores, budget_s=20.0):
+    """The reference's CPU implementation of the path on the host cores, bounded sample."""
+    from oracle import cpu_bench
+    kind = cpu_kind()
+    wl = CPU_WORKLOAD.get(workload, workload)
+    pool = cpu_bench.Pool(cores, kind)
+    slots, secs = pool.step(wl, 1, True, 7)       # one slot per core per round; rounds sized to the budget from this probe
     rounds = max(0, min(3, int(budget_s / max(secs, 1e-3)) - 1))
     for r in range(rounds):
-        s2, t2 = cpu_bench.run_sample(workload, cores, 1, faithful=True, seed0=100 + r)
+        s2, t2 = pool.step(wl, 1, True, 100 + r)
         slots, secs = slots + s2, secs + t2
-    return {"value": slots / secs, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{slots} slots of {workload} (oracle/chanest_oracle.py faithful profile: simulate + LS + MMSE), "
-                      f"{cores} worker processes, BLAS 1 thread each, {secs:.1f} s wall"}
+    pool.close()
+    return {"value": slots / secs, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{slots} {cpu_sample_text(kind, wl)}, {cores} worker processes, BLAS 1 thread each, {secs:.1f} s wall"}
+
+
+def workload_config(args):
+    """`config` of the JSON line: identical in both arms (arm-specific details go under `arm`)."""
+    return {"workload": f"{args.workload}: {WORKLOADS[args.workload]['desc']}"}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot
-    travel to the GPU box) on all host cores, same metric/config as the b200 arm."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref when staged, else the oracle
+    port) on all host cores, same metric / workload as the b200 arm."""
     if rank != 0:
         return
     from oracle import cpu_bench
     cores = host_cores()
-    ntx, nrx, model, fd, dens, desc = WORKLOADS[args.workload]
-    pool = cpu_bench.Pool(cores)
-    # One step = one slot per worker process (the smallest sample that keeps every host core busy), ~2-4 s each.
+    kind = cpu_kind()
+    wl = CPU_WORKLOAD.get(args.workload, args.workload)
+    pool = cpu_bench.Pool(cores, kind)
+    # One step = one slot per worker process (the smallest sample that keeps every host core busy), ~2-7 s each.
     # A step count that would overrun the wall budget is cut short and the line reports the steps actually timed.
     t_start = time.perf_counter()
     for w in range(args.warmup):
-        pool.step(args.workload, 1, True, 10 + w)
+        pool.step(wl, 1, True, 10 + w)
     slots = secs = 0.0
     done = 0
     for k in range(args.steps):
-        s, t = pool.step(args.workload, 1, True, 1000 + k)
+        s, t = pool.step(wl, 1, True, 1000 + k)
         slots, secs, done = slots + s, secs + t, done + 1
         if time.perf_counter() - t_start + 1.5 * t > args.reference_budget:
             break
@@ -148,18 +207,38 @@ def run_reference(args, rank, world):
     truncated = done < args.steps
     args.steps = done
     value = slots / secs
-    sample = (f"each step = {cores} slots of {args.workload} (one per worker process), oracle port of "
-              f"simulate_transmission + LSEstimator('linear') + MMSEEstimator() in its cost-faithful profile")
+    sample = f"each step = {cores} {cpu_sample_text(kind, wl)}, one per worker process"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "slots_per_step": cores, "rng": "numpy Generator",
-                   "note": (f"stopped after {done} timed steps: wall budget {args.reference_budget:.0f} s" if truncated else "all steps timed")},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args),
+        "arm": {"slots_per_step": cores, "rng": "numpy global RandomState (reference) / Generator (port)",
+                "cpu_sample_workload": wl,
+                "note": (f"stopped after {done} timed steps: wall budget {args.reference_budget:.0f} s" if truncated else "all steps timed")},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
+
+
+def d2h_probe(torch, dev, nbytes, seconds=0.25):
+    """Bare pinned device->host copies of one chunk slab (one cudaMemcpyAsync each), back to back: the link's own
+    rate for exactly the transfer size the host pipeline issues.  Returns GB/s."""
+    src = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    dst = [torch.empty((nbytes,), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    st = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        for i in range(2):
+            dst[i].copy_(src, non_blocking=True)
+        st.synchronize()
+        n = max(2, int(seconds * 50e9 / nbytes))
+        t0 = time.perf_counter()
+        for i in range(n):
+            dst[i & 1].copy_(src, non_blocking=True)
+        st.synchronize()
+        dt = time.perf_counter() - t0
+    return n * nbytes / dt / 1e9
 
 
 def run_b200(args, rank, world, local_rank):
@@ -175,165 +254,336 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    from engine import SlotEngine
+    import _b2c
+    from dataset_generator import ChannelEstimationDataset, philox_param_choice, shard_range, sharded_statistics
+    from engine import SlotEngine, WienerBank
     from host_pipeline import HostPipeline, bind_to_gpu_numa_node
 
-    ntx, nrx, model, fd, dens, desc = WORKLOADS[args.workload]
+    W = WORKLOADS[args.workload]
+    ntx, nrx, want, dense = W["ntx"], W["nrx"], tuple(W["want"]), W["mmse"] == "dense"
     cfg = {"ofdm": {"fft_size": 1024, "cp_length": 72, "num_symbols": 14, "useful_subcarriers": 600,
-                    "subcarrier_spacing": 15000}, "mimo": {"num_tx_antennas": ntx, "num_rx_antennas": nrx}}
-    eng = SlotEngine(cfg)
-    pool = eng.random_pool([dens], per_density=1, seed=42)
-    B = args.batch
+                    "subcarrier_spacing": 15000}, "mimo": {"num_tx_antennas": ntx, "num_rx_antennas": nrx},
+           "channel": {"models": W["models"], "doppler_hz": W["dopplers"], "carrier_freq": 2.0e9},
+           "pilots": {"density": W["densities"]}, "simulation": {"snr_range": list(SNRS)}}
+    eng = SlotEngine(cfg, models=tuple(W["models"]))
     dev = eng.device
-    compact = args.layout == "compact"
-    out = eng.alloc_outputs(B, ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), compact=compact, pitch=args.pitch)
-    geom_out = eng._with_pitch(eng.geom, args.pitch)      # rows of the five arrays are args.pitch complex apart
-    ws = eng.workspace(B)
-    model_id = torch.full((B,), eng.models.index(model), dtype=torch.int32, device=dev)
-    doppler = torch.full((B,), fd, dtype=torch.float32, device=dev)
-    pattern = torch.zeros((B,), dtype=torch.int32, device=dev)
-    snr_idx = torch.arange(B, device=dev, dtype=torch.int32) % len(SNRS)
-    snr = torch.tensor(SNRS, dtype=torch.float32, device=dev)[snr_idx.long()]
-    bins = torch.zeros((len(SNRS), 12), dtype=torch.float64, device=dev)
-    per_rank_steps = args.warmup + args.steps
+    ppd = 1 if dense else args.patterns            # one Wiener matrix per (pattern, SNR): the dense workload keeps one pattern
+    t0 = time.perf_counter()
+    pool = eng.random_pool(W["densities"], per_density=ppd, seed=42)
+    pool_build_s = time.perf_counter() - t0
+    B = args.batch
+    stats_only = want == ("stats",)
+    compact = args.layout == "compact" and not stats_only and not dense
+    pitch = None if stats_only else args.pitch
+    NBUF = 1 if stats_only else 2                   # rotating output buffers (each >> the 126 MB L2)
+    outs = [eng.alloc_outputs(B, want, compact=compact, pitch=pitch) for _ in range(NBUF)]
+    wss = [eng.workspace(B) for _ in range(NBUF)]
 
-    import _b2c
-    from _b2c import check, dptr, lib, ref, rows_ptr, stream_ptr, Slots
-    L = lib()
+    # per-slot parameters of one batch (reused by every launch; Philox keys still differ: they follow the global slot index)
+    nm, nd, ns, nden = len(W["models"]), len(W["dopplers"]), len(SNRS), len(W["densities"])
+    idx = np.arange(B)
+    if args.workload == "c5_mixed":
+        mi, di, si, pi = philox_param_choice(args.seed, 0, B, (nm, nd, ns, nden))
+    elif args.workload == "c4_sweep":
+        mi, di, si, pi = np.zeros(B, np.int64), np.zeros(B, np.int64), idx % ns, (idx // ns) % nden
+    else:
+        mi, di, si, pi = np.zeros(B, np.int64), np.zeros(B, np.int64), idx % ns, np.zeros(B, np.int64)
+    pat = (pi * ppd + (idx // (ns * nden)) % ppd).astype(np.int32)
+    snr_host = np.asarray(SNRS, np.float32)[si]
+    model_id = torch.from_numpy(mi.astype(np.int32)).to(dev)
+    doppler = torch.from_numpy(np.asarray(W["dopplers"], np.float32)[di]).to(dev)
+    snr = torch.from_numpy(snr_host).to(dev)
+    pattern = torch.from_numpy(pat).to(dev)
+    nbins = ns * nden if args.workload == "c4_sweep" else ns
+    bin_id = torch.from_numpy((pi * ns + si if args.workload == "c4_sweep" else si).astype(np.int32)).to(dev)
+    bins = torch.zeros((nbins, _b2c.N_BINSTAT), dtype=torch.float64, device=dev)
 
-    # With --overlap, K1a (tap gains) of step i+1 runs on a second stream while the slot kernel of step i
-    # runs on the main stream (double-buffered gains workspace, CUDA-event hand-offs); by default both
-    # are enqueued on the main stream in order.
-    main = torch.cuda.current_stream()
-    aux = torch.cuda.Stream(device=dev) if args.overlap else main
-    wss = [ws, eng.workspace(B)] if args.overlap else [ws, ws]
-    ev_gains = [torch.cuda.Event() for _ in range(2)]
-    ev_slot = [torch.cuda.Event() for _ in range(2)]
+    bank = None
+    if dense:      # known covariance of the LS pilot estimates: exponential time / frequency correlation model
+        pidx = pool.pilot_indices[0]
+        ps, pk = pidx // eng.nsc, pidx % eng.nsc
+        R = 0.4 * np.exp(-np.abs(ps[:, None] - ps[None, :]) / 20.0 - np.abs(pk[:, None] - pk[None, :]) / 60.0) \
+            * np.exp(1j * 2 * np.pi * (pk[:, None] - pk[None, :]) * 3 / 1024)
+        bank = WienerBank(eng, pool, {0: R}, SNRS)
 
-    def slots_of(i):
-        slot0 = (rank * per_rank_steps + i) * B
-        return Slots(slot0, args.seed, model_id.data_ptr(), doppler.data_ptr(), snr.data_ptr(), pattern.data_ptr())
+    launches = [0]
 
-    def gains(i):
-        """K1a of step i into workspace i & 1 (on the aux stream)."""
-        w = wss[i & 1]
-        with torch.cuda.stream(aux):
-            aux.wait_event(ev_slot[i & 1])          # the slot kernel that last read this workspace
-            check(L.b2c_tap_gains(ref(eng.geom), ref(eng.prof), ref(slots_of(i)), None, B, dptr(w["gains"], "c64"),
-                                  dptr(w["noise_std"], "f32"), stream_ptr()))
-            ev_gains[i & 1].record(aux)
-
-    def step(i, ev=None, last=False):
-        """One pass: slots [slot0, slot0 + B) of this rank's range."""
-        w = wss[i & 1]
-        main.wait_event(ev_gains[i & 1])
-        if ev is not None:
-            ev[0].record()
-        P = args.pitch
-        check(L.b2c_slot_pipeline(ref(geom_out), ref(eng.prof), ref(pool.struct), ref(slots_of(i)), None, B,
-                                  dptr(w["gains"], "c64"), dptr(w["noise_std"], "f32"), rows_ptr(out["H_true"], P),
-                                  rows_ptr(out["rx"], P), rows_ptr(out["tx"], P), rows_ptr(out["H_ls"], P),
-                                  rows_ptr(out["H_mmse"], P), dptr(out["stats"], "f64"), int(compact), stream_ptr()))
-        if ev is not None:
-            ev[1].record()
-        ev_slot[i & 1].record(main)
-        if not last:
-            gains(i + 1)                            # overlaps the slot kernel just enqueued
-        check(L.b2c_stats_bins(ref(eng.geom), dptr(out["stats"], "f64"), dptr(snr_idx, "i32"), B, len(SNRS),
-                               dptr(bins, "f64"), stream_ptr()))
+    def one_pass(gslot, buf):
+        """One batch: global slots [gslot, gslot + B) of this rank through the engine's own launcher."""
+        if dense:
+            eng.run(B, model_id, doppler, snr_host, pat, pool, slot0=gslot, seed=args.seed, out=outs[buf], ws=wss[buf],
+                    mmse="dense", wiener=bank)
+            launches[0] += 3 + len(SNRS)             # K1a, slot kernel, one GEMM per SNR group, K3
+        else:
+            eng.run(B, model_id, doppler, snr, pattern, pool, slot0=gslot, seed=args.seed, out=outs[buf], ws=wss[buf],
+                    compact=compact)
+            launches[0] += 2
+        eng.stats_bins(outs[buf]["stats"], bin_id, nbins, bins, snr_db=snr)
+        launches[0] += 1
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- size the step: launches_per_step such that the timed region lasts >= --min-seconds ---------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    gains(0)
-    step(0)                                # first launch (module load) outside the sampled window
+    one_pass(0, 0)                                   # first launch (module load) outside the sampled window
     barrier()
     sampler.mark_begin()
-    for i in range(1, args.warmup):
-        step(i)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for i in range(3):
+        one_pass((1 + i) * B, i % NBUF)
+    ev[1].record()
     barrier()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    pass_ms = ev[0].elapsed_time(ev[1]) / 3
+    lps = args.launches_per_step or max(1, math.ceil(args.min_seconds * 1e3 / (pass_ms * args.steps)))
+    if world > 1:                                    # every rank runs the same number of launches
+        t = torch.tensor([lps], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lps = int(t.item())
+    per_rank_passes = (args.warmup + args.steps) * lps + 32
+    base = rank * per_rank_passes * B                # this rank's block of global slot indices
+
+    n = 4
+    for w in range(args.warmup):
+        for j in range(lps):
+            one_pass(base + n * B, n % NBUF)
+            n += 1
+    barrier()
+    bins.zero_()
+    launches[0] = 0
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_beg.record()
-    for i in range(args.steps):
-        step(args.warmup + i, kev[i], last=(i == args.steps - 1))
+    for s in range(args.steps):
+        for j in range(lps):
+            one_pass(base + n * B, n % NBUF)
+            n += 1
     if world > 1:
-        dist.all_reduce(bins)            # the path's only collective: per-SNR statistics over NVLink
+        dist.all_reduce(bins)            # the path's only collective: per-bin statistics over NVLink
     t_end.record()
     barrier()
     clocks = sampler.stop()
     ms = t_beg.elapsed_time(t_end)
-    kern_ms = [a.elapsed_time(b) for a, b in kev]
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * args.steps * B / (ms * 1e-3)
+    slots_total = world * args.steps * lps * B
+    value = slots_total / (ms * 1e-3)
+    timed_launches = launches[0]
+    nb = bins.cpu().numpy()
 
-    # ---- end-to-end through the host-buffer API: params from pinned memory, all arrays back to pinned memory
-    e2e_B = min(args.e2e_batch, B)
-    numa = None if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)     # before the pinned buffers exist
-    hp = HostPipeline(eng, pool, chunk=min(args.e2e_chunk, e2e_B), compact=not args.e2e_full)
-    par = (np.full(e2e_B, eng.models.index(model)), np.full(e2e_B, fd), np.asarray(SNRS, np.float32)[np.arange(e2e_B) % 8],
-           np.zeros(e2e_B))
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for i in range(2):
-        hp.run(*par, slot0=(rank * 100 + i) * e2e_B, seed=args.seed)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        hp.run(*par, slot0=(rank * 100 + 2 + i) * e2e_B, seed=args.seed)
+    # ---- dominant kernel alone, CUDA events on its stream, over rotating buffers (right after the timed region) --------
+    L = _b2c.lib()
+    from _b2c import Slots, check, dptr, ref, rows_ptr, stream_ptr
+    P = _b2c.row_pitch(outs[0]["H_true"]) if "H_true" in outs[0] else eng.nsc
+    g_out = eng._with_pitch(eng.geom, P)
+    kev = []
+    for i in range(14):
+        o, w = outs[i % NBUF], wss[i % NBUF]
+        sl = Slots(base + (n + i) * B, args.seed, model_id.data_ptr(), doppler.data_ptr(), snr.data_ptr(), pattern.data_ptr())
+        check(L.b2c_tap_gains(ref(eng.geom), ref(eng.prof), ref(sl), None, B, dptr(w["gains"], "c64"), dptr(w["noise_std"], "f32"), stream_ptr()))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(L.b2c_slot_pipeline(ref(g_out), ref(eng.prof), ref(pool.struct), ref(sl), None, B, dptr(w["gains"], "c64"),
+                                  dptr(w["noise_std"], "f32"), rows_ptr(o.get("H_true"), P, True), rows_ptr(o.get("rx"), P, True),
+                                  rows_ptr(o.get("tx"), P, True), rows_ptr(o.get("H_ls"), P, True),
+                                  None if dense else rows_ptr(o.get("H_mmse"), P, True), dptr(o["stats"], "f64"),
+                                  int(compact), None, stream_ptr()))
+        b.record()
+        if i >= 2:
+            kev.append((a, b))
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    slot_want = tuple(k for k in want if not (dense and k == "H_mmse"))
+    alg = slot_bytes(ntx, nrx, compact=compact, want=slot_want) * B
+
+    tensor = None
+    if dense:     # the GEMM of one SNR group, alone: useful flops = 8 np^2 per column; issued = 3x (3xTF32)
+        npil = int(pool.npilots_host[0])
+        ncols = (B // len(SNRS)) * nrx
+        hp, hm = wss[0]["hp"], wss[0]["hm"]
+        Wp = bank.prepared[(0, float(SNRS[0]))]
+        evs = []
+        for i in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            check(L.b2c_dense_apply_prepared(dptr(Wp.buf, "u8"), Wp.m, Wp.k, 1, dptr(hp, "c64"), dptr(hm, "c64"), ncols, hp.shape[1],
+                                             hp.shape[1], stream_ptr()))
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        g_ms = statistics.mean(a.elapsed_time(b) for a, b in evs[2:])
+        useful = 8.0 * npil * npil * ncols / (g_ms * 1e-3) / 1e12
+        tensor = {"gemm_ms": g_ms, "columns": ncols, "np": npil, "useful_tflops": useful, "issued_tf32_tflops": 3 * useful}
+
+    # ---- the same metric through the public API (dataset_generator.sharded_statistics), device resident ----------------
+    value_api = None
+    if not args.no_api and not dense:
+        ds = ChannelEstimationDataset(cfg, rng='philox', seed=args.seed, patterns_per_density=ppd)
+        ds._pool = pool
+        api_slots = max(B, min(slots_total // world, 40 * B))
+        arrays = tuple(k for k in want if k != "stats")
+        sharded_statistics(cfg, 2 * B, 0, 1, batch=B, seed=args.seed, want_arrays=arrays, dataset=ds)      # warm-up
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        api_bins = sharded_statistics(cfg, api_slots * world, rank, world, batch=B, seed=args.seed, want_arrays=arrays, dataset=ds)
+        if world > 1:
+            dist.all_reduce(api_bins)
+        b.record()
+        barrier()
+        api_ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([api_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            api_ms = float(t.item())
+        value_api = {"value": api_slots * world / (api_ms * 1e-3), "unit": UNIT, "slots": api_slots * world,
+                     "call": "dataset_generator.sharded_statistics(config, total_slots, rank, world_size, batch, want_arrays=...) "
+                             "(host loop: per-batch parameter draw + upload, engine launches, K5 fold; every slot's parameters "
+                             "drawn from Philox stream 3)"}
+
+    # ---- fixed-range statistics checksum: global slots 0..65535 whatever N is (outside the timed region) --------------
+    CHK = 65536
+    lo, hi = shard_range(CHK, rank, world)
+    qsum = torch.zeros((nrx * 6,), dtype=torch.int64, device=dev)
+    pos = lo
+    while pos < hi:
+        m = min(B, hi - pos)
+        j = np.arange(pos, pos + m)
+        o = eng.run(m, (j % nm).astype(np.int32), float(W["dopplers"][0]), np.asarray(SNRS, np.float32)[j % ns],
+                    ((j // ns) % nden * ppd).astype(np.int32), pool, slot0=pos, seed=args.seed, want=("stats",))
+        # per-slot sums are a pure function of the global slot index; rounded to 2^-20 they add exactly in int64, so the
+        # checksum is bit-identical however the range is split over ranks
+        qsum += torch.round(o["stats"].reshape(m, -1) * float(2 ** 20)).to(torch.int64).sum(dim=0)
+        pos += m
     if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * e2e_steps * e2e_B / e2e_s
+        dist.all_reduce(qsum)
+    chk = qsum.cpu().numpy()
+    checksum = {"slots": CHK, "range": "global slots [0, 65536), seed %d" % args.seed,
+                "sha1": hashlib.sha1(chk.tobytes()).hexdigest(), "int64_sums_first4": [int(v) for v in chk[:4]],
+                "how": "per-slot statistics (sum|H-H_ls|^2, sum|H-H_mmse|^2, sum|H|^2 per rx and group) rounded to 2^-20 and "
+                       "summed exactly in int64 over the shards, then all-reduced: equal across N iff every rank computes "
+                       "the same slots"}
+
+    # ---- end-to-end through the host-buffer API: params from pinned memory, arrays back to pinned memory ---------------
+    e2e = None
+    if not stats_only and not dense:
+        e2e_B = min(args.e2e_batch, B)
+        numa = None if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)     # before the pinned buffers exist
+        hp_ = HostPipeline(eng, pool, chunk=min(args.e2e_chunk, e2e_B), want=want, compact=not args.e2e_full, depth=args.e2e_depth)
+        par = (mi[:e2e_B], np.asarray(W["dopplers"], np.float32)[di[:e2e_B]], snr_host[:e2e_B], pat[:e2e_B])
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for i in range(2):
+            hp_.run(*par, slot0=(rank * 100 + i) * e2e_B, seed=args.seed)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            hp_.run(*par, slot0=(rank * 100 + 2 + i) * e2e_B, seed=args.seed)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        link = d2h_probe(torch, dev, hp_.slab_bytes)           # all ranks at once: the link under the same contention
+        barrier()
+        link_min = link_sum = link
+        if world > 1:
+            t = torch.tensor([e2e_s, -link], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s, link_min = float(t[0].item()), -float(t[1].item())
+            t = torch.tensor([link], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            link_sum = float(t.item())
+        e2e_value = world * e2e_steps * e2e_B / e2e_s
+        gbs = e2e_value * hp_.d2h_bytes_per_slot / 1e9
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp_.h2d_bytes_per_slot * e2e_B,
+               "d2h_bytes_per_step": hp_.d2h_bytes_per_slot * e2e_B, "slots_per_step": e2e_B, "steps": e2e_steps,
+               "numa_node_rank0": numa,
+               "roofline": {"bound": "pcie d2h", "achieved": gbs, "peak": link_sum, "unit": "GB/s", "frac": gbs / link_sum,
+                            "peak_source": f"bare pinned cudaMemcpyAsync D2H of one {hp_.slab_bytes / 1e6:.0f} MB chunk slab, back to back, "
+                                           f"measured in this run on all {world} rank(s) at once (sum over ranks; slowest rank {link_min:.1f} GB/s)"},
+               "note": ("HostPipeline: params from pinned host memory, arrays + stats back to pinned host memory, one cudaMemcpyAsync per "
+                        f"{hp_.chunk}-slot chunk, {hp_.depth} chunks in flight (PCIe-bound); "
+                        + ("full replicated arrays cross PCIe" if args.e2e_full else
+                           "tx-replicated arrays (H_ls, H_mmse, tx) are written and cross PCIe once and are exposed as full-shape NumPy broadcast views"))}
 
     if rank == 0:
-        peak, peak_kind = measured_peaks()
-        k_ms = statistics.mean(kern_ms)
-        alg = slot_bytes(ntx, nrx, compact=compact) * B
-        achieved = alg / (k_ms * 1e-3) / 1e9
-        traffic = None
+        peaks = measured_peaks()
+        peak = peaks["hbm_gbs"]
+        achieved = alg / (k_ms * 1e-3) / 1e9 if alg else 0.0
+        traffic, traffic_note = None, "not captured for this workload / layout"
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 tj = json.load(fh)
-            per_slot = tj.get(args.workload, {}).get("dram_bytes_per_slot")
-            traffic = per_slot * B if per_slot else None
-        nb = bins.cpu().numpy()
+            ent = tj.get(f"{args.workload}:{args.layout}" if args.layout != "full" else args.workload, {})
+            if ent.get("dram_bytes_per_slot"):
+                traffic = ent["dram_bytes_per_slot"] * B
+                traffic_note = (f"static: dram__bytes_read + dram__bytes_write per slot from the ncu capture {ent.get('capture', '?')} "
+                                f"(profiles/), x {B} slots; not re-measured in this run")
+        kname = "slot_kernel<%d, ..., 599, FAST, pitch %s%s%s>" % (ntx, P, ", compact" if compact else "",
+                                                                   ", store-free (statistics only)" if stats_only else "")
+        share = k_ms * lps * args.steps / ms
+        if stats_only:
+            roof = {"bound": "issue", "kernel": kname, "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                    "note": "statistics-only sweep: the kernel writes 192 B per slot; it is bound by instruction issue / the FMA and LSU "
+                            "pipes (see profiles/), not by a memory roofline", "kernel_ms": k_ms, "kernel_share_of_step": share}
+        else:
+            roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "traffic_source": traffic_note, "peak_source": peaks["source"],
+                    "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
+                    "kernel_ms_source": "CUDA events on the launching stream around the kernel alone, mean of 12 launches over rotating "
+                                        "buffers right after the timed region",
+                    "kernel_share_of_step": share}
+        if tensor is not None:
+            tf32_peak = peaks["bf16_tflops"] / 2 if peaks["bf16_tflops"] else None
+            tensor.update({"bound": "tensor", "kernel": "dense_tc_ws_kernel<false> (tcgen05.mma kind::tf32, 3xTF32 split)",
+                           "achieved": tensor["issued_tf32_tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+                           "frac": tensor["issued_tf32_tflops"] / tf32_peak if tf32_peak else None,
+                           "peak_source": "measured bf16 dense burst peak / 2 (kind::tf32 issues at half the bf16 rate); "
+                                          "MEASURED_PEAKS.json holds no TF32 figure",
+                           "gemm_share_of_step": tensor["gemm_ms"] * len(SNRS) * lps * args.steps / ms})
+            roof["tensor"] = tensor
+        per_snr = {}
+        for j, s in enumerate(SNRS):
+            rows = nb[j::ns] if args.workload == "c4_sweep" else nb[j:j + 1]
+            c = max(rows[:, 0].sum(), 1)
+            per_snr[str(s)] = [float(10 * np.log10(rows[:, 3].sum() / c + 1e-12)), float(10 * np.log10(rows[:, 4].sum() / c + 1e-12))]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}, SNR cycling over {list(SNRS)} dB, simulate+LS(linear)+MMSE(default)",
-                       "slots_per_step": B, "slots_total": world * args.steps * B, "rng": "philox4x32-10 keyed by global slot index",
-                       "pilot_patterns": "1 fixed scattered pattern (838 pilots)", "parallelism": f"dp{world} (slots sharded, NCCL all-reduce of per-SNR stats)",
-                       "l2_policy": f"outputs per step = {alg / 1e9:.1f} GB >> 126 MB L2; no flush needed",
-                       "layout": args.layout + (" (H_ls, H_mmse, tx written once; stride-0 views over tx)" if compact else " (reference shapes, tx-replicated arrays written ntx times)"),
-                       "hbm_layout": (f"rows of 599 complex64 at pitch {args.pitch}" + (" (one padding element per row: 16-byte stores; "
-                                      "algorithmic bytes count 599)" if args.pitch != 599 else " (contiguous)"))},
-            "roofline": {"bound": "hbm", "kernel": (f"slot_kernel<{ntx}, ..., 599, FAST, pitch {args.pitch}> (16-byte stores)" if args.pitch != 599 else f"slot_kernel<{ntx}, ..., 599, FAST> (8-byte stores)"), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                         "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / ms},
+            "config": workload_config(args),
+            "arm": {"slots_per_launch": B, "launches_per_step": lps, "slots_per_step": B * lps, "slots_total": slots_total,
+                    "timed_seconds": ms * 1e-3, "rng": "philox4x32-10 keyed by global slot index",
+                    "pilot_patterns": f"pool of {len(pool)} scattered patterns ({ppd} per density, RandomState(42)) rotated over the slots, "
+                                      f"up to {pool.np_max} pilots; plans built in {pool_build_s:.1f} s",
+                    "parallelism": f"dp{world} (slots sharded, NCCL all-reduce of per-bin stats)",
+                    "l2_policy": (f"outputs per launch = {alg / 1e9:.1f} GB >> 126 MB L2, {NBUF} rotating buffers; no flush needed" if alg else
+                                  "no output arrays; tables (plans, twiddles) are meant to stay L2-resident"),
+                    "layout": args.layout + (" (H_ls, H_mmse, tx written once; stride-0 views over tx)" if compact else
+                                             " (reference shapes, tx-replicated arrays written ntx times)"),
+                    "hbm_layout": (f"rows of 599 complex64 at pitch {P}" + (" (one padding element per row: 16-byte stores; "
+                                   "algorithmic bytes count 599)" if P != 599 else " (contiguous)"))},
+            "roofline": roof,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes_per_slot * e2e_B,
-                    "d2h_bytes_per_step": hp.d2h_bytes_per_slot * e2e_B, "slots_per_step": e2e_B, "steps": e2e_steps,
-                    "numa_node_rank0": numa,
-                    "note": ("HostPipeline: params from pinned host memory, all five arrays + stats back to pinned host memory (PCIe-bound); "
-                             + ("full replicated arrays cross PCIe" if args.e2e_full else
-                                "tx-replicated arrays (H_ls, H_mmse, tx) cross PCIe once and are exposed as full-shape NumPy broadcast views"))},
-            "gpu_launches": 3 * args.steps,
+            "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                "note": "no host-buffer leg for this workload (statistics-only sweep / dense pipeline)"},
+            "value_api": value_api,
+            "stats_checksum": checksum,
+            "gpu_launches": timed_launches,
             "clocks": clocks,
-            "per_snr_nmse_db": {str(s): [float(10 * np.log10(nb[j, 3] / max(nb[j, 0], 1) + 1e-12)),
-                                         float(10 * np.log10(nb[j, 4] / max(nb[j, 0], 1) + 1e-12))] for j, s in enumerate(SNRS)},
+            "per_snr_nmse_db": per_snr,
         }
+        if args.workload == "c4_sweep":
+            def cell(d, s, c):
+                return float(nb[d * ns + s, c] / max(nb[d * ns + s, 0], 1))
+            line["curves"] = {"density_pct": [round(100 * d) for d in W["densities"]], "snr_db": list(SNRS),
+                              "nmse00_ls_db": [[float(10 * np.log10(cell(d, s, 8) + 1e-12)) for s in range(ns)] for d in range(nden)],
+                              "ber_proxy_ls": [[cell(d, s, 12) for s in range(ns)] for d in range(nden)],
+                              "ber_proxy_mmse": [[cell(d, s, 13) for s in range(ns)] for d in range(nden)]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -342,34 +592,37 @@ def run_b200(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 150; 6 for --impl reference)")
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 50; 6 for --impl reference)")
     ap.add_argument("--warmup", type=int, default=None, help="warm-up steps (default 3; 1 for --impl reference)")
+    ap.add_argument("--min-seconds", type=float, default=0.6,
+                    help="lower bound of the timed region: launches per step are sized in the warm-up to reach it")
+    ap.add_argument("--launches-per-step", type=int, default=0, help="fix the launches per step instead of sizing them")
     ap.add_argument("--reference-budget", type=float, default=240.0,
                     help="--impl reference: wall-clock budget in seconds; the step loop stops early rather than overrun it")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_4x4_etu", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=4096, help="slots per step per GPU")
+    ap.add_argument("--batch", type=int, default=4096, help="slots per launch per GPU")
     ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--patterns", type=int, default=64, help="pilot patterns per density in the pool (the reference draws one per sample)")
     ap.add_argument("--pitch", type=int, default=600, choices=[599, 600],
                     help="row pitch of the output arrays in HBM: 600 = padded rows / 16-byte stores (default), 599 = contiguous")
     ap.add_argument("--layout", default="full", choices=["full", "compact"],
                     help="full: the five arrays in the reference's shapes; compact: each unique value written once")
     ap.add_argument("--e2e-batch", type=int, default=2048)
-    ap.add_argument("--e2e-chunk", type=int, default=256)
+    ap.add_argument("--e2e-chunk", type=int, default=128)
+    ap.add_argument("--e2e-depth", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-full", action="store_true", help="copy the tx-replicated arrays in full instead of once")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA node for the e2e leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap", action="store_true",
-                    help="run K1a of step i+1 on a second stream under the slot kernel of step i (measured: no gain, "
-                         "the slot kernel slows down by the same amount; default off)")
+    ap.add_argument("--no-api", action="store_true", help="skip the value_api leg (sharded_statistics)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.steps is None:
-        args.steps = 150 if args.impl == "b200" else 6
+        args.steps = 50 if args.impl == "b200" else 6
     if args.warmup is None:
         args.warmup = 3 if args.impl == "b200" else 1
     if args.warmup < 3 and args.impl == "b200":

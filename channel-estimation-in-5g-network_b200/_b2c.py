@@ -11,7 +11,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2c.so")
 
-MAX_TAPS, MAX_ANT, MAX_SYM, N_OSC, N_STAT, N_BINSTAT = 16, 8, 16, 20, 3, 12
+MAX_TAPS, MAX_ANT, MAX_SYM, N_OSC, N_STAT, N_BINSTAT = 16, 8, 16, 20, 3, 14
 ABI_VERSION = 3
 WIDE_PITCH = 600      # padded row pitch b2c_slot_pipeline accepts in its throughput configuration
 EXPORTS = ["b2c_last_error_string", "b2c_abi_version", "b2c_tap_gains", "b2c_slot_pipeline",
@@ -48,6 +48,10 @@ class Slots(C.Structure):
                 ("doppler_hz", C.c_void_p), ("snr_db", C.c_void_p), ("pattern_id", C.c_void_p)]
 
 
+class PilotIO(C.Structure):
+    _fields_ = [("hp", C.c_void_p), ("col", C.c_void_p), ("ld", C.c_int64)]
+
+
 class Inject(C.Structure):
     _fields_ = [("jakes_u", C.c_void_p), ("p_max", C.c_int32), ("sym_turns", C.c_void_p),
                 ("noise", C.c_void_p)]
@@ -69,12 +73,12 @@ def lib():
         P, I64, I32, F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
         sig = {
             "b2c_tap_gains": [P, P, P, P, I64, P, P, P],
-            "b2c_slot_pipeline": [P, P, P, P, P, I64, P, P, P, P, P, P, P, P, I32, P],
-            "b2c_ls_interp": [P, P, P, P, I64, P, P, I64, P, I32, P, P, P, P, P, P],
+            "b2c_slot_pipeline": [P, P, P, P, P, I64, P, P, P, P, P, P, P, P, I32, P, P],
+            "b2c_ls_interp": [P, P, P, P, I64, P, P, I64, P, I32, P, P, P, P, P, P, I64, P],
             "b2c_pilot_vectors": [P, P, I64, I32, F, I32, P, P],
             "b2c_mmse_dense": [P, I32, P, P, I64, I64, P],
             "b2c_dense_real_apply": [P, I32, I32, P, P, I64, I64, I64, P],
-            "b2c_stats_bins": [P, P, P, I64, I32, P, P],
+            "b2c_stats_bins": [P, P, P, P, I64, I32, P, P],
             "b2c_ofdm_modulate": [P, P, P, I64, P],
             "b2c_ofdm_demodulate": [P, P, P, I64, P],
             "b2c_apply_channel": [P, P, P, I64, P, P, P, P, P],

@@ -11,6 +11,7 @@ batch is done on the GPU (b2c_ls_interp / b2c_slot_pipeline); this module only b
 from __future__ import annotations
 
 import hashlib
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -189,3 +190,112 @@ def cached_plan(pilot_indices, nsym, nsc, method="linear", cache_size=256):
     while len(_PLAN_CACHE) > cache_size:
         _PLAN_CACHE.popitem(last=False)
     return plan
+
+
+# ---- pools of plans: built in parallel, cached on disk -------------------------------------------------------------
+def _plan_cache_dir():
+    d = os.environ.get("B2C_PLAN_CACHE", os.path.join(os.path.expanduser("~"), ".cache", "b2c_plans"))
+    if d in ("", "0", "off"):
+        return None
+    try:
+        os.makedirs(d, exist_ok=True)
+        return d
+    except OSError:
+        return None
+
+
+def _plan_key(idx, nsym, nsc, method):
+    return f"{hashlib.sha1(idx.tobytes()).hexdigest()}_{nsym}x{nsc}_{method}"
+
+
+def _build_plans(job):
+    """Worker of plans_for (also run in-process): [(pilot index array)] -> [plan]."""
+    idx_list, nsym, nsc, method = job
+    return [interpolation_plan(np.unravel_index(i, (nsym, nsc)), nsym, nsc, method) for i in idx_list]
+
+
+def _build_plans_subprocess(idx_list, nsym, nsc, method, workers):
+    """Fan the patterns out over `workers` fresh interpreters running this file as a script (no fork of a process
+    that holds a CUDA context, no re-import of the caller's __main__): job and result travel as .npz / .npy files."""
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory(prefix="b2c_plans_") as tmp:
+        procs = []
+        for w in range(workers):
+            mine = idx_list[w::workers]
+            job, res = os.path.join(tmp, f"job{w}.npz"), os.path.join(tmp, f"res{w}.npy")
+            np.savez(job, nsym=nsym, nsc=nsc, method=method, **{f"p{j}": a for j, a in enumerate(mine)})
+            procs.append((len(mine), res, subprocess.Popen([sys.executable, os.path.abspath(__file__), "--build-plans", job, res])))
+        out = [None] * len(idx_list)
+        for w, (n, res, pr) in enumerate(procs):
+            if pr.wait() != 0:
+                raise RuntimeError(f"plan worker {w} failed (exit {pr.returncode})")
+            plans = np.load(res)
+            for j in range(n):
+                out[w + j * workers] = plans[j]
+    return out
+
+
+def plans_for(pilot_index_list, nsym, nsc, method="linear", workers=None):
+    """Plans of a whole pattern pool.  The reference draws a fresh pilot pattern per sample
+    (src/channel_simulator.py:391); a realistic pool therefore holds hundreds of patterns and a Qhull
+    triangulation + point location per pattern (~20-90 ms) adds up: plans missing from the in-memory and on-disk
+    caches (B2C_PLAN_CACHE, default ~/.cache/b2c_plans, keyed by the pilot set's SHA-1) are built by a pool of
+    worker interpreters (fresh processes, not forks: the parent usually holds a CUDA context)."""
+    idxs = [np.ascontiguousarray(np.asarray(p, dtype=np.int64)) for p in pilot_index_list]
+    out, todo = [None] * len(idxs), []
+    cdir = _plan_cache_dir()
+    for n, idx in enumerate(idxs):
+        key = (hashlib.sha1(idx.tobytes()).hexdigest(), nsym, nsc, method)
+        hit = _PLAN_CACHE.get(key)
+        if hit is None and cdir is not None:
+            path = os.path.join(cdir, _plan_key(idx, nsym, nsc, method) + ".npy")
+            if os.path.exists(path):
+                try:
+                    hit = np.load(path)
+                    if hit.dtype != PLAN_DTYPE or hit.shape != (nsym * nsc,):
+                        hit = None
+                except Exception:
+                    hit = None
+        if hit is None:
+            todo.append(n)
+        else:
+            out[n] = hit
+    if todo:
+        if workers is None:
+            try:
+                workers = len(os.sched_getaffinity(0))
+            except Exception:
+                workers = os.cpu_count() or 1
+        workers = max(1, min(int(workers), 32, len(todo) // 8))
+        if workers <= 1:
+            built = _build_plans(([idxs[n] for n in todo], nsym, nsc, method))
+        else:
+            built = _build_plans_subprocess([idxs[n] for n in todo], nsym, nsc, method, workers)
+        for n, plan in zip(todo, built):
+            out[n] = plan
+            if cdir is not None:
+                try:
+                    tmp = os.path.join(cdir, f".{os.getpid()}_{n}.npy")
+                    np.save(tmp, plan)
+                    os.replace(tmp, os.path.join(cdir, _plan_key(idxs[n], nsym, nsc, method) + ".npy"))
+                except OSError:
+                    pass
+    for idx, plan in zip(idxs, out):     # keep the small pools of the drop-in shims hot in memory
+        if len(idxs) <= 256:
+            _PLAN_CACHE[(hashlib.sha1(idx.tobytes()).hexdigest(), nsym, nsc, method)] = plan
+    while len(_PLAN_CACHE) > 256:
+        _PLAN_CACHE.popitem(last=False)
+    return out
+
+
+if __name__ == "__main__":      # plan worker of _build_plans_subprocess
+    import sys
+    if len(sys.argv) == 4 and sys.argv[1] == "--build-plans":
+        with np.load(sys.argv[2]) as z:
+            n = len([k for k in z.files if k.startswith("p")])
+            plans = _build_plans(([z[f"p{j}"] for j in range(n)], int(z["nsym"]), int(z["nsc"]), str(z["method"])))
+        np.save(sys.argv[3], np.stack(plans) if plans else np.zeros((0,), PLAN_DTYPE))
+    else:
+        sys.exit("usage: _tables.py --build-plans job.npz result.npy")

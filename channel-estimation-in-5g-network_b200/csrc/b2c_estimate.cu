@@ -16,7 +16,14 @@ struct LsArgs {
   int mmse_mode;
   float2 *H_ls, *H_mmse, *hp_out;
   double *stats;
+  const int32_t *hp_col;   // row of (slot b, rx 0) in hp_in (NULL: b * nrx)
+  int64_t hp_ld;           // row stride of hp_in
 };
+
+// mmse_mode 2 (hp_in = Wiener-filtered pilot estimates): the interpolated grid IS the MMSE estimate
+__device__ __forceinline__ const float2 *hp_in_row(const LsArgs &a, int64_t b, int rx) {
+  return a.hp_in + ((a.hp_col ? (int64_t)a.hp_col[b] : b * a.g.nrx) + rx) * a.hp_ld;
+}
 
 // One CTA per (slot, rx antenna).  The reference's rx_4d is rx replicated over tx
 // (src/dataset_generator.py:63-64), so the LS/MMSE grids are computed once per (slot, rx) and
@@ -36,11 +43,13 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
   const int *pre = a.pat.pilot_re + (int64_t)pid * a.pat.np_max;
 
   // h_p = y_p / (x_p + 1e-12), row-major pilot order (src/baseline_estimators.py:109-110)
+  const float2 *const hp_row = a.hp_in ? hp_in_row(a, b, rx) : nullptr;
+  const bool m2 = a.mmse_mode == 2;
   float psum = 0.f;
   for (int j = threadIdx.x; j < np; j += EST_THREADS) {
     float2 h;
     if (a.hp_in) {
-      h = __ldg(a.hp_in + (b * nrx + rx) * (int64_t)a.pat.np_max + j);
+      h = __ldg(hp_row + j);
     } else {
       int e = __ldg(pre + j);
       int s = e / nsc, k = e - s * nsc;
@@ -58,6 +67,7 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
     float sig2 = exp10f(-0.1f * a.snr_db[b]);    // noise_variance = 1/snr_linear (:174-175)
     alpha = P / (P + sig2);
   }
+  if (m2) alpha = 1.f;
 
   float st[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // [0] antenna pair (rx, 0), [1] all tx of this rx
 
@@ -68,7 +78,7 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
   const int nre = nsym * nsc;
   const uint4 *plan = reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)pid * (nre + 1);
   const int64_t slot_h = (int64_t)nsym * nrx * ntx * nsc;
-  float2 *const Lb = a.H_ls ? a.H_ls + b * slot_h : nullptr;
+  float2 *const Lb = (a.H_ls && !m2) ? a.H_ls + b * slot_h : nullptr;
   float2 *const Mb = a.H_mmse ? a.H_mmse + b * slot_h : nullptr;
   const float2 *const Tb = (a.H_true && a.stats) ? a.H_true + b * slot_h : nullptr;
   const int k0 = threadIdx.x;
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_kernel(LsArgs a) {
     if (threadIdx.x < 6) {
       double acc = 0.0;
       for (int w = 0; w < EST_THREADS / 32; ++w) acc += (double)ssm[w][threadIdx.x];
-      a.stats[(b * nrx + rx) * 6 + threadIdx.x] = acc;
+      if (!m2 || threadIdx.x % 3 == 1) a.stats[(b * nrx + rx) * 6 + threadIdx.x] = acc;
     }
   }
 }
@@ -161,11 +171,13 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_wide_kernel(LsArgs a
   const int np = a.pat.npilots[pid];
   const int *pre = a.pat.pilot_re + (int64_t)pid * a.pat.np_max;
 
+  const float2 *const hp_row = a.hp_in ? hp_in_row(a, b, rx) : nullptr;
+  const bool m2 = a.mmse_mode == 2;
   float psum = 0.f;
   for (int j = threadIdx.x; j < np; j += EST_THREADS) {
     float2 h;
     if (a.hp_in) {
-      h = __ldg(a.hp_in + (b * nrx + rx) * (int64_t)a.pat.np_max + j);
+      h = __ldg(hp_row + j);
     } else {
       int e = __ldg(pre + j);
       int s = e / NSC, k = e - s * NSC;
@@ -180,12 +192,13 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_wide_kernel(LsArgs a
   float P = block_sum(psum, red) / (float)np;
   float alpha = 0.f;
   if (a.mmse_mode == 1) alpha = P / (P + exp10f(-0.1f * a.snr_db[b]));
+  if (m2) alpha = 1.f;
 
   float st[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
   const int nre = nsym * NSC;
   const uint4 *plan = reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)pid * (nre + 1);
   const int64_t slot_h = (int64_t)nsym * nrx * NTX * PITCH;
-  float2 *const Lb = a.H_ls ? a.H_ls + b * slot_h : nullptr;
+  float2 *const Lb = (a.H_ls && !m2) ? a.H_ls + b * slot_h : nullptr;
   float2 *const Mb = a.H_mmse ? a.H_mmse + b * slot_h : nullptr;
   const float2 *const Tb = (a.H_true && a.stats) ? a.H_true + b * slot_h : nullptr;
   const int t = threadIdx.x;
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(EST_THREADS, 2) ls_interp_wide_kernel(LsArgs a
     if (threadIdx.x < 6) {
       double acc = 0.0;
       for (int w = 0; w < EST_THREADS / 32; ++w) acc += (double)ssm[w][threadIdx.x];
-      a.stats[(b * nrx + rx) * 6 + threadIdx.x] = acc;
+      if (!m2 || threadIdx.x % 3 == 1) a.stats[(b * nrx + rx) * 6 + threadIdx.x] = acc;
     }
   }
 }
@@ -295,7 +308,7 @@ constexpr int BIN_THREADS = 1024;   // one CTA per bin scans every slot: latency
 
 __global__ void __launch_bounds__(BIN_THREADS)
 stats_bins_kernel(b2c_geom g, const double *__restrict__ stats, const int32_t *__restrict__ bin_id,
-                  int64_t B, double *__restrict__ bins) {
+                  const float *__restrict__ snr_db, int64_t B, double *__restrict__ bins) {
   __shared__ double sm[BIN_THREADS / 32][B2C_N_BINSTAT];
   const int bin = blockIdx.x;
   const double n_all = (double)g.nsym * g.nrx * g.ntx * g.nsc, n_pair = (double)g.nsym * g.nsc;
@@ -329,6 +342,15 @@ stats_bins_kernel(b2c_geom g, const double *__restrict__ stats, const int32_t *_
     acc[9] += n00_ls * n00_ls;
     acc[10] += n00_mm;
     acc[11] += n00_mm * n00_mm;
+    if (snr_db) {
+      // compute_ber_approximation (run_phase5_evaluation.py:57-68): QPSK BER proxy from the estimation NMSE,
+      // effective_snr = snr / (1 + snr * nmse), ber = clip(0.5 exp(-effective_snr / 2), 1e-10, 0.5)
+      const double snr_lin = pow(10.0, (double)snr_db[b] / 10.0);
+      const double b_ls = 0.5 * exp(-0.5 * snr_lin / (1.0 + snr_lin * n00_ls));
+      const double b_mm = 0.5 * exp(-0.5 * snr_lin / (1.0 + snr_lin * n00_mm));
+      acc[12] += fmin(fmax(b_ls, 1e-10), 0.5);
+      acc[13] += fmin(fmax(b_mm, 1e-10), 0.5);
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -354,7 +376,7 @@ extern "C" int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const i
                              const float *snr_db, int64_t B, const float *rx, const float *pilots,
                              int64_t pilots_stride, const float *hp_in, int32_t mmse_mode,
                              const float *H_true, float *H_ls, float *H_mmse, float *hp_out, double *stats,
-                             void *stream) {
+                             const int32_t *hp_col, int64_t hp_ld, void *stream) {
   B2C_REQUIRE(g && pat && pattern_id, B2C_E_ARG, "b2c_ls_interp: null argument");
   B2C_REQUIRE(g->nsym >= 1 && g->nsc >= 1 && g->nsc <= 2 * EST_THREADS && g->ntx >= 1 &&
                   g->ntx <= B2C_MAX_ANT && g->nrx >= 1 && g->nrx <= B2C_MAX_ANT * B2C_MAX_ANT,
@@ -362,8 +384,11 @@ extern "C" int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const i
               g->ntx, g->nrx);
   B2C_REQUIRE(pat->plan && pat->pilot_re && pat->npilots, B2C_E_ARG, "b2c_ls_interp: incomplete pattern pool");
   B2C_REQUIRE(hp_in || (rx && pilots), B2C_E_ARG, "b2c_ls_interp: need rx and pilots (or hp_in)");
-  B2C_REQUIRE(mmse_mode == 0 || (mmse_mode == 1 && snr_db), B2C_E_ARG, "b2c_ls_interp: mmse_mode=%d invalid or snr_db missing", mmse_mode);
-  B2C_REQUIRE(mmse_mode == 1 || !H_mmse, B2C_E_ARG, "b2c_ls_interp: H_mmse requested with mmse_mode=0");
+  B2C_REQUIRE(mmse_mode == 0 || (mmse_mode == 1 && snr_db) || (mmse_mode == 2 && hp_in), B2C_E_ARG,
+              "b2c_ls_interp: mmse_mode=%d invalid, or snr_db (mode 1) / hp_in (mode 2) missing", mmse_mode);
+  B2C_REQUIRE(mmse_mode != 0 || !H_mmse, B2C_E_ARG, "b2c_ls_interp: H_mmse requested with mmse_mode=0");
+  B2C_REQUIRE((!hp_col && hp_ld == 0) || (hp_in && (hp_ld == 0 || hp_ld >= pat->np_max)), B2C_E_ARG,
+              "b2c_ls_interp: hp_col / hp_ld describe hp_in (hp_ld >= np_max)");
   B2C_REQUIRE(!stats || H_true, B2C_E_ARG, "b2c_ls_interp: stats need H_true");
   B2C_REQUIRE(B >= 0 && B * g->nrx < (1ll << 31), B2C_E_ARG, "b2c_ls_interp: B=%lld out of range", (long long)B);
   B2C_REQUIRE(pat->np_max >= 1 && pat->np_max <= 65534 && (size_t)pat->np_max * 8 <= 100 * 1024, B2C_E_UNSUPPORTED,
@@ -384,6 +409,8 @@ extern "C" int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const i
   a.H_mmse = reinterpret_cast<float2 *>(H_mmse);
   a.hp_out = reinterpret_cast<float2 *>(hp_out);
   a.stats = stats;
+  a.hp_col = hp_col;
+  a.hp_ld = hp_ld ? hp_ld : pat->np_max;
   cudaStream_t st = (cudaStream_t)stream;
   if (g->pitch != 0 && g->pitch != g->nsc) {   // padded rows (rx, H_true, H_ls, H_mmse alike): wide kernel
     B2C_REQUIRE(g->nsc == 599 && g->pitch == 600 && (g->ntx == 1 || g->ntx == 2 || g->ntx == 4 || g->ntx == 8), B2C_E_UNSUPPORTED,
@@ -405,13 +432,13 @@ extern "C" int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const i
   return launch_ls<8, false, 0>(a, B, st);
 }
 
-extern "C" int b2c_stats_bins(const b2c_geom *g, const double *stats, const int32_t *bin_id, int64_t B,
-                              int32_t nbins, double *bins, void *stream) {
+extern "C" int b2c_stats_bins(const b2c_geom *g, const double *stats, const int32_t *bin_id, const float *snr_db,
+                              int64_t B, int32_t nbins, double *bins, void *stream) {
   B2C_REQUIRE(g && stats && bin_id && bins, B2C_E_ARG, "b2c_stats_bins: null argument");
   if (int rc = check_geom(g)) return rc;
   B2C_REQUIRE(nbins >= 1 && B >= 0, B2C_E_ARG, "b2c_stats_bins: nbins=%d B=%lld", nbins, (long long)B);
   if (B == 0) return B2C_OK;
-  stats_bins_kernel<<<nbins, BIN_THREADS, 0, (cudaStream_t)stream>>>(*g, stats, bin_id, B, bins);
+  stats_bins_kernel<<<nbins, BIN_THREADS, 0, (cudaStream_t)stream>>>(*g, stats, bin_id, snr_db, B, bins);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }

@@ -181,6 +181,9 @@ struct SlotArgs {
   float2 *H_true, *rx, *tx, *H_ls, *H_mmse;
   double *stats;
   int compact;   // 1: tx-replicated outputs written once (H_ls/H_mmse [B][nsym][nrx][nsc], tx [B][nsym][nsc])
+  float2 *hp_out;          // b2c_pilot_io: h_ls at the pilots, row hp_col[b] + rx (NULL: not written)
+  const int32_t *hp_col;
+  int64_t hp_ld;
 };
 
 struct SlotCtx {
@@ -228,6 +231,7 @@ __device__ __forceinline__ void pilot_phase(const SlotArgs &a, SlotCtx &c, const
   const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * nsc;
   float psum = 0.f;
   if (threadIdx.x == 0) hp[a.pat.np_max] = make_float2(0.f, 0.f);   // the plan's "outside the hull" slot
+  float2 *const hp_g = a.hp_out ? a.hp_out + ((a.hp_col ? (int64_t)a.hp_col[c.b] : c.b * a.g.nrx) + c.rx) * a.hp_ld : nullptr;
   // A pilot costs two dependent L2 round trips (its RE index, then its T twiddles).  Pilots are taken PB at a time per
   // thread -- all PB indices first, then all PB * T twiddles, then the arithmetic -- so a CTA pays two round trips per
   // PB * 320 pilots instead of two per 320 (838 pilots: 2 instead of 6).
@@ -258,6 +262,7 @@ __device__ __forceinline__ void pilot_phase(const SlotArgs &a, SlotCtx &c, const
         const float2 y = cmul(hsum, x);
         const float2 h = ls_divide(make_float2(fmaf(c.sigma, n.x, y.x), fmaf(c.sigma, n.y, y.y)), x);
         hp[j] = h;
+        if (hp_g) hp_g[j] = h;
         psum += cabs2(h);
       }
     }
@@ -809,12 +814,14 @@ extern "C" int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, co
                                  const b2c_slots *slots, const b2c_inject *inj, int64_t B,
                                  const float *gains, const float *noise_std, float *H_true, float *rx,
                                  float *tx, float *H_ls, float *H_mmse, double *stats, int32_t compact,
-                                 void *stream) {
+                                 const b2c_pilot_io *pilots_out, void *stream) {
   B2C_REQUIRE(g && prof && slots && gains && noise_std, B2C_E_ARG, "b2c_slot_pipeline: null argument");
   if (int rc = check_geom(g, /*allow_pitch=*/true)) return rc;
   B2C_REQUIRE(B >= 0 && B * g->nrx < (1ll << 31), B2C_E_ARG, "b2c_slot_pipeline: B=%lld out of range",
               (long long)B);
-  const bool est = H_ls || H_mmse || stats;
+  const bool est = H_ls || H_mmse || stats || pilots_out;
+  B2C_REQUIRE(!pilots_out || (pilots_out->hp && pat && pilots_out->ld >= pat->np_max), B2C_E_ARG,
+              "b2c_slot_pipeline: pilots_out needs hp and ld >= np_max");
   B2C_REQUIRE(!est || (pat && pat->plan && pat->pilot_re && pat->npilots && slots->pattern_id), B2C_E_ARG,
               "b2c_slot_pipeline: estimation outputs requested without a pattern pool");
   B2C_REQUIRE(!inj || !(est || rx || tx) || (inj->sym_turns && inj->noise), B2C_E_ARG,
@@ -837,6 +844,11 @@ extern "C" int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, co
   a.H_mmse = reinterpret_cast<float2 *>(H_mmse);
   a.stats = stats;
   a.compact = compact != 0;
+  if (pilots_out) {
+    a.hp_out = reinterpret_cast<float2 *>(pilots_out->hp);
+    a.hp_col = pilots_out->col;
+    a.hp_ld = pilots_out->ld;
+  }
   size_t smem = slot_smem_bytes(g, est ? pat->np_max : 0);
   B2C_REQUIRE(smem <= 100 * 1024, B2C_E_UNSUPPORTED, "b2c_slot_pipeline: %zu B shared memory needed", smem);
   return est ? launch_slot_ntx<true>(a, B, smem, (cudaStream_t)stream)

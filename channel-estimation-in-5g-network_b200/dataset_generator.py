@@ -19,6 +19,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
+import _b2c
 import _tables
 from engine import SlotEngine
 
@@ -226,7 +227,7 @@ def sharded_statistics(config: Dict, total_slots: int, rank: int = 0, world_size
                        seed: int = 42, bin_by: str = "snr", want_arrays=(), on_batch=None, dataset: Optional[ChannelEstimationDataset] = None):
     """Multi-GPU dataset statistics: rank r simulates + estimates global samples
     [r*N/R, (r+1)*N/R) in batches and folds MSE/NMSE into per-bin float64 accumulators on its
-    GPU; the caller all-reduces the returned [nbins, 12] tensor (see reduce_bins).  Philox keyed
+    GPU; the caller all-reduces the returned [nbins, 14] tensor (see reduce_bins).  Philox keyed
     by the global sample index makes the result independent of world_size."""
     ds = dataset if dataset is not None else ChannelEstimationDataset(config, rng='philox', seed=seed)
     eng = ds.engine
@@ -234,18 +235,19 @@ def sharded_statistics(config: Dict, total_slots: int, rank: int = 0, world_size
     sizes = {"snr": len(snrs), "model": len(models), "density": len(dens), "doppler": len(dopplers)}
     nbins = sizes[bin_by]
     lo, hi = shard_range(total_slots, rank, world_size)
-    bins = torch.zeros((nbins, 12), dtype=torch.float64, device=eng.device)
+    bins = torch.zeros((nbins, _b2c.N_BINSTAT), dtype=torch.float64, device=eng.device)
     want = tuple(set(("stats",) + tuple(want_arrays)))
     out = ws = None
     pos = lo
     while pos < hi:
         n = min(batch, hi - pos)
         if out is None or n != batch:
-            # all five arrays requested: the row-padded throughput layout (wide-store kernel); callers see 599-wide views
-            full = all(k in want for k in ("H_true", "rx", "tx", "H_ls", "H_mmse"))
-            out, ws = eng.alloc_outputs(n, want, pitch=600 if (full and eng.nsc == 599 and eng.nsym % 2 == 0 and eng.ntx in (1, 2, 4, 8)) else None), eng.workspace(n)
+            # H_true + rx + tx + H_ls requested (the dataset arrays; H_mmse optional): the row-padded throughput layout
+            # (wide-store kernel); callers see 599-wide views
+            wide = all(k in want for k in ("H_true", "rx", "tx", "H_ls"))
+            out, ws = eng.alloc_outputs(n, want, pitch=600 if (wide and eng.nsc == 599 and eng.nsym % 2 == 0 and eng.ntx in (1, 2, 4, 8)) else None), eng.workspace(n)
         res, par = ds.generate_batch(n, pos, want=want, out=out, ws=ws)
-        eng.stats_bins(res["stats"], par[bin_by].astype(np.int32), nbins, bins)
+        eng.stats_bins(res["stats"], par[bin_by].astype(np.int32), nbins, bins, snr_db=np.asarray(snrs, np.float32)[par["snr"]])
         if on_batch is not None:
             on_batch(pos, res, par)
         pos += n
@@ -280,6 +282,8 @@ def summarize_bins(bins) -> List[Dict]:
         m["mse_mmse_db"] = 10 * np.log10(m["mse_mmse"] + 1e-12)
         m["nmse00_ls_db"] = 10 * np.log10(m["nmse00_ls_mean"] + 1e-12)
         m["nmse00_ls_std"] = float(np.sqrt(max(r[9] / n - (r[8] / n) ** 2, 0.0)))
+        if len(r) > 13:      # QPSK BER proxy of run_phase5_evaluation.py:57-68 (folded when the SNRs were given)
+            m["ber_proxy_ls"], m["ber_proxy_mmse"] = r[12] / n, r[13] / n
         rows.append(m)
     return rows
 

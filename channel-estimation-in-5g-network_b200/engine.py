@@ -14,12 +14,12 @@ import torch
 
 import _b2c
 import _tables
-from _b2c import Geom, Inject, Patterns, Profiles, Slots, check, dptr, lib, ref, row_pitch, rows_ptr, stream_ptr
+from _b2c import Geom, Inject, Patterns, PilotIO, Profiles, Slots, check, dptr, lib, ref, row_pitch, rows_ptr, stream_ptr
 
 DEFAULT_MODELS = ("EPA", "EVA", "ETU")
 BIN_FIELDS = ("count", "sum_mse_ls", "sum_mse_mmse", "sum_nmse_ls", "sum_nmse_mmse", "sum_nmse_ls_sq",
               "sum_nmse_mmse_sq", "sum_power", "sum_nmse00_ls", "sum_nmse00_ls_sq", "sum_nmse00_mmse",
-              "sum_nmse00_mmse_sq")
+              "sum_nmse00_mmse_sq", "sum_ber_proxy_ls", "sum_ber_proxy_mmse")
 
 
 def _cuda_device(device=None):
@@ -40,9 +40,10 @@ class PatternPool:
         self.np_max = int(self.npilots_host.max())
         pre = np.zeros((n, self.np_max), dtype=np.int32)
         plans = np.zeros((n + 1, nsym * nsc + 1), dtype=_tables.PLAN_DTYPE)   # +1 pattern of padding: kernels prefetch one symbol ahead
+        built = _tables.plans_for(self.pilot_indices, nsym, nsc, method)     # parallel + disk-cached for large pools
         for i, p in enumerate(self.pilot_indices):
             pre[i, :len(p)] = p
-            plans[i] = _tables.finalize_plan(_tables.cached_plan(p, nsym, nsc, method), self.np_max)
+            plans[i] = _tables.finalize_plan(built[i], self.np_max)
         self.npilots = torch.from_numpy(self.npilots_host).to(self.device)
         self.pilot_re = torch.from_numpy(pre).to(self.device)
         self.plan = torch.from_numpy(plans.view(np.uint8).reshape(n + 1, (nsym * nsc + 1) * 16)).to(self.device)
@@ -62,6 +63,50 @@ class PreparedDense:
 
     def __init__(self, buf, m, k, is_complex):
         self.buf, self.m, self.k, self.is_complex = buf, int(m), int(k), bool(is_complex)
+
+
+class WienerBank:
+    """Known-covariance MMSE filters of a batch: W = R (R + sigma^2 I)^-1 per (pilot pattern, SNR), built ONCE in
+    float64 on the host (src/baseline_estimators.py:174-190, noise_variance = 1 / snr_linear) and kept on the device
+    as prepared tensor-core operands (b2c_dense_prepare).  SlotEngine.run(mmse="dense", wiener=bank) then applies
+    each W to all pilot vectors of its (pattern, SNR) group with one GEMM.
+
+    covariances: {pattern_id: R [np, np] complex} (np = that pattern's pilot count); snrs: the SNR values (dB) the
+    batch may contain."""
+
+    def __init__(self, engine, pool, covariances, snrs):
+        self.pool = pool
+        self.prepared, self.W_host = {}, {}
+        for pid, R in covariances.items():
+            R = np.asarray(R)
+            n = int(pool.npilots_host[pid])
+            if R.shape != (n, n):
+                raise ValueError(f"covariance of pattern {pid} has shape {R.shape}, its pilot set has {n} pilots")
+            for snr in snrs:
+                sigma2 = 1.0 / (10.0 ** (float(snr) / 10.0))
+                Ry = R + sigma2 * np.eye(n)
+                try:
+                    W = R @ np.linalg.inv(Ry)
+                except np.linalg.LinAlgError:                       # the reference's regularised fallback (:191-194)
+                    W = R @ np.linalg.inv(Ry + 1e-6 * np.eye(n))
+                key = (int(pid), float(snr))
+                self.W_host[key] = W
+                self.prepared[key] = engine.prepare_dense(torch.from_numpy(np.ascontiguousarray(W.astype(np.complex64))).to(engine.device))
+
+    def groups(self, pattern_id, snr_db):
+        """Host-side grouping of a batch: (order, starts, keys) with `order` the slot indices sorted by
+        (pattern, SNR) group and group g = order[starts[g]:starts[g+1]] using the filter keys[g]."""
+        pid = np.asarray(pattern_id).astype(np.int64)
+        snr = np.asarray(snr_db, dtype=np.float64)
+        uniq, inv = np.unique(np.stack([pid.astype(np.float64), snr], axis=1), axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        keys = [(int(u[0]), float(u[1])) for u in uniq]
+        for k in keys:
+            if k not in self.prepared:
+                raise KeyError(f"no Wiener matrix for pattern {k[0]} at {k[1]} dB in this bank")
+        order = np.argsort(inv, kind="stable")
+        starts = np.concatenate([[0], np.cumsum(np.bincount(inv, minlength=len(keys)))])
+        return order, starts, keys
 
 
 class SlotEngine:
@@ -159,12 +204,30 @@ class SlotEngine:
 
     # ---- K1a + fused slot kernel -------------------------------------------------------------------
     def run(self, B, model_id, doppler_hz, snr_db, pattern_id=0, pool=None, slot0=0, seed=42, inject=None,
-            want=("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), out=None, ws=None, compact=False, pitch=None):
+            want=("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), out=None, ws=None, compact=False, pitch=None,
+            mmse="default", wiener=None):
         """Simulate B slots and (if any of H_ls/H_mmse/stats is wanted) estimate them.
         Per-slot parameters are scalars or length-B arrays/tensors.  Returns dict of CUDA tensors.
         compact=True writes the tx-replicated arrays once (see alloc_outputs); expand_compact() turns
         them into full-shape stride-0 views.  pitch=600 (or `out` from alloc_outputs(pitch=600)) selects the
-        padded-row layout of the wide-store kernel (throughput configuration only, see include/b2c.h)."""
+        padded-row layout of the wide-store kernel (throughput configuration only, see include/b2c.h).
+        mmse="default": MMSEEstimator()'s alpha * LS (src/baseline_estimators.py:177-180), fused in the slot kernel.
+        mmse="dense" + wiener=WienerBank: the known-covariance branch (:181-190) for the whole batch -- the slot
+        kernel also hands out h_ls at the pilots grouped by (pattern, SNR), one tensor-core GEMM per group applies
+        W, and K3 interpolates the filtered pilots into H_mmse and scores them (pattern_id / snr_db must then be
+        host values: they decide the grouping)."""
+        if mmse not in ("default", "dense"):
+            raise ValueError(f"Unknown mmse mode: {mmse}")
+        dense = mmse == "dense" and any(k in (out if out is not None else want) for k in ("H_mmse", "stats"))
+        if dense:
+            if wiener is None or pool is None:
+                raise ValueError('mmse="dense" needs a WienerBank and its PatternPool')
+            if compact:
+                raise ValueError('mmse="dense" writes H_mmse in the full layout')
+            if isinstance(pattern_id, torch.Tensor) or isinstance(snr_db, torch.Tensor):
+                raise ValueError('mmse="dense" groups slots by (pattern, SNR) on the host: pass host values')
+            if out is None:
+                want = tuple(want) + tuple(k for k in ("H_true", "H_ls") if k not in want)   # K3 scores against H_true
         if out is None:
             out = self.alloc_outputs(B, want, compact, pitch)
         if ws is None:
@@ -180,14 +243,42 @@ class SlotEngine:
         arrays = [out[k] for k in ("H_true", "rx", "tx", "H_ls", "H_mmse") if k in out]
         P = row_pitch(arrays[0]) if arrays else self.nsc
         g = self._with_pitch(self.geom, P)
+        pio = None
+        if dense:
+            if "H_true" not in out:
+                raise ValueError('mmse="dense" needs H_true among the outputs (the MMSE error sums are taken against it)')
+            order, starts, keys = wiener.groups(np.broadcast_to(np.asarray(pattern_id), (B,)), np.broadcast_to(np.asarray(snr_db), (B,)))
+            rank = np.empty(B, dtype=np.int64)
+            rank[order] = np.arange(B)
+            col = torch.from_numpy((rank * self.nrx).astype(np.int32)).to(self.device)
+            ld = pool.np_max
+            hp = ws.get("hp")
+            if hp is None or hp.shape[0] < B * self.nrx or hp.shape[1] != ld:
+                hp = ws["hp"] = torch.empty((B * self.nrx, ld), dtype=torch.complex64, device=self.device)
+                ws["hm"] = torch.empty_like(hp)
+            pio = PilotIO(hp.data_ptr(), col.data_ptr(), ld)
         check(L.b2c_tap_gains(ref(self.geom), ref(self.prof), ref(slots), ref(ij), B,
                               dptr(ws["gains"], "c64"), dptr(ws["noise_std"], "f32"), stream_ptr()), "b2c_tap_gains")
         check(L.b2c_slot_pipeline(ref(g), ref(self.prof), ref(pool.struct) if pool is not None else None,
                                   ref(slots), ref(ij), B, dptr(ws["gains"], "c64"), dptr(ws["noise_std"], "f32"),
                                   rows_ptr(out.get("H_true"), P, True), rows_ptr(out.get("rx"), P, True),
                                   rows_ptr(out.get("tx"), P, True), rows_ptr(out.get("H_ls"), P, True),
-                                  rows_ptr(out.get("H_mmse"), P, True), dptr(out.get("stats"), "f64", True),
-                                  1 if compact else 0, stream_ptr()), "b2c_slot_pipeline")
+                                  None if dense else rows_ptr(out.get("H_mmse"), P, True), dptr(out.get("stats"), "f64", True),
+                                  1 if compact else 0, ref(pio), stream_ptr()), "b2c_slot_pipeline")
+        if dense:
+            hm = ws["hm"]
+            for gi, key in enumerate(keys):                       # one GEMM per (pattern, SNR) group
+                r0, r1 = int(starts[gi]) * self.nrx, int(starts[gi + 1]) * self.nrx
+                W = wiener.prepared[key]
+                check(L.b2c_dense_apply_prepared(dptr(W.buf, "u8"), W.m, W.k, 1, C.c_void_p(hp.data_ptr() + r0 * ld * 8),
+                                                 C.c_void_p(hm.data_ptr() + r0 * ld * 8), r1 - r0, ld, ld, stream_ptr()),
+                      "b2c_dense_apply_prepared")
+            # K3, mode 2: interpolate the filtered pilots into H_mmse, MMSE error sums into stats[..., 1]
+            check(L.b2c_ls_interp(ref(g), ref(pool.struct), keep[3].data_ptr(), None, B, None, None, 0, dptr(hm, "c64"), 2,
+                                  rows_ptr(out["H_true"], P) if "stats" in out else None, None,
+                                  rows_ptr(out.get("H_mmse"), P, True), None, dptr(out.get("stats"), "f64", True),
+                                  dptr(col, "i32"), ld, stream_ptr()), "b2c_ls_interp")
+            keep = keep + (col,)
         out["_keepalive"] = (keep, keep_inj, ws)
         return out
 
@@ -207,13 +298,13 @@ class SlotEngine:
 
     # ---- K3 ------------------------------------------------------------------------------------------
     def ls_interp(self, rx, pilots, pool, pattern_id=0, snr_db=None, mmse=False, H_true=None, hp_in=None,
-                  want=("H_ls",), geom=None, out=None):
+                  want=("H_ls",), geom=None, out=None, pitch=None):
         """rx [B,nsym,nrx,nsc] c64, pilots [B or 1, np_max] c64.  want subset of H_ls, H_mmse, hp, stats.
         If rx (and H_true) are padded-row views (pitch 600, as run(pitch=600) returns them) the outputs are
         padded the same way and the wide-access kernel runs."""
         g = geom if geom is not None else self.geom
         B = rx.shape[0] if rx is not None else hp_in.shape[0]
-        P = row_pitch(rx) if rx is not None else g.nsc
+        P = row_pitch(rx) if rx is not None else (g.nsc if pitch is None else int(pitch))
         g = self._with_pitch(g, P)
         pid = self._vec(pattern_id, B, torch.int32)
         snr = self._vec(snr_db, B, torch.float32) if snr_db is not None else None
@@ -232,7 +323,7 @@ class SlotEngine:
                                   rows_ptr(rx, P, True), dptr(pilots, "c64", True), stride, dptr(hp_in, "c64", True),
                                   1 if mmse else 0, rows_ptr(H_true, P, True), rows_ptr(out.get("H_ls"), P, True),
                                   rows_ptr(out.get("H_mmse"), P, True), dptr(out.get("hp"), "c64", True),
-                                  dptr(out.get("stats"), "f64", True), stream_ptr()), "b2c_ls_interp")
+                                  dptr(out.get("stats"), "f64", True), None, 0, stream_ptr()), "b2c_ls_interp")
         return out
 
     def pilot_vectors(self, y, x, snr_db=0.0, mmse=False):
@@ -321,13 +412,16 @@ class SlotEngine:
         return out
 
     # ---- K5 ------------------------------------------------------------------------------------------
-    def stats_bins(self, stats, bin_id, nbins, bins=None, geom=None):
+    def stats_bins(self, stats, bin_id, nbins, bins=None, geom=None, snr_db=None):
+        """Fold per-slot statistics into [nbins, 14] float64 accumulators (BIN_FIELDS).  snr_db (per slot) also folds
+        the QPSK BER proxy of run_phase5_evaluation.py:57-68 (fields 12, 13)."""
         g = geom if geom is not None else self.geom
         B = stats.shape[0]
         if bins is None:
             bins = torch.zeros((nbins, _b2c.N_BINSTAT), dtype=torch.float64, device=self.device)
         bid = self._vec(bin_id, B, torch.int32)
-        check(lib().b2c_stats_bins(ref(g), dptr(stats, "f64"), dptr(bid, "i32"), B, nbins, dptr(bins, "f64"),
+        snr = None if snr_db is None else self._vec(snr_db, B, torch.float32)
+        check(lib().b2c_stats_bins(ref(g), dptr(stats, "f64"), dptr(bid, "i32"), dptr(snr, "f32", True), B, nbins, dptr(bins, "f64"),
                                    stream_ptr()), "b2c_stats_bins")
         return bins
 

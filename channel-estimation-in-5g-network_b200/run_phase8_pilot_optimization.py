@@ -46,7 +46,7 @@ class PilotOptimizer:
         ds = ChannelEstimationDataset(self.config, rng=self.rng, seed=self.seed,
                                       lists=([channel_type], [doppler_hz], list(snr_values), list(pilot_densities)))
         eng = ds.engine
-        bins = torch.zeros((nd * ns, 12), dtype=torch.float64, device=eng.device)
+        bins = torch.zeros((nd * ns, 14), dtype=torch.float64, device=eng.device)
         if self.rng == 'philox':
             pool = ds.pattern_pool()
             B = nd * ns * num_samples
@@ -58,14 +58,14 @@ class PilotOptimizer:
                 sl = slice(pos, pos + n)
                 out = eng.run(n, 0, float(doppler_hz), np.asarray(snr_values, np.float32)[snr_i[sl]], dens_i[sl].astype(np.int32),
                               pool, slot0=pos, seed=self.seed, want=("stats",))
-                eng.stats_bins(out["stats"], cell[sl].astype(np.int32), nd * ns, bins)
+                eng.stats_bins(out["stats"], cell[sl].astype(np.int32), nd * ns, bins, snr_db=np.asarray(snr_values, np.float32)[snr_i[sl]])
                 pos += n
         else:
             for di, dens in enumerate(pilot_densities):
                 for si, snr in enumerate(snr_values):
                     samples = ds._numpy_batch([(channel_type, doppler_hz, snr, dens)] * num_samples, draw_params=False,
                                               want_stats=True)
-                    eng.stats_bins(samples, np.full(len(samples), di * ns + si, np.int32), nd * ns, bins)
+                    eng.stats_bins(samples, np.full(len(samples), di * ns + si, np.int32), nd * ns, bins, snr_db=float(snr))
         b = bins.cpu().numpy()
         summary = {'pilot_densities': pilot_densities, 'snr_values': snr_values, 'methods': {'LS': {}, 'MMSE': {}}}
         for name, (c1, c2) in (('LS', (8, 9)), ('MMSE', (10, 11))):
@@ -77,5 +77,7 @@ class PilotOptimizer:
                         mean = r[c1] / r[0]
                         summary['methods'][name][snr][dens] = {
                             'nmse_mean': float(mean), 'nmse_db': float(linear2db(mean)),
-                            'nmse_std': float(np.sqrt(max(r[c2] / r[0] - mean * mean, 0.0)))}
+                            'nmse_std': float(np.sqrt(max(r[c2] / r[0] - mean * mean, 0.0))),
+                            # the sweep's BER curve: mean over the cell of compute_ber_approximation (run_phase5_evaluation.py:57-68)
+                            'ber_proxy': float(r[12 if name == 'LS' else 13] / r[0])}
         return summary

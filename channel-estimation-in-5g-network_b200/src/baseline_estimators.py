@@ -1,0 +1,5 @@
+"""src.baseline_estimators of the reference -> the B200 drop-in module of the same name (see src/__init__.py)."""
+import baseline_estimators as _impl
+from baseline_estimators import *  # noqa: F401,F403
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

@@ -129,6 +129,17 @@ typedef struct b2c_inject {
   const float *noise;
 } b2c_inject;
 
+/* Pilot-vector output of b2c_slot_pipeline for the dense-Wiener (known-covariance MMSE) pipeline
+ * (src/baseline_estimators.py:169-190): h_ls at the pilots of (slot b, rx) is written to row col[b] + rx of
+ *   hp [rows][ld] complex, elements j < npilots (the row's remaining elements are left as they are).
+ * `col` lets the caller lay the vectors out grouped by Wiener matrix (one (pattern, SNR) group = one contiguous
+ * block of rows = one GEMM); NULL = b * nrx.                                                             */
+typedef struct b2c_pilot_io {
+  float *hp;
+  const int32_t *col;       /* [B] or NULL                                                    */
+  int64_t ld;               /* complex elements between rows, >= np_max                       */
+} b2c_pilot_io;
+
 const char *b2c_last_error_string(void);
 int b2c_abi_version(void);
 
@@ -158,13 +169,14 @@ int b2c_tap_gains(const b2c_geom *g, const b2c_profiles *prof, const b2c_slots *
  *   tx requested and H_ls when estimating -- H_mmse and stats stay optional --; B2C_E_UNSUPPORTED
  *   otherwise): the last axis of the five arrays
  *   is 600 elements apart in memory (element 599 is padding) and every lane writes 16 aligned bytes per row;
+ *   pilots_out (optional, needs estimation): also hand out h_ls at the pilots, see b2c_pilot_io.
  *   same values as the contiguous layout, bit for bit.  compact = 1 combines with it: each unique value is written
  *   once (1 945 552 B per 4x4 slot instead of 3 756 928), in padded rows.                                  */
 int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat,
                       const b2c_slots *slots, const b2c_inject *inj, int64_t B,
                       const float *gains, const float *noise_std,
                       float *H_true, float *rx, float *tx, float *H_ls, float *H_mmse,
-                      double *stats, int32_t compact, void *stream);
+                      double *stats, int32_t compact, const b2c_pilot_io *pilots_out, void *stream);
 
 /* K3.  LS pilot division + plan interpolation on caller-supplied received grids.
  * Replaces LSEstimator.estimate (src/baseline_estimators.py:83-117) and, with mmse_mode=1,
@@ -173,14 +185,19 @@ int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, const b2c_pat
  *   pilots   [B or 1][np_max] complex transmitted pilot symbols; pilots_stride = np_max or 0
  *   hp_in    optional [B][nrx][np_max] complex: use these pilot-position values instead of
  *            rx/pilots (the dense-Wiener path feeds W h_ls here)
- *   mmse_mode 0: H_mmse not produced; 1: alpha = P/(P+10^(-snr/10)), P = mean|h_ls|^2 (:174-180)
+ *            hp_col / hp_ld (optional): row of (slot b, rx) in hp_in is hp_col[b] + rx and rows are hp_ld
+ *            elements apart (NULL / 0: b * nrx + rx, np_max) -- the layout b2c_pilot_io describes
+ *   mmse_mode 0: H_mmse not produced; 1: alpha = P/(P+10^(-snr/10)), P = mean|h_ls|^2 (:174-180);
+ *            2: hp_in holds Wiener-filtered pilot estimates (known-covariance branch, :181-190): their
+ *               interpolation is written to H_mmse, and of the statistics only the MMSE error sums (entry 1 of
+ *               each group) are written -- the other entries keep what b2c_slot_pipeline put there
  *   H_true   optional, for stats.  hp_out optional [B][nrx][np_max]: h_ls at the pilots (:110).
  *   g->pitch = 600 (nsc = 599, ntx in {1,2,4,8}): rx, H_true, H_ls and H_mmse all have padded rows.       */
 int b2c_ls_interp(const b2c_geom *g, const b2c_patterns *pat, const int32_t *pattern_id,
                   const float *snr_db, int64_t B, const float *rx, const float *pilots,
                   int64_t pilots_stride, const float *hp_in, int32_t mmse_mode,
                   const float *H_true, float *H_ls, float *H_mmse, float *hp_out, double *stats,
-                  void *stream);
+                  const int32_t *hp_col, int64_t hp_ld, void *stream);
 
 /* LS / default-MMSE on bare pilot vectors: out[v][j] = alpha_v * y[v][j] / (x[j] + 1e-12).
  * Replaces LSEstimator.estimate_at_pilots (src/baseline_estimators.py:23-42) with mmse_mode=0 and
@@ -223,9 +240,12 @@ int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t k, int32_t
  *   bins  [nbins][B2C_N_BINSTAT] double, ACCUMULATED INTO (zero it first):
  *     0 count  1 sum mse_ls  2 sum mse_mmse  3 sum nmse_ls  4 sum nmse_mmse  5 sum nmse_ls^2
  *     6 sum nmse_mmse^2  7 sum mean|H|^2  8 sum nmse00_ls  9 sum nmse00_ls^2  10 sum nmse00_mmse
- *     11 sum nmse00_mmse^2       (nmse: /(pow+1e-12); nmse00: antenna pair (0,0), /(pow+1e-10)) */
-#define B2C_N_BINSTAT 12
-int b2c_stats_bins(const b2c_geom *g, const double *stats, const int32_t *bin_id, int64_t B,
+ *     11 sum nmse00_mmse^2       (nmse: /(pow+1e-12); nmse00: antenna pair (0,0), /(pow+1e-10))
+ *     12 sum ber_proxy_ls  13 sum ber_proxy_mmse: compute_ber_approximation (run_phase5_evaluation.py:57-68) of the
+ *     pair-(0,0) NMSE at the slot's SNR, the "BER curve" of the pilot-density sweep; only when snr_db [B] is given
+ *     (NULL: entries 12, 13 are left untouched)                                                        */
+#define B2C_N_BINSTAT 14
+int b2c_stats_bins(const b2c_geom *g, const double *stats, const int32_t *bin_id, const float *snr_db, int64_t B,
                    int32_t nbins, double *bins, void *stream);
 
 /* K2.  OFDM modulate / demodulate, batched over rows (one row = one OFDM symbol of one antenna).

@@ -147,6 +147,35 @@ def dense_mmse_case(name, seed):
     print(f"{name}: Np={n_p}")
 
 
+def model_covariance(pilot_positions):
+    """The formula-defined pilot covariance of the dense-MMSE fixtures (reproduced in the tests)."""
+    ds = pilot_positions[0][:, None] - pilot_positions[0][None, :]
+    dk = pilot_positions[1][:, None] - pilot_positions[1][None, :]
+    return 0.4 * np.exp(-np.abs(ds) / 20.0 - np.abs(dk) / 60.0) * np.exp(1j * 2 * np.pi * dk * 3 / 1024)
+
+
+def dense_from_slot_case(name, source):
+    """Known-covariance MMSE of the reference on the slot an existing fixture holds (same draws, same rx):
+    only the estimate is stored, so the batched dense pipeline can be driven with the source fixture's draws."""
+    import baseline_estimators as be
+    with np.load(os.path.join(OUT, source + ".npz")) as z:
+        g = {k: z[k] for k in z.files}
+    ntx, nrx, nsc = int(g["ntx"]), int(g["nrx"]), g["pilot_mask"].shape[1]
+    idx = g["pilot_indices"]
+    pos = (idx // nsc, idx % nsc)
+    R = model_covariance(pos)
+    rx = g["rx_symbols"]
+    rx4d = np.repeat(rx.reshape(rx.shape[0], nrx, 1, rx.shape[2]), ntx, axis=2)
+    est = be.MMSEEstimator(channel_covariance=R, estimate_statistics=False)
+    H_mm = est.estimate(rx4d, g["pilot_symbols"], g["pilot_mask"], pos, snr_db=float(g["snr_db"]))
+    for t in range(1, ntx):
+        assert np.array_equal(H_mm[:, :, t], H_mm[:, :, 0])
+    m = be.evaluate_estimator(g["channel"], H_mm)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), source=source, H_mmse_tx0=H_mm[:, :, 0],
+                        metrics_mmse=np.array([m["mse"], m["nmse"], m["nmse_db"]]))
+    print(f"{name}: Np={idx.size} dense MMSE {m['nmse_db']:.2f} dB")
+
+
 def ofdm_case(name, seed):
     import channel_simulator as cs
     rng = np.random.RandomState(seed)
@@ -317,6 +346,7 @@ def main():
     # another grid: 7 symbols x 299 used bins, 3 TX x 2 RX (the generic kernels, odd symbol count, ntx not a power of two)
     slot_case("slot_3x2_eva_7x299", 606, 3, 2, "EVA", 70, 8, 0.08, extra_methods=("nearest",), nsym=7, useful=300)
     dense_mmse_case("mmse_dense_2x2", 606)
+    dense_from_slot_case("mmse_dense_4x4_etu", "slot_4x4_etu")
     ofdm_case("ofdm_modem", 707)
     tdl_case("tdl_standalone", 808)
     cubic_case("ls_cubic")

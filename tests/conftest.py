@@ -45,3 +45,17 @@ def relerr(a, b):
     """Norm-wise relative error max|a-b| / max|b| used by the float parity checks."""
     a, b = np.asarray(a), np.asarray(b)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def assert_close_elementwise(a, b, rtol=1e-4, floor=1e-6, what=""):
+    """Element-wise companion of relerr: |a - b| <= rtol * |b| + floor * max|b| for EVERY element, so that a
+    systematic error on the small-magnitude resource elements (deep fades, hull edges) cannot hide behind the
+    array's largest value.  The floor (1e-6 of the largest magnitude, ~10 fp32 ulps of it) is what fp32 storage of a
+    sum of O(1) terms can resolve; exact zeros of `b` (outside the pilots' hull) must be within it."""
+    a, b = np.asarray(a), np.asarray(b)
+    bound = rtol * np.abs(b) + floor * max(float(np.max(np.abs(b))), 1e-300)
+    bad = np.abs(a - b) > bound
+    if bad.any():
+        i = np.unravel_index(np.argmax(np.abs(a - b) - bound), a.shape)
+        raise AssertionError(f"{what}: {int(bad.sum())} of {a.size} elements outside |a-b| <= {rtol}|b| + {floor} max|b|; "
+                             f"worst at {i}: got {a[i]}, want {b[i]}")

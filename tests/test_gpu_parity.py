@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import OFDM_CFG, ROOT, SLOT_CASES, full_config, golden_draws, load_golden, relerr
+from conftest import OFDM_CFG, ROOT, SLOT_CASES, assert_close_elementwise, full_config, golden_draws, load_golden, relerr
 from oracle import chanest_oracle as orc
 from oracle import philox as opx
 
@@ -82,6 +82,13 @@ def test_fused_pipeline_on_reference_draws(name, engines):
     diag(test="fused_injected", case=name, **errs)
     for k, v in errs.items():
         assert v < RTOL, (k, v)
+    # element-wise as well: |a - b| <= 1e-4 |b| + 1e-6 max|b| on every resource element (deep fades, hull edges)
+    assert_close_elementwise(H, g["channel"], what="H_true")
+    assert_close_elementwise(rx, g["rx_symbols"], what="rx")
+    for t in range(ntx):
+        assert_close_elementwise(tx[:, t], g["tx_grid"], what="tx")
+        assert_close_elementwise(H_ls[:, :, t], g["H_ls_tx0"], what="H_ls")
+        assert_close_elementwise(H_mm[:, :, t], g["H_mmse_tx0"], what="H_mmse")
     # exact zeros outside the pilots' convex hull (griddata fill_value = 0.0)
     assert np.array_equal(H_ls[:, :, 0] == 0, g["H_ls_tx0"] == 0)
     # statistics vs evaluate_estimator on the reference's arrays
@@ -152,6 +159,10 @@ def test_philox_mode_matches_oracle_on_twin_draws(ntx, nrx, model, fd, snr, dens
              "H_mmse": relerr(got["H_mmse"], ref["H_mmse"])}
         for k, v in e.items():
             worst[k] = max(worst.get(k, 0), v)
+        # element-wise too.  The floor is 4e-6 max|b| here (1e-6 on injected draws): the Philox path evaluates
+        # Box-Muller / symbol phases on the SFU (lg2.approx, sin/cos.approx: ~4e-7 absolute per unit amplitude).
+        for k, rk in (("H_true", "channel"), ("rx", "rx_symbols"), ("tx", "tx_symbols"), ("H_ls", "H_ls"), ("H_mmse", "H_mmse")):
+            assert_close_elementwise(got[k], ref[rk], floor=4e-6, what=k)
         st = out["stats"][i].cpu().numpy()[:, 1].sum(axis=0) / ref["channel"].size
         m_ls, m_mm = orc.evaluate(ref["channel"], ref["H_ls"]), orc.evaluate(ref["channel"], ref["H_mmse"])
         assert abs(db(st[0] / (st[2] + 1e-12)) - m_ls["nmse_db"]) < DB_TOL
@@ -236,18 +247,23 @@ def test_stats_bins_against_numpy(engines):
     out = eng.run(B, 1, 50.0, snr, 0, pool, slot0=0, seed=77)
     bin_id = snr_idx.astype(np.int32).copy()
     bin_id[5] = -1                                        # skipped slot
-    bins = eng.stats_bins(out["stats"], bin_id, 8).cpu().numpy()
+    bins = eng.stats_bins(out["stats"], bin_id, 8, snr_db=snr).cpu().numpy()
     H, Hl, Hm = (out[k].cpu().numpy().astype(np.complex128) for k in ("H_true", "H_ls", "H_mmse"))
-    want = np.zeros((8, 12))
+    want = np.zeros((8, 14))
     for b in range(B):
         if bin_id[b] < 0:
             continue
         ls, mm = orc.evaluate(H[b], Hl[b]), orc.evaluate(H[b], Hm[b])
         n00l, n00m = orc.nmse_pair00(Hl[b], H[b]), orc.nmse_pair00(Hm[b], H[b])
+        # the BER proxy of run_phase5_evaluation.py:57-68 on the pair-(0,0) rows (oracle restatement: ber_approximation)
+        bl = orc.ber_approximation(Hl[b][:, 0, 0], H[b][:, 0, 0], float(snr[b]))
+        bm = orc.ber_approximation(Hm[b][:, 0, 0], H[b][:, 0, 0], float(snr[b]))
         want[bin_id[b]] += [1, ls["mse"], mm["mse"], ls["nmse"], mm["nmse"], ls["nmse"] ** 2, mm["nmse"] ** 2,
-                            np.mean(np.abs(H[b]) ** 2), n00l, n00l ** 2, n00m, n00m ** 2]
+                            np.mean(np.abs(H[b]) ** 2), n00l, n00l ** 2, n00m, n00m ** 2, bl, bm]
     assert np.array_equal(bins[:, 0], want[:, 0])
     assert np.allclose(bins, want, rtol=2e-5), np.abs(bins / want - 1).max()
+    no_snr = eng.stats_bins(out["stats"], bin_id, 8).cpu().numpy()          # without SNRs the proxy fields stay zero
+    assert np.array_equal(no_snr[:, :12], bins[:, :12]) and not no_snr[:, 12:].any()
     # accumulate-into semantics and determinism
     again = eng.stats_bins(out["stats"], bin_id, 8, torch.from_numpy(bins).to(eng.device)).cpu().numpy()
     assert np.array_equal(again, 2 * bins)
@@ -370,6 +386,80 @@ def test_dense_wiener_path(engines):
     small = torch.from_numpy(rng.standard_normal((167, 167)) + 1j * rng.standard_normal((167, 167))).to(dev, torch.complex64)
     xs = torch.from_numpy(rng.standard_normal((77, 167)) + 1j * rng.standard_normal((77, 167))).to(dev, torch.complex64)
     assert torch.equal(eng.mmse_dense(eng.prepare_dense(small), xs), eng.mmse_dense(small, xs))
+
+
+def model_cov(idx, nsc=599):
+    """The formula-defined pilot covariance of the dense-MMSE fixtures (oracle/make_golden.py model_covariance)."""
+    ps, pk = idx // nsc, idx % nsc
+    ds, dk = ps[:, None] - ps[None, :], pk[:, None] - pk[None, :]
+    return 0.4 * np.exp(-np.abs(ds) / 20.0 - np.abs(dk) / 60.0) * np.exp(1j * 2 * np.pi * dk * 3 / 1024)
+
+
+def test_batched_dense_wiener_pipeline_on_reference_draws(engines):
+    """SlotEngine.run(mmse="dense"): slot kernel (pilot vectors out) -> one GEMM per (pattern, SNR) -> K3 mode 2,
+    driven with the reference's recorded draws of the 4x4 ETU slot, against the reference's known-covariance
+    MMSEEstimator (838 x 838 Wiener matrix, tests/golden/mmse_dense_4x4_etu.npz)."""
+    from engine import WienerBank
+    g, d = load_golden("slot_4x4_etu"), load_golden("mmse_dense_4x4_etu")
+    eng = engines(4, 4)
+    pool = eng.pool([g["pilot_indices"]])
+    snr = float(g["snr_db"])
+    bank = WienerBank(eng, pool, {0: model_cov(g["pilot_indices"])}, [snr])
+    out = eng.run(1, eng.models.index("ETU"), float(g["doppler_hz"]), snr, 0, pool, inject=inject_from_golden(eng, g),
+                  mmse="dense", wiener=bank)
+    torch.cuda.synchronize()
+    H_mm = out["H_mmse"][0].cpu().numpy()
+    errs = [relerr(H_mm[:, :, t], d["H_mmse_tx0"]) for t in range(4)]
+    diag(test="dense_pipeline_injected", worst=max(errs))
+    assert max(errs) < RTOL
+    assert_close_elementwise(H_mm[:, :, 0], d["H_mmse_tx0"])
+    assert relerr(out["H_ls"][0, :, :, 0].cpu().numpy(), g["H_ls_tx0"]) < RTOL          # LS part untouched
+    st = out["stats"][0].cpu().numpy()[:, 1].sum(axis=0)
+    n = g["channel"].size
+    assert abs(db(st[1] / n / (st[2] / n + 1e-12)) - d["metrics_mmse"][2]) < DB_TOL     # dense MMSE NMSE
+    assert abs(db(st[0] / n / (st[2] / n + 1e-12)) - g["metrics_ls"][2]) < DB_TOL       # LS NMSE from the slot kernel
+
+
+@pytest.mark.parametrize("pitch", [600, None])
+def test_batched_dense_wiener_pipeline_groups(pitch, engines):
+    """A mixed batch (2 patterns of different pilot counts x 3 SNRs, shuffled) through the dense pipeline: every slot
+    must get the filter of ITS (pattern, SNR) group -- checked against the oracle's W @ h_ls + interpolation on the
+    GPU's own LS pilot estimates, and H_true / rx / tx / H_ls must equal the default-MMSE run bit for bit."""
+    from engine import WienerBank
+    eng = engines(2, 2)
+    pool = eng.random_pool([0.05, 0.02], seed=9)
+    snrs = [0.0, 10.0, 20.0]
+    covs = {i: model_cov(pool.pilot_indices[i]) for i in range(2)}
+    bank = WienerBank(eng, pool, covs, snrs)
+    B = 13
+    rng = np.random.default_rng(5)
+    pid = rng.integers(0, 2, B).astype(np.int32)
+    snr = np.asarray(snrs, np.float32)[rng.integers(0, 3, B)]
+    args = dict(model_id=1, doppler_hz=50.0, snr_db=snr, pattern_id=pid, pool=pool, slot0=4242, seed=6)
+    base = eng.run(B, pitch=pitch, **args)
+    out = eng.run(B, pitch=pitch, mmse="dense", wiener=bank, **args)
+    torch.cuda.synchronize()
+    for k in ("H_true", "rx", "tx", "H_ls"):
+        assert torch.equal(out[k], base[k]), k
+    assert torch.equal(out["stats"][..., 0], base["stats"][..., 0]) and torch.equal(out["stats"][..., 2], base["stats"][..., 2])
+    H_ls = out["H_ls"].cpu().numpy()
+    H_true = out["H_true"].cpu().numpy().astype(np.complex128)
+    H_mm = out["H_mmse"].cpu().numpy()
+    stats = out["stats"].cpu().numpy()
+    plans = {}
+    for b in range(B):
+        idx = pool.pilot_indices[pid[b]]
+        pos = (idx // 599, idx % 599)
+        if pid[b] not in plans:
+            plans[pid[b]] = orc.linear_plan(pos, 14, 599)
+        W = orc.wiener_matrix(covs[pid[b]], float(snr[b]))
+        for r in range(2):
+            h_ls_p = H_ls[b, :, r, 0].reshape(-1)[idx].astype(np.complex128)      # LS interpolation is exact at the pilots
+            ref = orc.plan_apply(*plans[pid[b]], W @ h_ls_p, 14, 599)
+            for t in range(2):
+                assert relerr(H_mm[b, :, r, t], ref) < RTOL, (b, r, t)
+            e = sum((np.abs(H_true[b, :, r, t] - ref) ** 2).sum() for t in range(2))
+            assert abs(stats[b, r, 1, 1] / e - 1) < 1e-3, (b, r)
 
 
 def test_error_reporting(engines):

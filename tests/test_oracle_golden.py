@@ -83,6 +83,24 @@ def test_dense_covariance_mmse_matches_reference():
         assert relerr(orc.plan_apply(idx, w, h, 14, 599), g["H_mmse_tx0"][:, r]) < 1e-10
 
 
+def test_dense_covariance_mmse_4x4_matches_reference():
+    """838-pilot Wiener filter on the 4x4 ETU fixture's slot (reference run: oracle/make_golden.py
+    dense_from_slot_case): the oracle's W @ h_ls + plan route against the reference's estimate."""
+    g, d = load_golden("slot_4x4_etu"), load_golden("mmse_dense_4x4_etu")
+    pos = np.unravel_index(g["pilot_indices"], g["pilot_mask"].shape)
+    ds = pos[0][:, None] - pos[0][None, :]
+    dk = pos[1][:, None] - pos[1][None, :]
+    R = 0.4 * np.exp(-np.abs(ds) / 20.0 - np.abs(dk) / 60.0) * np.exp(1j * 2 * np.pi * dk * 3 / 1024)
+    W = orc.wiener_matrix(R, float(g["snr_db"]))
+    idx, w = orc.linear_plan(pos, 14, 599)
+    for r in range(4):
+        h = W @ orc.ls_at_pilots(g["rx_symbols"][:, r], g["pilot_symbols"], g["pilot_mask"])
+        assert relerr(orc.plan_apply(idx, w, h, 14, 599), d["H_mmse_tx0"][:, r]) < 1e-9
+    H = np.repeat(d["H_mmse_tx0"][:, :, None, :], 4, axis=2)
+    m = orc.evaluate(g["channel"], H)
+    assert abs(m["nmse_db"] - d["metrics_mmse"][2]) < 1e-9
+
+
 def test_ofdm_modem_matches_reference():
     g = load_golden("ofdm_modem")
     assert np.array_equal(orc.used_bins(1024, 600), g["used_indices"])

@@ -26,7 +26,7 @@ def _fake_bins(lo, hi, seed, sizes, nbins):
     mi, di, si, pi = dg.philox_param_choice(seed, lo, hi - lo, sizes)
     g = np.arange(lo, hi, dtype=np.float64)
     nmse = 0.1 + (g % 97) / 97.0
-    bins = np.zeros((nbins, 12))
+    bins = np.zeros((nbins, 14))
     np.add.at(bins[:, 0], si, 1.0)
     np.add.at(bins[:, 3], si, nmse)
     np.add.at(bins[:, 5], si, nmse ** 2)
@@ -62,5 +62,5 @@ def test_two_rank_sharding_and_reduction(world, tmp_path):
 
 def test_reduce_bins_is_identity_without_a_process_group():
     import dataset_generator as dg
-    b = torch.arange(24, dtype=torch.float64).reshape(2, 12)
+    b = torch.arange(28, dtype=torch.float64).reshape(2, 14)
     assert torch.equal(dg.reduce_bins(b.clone()), b)
