@@ -42,9 +42,23 @@ __device__ __forceinline__ uint4 draw(const PhiloxKey &k, uint32_t stream, uint3
   return philox4x32_10(index, stream, k.s0, k.s1, k.k0, k.k1);
 }
 
-// 23-bit uniform in (0,1); every step is exact in fp32 so the CPU twin matches bit for bit.
-__device__ __forceinline__ float u01(uint32_t w) {
-  return ((float)(w >> 9) + 0.5f) * 1.1920928955078125e-07f;
+// 23-bit uniform u = (m + 1/2) 2^-23 in (0,1), m = the word's top 23 bits.  Built from the bits of 1 + m 2^-23 (one
+// shift, one OR) instead of an int -> float conversion and a multiply; every step is exact in fp32 (the result has 24
+// significant bits), so the CPU twin matches bit for bit.
+__device__ __forceinline__ float one_plus_m(uint32_t w) { return __uint_as_float(0x3f800000u | (w >> 9)); }
+__device__ __forceinline__ float u01(uint32_t w) { return one_plus_m(w) - 0.99999994039535522f; }   // 1 - 2^-24
+
+// 2 pi (u - 1/2) for the same u: (1 + m 2^-23) - 3/2 is exact, the half-step 2^-24 rides in the FMA's addend.
+__device__ __forceinline__ float two_pi_u_centered(uint32_t w) {
+  return fmaf(6.283185307179586f, one_plus_m(w) - 1.5f, 6.283185307179586f * 5.9604644775390625e-08f);
+}
+
+// exp(j 2 pi u) for the uniform of word w.  The SFU wants its argument in [-pi, pi]: flipping the top mantissa bit
+// of m gives u' = u +- 1/2 (mod 1), and 2 pi (u' - 1/2) is the same angle in (-pi, pi) -- no round / subtract.
+__device__ __forceinline__ float2 cis_u01(uint32_t w) {
+  float s, c;
+  __sincosf(two_pi_u_centered(w ^ 0x80000000u), &s, &c);
+  return make_float2(c, s);
 }
 
 // Box-Muller pair -> one complex normal with unit variance per component.
@@ -53,9 +67,8 @@ __device__ __forceinline__ float2 normal_pair(uint32_t w1, uint32_t w2) {
   // clamp keeps r finite should the approximation round ln u to +0 for u within 1e-7 of 1.
   float x = fmaxf(-1.3862943611198906f * __log2f(u01(w1)), 1e-30f);
   float r = x * rsqrtf(x);
-  float v = u01(w2) - 0.5f;           // cos(2 pi u) = -cos(2 pi (u - 1/2)), same for sin
-  float s, c;
-  __sincosf(6.283185307179586f * v, &s, &c);
+  float s, c;                         // cos(2 pi u) = -cos(2 pi (u - 1/2)), same for sin
+  __sincosf(two_pi_u_centered(w2), &s, &c);
   return make_float2(-r * c, -r * s);
 }
 

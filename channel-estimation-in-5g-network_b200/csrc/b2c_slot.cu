@@ -209,7 +209,7 @@ __device__ __forceinline__ float2 draw_symbol(const SlotArgs &a, const SlotCtx &
   int l, h;
   rng_lane(k, a.g.nsc, l, h);
   uint4 w = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 1) * RNG_LANES + l));
-  return cis_turns(u01(pick(w, (s & 1) * 2 + h)));
+  return cis_u01(pick(w, (s & 1) * 2 + h));
 }
 __device__ __forceinline__ float2 draw_noise(const SlotArgs &a, const SlotCtx &c, int s, int k) {
   if (a.has_inj)
@@ -427,8 +427,8 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
             n1 = __ldg(inj_noise + oI + k1);
           } else {
             if (j == 0) ws = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 1) * RNG_LANES + t_));
-            x0 = cis_turns(u01(j ? ws.z : ws.x));
-            x1 = cis_turns(u01(j ? ws.w : ws.y));
+            x0 = cis_u01(j ? ws.z : ws.x);
+            x1 = cis_u01(j ? ws.w : ws.y);
             const uint4 wn = draw(c.key, STREAM_NOISE, (uint32_t)((s * nrx + c.rx) * RNG_LANES + t_));
             n0 = normal_pair(wn.x, wn.y);
             n1 = normal_pair(wn.z, wn.w);
@@ -475,6 +475,9 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
 // 8-byte form -- the kernel's ceiling moves from the store path to its arithmetic.
 // STORE = false: statistics-only sweeps (pilot-density / SNR curves, sharded statistics): no array is written, so the
 // grid symbols, the noise and the lane exchanges that only feed stores are skipped altogether.
+// ntx >= 4: the wide kernel takes the error sums over all tx from the tx-summed CFR instead of per-tx differences
+__host__ __device__ constexpr bool wide_fold(int ntx) { return ntx >= 4; }
+
 // COMPACT: the tx-replicated outputs are written once, in rx's row layout: H_ls / H_mmse [B][nsym][nrx][PITCH] and
 // tx [B][nsym][PITCH] (1 945 552 unique bytes per 4x4 slot instead of 3 756 928).
 template <int T, int NTX, bool EST, int PITCH, bool STORE, bool COMPACT>
@@ -491,6 +494,7 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
 
   const float2 *tw = reinterpret_cast<const float2 *>(a.prof.tap_tw) + (int64_t)c.m * MAXT * NSC;
   const float2 zero2 = make_float2(0.f, 0.f), neg1 = make_float2(-1.f, -1.f), nalpha = make_float2(-c.alpha, -c.alpha);
+  constexpr bool FOLD = wide_fold(NTX);                          // error sums over all tx from the tx-summed CFR (below)
   float2 twp[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) twp[t] = act ? __ldg(tw + t * NSC + K) : zero2;
@@ -521,13 +525,19 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
   // (the kernel's top stall when they were plain loads behind an L1 prefetch) is spent under the previous symbol's work
   // and costs no registers.  A thread reads back only what it copied itself, so cp.async.wait_group is all the
   // synchronisation needed.  The last iteration stages the row after the pattern's plan: in bounds (padded pool).
-  uint4 *const ps = c.pstage + t_;
+  // shared-window address of this thread's staging slots: explicit ld.shared / cp.async on it (through the generic
+  // pointer the compiler emitted generic LD.E.128, which pays the address-space check on every access)
+  const uint32_t ps_s = (uint32_t)__cvta_generic_to_shared(c.pstage + t_);
+  constexpr uint32_t PS_SLOT = SLOT_THREADS * sizeof(uint4);
   auto stage_plan = [&](int buf) {
-    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(ps + (buf * 2 + 0) * SLOT_THREADS);
-    const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(ps + (buf * 2 + 1) * SLOT_THREADS);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d0), "l"(plan + oPK) : "memory");
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d1), "l"(plan + oPS) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(ps_s + (buf * 2 + 0) * PS_SLOT), "l"(plan + oPK) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(ps_s + (buf * 2 + 1) * PS_SLOT), "l"(plan + oPS) : "memory");
     asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  auto staged = [&](int slot) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ps_s + slot * PS_SLOT) : "memory");
+    return v;
   };
   if (EST) stage_plan(0);
   auto xchg = [](float2 v) {     // value of this lane's S bin -> the neighbour that stores it as K+1
@@ -544,8 +554,8 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
         oPS += dPS;
         stage_plan(j ^ 1);                                   // next symbol's entries (s2 is even: buffer = s & 1 = j)
         asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-        lK = plan_apply(plan_decode(ps[(j * 2 + 0) * SLOT_THREADS]), c.hp);
-        lS = plan_apply(plan_decode(ps[(j * 2 + 1) * SLOT_THREADS]), c.hp);
+        lK = plan_apply(plan_decode(staged(j * 2 + 0)), c.hp);
+        lS = plan_apply(plan_decode(staged(j * 2 + 1)), c.hp);
       }
       if (EST && STORE) {
         // H_ls / H_mmse rows are the same for every tx: written here, so that only lK / lS stay live below
@@ -580,18 +590,42 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
           if (act) st16(pH + tx * PITCH, hK, hN);
         }
         if (EST) {
-          float2 (&acc)[3] = st[tx == 0 ? 0 : 1];
-          float2 d = __ffma2_rn(lK, neg1, hK);
-          acc[0] = __ffma2_rn(d, d, acc[0]);
-          d = __ffma2_rn(lS, neg1, hS);
-          acc[0] = __ffma2_rn(d, d, acc[0]);
-          d = __ffma2_rn(lK, nalpha, hK);
-          acc[1] = __ffma2_rn(d, d, acc[1]);
-          d = __ffma2_rn(lS, nalpha, hS);
-          acc[1] = __ffma2_rn(d, d, acc[1]);
-          acc[2] = __ffma2_rn(hK, hK, acc[2]);
-          acc[2] = __ffma2_rn(hS, hS, acc[2]);
+          if (!FOLD) {
+            float2 (&acc)[3] = st[tx == 0 ? 0 : 1];
+            float2 d = __ffma2_rn(lK, neg1, hK);
+            acc[0] = __ffma2_rn(d, d, acc[0]);
+            d = __ffma2_rn(lS, neg1, hS);
+            acc[0] = __ffma2_rn(d, d, acc[0]);
+            d = __ffma2_rn(lK, nalpha, hK);
+            acc[1] = __ffma2_rn(d, d, acc[1]);
+            d = __ffma2_rn(lS, nalpha, hS);
+            acc[1] = __ffma2_rn(d, d, acc[1]);
+            acc[2] = __ffma2_rn(hK, hK, acc[2]);
+            acc[2] = __ffma2_rn(hS, hS, acc[2]);
+          } else {
+            // folded form (ntx >= 4), see below: per tx only the power; tx 0 also its own cross term (pair (rx, 0))
+            float2 &pw = st[tx == 0 ? 0 : 1][2];
+            pw = __ffma2_rn(hK, hK, pw);
+            pw = __ffma2_rn(hS, hS, pw);
+            if (tx == 0) {
+              st[0][0] = __ffma2_rn(lK, hK, st[0][0]);
+              st[0][0] = __ffma2_rn(lS, hS, st[0][0]);
+            }
+          }
         }
+      }
+      if (EST && FOLD) {
+        // sum_tx |h_tx - c l|^2 = sum_tx |h_tx|^2 - 2 c Re(conj(l) sum_tx h_tx) + ntx c^2 |l|^2   (c = 1: LS, c = alpha: MMSE).
+        // l is the same for every tx, so the error sums over ALL tx need only the power, the cross term with the tx-SUMMED
+        // CFR (hsK / hsS, which the received grid needs anyway) and |l|^2: 2 packed ops per tx + 6 per symbol instead
+        // of 12 per tx.  The kernel accumulates the three raw sums; the flush combines them in double.  For ntx > 1 the
+        // result is of the order of the power itself (the LS estimate is the tx-SUM, src/channel_simulator.py:402-404),
+        // so nothing cancels.  Accumulators: st[0][0] = sum Re(conj(l) h_0) (packed re / im products), st[0][2] = |h_0|^2,
+        // st[1][0] = sum Re(conj(l) sum_tx h), st[1][1] = sum |l|^2, st[1][2] = sum_{tx >= 1} |h_tx|^2.
+        st[1][0] = __ffma2_rn(lK, hsK, st[1][0]);
+        st[1][0] = __ffma2_rn(lS, hsS, st[1][0]);
+        st[1][1] = __ffma2_rn(lK, lK, st[1][1]);
+        st[1][1] = __ffma2_rn(lS, lS, st[1][1]);
       }
       if (!STORE) {
         gps += NTX * MAXT;
@@ -600,7 +634,7 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
       // ---- draws: Philox lane t serves both bins of the mirror pair; word half h = (f > 0) -------------
       if (j == 0) ws = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 1) * RNG_LANES + t_));
       const uint32_t wm = j ? ws.z : ws.x, wp = j ? ws.w : ws.y;               // -f, +f
-      const float2 xK = cis_turns(u01(odd ? wm : wp)), xS = cis_turns(u01(odd ? wp : wm));
+      const float2 xK = cis_u01(odd ? wm : wp), xS = cis_u01(odd ? wp : wm);
       const uint4 wn = draw(c.key, STREAM_NOISE, (uint32_t)((s * nrx + c.rx) * RNG_LANES + t_));
       const float2 nK = normal_pair(odd ? wn.x : wn.z, odd ? wn.y : wn.w);
       const float2 nS = normal_pair(odd ? wn.z : wn.x, odd ? wn.w : wn.y);
@@ -704,11 +738,32 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
         // [0] = pair (rx, 0); [1] = all tx of this rx = tx 0 + the rest
         float v = st[0][j].x + st[0][j].y;
         if (q == 1) v += st[1][j].x + st[1][j].y;
+        if constexpr (WIDE != 0 && wide_fold(NTX)) v = st[q][j].x + st[q][j].y;      // raw sums, combined below
         v = warp_sum(v);
         if (lane == 0) ssm[warp][q * 3 + j] = v;
       }
     __syncthreads();
-    if (threadIdx.x < 6) {
+    if constexpr (WIDE != 0 && wide_fold(NTX)) {
+      // folded form of slot_body_wide: [0][0] = T0 = sum Re(conj(l) h_0), [0][2] = P0 = sum |h_0|^2, [1][0] = T = sum
+      // Re(conj(l) sum_tx h), [1][1] = U = sum |l|^2, [1][2] = P1 = sum_{tx >= 1} |h|^2.
+      //   pair (rx, 0): e_ls = P0 - 2 T0 + U          e_mmse = P0 - 2 alpha T0 + alpha^2 U            power = P0
+      //   all tx      : e_ls = P - 2 T + ntx U        e_mmse = P - 2 alpha T + ntx alpha^2 U          power = P = P0 + P1
+      if (threadIdx.x < 6) {
+        double r[6];
+        for (int i = 0; i < 6; ++i) {
+          double acc = 0.0;
+          for (int w = 0; w < SLOT_THREADS / 32; ++w) acc += (double)ssm[w][i];
+          r[i] = acc;
+        }
+        const double T0 = r[0], P0 = r[2], T = r[3], U = r[4], P = r[2] + r[5], al = (double)c.alpha, n = (double)NTX;
+        const int q = threadIdx.x / 3, j = threadIdx.x - 3 * q;
+        const double cc = j == 0 ? 1.0 : al;
+        double v;
+        if (j == 2) v = q ? P : P0;
+        else v = q ? P - 2.0 * cc * T + n * cc * cc * U : P0 - 2.0 * cc * T0 + cc * cc * U;
+        a.stats[(c.b * nrx + c.rx) * 6 + threadIdx.x] = v;
+      }
+    } else if (threadIdx.x < 6) {
       double acc = 0.0;
       for (int w = 0; w < SLOT_THREADS / 32; ++w) acc += (double)ssm[w][threadIdx.x];
       a.stats[(c.b * nrx + c.rx) * 6 + threadIdx.x] = acc;

@@ -265,7 +265,7 @@ def test_stats_bins_against_numpy(engines):
     no_snr = eng.stats_bins(out["stats"], bin_id, 8).cpu().numpy()          # without SNRs the proxy fields stay zero
     assert np.array_equal(no_snr[:, :12], bins[:, :12]) and not no_snr[:, 12:].any()
     # accumulate-into semantics and determinism
-    again = eng.stats_bins(out["stats"], bin_id, 8, torch.from_numpy(bins).to(eng.device)).cpu().numpy()
+    again = eng.stats_bins(out["stats"], bin_id, 8, torch.from_numpy(bins).to(eng.device), snr_db=snr).cpu().numpy()
     assert np.array_equal(again, 2 * bins)
 
 
@@ -721,7 +721,9 @@ def test_padded_row_layout_matches_contiguous(ntx, nrx, model, engines):
         assert torch.equal(pad[k], ref[k]), k                      # same operations in the same order: bit-identical
         if k in sim_pad:
             assert torch.equal(sim_pad[k], sim_ref[k]), k
-    assert torch.allclose(pad["stats"], ref["stats"], rtol=1e-6, atol=0)
+    # ntx >= 4: the wide kernel folds the error sums over tx (sum|h|^2 - 2 Re(conj(l) sum h) + ntx |l|^2), same value
+    # to fp32 rounding of O(power)-sized terms
+    assert torch.allclose(pad["stats"], ref["stats"], rtol=1e-6 if ntx < 4 else 2e-5, atol=0)
     # dataset mode: what the reference's generate_sample returns (no H_mmse, no statistics), same wide-store kernel
     dm = eng.run(B, want=("H_true", "rx", "tx", "H_ls"), pitch=_b2c.WIDE_PITCH, **args)
     assert set(k for k in dm if not k.startswith("_")) == {"H_true", "rx", "tx", "H_ls"}
@@ -730,7 +732,7 @@ def test_padded_row_layout_matches_contiguous(ntx, nrx, model, engines):
     # statistics-only call (pilot-density / SNR sweeps): the store-free instantiation gives the same sums
     so = eng.run(B, want=("stats",), **args)
     assert set(k for k in so if not k.startswith("_")) == {"stats"}
-    assert torch.allclose(so["stats"], ref["stats"], rtol=1e-6, atol=0)
+    assert torch.allclose(so["stats"], ref["stats"], rtol=1e-6 if ntx < 4 else 2e-5, atol=0)
     # against the oracle on the Philox twin draws for one slot (the contiguous path is pinned the same way)
     assert relerr(pad["H_true"][3].cpu().numpy(), ref["H_true"][3].cpu().numpy()) == 0.0
     # pitch-aware readers
