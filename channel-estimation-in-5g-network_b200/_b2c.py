@@ -16,9 +16,9 @@ ABI_VERSION = 3
 WIDE_PITCH = 600      # padded row pitch b2c_slot_pipeline accepts in its throughput configuration
 EXPORTS = ["b2c_last_error_string", "b2c_abi_version", "b2c_tap_gains", "b2c_slot_pipeline",
            "b2c_ls_interp", "b2c_pilot_vectors", "b2c_mmse_dense", "b2c_dense_real_apply", "b2c_stats_bins",
-           "b2c_ofdm_modulate", "b2c_ofdm_demodulate", "b2c_apply_channel", "b2c_tdl_full", "b2c_equalize",
+           "b2c_ofdm_modulate", "b2c_ofdm_demodulate", "b2c_apply_channel", "b2c_tdl_full", "b2c_tdl_circular", "b2c_equalize",
            "b2c_qam_modulate", "b2c_qam_demodulate", "b2c_count_bit_errors", "b2c_pair00_moments", "b2c_pair00_errors", "b2c_count_nonfinite", "b2c_dense_prepared_bytes", "b2c_dense_prepare",
-           "b2c_dense_apply_prepared", "b2c_abs_diff_sum",
+           "b2c_dense_apply_prepared", "b2c_dense_apply_grouped", "b2c_abs_diff_sum",
            "b2c_ml_features"]
 
 
@@ -35,7 +35,7 @@ class Geom(C.Structure):
 class Profiles(C.Structure):
     _fields_ = [("n_models", C.c_int32), ("ntaps", C.c_void_p), ("npaths", C.c_void_p),
                 ("tap_path", C.c_void_p), ("tap_amp", C.c_void_p), ("tap_tw", C.c_void_p),
-                ("tap_corr", C.c_void_p)]
+                ("tap_corr", C.c_void_p), ("tap_delay", C.c_void_p)]
 
 
 class Patterns(C.Structure):
@@ -46,6 +46,10 @@ class Patterns(C.Structure):
 class Slots(C.Structure):
     _fields_ = [("slot0", C.c_int64), ("seed", C.c_uint64), ("model_id", C.c_void_p),
                 ("doppler_hz", C.c_void_p), ("snr_db", C.c_void_p), ("pattern_id", C.c_void_p)]
+
+
+class DenseGroup(C.Structure):
+    _fields_ = [("prepared", C.c_void_p), ("col0", C.c_int64), ("ncols", C.c_int64), ("np", C.c_int32)]
 
 
 class PilotIO(C.Structure):
@@ -83,6 +87,7 @@ def lib():
             "b2c_ofdm_demodulate": [P, P, P, I64, P],
             "b2c_apply_channel": [P, P, P, I64, P, P, P, P, P],
             "b2c_tdl_full": [P, P, I32, F, F, I64, I32, P, I32, P, C.c_uint64, I64, P, P],
+            "b2c_tdl_circular": [P, P, P, I64, P, P, P, P],
             "b2c_equalize": [P, I64, P, P, P, C.c_double, I32, P],
             "b2c_qam_modulate": [P, I64, I32, P, P],
             "b2c_qam_demodulate": [P, I64, I32, I32, P, P],
@@ -93,6 +98,7 @@ def lib():
             "b2c_abs_diff_sum": [P, P, I64, P, P],
             "b2c_dense_prepare": [P, I32, I32, I32, P, P],
             "b2c_dense_apply_prepared": [P, I32, I32, I32, P, P, I64, I64, I64, P],
+            "b2c_dense_apply_grouped": [P, I32, P, P, I64, P],
             "b2c_ml_features": [P, P, P, I64, P, P, P, I64, I32, I32, P, P, P, P],
         }
         L.b2c_dense_prepared_bytes.argtypes = [I32, I32, I32]

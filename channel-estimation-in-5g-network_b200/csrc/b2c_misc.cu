@@ -117,9 +117,69 @@ __global__ void __launch_bounds__(256) tdl_full_kernel(TdlArgs a) {
   a.out[((n * a.nrx + rx) * a.ntx + tx) * (int64_t)a.L + a.tap_delay[t]] = make_float2(amp * ar, amp * ai);
 }
 
+// ---- time-domain TDL convolution (per-symbol, circular) ---------------------------------------------------------------
+// y[s][rx][n] = sum_tx sum_taps g[rx][s][tx][t] * x[s][tx][(n - d_t) mod N]   on the N-sample symbol bodies, prefix re-attached.
+// The reference never convolves in time: it multiplies the CFR of the symbol-start gains into the grid per bin
+// (src/channel_simulator.py:274-345), which is EXACTLY a circular convolution of each symbol body with that symbol's
+// taps (a linear one would leak the ETU taps at delay 77 > CP 72 into the next symbol and could not reproduce the
+// reference).  modulate -> this kernel -> demodulate therefore lands on the frequency-domain rx (noise aside): the
+// time-domain statement of north_star kernel 1 and an in-situ exercise of the OFDM modem (K2).
+// One CTA per (slot, symbol, rx): the ntx symbol bodies staged in shared memory, 4 outputs per thread.
+constexpr int TDC_THREADS = 256;
+__global__ void __launch_bounds__(TDC_THREADS) tdl_circular_kernel(b2c_geom g, b2c_profiles prof, const int32_t *__restrict__ model_id,
+                                                                  const float2 *__restrict__ gains, const float2 *__restrict__ x,
+                                                                  float2 *__restrict__ y) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *xs = reinterpret_cast<float2 *>(smem_raw);          // [ntx][N]
+  __shared__ float2 gs[B2C_MAX_ANT * MAXT];
+  __shared__ int ds[MAXT];
+  const int N = g.fft_size, cp = g.cp_length, T = N + cp;
+  const int rx = blockIdx.x % g.nrx;
+  const int64_t bs = blockIdx.x / g.nrx;                        // b * nsym + s
+  const int64_t b = bs / g.nsym;
+  const int s = (int)(bs - b * g.nsym);
+  const int m = model_id[b];
+  const int ntaps = prof.ntaps[m];
+  for (int i = threadIdx.x; i < g.ntx * N; i += TDC_THREADS) {
+    const int tx = i / N, n = i - tx * N;
+    xs[i] = __ldg(x + (bs * g.ntx + tx) * (int64_t)T + cp + n);                 // symbol body (prefix stripped)
+  }
+  if (threadIdx.x < g.ntx * MAXT)
+    gs[threadIdx.x] = __ldg(gains + (((b * g.nrx + rx) * g.nsym + s) * g.ntx) * (int64_t)MAXT + threadIdx.x);
+  if (threadIdx.x < MAXT) ds[threadIdx.x] = threadIdx.x < ntaps ? prof.tap_delay[m * MAXT + threadIdx.x] : 0;
+  __syncthreads();
+  float2 *yr = y + (bs * g.nrx + rx) * (int64_t)T;
+  for (int n = threadIdx.x; n < N; n += TDC_THREADS) {
+    float2 acc = make_float2(0.f, 0.f);
+    for (int tx = 0; tx < g.ntx; ++tx)
+      for (int t = 0; t < ntaps; ++t) acc = cadd(acc, cmul(gs[tx * MAXT + t], xs[tx * N + ((n - ds[t]) & (N - 1))]));
+    yr[cp + n] = acc;
+    if (n >= N - cp) yr[n - (N - cp)] = acc;                                    // cyclic prefix = the last cp samples
+  }
+}
+
 }  // namespace b2c
 
 using namespace b2c;
+
+extern "C" int b2c_tdl_circular(const b2c_geom *g, const b2c_profiles *prof, const int32_t *model_id, int64_t B, const float *gains,
+                                const float *x_time, float *y_time, void *stream) {
+  B2C_REQUIRE(g && prof && model_id && gains && x_time && y_time, B2C_E_ARG, "b2c_tdl_circular: null argument");
+  if (int rc = check_geom(g)) return rc;
+  B2C_REQUIRE(prof->tap_delay, B2C_E_ARG, "b2c_tdl_circular: b2c_profiles.tap_delay missing");
+  B2C_REQUIRE(g->fft_size >= 64 && (g->fft_size & (g->fft_size - 1)) == 0 && g->cp_length >= 0 && g->cp_length <= g->fft_size, B2C_E_UNSUPPORTED,
+              "b2c_tdl_circular: fft_size=%d must be a power of two, cp=%d", g->fft_size, g->cp_length);
+  B2C_REQUIRE(B >= 0 && B * g->nsym * g->nrx < (1ll << 31), B2C_E_ARG, "b2c_tdl_circular: B=%lld out of range", (long long)B);
+  if (B == 0) return B2C_OK;
+  const size_t smem = (size_t)g->ntx * g->fft_size * sizeof(float2);
+  B2C_REQUIRE(smem <= 200 * 1024, B2C_E_UNSUPPORTED, "b2c_tdl_circular: %zu B shared memory needed", smem);
+  if (smem > 48 * 1024) B2C_CUDA(set_max_smem<tdl_circular_kernel>(smem));
+  tdl_circular_kernel<<<(unsigned)(B * g->nsym * g->nrx), TDC_THREADS, smem, (cudaStream_t)stream>>>(
+      *g, *prof, model_id, reinterpret_cast<const float2 *>(gains), reinterpret_cast<const float2 *>(x_time),
+      reinterpret_cast<float2 *>(y_time));
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
 
 extern "C" int b2c_apply_channel(const b2c_geom *g, const b2c_slots *slots, const b2c_inject *inj, int64_t B,
                                  const float *tx, const float *H, float *rx, double *power_scratch, void *stream) {

@@ -528,10 +528,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // REALW = false: complex W [np][np] embedded as a real 2np x 2np operand (m = k = np), a tile covers 256 columns.
 // REALW = true : real W [m][k] applied to re / im alike, a tile covers 128 complex columns (= 256 GEMM columns).
-template <bool REALW>
+// Grouped launch: several independent products (one Wiener matrix per (pattern, SNR) group of the batch, each applied to
+// its own contiguous block of columns) share ONE grid, so that the small per-group tile counts (14 row tiles x a few
+// column tiles) fill the 148 SMs together instead of one partial wave each.
+constexpr int MAX_GROUPS = 32;
+struct GroupTable {
+  int ngroups;                          // 0: plain launch, blockIdx.x = row tile, blockIdx.y = column tile
+  int tile_end[MAX_GROUPS];             // running sum of tiles (row tiles x column tiles) over the groups
+  int tiles_m[MAX_GROUPS];
+  int np[MAX_GROUPS];
+  long long col0[MAX_GROUPS], ncols[MAX_GROUPS];
+  const float *prepared[MAX_GROUPS];
+};
+
+template <bool REALW, bool GROUPED = false>
 __global__ void __launch_bounds__(WS_THREADS, 1) dense_tc_ws_kernel(const float *__restrict__ prepared, int m, int k,
                                                                    const float2 *__restrict__ in, float *__restrict__ out,
-                                                                   int64_t ncols, int64_t ld_in, int64_t ld_out) {
+                                                                   int64_t ncols, int64_t ld_in, int64_t ld_out,
+                                                                   const __grid_constant__ GroupTable gt) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ uint32_t tmem_base_sm;
   __shared__ __align__(8) uint64_t full_a[2], full_b[2], empty[2], acc_bar;
@@ -539,7 +553,35 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dense_tc_ws_kernel(const float 
   unsigned char *sp = smem_dyn + (s0 - smem_u32(smem_dyn));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t c0 = (int64_t)blockIdx.y * (REALW ? T2_BN / 2 : T2_BN);     // first (complex) column of the tile
+  int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  if constexpr (GROUPED) {
+    // which group owns linear tile blockIdx.x, and which (row, column) tile of that group it is; selects over the
+    // unrolled table keep every access to the kernel parameters statically indexed
+    const int tile = blockIdx.x;
+    int g = 0;
+#pragma unroll
+    for (int i = 0; i < MAX_GROUPS; ++i)
+      if (i < gt.ngroups - 1 && tile >= gt.tile_end[i]) g = i + 1;
+    int begin = 0, tm_count = 1;
+    long long col0 = 0;
+#pragma unroll
+    for (int i = 0; i < MAX_GROUPS; ++i) {
+      if (i == g) {
+        begin = i ? gt.tile_end[i - 1] : 0;
+        tm_count = gt.tiles_m[i];
+        m = k = gt.np[i];
+        col0 = gt.col0[i];
+        ncols = gt.ncols[i];
+        prepared = gt.prepared[i];
+      }
+    }
+    const int local = tile - begin;
+    tile_n = local / tm_count;
+    tile_m = local - tile_n * tm_count;
+    in += col0 * ld_in;
+    out += 2 * col0 * ld_out;
+  }
+  const int64_t c0 = (int64_t)tile_n * (REALW ? T2_BN / 2 : T2_BN);     // first (complex) column of the tile
   const int np = k, kreal = REALW ? k : 2 * k;
   const int mreal = REALW ? m : 2 * k;
   const int64_t ld = ld_in;
@@ -590,7 +632,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dense_tc_ws_kernel(const float 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const unsigned char *prep = reinterpret_cast<const unsigned char *>(prepared) + (int64_t)blockIdx.x * nstages * (2 * TC_TILE_A);
+      const unsigned char *prep = reinterpret_cast<const unsigned char *>(prepared) + (int64_t)tile_m * nstages * (2 * TC_TILE_A);
       for (int st = 0; st < nstages; ++st) {
         const int b = st & 1;
         if (st >= 2) mbar_wait(smem_u32(&empty[b]), (uint32_t)((st >> 1) - 1) & 1u);
@@ -677,7 +719,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dense_tc_ws_kernel(const float 
     // epilogue: TMEM lanes 32 (warp & 3) .. + 31 (this warp's hardware quarter), columns 128 (pw >> 2) .. + 127
     mbar_wait(smem_u32(&acc_bar), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const int ip = blockIdx.x * TC_BM + (warp & 3) * 32 + lane;
+    const int ip = tile_m * TC_BM + (warp & 3) * 32 + lane;
     const int chalf = (pw >> 2) * 128;
     const int64_t ld2 = 2 * ld_out;
 #pragma unroll 1
@@ -715,6 +757,248 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dense_tc_ws_kernel(const float 
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)T2_BN));
+}
+
+
+// ---- data operand in TMEM ("TS" form) ----------------------------------------------------------------------------------
+// The warp-specialised SS kernel above is bound by the shared-memory pipe (ncu: L1/shared data pipe 79-81 %, tensor pipe
+// 63 %): every K step the three MMAs read A (4 KB) and B (8 KB) from shared memory, and the data operand is first WRITTEN
+// there by the CUDA cores (64 KB of hi / lo tiles per stage).  Here the roles are swapped:
+//     D[c][i'] = sum_j' X[c][j'] * Wt[i'][j']        M = 128 data columns c,  N = 2 x 128 real output rows i'
+//   * A = the data, straight from global memory into registers, split into TF32 hi / lo and stored to TENSOR MEMORY with
+//     tcgen05.st (one lane per column c, 32 K-columns per stage): it never touches shared memory;
+//   * B = the prepared Wiener tiles (b2c_dense_prepare's hi / lo pairs, unchanged), two 128-row tiles per CTA fetched by
+//     cp.async.bulk into a three-stage ring: the only shared-memory traffic left is the bulk write and the MMAs' B reads
+//     (107 B/clk/SM at full tensor rate instead of 159 of the 128 the pipe can carry).
+//   * the accumulator row of a thread is one column c with 256 consecutive output reals: 16-byte stores.
+// warp 0: MMA issuer, warp 1: bulk producer, warps 2-5: data producers (their TMEM lane quarter) and epilogue.
+constexpr int TA_THREADS = 192;
+constexpr int TA_NST = 3;
+constexpr int TA_STAGE = 2 * (2 * TC_TILE_A);                 // two W row tiles, hi + lo each: 64 KB
+constexpr int TA_SMEM = TA_NST * TA_STAGE + 1024;
+constexpr int TA_BM = 128;                                    // data columns per CTA (TMEM lanes)
+constexpr uint32_t TA_COL_D = 0, TA_COL_A = 256, TA_COLS = 512;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+
+template <bool GROUPED>
+__global__ void __launch_bounds__(TA_THREADS, 1) dense_tc_ta_kernel(const float *__restrict__ prepared, int np,
+                                                                   const float2 *__restrict__ in, float *__restrict__ out,
+                                                                   int64_t ncols, int64_t ld,
+                                                                   const __grid_constant__ GroupTable gt) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ uint32_t tmem_base_sm;
+  __shared__ __align__(8) uint64_t full_a[TA_NST], full_b[TA_NST], empty[TA_NST], acc_bar;
+  const uint32_t s0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int pair = blockIdx.x, tile_n = blockIdx.y;
+  if constexpr (GROUPED) {
+    const int tile = blockIdx.x;
+    int g = 0;
+#pragma unroll
+    for (int i = 0; i < MAX_GROUPS; ++i)
+      if (i < gt.ngroups - 1 && tile >= gt.tile_end[i]) g = i + 1;
+    int begin = 0, pairs = 1;
+    long long col0 = 0;
+#pragma unroll
+    for (int i = 0; i < MAX_GROUPS; ++i) {
+      if (i == g) {
+        begin = i ? gt.tile_end[i - 1] : 0;
+        pairs = gt.tiles_m[i];                      // here: PAIRS of W row tiles
+        np = gt.np[i];
+        col0 = gt.col0[i];
+        ncols = gt.ncols[i];
+        prepared = gt.prepared[i];
+      }
+    }
+    const int local = tile - begin;
+    tile_n = local / pairs;
+    pair = local - tile_n * pairs;
+    in += col0 * ld;
+    out += 2 * col0 * ld;
+  }
+  const int kreal = 2 * np;                                   // K and the output rows are both the 2 np real indices
+  const int nstages = (kreal + TC_BK - 1) / TC_BK;
+  const int tiles_w = (kreal + TC_BM - 1) / TC_BM;
+  const int tm0 = 2 * pair;
+  const bool has2 = tm0 + 1 < tiles_w;
+  const int64_t c0 = (int64_t)tile_n * TA_BM;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "r"(TA_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < TA_NST; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;\n" ::"r"(smem_u32(&full_a[b])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&full_b[b])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&empty[b])));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&acc_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base_sm;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int st = 0; st < nstages; ++st) {
+        const int b = st % TA_NST;
+        const uint32_t ph = (uint32_t)(st / TA_NST) & 1u;
+        mbar_wait(smem_u32(&full_a[b]), ph);
+        mbar_wait(smem_u32(&full_b[b]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t aA = tmem + TA_COL_A + (uint32_t)b * 64u;              // hi: 32 columns, lo: the next 32
+        const uint32_t sB = s0 + b * TA_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 0 || has2) {
+              const uint32_t bh = sB + h * (2 * TC_TILE_A), bl = bh + TC_TILE_A;
+              const uint64_t dBh = umma_desc(bh + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+              const uint64_t dBl = umma_desc(bl + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+              const uint32_t d = tmem + TA_COL_D + (uint32_t)h * 128u;
+              // same three products in the same order as the SS kernels (W hi x hi, W hi x lo, W lo x hi)
+              umma_tf32_ts(d, aA + kk * 8, dBh, (st | kk) != 0);
+              umma_tf32_ts(d, aA + 32 + kk * 8, dBh, 1u);
+              umma_tf32_ts(d, aA + kk * 8, dBl, 1u);
+            }
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&empty[b])) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&acc_bar)) : "memory");
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const unsigned char *prep = reinterpret_cast<const unsigned char *>(prepared);
+      const uint32_t bytes = has2 ? 2u * (2u * TC_TILE_A) : 2u * TC_TILE_A;
+      for (int st = 0; st < nstages; ++st) {
+        const int b = st % TA_NST;
+        if (st >= TA_NST) mbar_wait(smem_u32(&empty[b]), (uint32_t)(st / TA_NST - 1) & 1u);
+        const uint32_t bar = smem_u32(&full_b[b]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+        for (int h = 0; h < (has2 ? 2 : 1); ++h)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                           s0 + b * TA_STAGE + h * (2 * TC_TILE_A)),
+                       "l"(prep + ((int64_t)(tm0 + h) * nstages + st) * (2 * TC_TILE_A)), "r"(2u * TC_TILE_A), "r"(bar)
+                       : "memory");
+      }
+    }
+  } else {
+    // data producers: this thread owns data column c (TMEM lane 32 q + lane of its warp's quarter q = warp % 4)
+    const int q = warp & 3;
+    const int64_t c = c0 + q * 32 + lane;
+    const bool cvalid = c < ncols;
+    const float *row = reinterpret_cast<const float *>(in) + c * 2 * ld;
+    const int64_t row_floats = 2 * ld;
+    float4 cur[8], nxt[8];
+    auto load_stage = [&](int st, float4 (&r)[8]) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int e = st * TC_BK + 4 * i;
+        r[i] = (cvalid && e + 4 <= row_floats && e < kreal) ? __ldg(reinterpret_cast<const float4 *>(row + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e + 4 > kreal) {                       // the K tail: elements past 2 np never enter the product
+          if (e + 0 >= kreal) r[i].x = 0.f;
+          if (e + 1 >= kreal) r[i].y = 0.f;
+          if (e + 2 >= kreal) r[i].z = 0.f;
+          if (e + 3 >= kreal) r[i].w = 0.f;
+        }
+      }
+    };
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    load_stage(0, cur);
+    for (int st = 0; st < nstages; ++st) {
+      const int b = st % TA_NST;
+      if (st + 1 < nstages) load_stage(st + 1, nxt);
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float v[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float h, l;
+          split_tf32(v[j], h, l);
+          hi[4 * i + j] = __float_as_uint(h);
+          lo[4 * i + j] = __float_as_uint(l);
+        }
+      }
+      if (st >= TA_NST) {
+        mbar_wait(smem_u32(&empty[b]), (uint32_t)(st / TA_NST - 1) & 1u);       // the MMAs that read this TMEM stage are done
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      }
+      tmem_st32(lane_base + TA_COL_A + (uint32_t)b * 64u, hi);
+      tmem_st32(lane_base + TA_COL_A + (uint32_t)b * 64u + 32u, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_a[b])) : "memory");
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+    }
+
+    // epilogue: this thread's accumulator row = column c, 256 consecutive output reals
+    mbar_wait(smem_u32(&acc_bar), 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    float *orow = out + c * 2 * ld;
+    const bool vec_ok = ((2 * ld) & 3) == 0;
+#pragma unroll 1
+    for (int cb = 0; cb < (has2 ? 256 : 128); cb += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = lane_base + TA_COL_D + (uint32_t)cb;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      if (cvalid) {
+        const int i0 = tm0 * TC_BM + cb;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const int ip = i0 + e;
+          if (vec_ok && ip + 4 <= kreal) {
+            *reinterpret_cast<float4 *>(orow + ip) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]),
+                                                                 __uint_as_float(r[e + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (ip + j < kreal) orow[ip + j] = __uint_as_float(r[e + j]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TA_COLS));
 }
 
 }  // namespace b2c
@@ -797,6 +1081,16 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
     // wave quantisation at this column count, so take the shape whose last wave is fuller.
     int sm_count = 0;
     B2C_CUDA((cudaError_t)sm_count_current(&sm_count));
+    if (ncols >= TA_BM && (ld_in & 1) == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 && !getenv("B2C_DENSE_SS")) {
+      // data operand in tensor memory (see dense_tc_ta_kernel): one CTA per pair of W row tiles x 128 columns
+      dim3 grid((unsigned)((tiles_m + 1) / 2), (unsigned)((ncols + TA_BM - 1) / TA_BM));
+      B2C_REQUIRE(grid.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
+      B2C_CUDA((set_max_smem<dense_tc_ta_kernel<false>>(TA_SMEM)));
+      dense_tc_ta_kernel<false><<<grid, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(P, k, reinterpret_cast<const float2 *>(in), out, ncols, ld_in,
+                                                                                     GroupTable{});
+      B2C_CUDA(cudaGetLastError());
+      return B2C_OK;
+    }
     auto wave_eff = [&](int64_t tiles, int per_sm) {
       const int64_t slots = (int64_t)sm_count * per_sm;
       return (double)tiles / (double)(((tiles + slots - 1) / slots) * slots);
@@ -810,7 +1104,7 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
       B2C_REQUIRE(grid2.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
       B2C_CUDA((set_max_smem<dense_tc_ws_kernel<false>>(WS_SMEM)));
       dense_tc_ws_kernel<false><<<grid2, WS_THREADS, WS_SMEM, (cudaStream_t)stream>>>(P, k, k, reinterpret_cast<const float2 *>(in), out,
-                                                                                      ncols, ld_in, ld_out);
+                                                                                      ncols, ld_in, ld_out, GroupTable{});
       B2C_CUDA(cudaGetLastError());
       return B2C_OK;
     }
@@ -833,7 +1127,7 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
       B2C_REQUIRE(grid2.y <= 65535, B2C_E_UNSUPPORTED, "b2c_dense_apply_prepared: ncols=%lld too large for one launch", (long long)ncols);
       B2C_CUDA((set_max_smem<dense_tc_ws_kernel<true>>(WS_SMEM)));
       dense_tc_ws_kernel<true><<<grid2, WS_THREADS, WS_SMEM, (cudaStream_t)stream>>>(P, m, k, reinterpret_cast<const float2 *>(in), out, ncols,
-                                                                                     ld_in, ld_out);
+                                                                                     ld_in, ld_out, GroupTable{});
       B2C_CUDA(cudaGetLastError());
       return B2C_OK;
     }
@@ -843,6 +1137,51 @@ extern "C" int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t
     dense_tc_kernel<true, true><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(P, m, k, reinterpret_cast<const float2 *>(in), out,
                                                                                       ncols, ld_in, ld_out);
   }
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_dense_apply_grouped(const b2c_dense_group *groups_host, int32_t ngroups, const float *in, float *out, int64_t ld,
+                                       void *stream) {
+  B2C_REQUIRE(groups_host && in && out && in != out, B2C_E_ARG, "b2c_dense_apply_grouped: null argument or in-place");
+  B2C_REQUIRE(ngroups >= 0 && ngroups <= MAX_GROUPS, B2C_E_UNSUPPORTED, "b2c_dense_apply_grouped: %d groups (at most %d per call)", ngroups,
+              MAX_GROUPS);
+  GroupTable gt = {};
+  int tiles = 0;
+  bool ta = (ld & 1) == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 && !getenv("B2C_DENSE_SS");
+  for (int g = 0; g < ngroups; ++g) ta = ta && ((groups_host[g].col0 * ld) & 1) == 0;
+  for (int g = 0; g < ngroups; ++g) {
+    const b2c_dense_group &q = groups_host[g];
+    B2C_REQUIRE(q.prepared && q.np >= 1 && q.ncols >= 0 && q.col0 >= 0 && ld >= q.np, B2C_E_ARG,
+                "b2c_dense_apply_grouped: group %d: np=%d col0=%lld ncols=%lld ld=%lld", g, q.np, (long long)q.col0, (long long)q.ncols,
+                (long long)ld);
+    B2C_REQUIRE(((uintptr_t)q.prepared & 15) == 0, B2C_E_ARG, "b2c_dense_apply_grouped: prepared operand must be 16-byte aligned");
+    if (q.ncols == 0) continue;                    // empty groups take no tiles
+    int tm, nst;
+    prep_dims(q.np, q.np, 1, tm, nst);
+    if (ta) tm = (tm + 1) / 2;                     // TS kernel: a CTA takes a PAIR of W row tiles x 128 columns
+    const int64_t tn = ta ? (q.ncols + TA_BM - 1) / TA_BM : (q.ncols + T2_BN - 1) / T2_BN;
+    B2C_REQUIRE(tiles + tm * tn < (1ll << 30), B2C_E_UNSUPPORTED, "b2c_dense_apply_grouped: too many tiles");
+    const int i = gt.ngroups++;
+    tiles += (int)(tm * tn);
+    gt.tile_end[i] = tiles;
+    gt.tiles_m[i] = tm;
+    gt.np[i] = q.np;
+    gt.col0[i] = q.col0;
+    gt.ncols[i] = q.ncols;
+    gt.prepared[i] = static_cast<const float *>(q.prepared);
+  }
+  if (tiles == 0) return B2C_OK;
+  if (ta) {
+    B2C_CUDA((set_max_smem<dense_tc_ta_kernel<true>>(TA_SMEM)));
+    dense_tc_ta_kernel<true><<<(unsigned)tiles, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(nullptr, 0, reinterpret_cast<const float2 *>(in), out,
+                                                                                            0, ld, gt);
+    B2C_CUDA(cudaGetLastError());
+    return B2C_OK;
+  }
+  B2C_CUDA((set_max_smem<dense_tc_ws_kernel<false, true>>(WS_SMEM)));
+  dense_tc_ws_kernel<false, true><<<(unsigned)tiles, WS_THREADS, WS_SMEM, (cudaStream_t)stream>>>(
+      nullptr, 0, 0, reinterpret_cast<const float2 *>(in), out, 0, ld, ld, gt);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }

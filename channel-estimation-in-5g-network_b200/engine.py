@@ -14,7 +14,7 @@ import torch
 
 import _b2c
 import _tables
-from _b2c import Geom, Inject, Patterns, PilotIO, Profiles, Slots, check, dptr, lib, ref, row_pitch, rows_ptr, stream_ptr
+from _b2c import DenseGroup, Geom, Inject, Patterns, PilotIO, Profiles, Slots, check, dptr, lib, ref, row_pitch, rows_ptr, stream_ptr
 
 DEFAULT_MODELS = ("EPA", "EVA", "ETU")
 BIN_FIELDS = ("count", "sum_mse_ls", "sum_mse_mmse", "sum_nmse_ls", "sum_nmse_mmse", "sum_nmse_ls_sq",
@@ -108,6 +108,29 @@ class WienerBank:
         starts = np.concatenate([[0], np.cumsum(np.bincount(inv, minlength=len(keys)))])
         return order, starts, keys
 
+    def plan_batch(self, engine, pattern_id, snr_db, B):
+        """Grouping of one batch as the kernels consume it: the device column map (slot b's pilot vectors live in rows
+        col[b] .. col[b] + nrx - 1 of the grouped pilot matrix) and the per-group GEMM descriptors.  A plan depends only on
+        the batch's (pattern, SNR) values: build it once and pass it to every SlotEngine.run(dense_plan=...) that
+        repeats them (the grouping is host work: np.unique + argsort + one upload)."""
+        order, starts, keys = self.groups(np.broadcast_to(np.asarray(pattern_id), (B,)), np.broadcast_to(np.asarray(snr_db), (B,)))
+        rank = np.empty(B, dtype=np.int64)
+        rank[order] = np.arange(B)
+        nrx = engine.nrx
+        plan = DenseBatchPlan()
+        plan.B, plan.keys = B, keys
+        plan.col = torch.from_numpy((rank * nrx).astype(np.int32)).to(engine.device)
+        plan.groups = (DenseGroup * len(keys))()
+        for gi, key in enumerate(keys):
+            W = self.prepared[key]
+            plan.groups[gi] = DenseGroup(W.buf.data_ptr(), int(starts[gi]) * nrx, int(starts[gi + 1] - starts[gi]) * nrx, W.m)
+        plan.keepalive = [self.prepared[k] for k in keys]
+        return plan
+
+
+class DenseBatchPlan:
+    """See WienerBank.plan_batch."""
+
 
 class SlotEngine:
     """Geometry + TDL profile tables on one GPU, and launchers for every libb2c entry point."""
@@ -129,7 +152,7 @@ class SlotEngine:
         self._dev = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in t.items()}
         self.prof = Profiles(len(self.models), self._dev["ntaps"].data_ptr(), self._dev["npaths"].data_ptr(),
                              self._dev["tap_path"].data_ptr(), self._dev["tap_amp"].data_ptr(),
-                             self._dev["tap_tw"].data_ptr(), self._dev["tap_corr"].data_ptr())
+                             self._dev["tap_tw"].data_ptr(), self._dev["tap_corr"].data_ptr(), self._dev["tap_delay"].data_ptr())
         self.p_max = int(t["npaths"].max())
         self._cubic, self._ident = {}, {}
 
@@ -205,7 +228,7 @@ class SlotEngine:
     # ---- K1a + fused slot kernel -------------------------------------------------------------------
     def run(self, B, model_id, doppler_hz, snr_db, pattern_id=0, pool=None, slot0=0, seed=42, inject=None,
             want=("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), out=None, ws=None, compact=False, pitch=None,
-            mmse="default", wiener=None):
+            mmse="default", wiener=None, dense_plan=None):
         """Simulate B slots and (if any of H_ls/H_mmse/stats is wanted) estimate them.
         Per-slot parameters are scalars or length-B arrays/tensors.  Returns dict of CUDA tensors.
         compact=True writes the tx-replicated arrays once (see alloc_outputs); expand_compact() turns
@@ -214,8 +237,9 @@ class SlotEngine:
         mmse="default": MMSEEstimator()'s alpha * LS (src/baseline_estimators.py:177-180), fused in the slot kernel.
         mmse="dense" + wiener=WienerBank: the known-covariance branch (:181-190) for the whole batch -- the slot
         kernel also hands out h_ls at the pilots grouped by (pattern, SNR), one tensor-core GEMM per group applies
-        W, and K3 interpolates the filtered pilots into H_mmse and scores them (pattern_id / snr_db must then be
-        host values: they decide the grouping)."""
+        W, and K3 interpolates the filtered pilots into H_mmse and scores them.  The grouping is decided on the host:
+        either pattern_id / snr_db are host values, or dense_plan = wiener.plan_batch(...) built once for batches that
+        repeat the same (pattern, SNR) values."""
         if mmse not in ("default", "dense"):
             raise ValueError(f"Unknown mmse mode: {mmse}")
         dense = mmse == "dense" and any(k in (out if out is not None else want) for k in ("H_mmse", "stats"))
@@ -224,8 +248,8 @@ class SlotEngine:
                 raise ValueError('mmse="dense" needs a WienerBank and its PatternPool')
             if compact:
                 raise ValueError('mmse="dense" writes H_mmse in the full layout')
-            if isinstance(pattern_id, torch.Tensor) or isinstance(snr_db, torch.Tensor):
-                raise ValueError('mmse="dense" groups slots by (pattern, SNR) on the host: pass host values')
+            if dense_plan is None and (isinstance(pattern_id, torch.Tensor) or isinstance(snr_db, torch.Tensor)):
+                raise ValueError('mmse="dense" groups slots by (pattern, SNR) on the host: pass host values or a dense_plan')
             if out is None:
                 want = tuple(want) + tuple(k for k in ("H_true", "H_ls") if k not in want)   # K3 scores against H_true
         if out is None:
@@ -247,10 +271,11 @@ class SlotEngine:
         if dense:
             if "H_true" not in out:
                 raise ValueError('mmse="dense" needs H_true among the outputs (the MMSE error sums are taken against it)')
-            order, starts, keys = wiener.groups(np.broadcast_to(np.asarray(pattern_id), (B,)), np.broadcast_to(np.asarray(snr_db), (B,)))
-            rank = np.empty(B, dtype=np.int64)
-            rank[order] = np.arange(B)
-            col = torch.from_numpy((rank * self.nrx).astype(np.int32)).to(self.device)
+            if dense_plan is None:
+                dense_plan = wiener.plan_batch(self, pattern_id, snr_db, B)
+            if dense_plan.B != B:
+                raise ValueError(f"dense_plan was built for {dense_plan.B} slots, this batch has {B}")
+            col = dense_plan.col
             ld = pool.np_max
             hp = ws.get("hp")
             if hp is None or hp.shape[0] < B * self.nrx or hp.shape[1] != ld:
@@ -267,18 +292,17 @@ class SlotEngine:
                                   1 if compact else 0, ref(pio), stream_ptr()), "b2c_slot_pipeline")
         if dense:
             hm = ws["hm"]
-            for gi, key in enumerate(keys):                       # one GEMM per (pattern, SNR) group
-                r0, r1 = int(starts[gi]) * self.nrx, int(starts[gi + 1]) * self.nrx
-                W = wiener.prepared[key]
-                check(L.b2c_dense_apply_prepared(dptr(W.buf, "u8"), W.m, W.k, 1, C.c_void_p(hp.data_ptr() + r0 * ld * 8),
-                                                 C.c_void_p(hm.data_ptr() + r0 * ld * 8), r1 - r0, ld, ld, stream_ptr()),
-                      "b2c_dense_apply_prepared")
+            ng = len(dense_plan.groups)
+            for g0 in range(0, ng, 32):                           # every (pattern, SNR) group's GEMM in one launch (32 groups per call)
+                n = min(32, ng - g0)
+                check(L.b2c_dense_apply_grouped(C.byref(dense_plan.groups, g0 * C.sizeof(DenseGroup)), n, dptr(hp, "c64"), dptr(hm, "c64"),
+                                                ld, stream_ptr()), "b2c_dense_apply_grouped")
             # K3, mode 2: interpolate the filtered pilots into H_mmse, MMSE error sums into stats[..., 1]
             check(L.b2c_ls_interp(ref(g), ref(pool.struct), keep[3].data_ptr(), None, B, None, None, 0, dptr(hm, "c64"), 2,
                                   rows_ptr(out["H_true"], P) if "stats" in out else None, None,
                                   rows_ptr(out.get("H_mmse"), P, True), None, dptr(out.get("stats"), "f64", True),
                                   dptr(col, "i32"), ld, stream_ptr()), "b2c_ls_interp")
-            keep = keep + (col,)
+            keep = keep + (dense_plan,)
         out["_keepalive"] = (keep, keep_inj, ws)
         return out
 
@@ -439,6 +463,31 @@ class SlotEngine:
         check(lib().b2c_ofdm_demodulate(ref(self.geom), dptr(sig, "c64"), dptr(out, "c64"), rows, stream_ptr()),
               "b2c_ofdm_demodulate")
         return out
+
+    # ---- time-domain statement of the slot (north_star kernels 1 / 2 as written) -------------------------------------
+    def time_domain_slot(self, B, model_id, doppler_hz, tx=None, slot0=0, seed=42, inject=None):
+        """OFDM-modulate the transmit grids, convolve every symbol body circularly with that symbol's tap gains (K1a,
+        the very gains the fused kernel uses) and demodulate: the received grid of the frequency-domain pipeline
+        WITHOUT noise, obtained through src/channel_simulator.py:150-203's modem (K2) and a time-domain TDL.
+        tx [B, nsym, ntx, nsc] complex64 CUDA (default: the slot pipeline's own Philox grid).  Returns dict with
+        rx [B, nsym, nrx, nsc], x_time / y_time [B, nsym, ant, fft + cp] and the tx used."""
+        ws = self.workspace(B)
+        slots, keep = self._slots(B, model_id, doppler_hz, 300.0, 0, slot0, seed)
+        ij, keep_inj = self._inject(inject)
+        L = lib()
+        check(L.b2c_tap_gains(ref(self.geom), ref(self.prof), ref(slots), ref(ij), B, dptr(ws["gains"], "c64"),
+                              dptr(ws["noise_std"], "f32"), stream_ptr()), "b2c_tap_gains")
+        if tx is None:
+            tx = self.run(B, model_id, doppler_hz, 300.0, slot0=slot0, seed=seed, inject=inject, want=("H_true", "rx", "tx"))["tx"]
+        tx = tx.contiguous()
+        x_time = self.ofdm_modulate(tx.reshape(B * self.nsym * self.ntx, self.nsc))
+        y_time = torch.empty((B * self.nsym * self.nrx, self.fft_size + self.cp), dtype=torch.complex64, device=self.device)
+        check(L.b2c_tdl_circular(ref(self.geom), ref(self.prof), keep[0].data_ptr(), B, dptr(ws["gains"], "c64"), dptr(x_time, "c64"),
+                                 dptr(y_time, "c64"), stream_ptr()), "b2c_tdl_circular")
+        rx = self.ofdm_demodulate(y_time).reshape(B, self.nsym, self.nrx, self.nsc)
+        T = self.fft_size + self.cp
+        return {"rx": rx, "tx": tx, "x_time": x_time.reshape(B, self.nsym, self.ntx, T), "y_time": y_time.reshape(B, self.nsym, self.nrx, T),
+                "_keepalive": (keep, keep_inj, ws)}
 
     # ---- a8 / a3 stand-alone -----------------------------------------------------------------------------
     def apply_channel(self, tx, H, snr_db, noise=None, slot0=0, seed=42, geom=None):

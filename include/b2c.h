@@ -88,6 +88,7 @@ typedef struct b2c_profiles {
   const float *tap_amp;     /* [M][B2C_MAX_TAPS]      sqrt(P_path) / sqrt(2*20)                */
   const float *tap_tw;      /* [M][B2C_MAX_TAPS][nsc] complex: exp(-j 2 pi (i_k - N/2) d / N)  */
   const float *tap_corr;    /* [M][B2C_MAX_TAPS][B2C_MAX_TAPS] complex: sum_k T[p,k] conj(T[q,k]) */
+  const int32_t *tap_delay; /* [M][B2C_MAX_TAPS]      sample delay of the tap (b2c_tdl_circular) */
 } b2c_profiles;
 
 /* Pool of pilot patterns with their interpolation plans.  PilotPattern
@@ -233,6 +234,20 @@ int b2c_dense_prepare(const float *W, int32_t m, int32_t k, int32_t is_complex, 
 int b2c_dense_apply_prepared(const void *prepared, int32_t m, int32_t k, int32_t is_complex, const float *in,
                              float *out, int64_t ncols, int64_t ld_in, int64_t ld_out, void *stream);
 
+/* K4, grouped.  Several prepared complex products in ONE launch: group g applies its Wiener matrix (np_g x np_g, in
+ * b2c_dense_prepare's form) to columns [col0_g, col0_g + ncols_g) of in / out [.][ld] -- the (pattern, SNR) groups of a
+ * batch in the dense-Wiener pipeline (W = R (R + sigma^2 I)^-1 "built once, then applied to the batch",
+ * src/baseline_estimators.py:181-190).  One grid over the tiles of all groups: the small per-group tile counts fill
+ * the SMs together.  groups_host is a HOST array (read during the call); at most 32 groups per call.  Same results as
+ * ngroups calls of b2c_dense_apply_prepared, bit for bit.                                                    */
+typedef struct b2c_dense_group {
+  const void *prepared;     /* b2c_dense_prepare(W, np, np, 1, ...) workspace (device)         */
+  int64_t col0, ncols;      /* this group's block of columns                                  */
+  int32_t np;
+} b2c_dense_group;
+int b2c_dense_apply_grouped(const b2c_dense_group *groups_host, int32_t ngroups, const float *in, float *out, int64_t ld,
+                            void *stream);
+
 /* K5.  Fold per-slot statistics into per-bin float64 accumulators (deterministic order).
  * Replaces the per-sample evaluate_estimator / compute_nmse + list aggregation of
  * src/baseline_estimators.py:326-337 and run_phase8_pilot_optimization.py:32-37,186-206.
@@ -273,6 +288,16 @@ int b2c_apply_channel(const b2c_geom *g, const b2c_slots *slots, const b2c_injec
 int b2c_tdl_full(const b2c_geom *g, const b2c_profiles *prof, int32_t model_id, float doppler_hz,
                  float sample_period_s, int64_t num_samples, int32_t L, const int32_t *tap_delay_host,
                  int32_t ntaps, const float *jakes_u, uint64_t seed, int64_t slot, float *out, void *stream);
+
+/* Time-domain statement of the channel: per-symbol CIRCULAR convolution of the modulated symbols with the tap gains of
+ * b2c_tap_gains, y[s][rx][n] = sum_tx sum_t g[rx][s][tx][t] x[s][tx][(n - d_t) mod N] on the N-sample bodies, cyclic
+ * prefix re-attached.  b2c_ofdm_modulate -> this -> b2c_ofdm_demodulate equals the frequency-domain product
+ * MIMOChannel.apply_channel forms per bin (src/channel_simulator.py:274-345, noise aside): the reference samples the
+ * channel once per symbol and multiplies CFRs, which is a circular convolution per symbol (a linear one cannot
+ * reproduce it: ETU's last tap, 77 samples, exceeds the 72-sample prefix).
+ *   gains [B][nrx][nsym][ntx][B2C_MAX_TAPS] (b2c_tap_gains), x_time [B][nsym][ntx][fft+cp], y_time [B][nsym][nrx][fft+cp]  */
+int b2c_tdl_circular(const b2c_geom *g, const b2c_profiles *prof, const int32_t *model_id, int64_t B, const float *gains,
+                     const float *x_time, float *y_time, void *stream);
 
 /* ---- "next" rows either side of the path ------------------------------- */
 

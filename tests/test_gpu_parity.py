@@ -374,15 +374,30 @@ def test_dense_wiener_path(engines):
     assert relerr(Y[:, :n], X[:, :n] @ A.T) < 5e-5 and not Y[:, n:].any()
     # prepared operand (pre-split tiles fetched by bulk copy): same MMAs on the same bits
     prep = eng.prepare_dense(At)
+    # (>= 128 columns with 16-byte aligned rows take the TS kernel -- data operand in tensor memory --, the one-shot call
+    # the SS kernel: same three TF32 products per K step, accumulated by different instruction shapes)
     for _ in range(2):                      # second call: the prepared buffer is reusable
+        Yp = eng.mmse_dense(prep, Xt).cpu().numpy()
+        assert relerr(Yp, Y) < 2e-6 and not Yp[:, n:].any()
+    os.environ["B2C_DENSE_SS"] = "1"        # force the shared-memory-operand kernels: bit-identical to the one-shot form
+    try:
         assert torch.equal(eng.mmse_dense(prep, Xt), torch.from_numpy(Y).to(dev))
+    finally:
+        del os.environ["B2C_DENSE_SS"]
     # 4000 columns: the 128 x 256 tile form is chosen (fuller last wave), ragged last tile, padded leading dimension
     Xw = np.zeros((4000, ld), complex)
     Xw[:, :n] = rng.standard_normal((4000, n)) + 1j * rng.standard_normal((4000, n))
     Xwt = torch.from_numpy(Xw).to(dev, torch.complex64)
     Yw = eng.mmse_dense(prep, Xwt)
     assert relerr(Yw.cpu().numpy()[:, :n], Xw[:, :n] @ A.T) < 5e-5 and not Yw[:, n:].abs().max().item()
-    assert torch.equal(Yw, eng.mmse_dense(At, Xwt))             # same products accumulated in the same order
+    assert relerr(Yw.cpu().numpy(), eng.mmse_dense(At, Xwt).cpu().numpy()) < 2e-6      # TS kernel vs one-shot SS kernel
+    # ragged everything on the TS kernel: odd pilot count (K tail inside a 16-byte load), 131 columns, padded rows
+    n2, c2, ld2 = 419, 131, 420
+    A2 = (rng.standard_normal((n2, n2)) + 1j * rng.standard_normal((n2, n2))) / np.sqrt(n2)
+    X2 = np.full((c2, ld2), np.nan + 0j)                       # the padding element of each row must never be read into a result
+    X2[:, :n2] = rng.standard_normal((c2, n2)) + 1j * rng.standard_normal((c2, n2))
+    Y2 = eng.mmse_dense(eng.prepare_dense(torch.from_numpy(A2).to(dev, torch.complex64)), torch.from_numpy(X2).to(dev, torch.complex64)).cpu().numpy()
+    assert relerr(Y2[:, :n2], X2[:, :n2] @ A2.T) < 5e-5 and not Y2[:, n2:].any()
     small = torch.from_numpy(rng.standard_normal((167, 167)) + 1j * rng.standard_normal((167, 167))).to(dev, torch.complex64)
     xs = torch.from_numpy(rng.standard_normal((77, 167)) + 1j * rng.standard_normal((77, 167))).to(dev, torch.complex64)
     assert torch.equal(eng.mmse_dense(eng.prepare_dense(small), xs), eng.mmse_dense(small, xs))
@@ -460,6 +475,54 @@ def test_batched_dense_wiener_pipeline_groups(pitch, engines):
                 assert relerr(H_mm[b, :, r, t], ref) < RTOL, (b, r, t)
             e = sum((np.abs(H_true[b, :, r, t] - ref) ** 2).sum() for t in range(2))
             assert abs(stats[b, r, 1, 1] / e - 1) < 1e-3, (b, r)
+    # a prebuilt plan (grouping done once on the host) with device-resident parameters: same launches, same bits
+    plan = bank.plan_batch(eng, pid, snr, B)
+    dev_args = dict(args, snr_db=torch.from_numpy(snr).to(eng.device), pattern_id=torch.from_numpy(pid).to(eng.device))
+    again = eng.run(B, pitch=pitch, mmse="dense", wiener=bank, dense_plan=plan, **dev_args)
+    torch.cuda.synchronize()
+    assert torch.equal(again["H_mmse"], out["H_mmse"]) and torch.equal(again["stats"], out["stats"])
+    with pytest.raises(ValueError):            # device parameters without a plan: the grouping needs host values
+        eng.run(B, pitch=pitch, mmse="dense", wiener=bank, **dev_args)
+    # the grouped launch equals one prepared product per group, bit for bit
+    hp = out["_keepalive"][2]["hp"]
+    hm_grouped = out["_keepalive"][2]["hm"].clone()
+    for gq in plan.groups:
+        key = [k for k in plan.keys if bank.prepared[k].buf.data_ptr() == gq.prepared][0]
+        rows = slice(gq.col0, gq.col0 + gq.ncols)
+        one = eng.mmse_dense(bank.prepared[key], hp[rows].contiguous())
+        n = bank.prepared[key].m
+        assert (one[:, :n] - hm_grouped[rows, :n]).abs().max().item() <= 2e-6 * one[:, :n].abs().max().item(), key
+
+
+@pytest.mark.parametrize("model,fd,ntx,nrx", [("EPA", 10.0, 1, 1), ("EVA", 50.0, 2, 2), ("ETU", 200.0, 4, 4)])
+def test_time_domain_path_lands_on_the_frequency_domain_grid(model, fd, ntx, nrx, engines):
+    """modulate (K2) -> per-symbol circular TDL convolution with the K1a tap gains -> demodulate (K2) reproduces the
+    received grid of the frequency-domain pipeline (noise off) within 1e-4 -- for ETU too, whose last tap (77 samples)
+    exceeds the 72-sample prefix: the reference's per-bin CFR product IS a circular convolution per symbol
+    (src/channel_simulator.py:274-345).  One symbol is also checked against a NumPy time-domain convolution."""
+    eng = engines(ntx, nrx)
+    B, m = 3, eng.models.index(model)
+    fq = eng.run(B, m, fd, 300.0, slot0=31, seed=12, want=("H_true", "rx", "tx"))          # 300 dB: the noise term is ~1e-15
+    td = eng.time_domain_slot(B, m, fd, tx=fq["tx"], slot0=31, seed=12)
+    torch.cuda.synchronize()
+    assert td["rx"].shape == fq["rx"].shape
+    err = relerr(td["rx"].cpu().numpy(), fq["rx"].cpu().numpy())
+    diag(test="time_domain", case=model, err=err)
+    assert err < RTOL
+    assert_close_elementwise(td["rx"].cpu().numpy(), fq["rx"].cpu().numpy(), floor=4e-6, what="rx (time domain)")
+    # time-domain samples against NumPy: y[n] = sum_tx sum_t g x[(n - d) mod N], prefix = last 72 samples
+    gains = td["_keepalive"][2]["gains"].cpu().numpy().astype(np.complex128)               # [B, nrx, nsym, ntx, 16]
+    delays = eng.host_tables["tap_delay"][m][:int(eng.host_tables["ntaps"][m])]
+    b, s = 1, 5
+    xt = orc.ofdm_modulate(fq["tx"][b, s].cpu().numpy().astype(np.complex128), 1024, 72, 600)   # [ntx, 1096]
+    assert relerr(td["x_time"][b, s].cpu().numpy(), xt) < RTOL
+    for r in range(nrx):
+        body = sum(gains[b, r, s, t, i] * np.roll(xt[t, 72:], int(d)) for t in range(ntx) for i, d in enumerate(delays))
+        want = np.concatenate([body[-72:], body])
+        assert relerr(td["y_time"][b, s, r].cpu().numpy(), want) < RTOL
+    # default transmit grid: the slot pipeline's own Philox grid for these slots
+    td2 = eng.time_domain_slot(B, m, fd, slot0=31, seed=12)
+    assert torch.equal(td2["tx"], fq["tx"]) and torch.equal(td2["rx"], td["rx"])
 
 
 def test_error_reporting(engines):
