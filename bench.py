@@ -269,7 +269,11 @@ def run_b200(args, rank, world, local_rank):
     dev = eng.device
     ppd = 1 if dense else args.patterns            # one Wiener matrix per (pattern, SNR): the dense workload keeps one pattern
     t0 = time.perf_counter()
+    if world > 1 and rank != 0:
+        dist.barrier()                     # rank 0 builds the plans first (they land in the on-disk cache), the others read them
     pool = eng.random_pool(W["densities"], per_density=ppd, seed=42)
+    if world > 1 and rank == 0:
+        dist.barrier()
     pool_build_s = time.perf_counter() - t0
     B = args.batch
     stats_only = want == ("stats",)
@@ -481,9 +485,27 @@ def run_b200(args, rank, world, local_rank):
         for i in range(2):
             hp_.run(*par, slot0=(rank * 100 + i) * e2e_B, seed=args.seed)
         barrier()
+        e2e_total = world * e2e_steps * e2e_B
+        mine = e2e_steps * e2e_B
         t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            hp_.run(*par, slot0=(rank * 100 + 2 + i) * e2e_B, seed=args.seed)
+        if world == 1:
+            for i in range(e2e_steps):
+                hp_.run(*par, slot0=(2 + i) * e2e_B, seed=args.seed)
+        else:
+            # the job's slots [0, e2e_total) are CLAIMED chunk by chunk (atomic add on the rendezvous store): the GPUs of a box
+            # feed host memory at different rates, a fixed shard would leave the fast links idle while the slow ones finish
+            store = dist.distributed_c10d._get_default_store()
+            par_np = np.stack([np.asarray(v, np.float32) for v in par])
+
+            def claim(k):
+                first = store.add("b2c_e2e_next", k) - k
+                return int(first) if first < e2e_total else None
+
+            def params_of(first, k):
+                k = min(k, e2e_total - first)
+                j = (first + np.arange(k)) % e2e_B
+                return par_np[:, j]
+            mine = hp_.run_dynamic(claim, params_of, seed=args.seed)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         barrier()
@@ -497,11 +519,20 @@ def run_b200(args, rank, world, local_rank):
             t = torch.tensor([link], dtype=torch.float64, device=dev)
             dist.all_reduce(t)
             link_sum = float(t.item())
-        e2e_value = world * e2e_steps * e2e_B / e2e_s
+        e2e_value = e2e_total / e2e_s
+        if world > 1:
+            t = torch.tensor([float(mine)], dtype=torch.float64, device=dev)
+            g = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            claimed = [int(v.item()) for v in g]
+            assert sum(claimed) == e2e_total, (claimed, e2e_total)
         gbs = e2e_value * hp_.d2h_bytes_per_slot / 1e9
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp_.h2d_bytes_per_slot * e2e_B,
                "d2h_bytes_per_step": hp_.d2h_bytes_per_slot * e2e_B, "slots_per_step": e2e_B, "steps": e2e_steps,
                "numa_node_rank0": numa,
+               "slots_per_rank": (claimed if world > 1 else [mine]),
+               "sharding": ("static" if world == 1 else "dynamic: ranks claim 128-slot chunks of the global index range from the "
+                            "rendezvous store as their buffers free up (Philox keyed by global index: same arrays whoever makes them)"),
                "roofline": {"bound": "pcie d2h", "achieved": gbs, "peak": link_sum, "unit": "GB/s", "frac": gbs / link_sum,
                             "peak_source": f"bare pinned cudaMemcpyAsync D2H of one {hp_.slab_bytes / 1e6:.0f} MB chunk slab, back to back, "
                                            f"measured in this run on all {world} rank(s) at once (sum over ranks; slowest rank {link_min:.1f} GB/s)"},
@@ -602,7 +633,8 @@ def main():
                     help="--impl reference: wall-clock budget in seconds; the step loop stops early rather than overrun it")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_4x4_etu", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=4096, help="slots per launch per GPU")
+    ap.add_argument("--batch", type=int, default=4144,
+                    help="slots per launch per GPU (4144 x 4 rx CTAs = 56 full waves of 296 resident CTAs on 148 SMs)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--patterns", type=int, default=64, help="pilot patterns per density in the pool (the reference draws one per sample)")
     ap.add_argument("--pitch", type=int, default=600, choices=[599, 600],

@@ -17,7 +17,7 @@ WIDE_PITCH = 600      # padded row pitch b2c_slot_pipeline accepts in its throug
 EXPORTS = ["b2c_last_error_string", "b2c_abi_version", "b2c_tap_gains", "b2c_slot_pipeline",
            "b2c_ls_interp", "b2c_pilot_vectors", "b2c_mmse_dense", "b2c_dense_real_apply", "b2c_stats_bins",
            "b2c_ofdm_modulate", "b2c_ofdm_demodulate", "b2c_apply_channel", "b2c_tdl_full", "b2c_tdl_circular", "b2c_equalize",
-           "b2c_qam_modulate", "b2c_qam_demodulate", "b2c_count_bit_errors", "b2c_pair00_moments", "b2c_pair00_errors", "b2c_count_nonfinite", "b2c_dense_prepared_bytes", "b2c_dense_prepare",
+           "b2c_qam_modulate", "b2c_qam_demodulate", "b2c_count_bit_errors", "b2c_bit_errors_per_slot", "b2c_pair00_moments", "b2c_pair00_errors", "b2c_count_nonfinite", "b2c_dense_prepared_bytes", "b2c_dense_prepare",
            "b2c_dense_apply_prepared", "b2c_dense_apply_grouped", "b2c_abs_diff_sum",
            "b2c_ml_features"]
 
@@ -45,7 +45,7 @@ class Patterns(C.Structure):
 
 class Slots(C.Structure):
     _fields_ = [("slot0", C.c_int64), ("seed", C.c_uint64), ("model_id", C.c_void_p),
-                ("doppler_hz", C.c_void_p), ("snr_db", C.c_void_p), ("pattern_id", C.c_void_p)]
+                ("doppler_hz", C.c_void_p), ("snr_db", C.c_void_p), ("pattern_id", C.c_void_p), ("qpsk", C.c_int32)]
 
 
 class DenseGroup(C.Structure):
@@ -92,6 +92,7 @@ def lib():
             "b2c_qam_modulate": [P, I64, I32, P, P],
             "b2c_qam_demodulate": [P, I64, I32, I32, P, P],
             "b2c_count_bit_errors": [P, P, I64, P, P],
+            "b2c_bit_errors_per_slot": [P, P, P, I64, P, P, I32, P, P],
             "b2c_pair00_moments": [P, I64, P, P, P, I64, P, P],
             "b2c_pair00_errors": [P, I64, P, P, I64, P, P, P],
             "b2c_count_nonfinite": [P, I64, I32, P, P],

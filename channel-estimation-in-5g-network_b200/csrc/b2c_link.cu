@@ -206,6 +206,41 @@ __global__ void __launch_bounds__(256) bit_errors_kernel(const uint8_t *__restri
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
 
+// Bit errors per slot on the data REs: one CTA per slot, the pilot set of the slot's pattern as a bitmap in shared memory.
+__global__ void __launch_bounds__(256) bit_errors_slot_kernel(b2c_geom g, b2c_patterns pat, const int32_t *__restrict__ pattern_id,
+                                                              const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, int bps,
+                                                              uint32_t *__restrict__ counts) {
+  extern __shared__ uint32_t pilot_bits[];                 // [(nre + 31) / 32]
+  __shared__ uint32_t wsum[8];
+  const int nre = g.nsym * g.nsc, nwords = (nre + 31) >> 5;
+  const int64_t s = blockIdx.x;
+  const int pid = pattern_id[s];
+  for (int i = threadIdx.x; i < nwords; i += 256) pilot_bits[i] = 0u;
+  __syncthreads();
+  const int np = pat.npilots[pid];
+  const int *pre = pat.pilot_re + (int64_t)pid * pat.np_max;
+  for (int j = threadIdx.x; j < np; j += 256) {
+    const int e = __ldg(pre + j);
+    atomicOr(&pilot_bits[e >> 5], 1u << (e & 31));
+  }
+  __syncthreads();
+  const uint8_t *pa = a + s * (int64_t)nre * bps, *pb = b + s * (int64_t)nre * bps;
+  uint32_t c = 0;
+  for (int i = threadIdx.x; i < nre * bps; i += 256) {
+    const int e = i / bps;
+    if (!((pilot_bits[e >> 5] >> (e & 31)) & 1u)) c += pa[i] != pb[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; ++w) t += wsum[w];
+    counts[s] = t;
+  }
+}
+
 // counts[0] += #NaN, counts[1] += #Inf among n elements (verify_phase3_datasets.py:98-111).  CPLX: elements are
 // complex64 and one counts as NaN / Inf when either part is, as numpy.isnan / numpy.isinf do.
 template <bool CPLX>
@@ -441,6 +476,19 @@ extern "C" int b2c_qam_demodulate(const void *symbols, int64_t nsymbols, int32_t
     qam_demod_kernel<double2><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const double2 *>(symbols), nsymbols, M, bps, bits);
   else
     qam_demod_kernel<float2><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float2 *>(symbols), nsymbols, M, bps, bits);
+  B2C_CUDA(cudaGetLastError());
+  return B2C_OK;
+}
+
+extern "C" int b2c_bit_errors_per_slot(const b2c_geom *g, const b2c_patterns *pat, const int32_t *pattern_id, int64_t B,
+                                       const uint8_t *a, const uint8_t *b, int32_t bps, uint32_t *counts, void *stream) {
+  B2C_REQUIRE(g && pat && pattern_id && a && b && counts, B2C_E_ARG, "b2c_bit_errors_per_slot: null argument");
+  B2C_REQUIRE(pat->pilot_re && pat->npilots, B2C_E_ARG, "b2c_bit_errors_per_slot: incomplete pattern pool");
+  B2C_REQUIRE(g->nsym >= 1 && g->nsc >= 1 && (int64_t)g->nsym * g->nsc <= 65535 * 4 && bps >= 1 && bps <= 8 && B >= 0 && B < (1ll << 31),
+              B2C_E_ARG, "b2c_bit_errors_per_slot: grid %dx%d bps=%d B=%lld", g->nsym, g->nsc, bps, (long long)B);
+  if (B == 0) return B2C_OK;
+  const size_t smem = (size_t)((g->nsym * g->nsc + 31) / 32) * sizeof(uint32_t);
+  bit_errors_slot_kernel<<<(unsigned)B, 256, smem, (cudaStream_t)stream>>>(*g, *pat, pattern_id, a, b, bps, counts);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }

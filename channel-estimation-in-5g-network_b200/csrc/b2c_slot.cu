@@ -181,6 +181,7 @@ struct SlotArgs {
   float2 *H_true, *rx, *tx, *H_ls, *H_mmse;
   double *stats;
   int compact;   // 1: tx-replicated outputs written once (H_ls/H_mmse [B][nsym][nrx][nsc], tx [B][nsym][nsc])
+  uint32_t sym_and, sym_or;   // symbol-word mask: (w & and) | or; identity, or the QPSK quantisation of b2c_slots.qpsk
   float2 *hp_out;          // b2c_pilot_io: h_ls at the pilots, row hp_col[b] + rx (NULL: not written)
   const int32_t *hp_col;
   int64_t hp_ld;
@@ -209,7 +210,7 @@ __device__ __forceinline__ float2 draw_symbol(const SlotArgs &a, const SlotCtx &
   int l, h;
   rng_lane(k, a.g.nsc, l, h);
   uint4 w = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s >> 1) * RNG_LANES + l));
-  return cis_u01(pick(w, (s & 1) * 2 + h));
+  return cis_u01((pick(w, (s & 1) * 2 + h) & a.sym_and) | a.sym_or);
 }
 __device__ __forceinline__ float2 draw_noise(const SlotArgs &a, const SlotCtx &c, int s, int k) {
   if (a.has_inj)
@@ -427,8 +428,8 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
             n1 = __ldg(inj_noise + oI + k1);
           } else {
             if (j == 0) ws = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 1) * RNG_LANES + t_));
-            x0 = cis_u01(j ? ws.z : ws.x);
-            x1 = cis_u01(j ? ws.w : ws.y);
+            x0 = cis_u01(((j ? ws.z : ws.x) & a.sym_and) | a.sym_or);
+            x1 = cis_u01(((j ? ws.w : ws.y) & a.sym_and) | a.sym_or);
             const uint4 wn = draw(c.key, STREAM_NOISE, (uint32_t)((s * nrx + c.rx) * RNG_LANES + t_));
             n0 = normal_pair(wn.x, wn.y);
             n1 = normal_pair(wn.z, wn.w);
@@ -634,7 +635,7 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
       // ---- draws: Philox lane t serves both bins of the mirror pair; word half h = (f > 0) -------------
       if (j == 0) ws = draw(c.key, STREAM_SYMBOLS, (uint32_t)((s2 >> 1) * RNG_LANES + t_));
       const uint32_t wm = j ? ws.z : ws.x, wp = j ? ws.w : ws.y;               // -f, +f
-      const float2 xK = cis_u01(odd ? wm : wp), xS = cis_u01(odd ? wp : wm);
+      const float2 xK = cis_u01(((odd ? wm : wp) & a.sym_and) | a.sym_or), xS = cis_u01(((odd ? wp : wm) & a.sym_and) | a.sym_or);
       const uint4 wn = draw(c.key, STREAM_NOISE, (uint32_t)((s * nrx + c.rx) * RNG_LANES + t_));
       const float2 nK = normal_pair(odd ? wn.x : wn.z, odd ? wn.y : wn.w);
       const float2 nS = normal_pair(odd ? wn.z : wn.x, odd ? wn.w : wn.y);
@@ -899,6 +900,10 @@ extern "C" int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, co
   a.H_mmse = reinterpret_cast<float2 *>(H_mmse);
   a.stats = stats;
   a.compact = compact != 0;
+  // QPSK grid: keep the word's top two bits (the quadrant) and put the phase at the quadrant's centre: the 23-bit
+  // mantissa becomes k 2^21 + 2^20, i.e. u = k/4 + 1/8 (+ 2^-24)
+  a.sym_and = slots->qpsk ? 0xC0000000u : 0xFFFFFFFFu;
+  a.sym_or = slots->qpsk ? 0x20000000u : 0u;
   if (pilots_out) {
     a.hp_out = reinterpret_cast<float2 *>(pilots_out->hp);
     a.hp_col = pilots_out->col;

@@ -180,10 +180,10 @@ class SlotEngine:
         a = np.array(np.broadcast_to(np.asarray(v), (B,)))     # writable copy (torch.from_numpy needs one)
         return torch.from_numpy(a).to(device=self.device, dtype=dtype)
 
-    def _slots(self, B, model_id, doppler_hz, snr_db, pattern_id, slot0, seed):
+    def _slots(self, B, model_id, doppler_hz, snr_db, pattern_id, slot0, seed, qpsk=False):
         keep = (self._vec(model_id, B, torch.int32), self._vec(doppler_hz, B, torch.float32),
                 self._vec(snr_db, B, torch.float32), self._vec(pattern_id, B, torch.int32))
-        s = Slots(int(slot0), int(seed) & 0xFFFFFFFFFFFFFFFF, *(k.data_ptr() for k in keep))
+        s = Slots(int(slot0), int(seed) & 0xFFFFFFFFFFFFFFFF, *(k.data_ptr() for k in keep), 1 if qpsk else 0)
         return s, keep
 
     def _inject(self, inject):
@@ -228,7 +228,7 @@ class SlotEngine:
     # ---- K1a + fused slot kernel -------------------------------------------------------------------
     def run(self, B, model_id, doppler_hz, snr_db, pattern_id=0, pool=None, slot0=0, seed=42, inject=None,
             want=("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"), out=None, ws=None, compact=False, pitch=None,
-            mmse="default", wiener=None, dense_plan=None):
+            mmse="default", wiener=None, dense_plan=None, qpsk=False):
         """Simulate B slots and (if any of H_ls/H_mmse/stats is wanted) estimate them.
         Per-slot parameters are scalars or length-B arrays/tensors.  Returns dict of CUDA tensors.
         compact=True writes the tx-replicated arrays once (see alloc_outputs); expand_compact() turns
@@ -239,7 +239,9 @@ class SlotEngine:
         kernel also hands out h_ls at the pilots grouped by (pattern, SNR), one tensor-core GEMM per group applies
         W, and K3 interpolates the filtered pilots into H_mmse and scores them.  The grouping is decided on the host:
         either pattern_id / snr_db are host values, or dense_plan = wiener.plan_batch(...) built once for batches that
-        repeat the same (pattern, SNR) values."""
+        repeat the same (pattern, SNR) values.
+        qpsk=True (Philox draws only): every resource element carries a QPSK point instead of a uniform phase, i.e. two
+        payload bits (b2c_slots.qpsk) -- the grid of the BER sweeps (ber_batch)."""
         if mmse not in ("default", "dense"):
             raise ValueError(f"Unknown mmse mode: {mmse}")
         dense = mmse == "dense" and any(k in (out if out is not None else want) for k in ("H_mmse", "stats"))
@@ -261,7 +263,9 @@ class SlotEngine:
             raise ValueError("estimation outputs need a PatternPool")
         if B == 0:
             return out
-        slots, keep = self._slots(B, model_id, doppler_hz, snr_db, pattern_id, slot0, seed)
+        if qpsk and inject is not None and inject.get("sym_turns") is not None:
+            raise ValueError("qpsk selects the Philox grid; with injected symbols inject the QPSK phases themselves")
+        slots, keep = self._slots(B, model_id, doppler_hz, snr_db, pattern_id, slot0, seed, qpsk)
         ij, keep_inj = self._inject(inject)
         L = lib()
         arrays = [out[k] for k in ("H_true", "rx", "tx", "H_ls", "H_mmse") if k in out]
@@ -565,6 +569,38 @@ class SlotEngine:
             check(lib().b2c_count_bit_errors(dptr(a, "u8"), dptr(b, "u8"), a.numel(), dptr(count, "i64"), stream_ptr()),
                   "b2c_count_bit_errors")
         return count
+
+    def bit_errors_per_slot(self, bits_a, bits_b, pool, pattern_id, B, bps=2, geom=None):
+        """int32 [B]: differing bits per slot on the DATA resource elements (pilots of the slot's pattern excluded).
+        bits_a / bits_b: uint8 [B * nsym * nsc * bps] as qam_demodulate writes them for [B, nsym, nsc] grids."""
+        g = geom if geom is not None else self.geom
+        if bits_a.numel() != bits_b.numel() or bits_a.numel() != B * g.nsym * g.nsc * bps:
+            raise ValueError("bit arrays do not match B x nsym x nsc x bps")
+        pid = self._vec(pattern_id, B, torch.int32)
+        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        if B:
+            check(lib().b2c_bit_errors_per_slot(ref(g), ref(pool.struct), dptr(pid, "i32"), B, dptr(bits_a, "u8"), dptr(bits_b, "u8"), bps,
+                                                C.c_void_p(counts.data_ptr()), stream_ptr()), "b2c_bit_errors_per_slot")
+        return counts
+
+    def ber_batch(self, B, model_id, doppler_hz, snr_db, pattern_id, pool, slot0=0, seed=42, method="zf",
+                  estimates=("H_ls", "H_mmse", "H_true"), inject=None):
+        """Link-level bit errors of B slots: a QPSK grid (2 payload bits per RE) through the slot pipeline, then for each
+        channel estimate  equalize_channel (src/baseline_estimators.py:273-312) -> qam_demodulation (src/utils.py:111-152)
+        -> bit errors against the transmitted bits on the data REs (calculate_ber, :155-157), all on the GPU.
+        Every TX antenna sends the same grid (src/channel_simulator.py:402-404), so the payload is read off TX 0.
+        `inject` (parity tests): recorded draws whose sym_turns are QPSK phases (2k+1)/8.
+        Returns {"errors": {estimate: int32 [B]}, "bits": int64 [B] data bits per slot, "stats": per-slot error sums}."""
+        out = self.run(B, model_id, doppler_hz, snr_db, pattern_id, pool, slot0=slot0, seed=seed, qpsk=inject is None, inject=inject)
+        tx0 = out["tx"][:, :, 0, :].contiguous()
+        bits_tx = self.qam_demodulate(tx0.reshape(-1), 4)
+        res = {}
+        for name in estimates:
+            xh = self.equalize(out["rx"].contiguous(), out[name].contiguous(), method)[:, :, 0, :].contiguous()
+            res[name] = self.bit_errors_per_slot(self.qam_demodulate(xh.reshape(-1), 4), bits_tx, pool, pattern_id, B)
+        pid = np.broadcast_to(np.asarray(pattern_id.cpu() if isinstance(pattern_id, torch.Tensor) else pattern_id), (B,))
+        nbits = 2 * (self.nsym * self.nsc - pool.npilots_host[pid].astype(np.int64))
+        return {"errors": res, "bits": nbits, "stats": out["stats"], "_keepalive": out}
 
     def count_nonfinite(self, x, counts=None):
         """(#NaN, #Inf) elements of a float32 / complex64 CUDA tensor (numpy.isnan / isinf semantics), accumulated

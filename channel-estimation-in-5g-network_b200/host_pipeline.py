@@ -115,10 +115,31 @@ class HostPipeline:
         """Process len(model_id) slots; `consume(first_slot, n, host_buffers)` is called once each
         chunk's arrays are complete in pinned memory (buffers are reused `depth` chunks later)."""
         total = len(model_id)
-        D = self.depth
-        pending = [None] * D
         par = np.stack([np.asarray(model_id, np.float32), np.asarray(doppler_hz, np.float32),
                         np.asarray(snr_db, np.float32), np.asarray(pattern_id, np.float32)])
+        chunks = ((slot0 + start, par[:, start:start + self.chunk]) for start in range(0, total, self.chunk))
+        return self._run_chunks(chunks, seed, consume)
+
+    def run_dynamic(self, claim, params_of, seed=42, consume=None):
+        """Work-sharing front end for several ranks feeding host memory at different link rates (on an 8-GPU box the
+        per-GPU device->host rate differs by 1.5x between PCIe domains): instead of a fixed shard, every rank CLAIMS
+        the next chunk of global slot indices when one of its buffers frees up -- `claim(n)` returns the first global
+        index of n fresh slots or None when the job is exhausted (e.g. an atomic add on the torch.distributed store),
+        `params_of(first, n)` the [4, n] parameter block (model, doppler, snr, pattern) of those slots.  Philox draws are
+        keyed by the global slot index, so the arrays do not depend on which rank produced them.  Returns the number
+        of slots this rank processed."""
+        def chunks():
+            while True:
+                first = claim(self.chunk)
+                if first is None:
+                    return
+                yield first, np.asarray(params_of(first, self.chunk), np.float32)
+        return self._run_chunks(chunks(), seed, consume)
+
+    def _run_chunks(self, chunks, seed, consume):
+        D = self.depth
+        pending = [None] * D
+        done = 0
 
         def retire(i):
             self.ev_copied[i].synchronize()
@@ -126,19 +147,19 @@ class HostPipeline:
                 consume(*pending[i], self.views(i, pending[i][1]))
             pending[i] = None
 
-        for c, start in enumerate(range(0, total, self.chunk)):
+        for c, (first, par) in enumerate(chunks):
             i = c % D
-            n = min(self.chunk, total - start)
+            n = par.shape[1]
             if pending[i] is not None:                 # buffer i still owned by an earlier chunk
                 retire(i)
-            self.par_host[i][:, :n] = torch.from_numpy(par[:, start:start + n])
+            self.par_host[i][:, :n] = torch.from_numpy(np.ascontiguousarray(par))
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(self.ev_copied[i])
                 self.par_dev[i].copy_(self.par_host[i], non_blocking=True)
                 p = self.par_dev[i]
                 ws = {k: v[:n] for k, v in self.ws[i].items()}
                 self.eng.run(n, p[0, :n].to(torch.int32), p[1, :n], p[2, :n], p[3, :n].to(torch.int32), self.pool,
-                             slot0=slot0 + start, seed=seed, want=self.want, out=self._payload(self.dev[i], n), ws=ws,
+                             slot0=first, seed=seed, want=self.want, out=self._payload(self.dev[i], n), ws=ws,
                              compact=self.compact)
                 self.ev_done[i].record(self.compute)
             with torch.cuda.stream(self.copy):
@@ -149,10 +170,11 @@ class HostPipeline:
                     for k, v in self.dev[i].items():
                         self.host[i][k][:n].copy_(v[:n], non_blocking=True)
                 self.ev_copied[i].record(self.copy)
-            pending[i] = (slot0 + start, n)
+            pending[i] = (first, n)
+            done += n
         for i in sorted((j for j in range(D) if pending[j] is not None), key=lambda j: pending[j][0]):
             retire(i)
-        return total
+        return done
 
     def views(self, i, n=None):
         """NumPy views of host buffer i (zero-copy; full reference shapes, stride 0 over tx if compact)."""

@@ -38,8 +38,14 @@ class PilotOptimizer:
         return {'rx_symbols': s['rx_symbols'], 'H_ls': s['H_ls'], 'H_true': s['H_true'], 'pilot_mask': s['pilot_mask'], 'snr_db': snr_db}
 
     def analyze_pilot_density(self, pilot_densities: list, snr_values: list = None, num_samples: int = 100,
-                              channel_type: str = 'EVA', doppler_hz: float = 50.0) -> dict:
-        """NMSE vs pilot density (run_phase8_pilot_optimization.py:110-208)."""
+                              channel_type: str = 'EVA', doppler_hz: float = 50.0, with_ber: bool = False,
+                              ber_samples: int = None) -> dict:
+        """NMSE vs pilot density (run_phase8_pilot_optimization.py:110-208).  Every cell also carries 'ber_proxy', the
+        mean of compute_ber_approximation (run_phase5_evaluation.py:57-68) over its samples.  with_ber=True (Philox
+        mode) adds 'ber': a measured bit-error rate per cell -- a QPSK grid through the same slot pipeline, ZF
+        equalisation with the cell's LS / MMSE estimate (equalize_channel), demapping and bit counting on the data
+        resource elements, `ber_samples` slots per cell (default min(num_samples, 64)); the method 'PERFECT' (the true
+        channel as the estimate) is the curve's floor."""
         if snr_values is None:
             snr_values = [5, 10, 15, 20]
         nd, ns = len(pilot_densities), len(snr_values)
@@ -66,8 +72,29 @@ class PilotOptimizer:
                     samples = ds._numpy_batch([(channel_type, doppler_hz, snr, dens)] * num_samples, draw_params=False,
                                               want_stats=True)
                     eng.stats_bins(samples, np.full(len(samples), di * ns + si, np.int32), nd * ns, bins, snr_db=float(snr))
+        ber = None
+        if with_ber:
+            if self.rng != 'philox':
+                raise ValueError("with_ber needs rng='philox' (the QPSK grid is a Philox-mode option)")
+            nb = int(ber_samples) if ber_samples is not None else min(int(num_samples), 64)
+            Bb = nd * ns * nb
+            cellb = np.arange(Bb) // nb
+            ber = {k: np.zeros(nd * ns, np.int64) for k in ('H_ls', 'H_mmse', 'H_true', 'bits')}
+            pos = 0
+            while pos < Bb:
+                n = min(512, Bb - pos)
+                sl = slice(pos, pos + n)
+                r = eng.ber_batch(n, 0, float(doppler_hz), np.asarray(snr_values, np.float32)[cellb[sl] % ns],
+                                  (cellb[sl] // ns).astype(np.int32), pool, slot0=(1 << 40) + pos, seed=self.seed)
+                for k in ('H_ls', 'H_mmse', 'H_true'):
+                    np.add.at(ber[k], cellb[sl], r['errors'][k].cpu().numpy().astype(np.int64))
+                np.add.at(ber['bits'], cellb[sl], r['bits'])
+                pos += n
         b = bins.cpu().numpy()
         summary = {'pilot_densities': pilot_densities, 'snr_values': snr_values, 'methods': {'LS': {}, 'MMSE': {}}}
+        if ber is not None:
+            summary['methods']['PERFECT'] = {snr: {dens: {'ber': float(ber['H_true'][di * ns + si] / max(ber['bits'][di * ns + si], 1))}
+                                                   for di, dens in enumerate(pilot_densities)} for si, snr in enumerate(snr_values)}
         for name, (c1, c2) in (('LS', (8, 9)), ('MMSE', (10, 11))):
             for si, snr in enumerate(snr_values):
                 summary['methods'][name][snr] = {}
@@ -80,4 +107,7 @@ class PilotOptimizer:
                             'nmse_std': float(np.sqrt(max(r[c2] / r[0] - mean * mean, 0.0))),
                             # the sweep's BER curve: mean over the cell of compute_ber_approximation (run_phase5_evaluation.py:57-68)
                             'ber_proxy': float(r[12 if name == 'LS' else 13] / r[0])}
+                        if ber is not None:
+                            c = di * ns + si
+                            summary['methods'][name][snr][dens]['ber'] = float(ber['H_ls' if name == 'LS' else 'H_mmse'][c] / max(ber['bits'][c], 1))
         return summary

@@ -116,6 +116,10 @@ typedef struct b2c_slots {
   const float *doppler_hz;
   const float *snr_db;
   const int32_t *pattern_id;/* index into b2c_patterns                                        */
+  int32_t qpsk;             /* Philox mode only.  0: every RE carries exp(j 2 pi u), u uniform -- the reference's grid
+                               (src/channel_simulator.py:394-399).  1: the phase is quantised to the QPSK points
+                               (2 floor(4u) + 1) pi / 4, i.e. the grid carries 2 random bits per RE, so that
+                               equalise -> demap -> count gives a real bit-error rate (b2c_bit_errors_per_slot)   */
 } b2c_slots;
 
 /* Injected draws (all nullable as a group: NULL struct pointer = Philox mode).
@@ -317,6 +321,13 @@ int b2c_qam_demodulate(const void *symbols, int64_t nsymbols, int32_t M, int32_t
 
 /* calculate_ber numerator (src/utils.py:155-157): *count += #{i : a[i] != b[i]}.                       */
 int b2c_count_bit_errors(const uint8_t *a, const uint8_t *b, int64_t n, uint64_t *count, void *stream);
+
+/* Per-slot bit errors on the DATA resource elements: counts[b] = #{ i : a[b][e][i] != b[b][e][i] } over the resource
+ * elements e of slot b that are not pilots of its pattern (pilots carry no payload).  a, b: [B][nsym*nsc][bps] bits
+ * (bytes 0 / 1) as b2c_qam_demodulate writes them for [B][nsym][nsc] grids; the per-(density, SNR) BER curves of the
+ * pilot sweep are sums of these counts (calculate_ber, src/utils.py:155-157, applied per cell).             */
+int b2c_bit_errors_per_slot(const b2c_geom *g, const b2c_patterns *pat, const int32_t *pattern_id, int64_t B,
+                            const uint8_t *a, const uint8_t *b, int32_t bps, uint32_t *counts, void *stream);
 
 /* Dataset integrity check (verify_phase3_datasets.py:98-111): counts[0] += #NaN, counts[1] += #Inf among n
  * elements; is_complex: elements are complex64 and count when either part is NaN / Inf (numpy.isnan / isinf). */

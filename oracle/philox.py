@@ -70,12 +70,16 @@ def _lane(k, nsc):
     return np.where(h == 1, k - half, half - 1 - k), h
 
 
-def symbol_u(seed, slot, nsym, nsc):
-    """u[nsym, nsc]: phase (in turns) of every resource element."""
+def symbol_u(seed, slot, nsym, nsc, qpsk=False):
+    """u[nsym, nsc]: phase (in turns) of every resource element.  qpsk (b2c_slots.qpsk): the word keeps its top two
+    bits (the quadrant) and the phase sits at the quadrant's centre, u = k/4 + 1/8 (+ 2^-24)."""
     s, k = np.meshgrid(np.arange(nsym), np.arange(nsc), indexing="ij")
     l, h = _lane(k, nsc)
     w = _block(seed, slot, STREAM_SYMBOLS, (s >> 1) * RNG_LANES + l)
-    return u01(np.take_along_axis(w, ((s & 1) * 2 + h)[..., None], axis=-1)[..., 0])
+    w = np.take_along_axis(w, ((s & 1) * 2 + h)[..., None], axis=-1)[..., 0]
+    if qpsk:
+        w = (w & np.uint32(0xC0000000)) | np.uint32(0x20000000)
+    return u01(w)
 
 
 def jakes_u(seed, slot, npaths, ntx, nrx, nosc=20):
@@ -107,10 +111,10 @@ def param_choice(seed, slot, n_model, n_doppler, n_snr, n_density):
                  enumerate((n_model, n_doppler, n_snr, n_density)))
 
 
-def slot_draws(seed, slot, cfg_nsym, nsc, npaths, ntx, nrx, pilot_mask):
+def slot_draws(seed, slot, cfg_nsym, nsc, npaths, ntx, nrx, pilot_mask, qpsk=False):
     """Draw dictionary for oracle.simulate(): same keys as a recorded reference run, but
     `perm` is replaced by an explicit pilot mask (the pattern comes from the host pool)."""
-    u = symbol_u(seed, slot, cfg_nsym, nsc)
+    u = symbol_u(seed, slot, cfg_nsym, nsc, qpsk)
     ph = 2 * np.pi * u
     nre, nim = noise(seed, slot, cfg_nsym, nrx, nsc)
     return {"pilot_phase": ph[pilot_mask], "data_phase": ph[~pilot_mask],

@@ -117,4 +117,35 @@ for tag, pitch in (("k1_simulate_only", 600), ("k1_simulate_only_contiguous", No
     res[tag] = {"ms": t * 1e3, "gbs": bs / t / 1e9, "frac_hbm": bs / t / 1e9 / PEAK_HBM, "slots_per_s": B / t,
                 "note": "includes K1a tap gains; " + ("rows at pitch 600, 16-byte stores" if pitch else "contiguous rows, 8-byte stores")}
     del o
+# unique-bytes (compact) forms of the same two modes: the tx grid written once, H_ls [B,14,nrx,600]
+for tag, want in (("k1_dataset_mode_compact", ("H_true", "rx", "tx", "H_ls")), ("k1_simulate_only_compact", ("H_true", "rx", "tx"))):
+    o = eng.alloc_outputs(B, want, compact=True, pitch=600)
+    kw = dict(pattern_id=0, pool=pool) if "H_ls" in want else {}
+    t = timeit(lambda: eng.run(B, 2, 200.0, 10.0, want=want, out=o, ws=ws, compact=True, **kw), n=5)
+    bs = B * sum(o[k][0].numel() for k in want) * 8
+    res[tag] = {"ms": t * 1e3, "gbs": bs / t / 1e9, "frac_hbm": bs / t / 1e9 / PEAK_HBM, "slots_per_s": B / t,
+                "note": "includes K1a; compact layout at pitch 600 (every unique value once)"}
+    del o
+torch.cuda.empty_cache()
+
+# time-domain statement of the slot: modulate -> circular TDL convolution -> demodulate (K2 exercised in situ)
+B = 1024
+fq = eng.run(B, 2, 200.0, 300.0, want=("H_true", "rx", "tx"))
+tx = fq["tx"].contiguous()
+t = timeit(lambda: eng.time_domain_slot(B, 2, 200.0, tx=tx), n=5)
+rows_tx, rows_rx = B * 14 * 4, B * 14 * 4
+bt = 8 * (rows_tx * (599 + 1096) + rows_tx * 1096 + rows_rx * 1096 + rows_rx * (1096 + 599))     # modulate + convolution + demodulate
+res["time_domain_slot_4x4_etu"] = {"ms": t * 1e3, "slots_per_s": B / t, "gbs": bt / t / 1e9, "frac_hbm": bt / t / 1e9 / PEAK_HBM,
+                                    "note": "K1a + K2 modulate + b2c_tdl_circular + K2 demodulate (incl. their output allocations); bytes = "
+                                            "reads + writes of the three kernels"}
+x_time = eng.ofdm_modulate(tx.reshape(-1, 599))
+ws2 = eng.workspace(B)
+from _b2c import check, dptr, lib, ref, stream_ptr  # noqa: E402
+y_time = torch.empty((rows_rx, 1096), dtype=torch.complex64, device=dev)
+mid = torch.full((B,), 2, dtype=torch.int32, device=dev)
+t = timeit(lambda: check(lib().b2c_tdl_circular(ref(eng.geom), ref(eng.prof), mid.data_ptr(), B, dptr(ws2["gains"], "c64"), dptr(x_time, "c64"),
+                                                 dptr(y_time, "c64"), stream_ptr())), n=5)
+bc = 8 * 1096 * (rows_tx + rows_rx)
+res["tdl_circular_4x4_etu"] = {"ms": t * 1e3, "gbs": bc / t / 1e9, "frac_hbm": bc / t / 1e9 / PEAK_HBM,
+                               "note": "reads x_time once per rx CTA from L2 (4 rx share it), writes y_time; 4x4x9 complex MACs per sample"}
 print(json.dumps(res))

@@ -525,6 +525,79 @@ def test_time_domain_path_lands_on_the_frequency_domain_grid(model, fd, ntx, nrx
     assert torch.equal(td2["tx"], fq["tx"]) and torch.equal(td2["rx"], td["rx"])
 
 
+@pytest.mark.parametrize("ntx,nrx,model,snr", [(1, 1, "EPA", 8.0), (2, 2, "EVA", 4.0), (4, 4, "ETU", 0.0)])
+def test_qpsk_bit_errors_against_the_oracle(ntx, nrx, model, snr, engines):
+    """BER path: QPSK grid -> slot pipeline -> equalize_channel('zf') with H_ls / H_mmse / H_true -> qam_demodulation ->
+    bit errors on the data REs, per slot.  (1) Philox mode: b2c_slots.qpsk against the oracle fed with the twin draws
+    (oracle/philox.py qpsk=True): same grid, same per-slot error counts (a bit whose soft value sits within fp32
+    rounding of a decision boundary may flip: <= 2 per slot allowed).  (2) injected QPSK phases: same check through
+    the generic kernels."""
+    eng = engines(ntx, nrx)
+    dens = 0.05
+    pool = eng.random_pool([dens], seed=3)
+    mask = pool.mask(0)
+    m, fd, B, seed, slot0 = eng.models.index(model), 70.0, 3, 77, 900
+    P = len(orc.TDL_NS[model])
+    perm = np.concatenate([pool.pilot_indices[0], np.setdiff1d(np.arange(14 * 599), pool.pilot_indices[0])])
+
+    def oracle_errors(d):
+        ref = orc.slot_pipeline(OFDM_CFG, ntx, nrx, model, fd, snr, dens, d)
+        tx0 = ref["tx_symbols"][:, 0]
+        bits_tx = orc.qam_demodulate(tx0, 4).reshape(14 * 599, 2)
+        out = {}
+        for name, H in (("H_ls", ref["H_ls"]), ("H_mmse", ref["H_mmse"]), ("H_true", ref["channel"])):
+            xh = orc.equalize(ref["rx_symbols"], H, "zf")[:, 0]
+            bits = orc.qam_demodulate(xh, 4).reshape(14 * 599, 2)
+            out[name] = int(((bits != bits_tx) & ~mask.reshape(-1, 1)).sum())
+        return ref, out
+
+    got = eng.ber_batch(B, m, fd, snr, 0, pool, slot0=slot0, seed=seed)
+    torch.cuda.synchronize()
+    assert np.array_equal(got["bits"], np.full(B, 2 * (14 * 599 - len(pool.pilot_indices[0]))))
+    tx_gpu = got["_keepalive"]["tx"].cpu().numpy()
+    total = 0
+    for i in range(B):
+        d = opx.slot_draws(seed, slot0 + i, 14, 599, P, ntx, nrx, mask, qpsk=True)
+        d["perm"] = perm
+        ref, want = oracle_errors(d)
+        assert relerr(tx_gpu[i], ref["tx_symbols"]) < RTOL
+        assert np.allclose(np.abs(np.angle(ref["tx_symbols"]) / (np.pi / 4)) % 2, 1.0, atol=1e-5)      # QPSK points
+        for name in ("H_ls", "H_mmse", "H_true"):
+            assert abs(int(got["errors"][name][i]) - want[name]) <= 2, (name, i, int(got["errors"][name][i]), want[name])
+        total += want["H_ls"]
+    assert total > 0                                                    # the case is noisy enough to exercise the counter
+    # injected QPSK phases (numpy draws) through the generic instantiation
+    rng = np.random.default_rng(5)
+    turns = (2 * rng.integers(0, 4, (1, 14, 599)) + 1) / 8.0
+    ju = np.zeros((1, eng.p_max, ntx, nrx, 2, 20))
+    ju[:, :P] = rng.random((1, P, ntx, nrx, 2, 20))
+    z = rng.standard_normal((2, 14, nrx, 599))
+    inj = {"jakes_u": torch.from_numpy(ju).to(eng.device, torch.float32), "sym_turns": torch.from_numpy(turns).to(eng.device, torch.float32),
+           "noise": torch.from_numpy((z[0] + 1j * z[1])[None]).to(eng.device, torch.complex64)}
+    got2 = eng.ber_batch(1, m, fd, snr, 0, pool, inject=inj)
+    ph = 2 * np.pi * turns[0]
+    d = {"perm": perm, "pilot_phase": ph[mask], "data_phase": ph[~mask], "jakes_u": ju[0, :P], "noise_re": z[0], "noise_im": z[1]}
+    _, want2 = oracle_errors(d)
+    for name in ("H_ls", "H_mmse", "H_true"):
+        assert abs(int(got2["errors"][name][0]) - want2[name]) <= 2, (name, int(got2["errors"][name][0]), want2[name])
+
+
+def test_pilot_sweep_ber_curves():
+    """PilotOptimizer.analyze_pilot_density(with_ber=True): the measured BER falls with SNR, the true channel is the
+    floor, and the proxy curve (compute_ber_approximation) is reported beside it."""
+    import run_phase8_pilot_optimization as p8
+    opt = p8.PilotOptimizer(rng='philox', seed=3)
+    opt.config['mimo'] = {'num_tx_antennas': 1, 'num_rx_antennas': 2}
+    res = opt.analyze_pilot_density([0.02, 0.10], [0, 10, 20], num_samples=24, channel_type='EPA', doppler_hz=10.0, with_ber=True, ber_samples=12)
+    for dens in (0.02, 0.10):
+        ls = [res['methods']['LS'][s][dens]['ber'] for s in (0, 10, 20)]
+        pf = [res['methods']['PERFECT'][s][dens]['ber'] for s in (0, 10, 20)]
+        assert ls[0] > ls[1] > ls[2] >= 0 and pf[0] > pf[1] >= pf[2]
+        assert all(p <= l + 1e-3 for p, l in zip(pf, ls))              # perfect CSI is the floor
+        assert 0 < ls[0] < 0.5 and 0 <= res['methods']['LS'][0][dens]['ber_proxy'] <= 0.5
+    assert res['methods']['LS'][10][0.10]['ber'] <= res['methods']['LS'][10][0.02]['ber'] + 5e-3     # more pilots do not hurt
+
+
 def test_error_reporting(engines):
     import _b2c
     eng = engines(2, 2)
@@ -645,6 +718,27 @@ def test_compact_layout_and_host_pipeline(engines):
             host = np.concatenate([got[k][f] for f in sorted(got[k])])
             assert host.shape == tuple(full[k].shape)
             assert np.abs(host - full[k].cpu().numpy()).max() < 2e-6, (k, compact)
+        if compact:
+            # work-sharing front end: chunks claimed from a shared counter (here a local one, claimed out of order by two
+            # interleaved "ranks") produce the same arrays as the static run -- results follow the global slot index
+            nxt, got2 = [0], {}
+
+            def claim(k):
+                first = nxt[0]
+                nxt[0] += k
+                return first + 500 if first < n else None
+
+            def params_of(first, k):
+                j = np.arange(first - 500, min(first - 500 + k, n))
+                return np.stack([np.full(len(j), 2.0), np.full(len(j), 200.0), snr[j], np.zeros(len(j))])
+
+            def consume2(first, cnt, host):
+                got2[first] = {k: np.array(v[:cnt]) for k, v in host.items()}
+            assert HostPipeline(eng, pool, chunk=16, compact=True, depth=3).run_dynamic(claim, params_of, seed=8, consume=consume2) == n
+            assert sorted(got2) == [500, 516, 532] and got2[532]["rx"].shape[0] == 5
+            for f in got2:
+                for k in ("H_true", "rx", "H_ls"):
+                    assert np.array_equal(got2[f][k], got[k][f]), (f, k)
         # what crosses the link: the unique bytes in padded rows (600 / 599) + statistics + 256-byte array alignment
         unique = (1945552 if compact else 3756928) * 600 / 599 + 192
         assert unique <= hp.d2h_bytes_per_slot <= unique + 6 * 256 / 16
