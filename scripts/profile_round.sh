@@ -1,20 +1,27 @@
 #!/bin/bash
-# One GPU call that produces the round's ncu evidence (each bench command is first run plain, then under ncu):
+# One GPU call that produces the round's ncu evidence (each bench command is first run plain, then under ncu).
+# Reports are reduced to CSV / JSON on the box (the .ncu-rep files with source are ~30 MB each; gpurun returns 64 MB).
 #   scripts/profile_round.sh OUT_DIR
-OUT=${1:-gpurun_out/r2p}; mkdir -p "$OUT"
+OUT=${1:-gpurun_out/r2p}; mkdir -p "$OUT"; TMP=$(mktemp -d)
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-api --launches-per-step 1 --batch 2048 --e2e-batch 256 --e2e-steps 1"
 $B > "$OUT/plain_full.json" 2> "$OUT/plain_full.err" || { tail -5 "$OUT/plain_full.err"; exit 1; }
-# launch list of the default bench command (kernel shares)
+# launch lists of the bench commands (kernel shares)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_full.csv" $B > "$OUT/ncu_l1.log" 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_compact.csv" $B --layout compact > "$OUT/ncu_l2.log" 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_dense.csv" $B --workload c2_2x2_eva_dense --batch 8192 > "$OUT/ncu_l3.log" 2>&1
-# full captures of the dominant kernels
-ncu --set full --clock-control none --import-source on -k regex:slot_kernel -s 4 -c 1 -o "$OUT/slot_full" $B > "$OUT/ncu_f1.log" 2>&1
-ncu --set full --clock-control none --import-source on -k regex:slot_kernel -s 4 -c 1 -o "$OUT/slot_compact" $B --layout compact > "$OUT/ncu_f2.log" 2>&1
-ncu --set full --clock-control none --import-source on -k regex:slot_kernel -s 4 -c 1 -o "$OUT/slot_c5_dataset" $B --workload c5_mixed > "$OUT/ncu_f3.log" 2>&1
-ncu --set full --clock-control none --import-source on -k regex:slot_kernel -s 4 -c 1 -o "$OUT/slot_c4_stats" $B --workload c4_sweep > "$OUT/ncu_f4.log" 2>&1
-ncu --set full --clock-control none --import-source on -k regex:dense_tc_ta -s 3 -c 1 -o "$OUT/gemm_ta" $B --workload c2_2x2_eva_dense --batch 16384 > "$OUT/ncu_f5.log" 2>&1
-ncu --set full --clock-control none --import-source on -k regex:ls_interp -s 3 -c 1 -o "$OUT/k3_mode2" $B --workload c2_2x2_eva_dense --batch 16384 > "$OUT/ncu_f6.log" 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tap_gains -s 3 -c 1 -o "$OUT/tap_gains" $B > "$OUT/ncu_f7.log" 2>&1
+cap() {   # name kernel-regex skip extra bench args...
+  local name=$1 rx=$2 skip=$3; shift 3
+  ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -f -o "$TMP/$name" $B "$@" > "$OUT/ncu_$name.log" 2>&1
+  ncu -i "$TMP/$name.ncu-rep" --page raw --csv > "$OUT/$name.raw.csv" 2>/dev/null
+  python scripts/sass_histogram.py "$TMP/$name.ncu-rep" > "$OUT/$name.sass.json" 2>/dev/null
+  rm -f "$TMP/$name.ncu-rep"
+}
+cap slot_full slot_kernel 4
+cap slot_compact slot_kernel 4 --layout compact
+cap slot_c5_dataset slot_kernel 4 --workload c5_mixed
+cap slot_c4_stats slot_kernel 4 --workload c4_sweep
+cap gemm_ta dense_tc_ta 3 --workload c2_2x2_eva_dense --batch 16384
+cap k3_mode2 ls_interp 3 --workload c2_2x2_eva_dense --batch 16384
+cap tap_gains tap_gains 3
 python scripts/bench_kernels.py > "$OUT/kernels.json" 2> "$OUT/kernels.err" || tail -5 "$OUT/kernels.err"
-ls -la "$OUT" | head -40
+rm -rf "$TMP"; du -sh "$OUT"; ls "$OUT"
