@@ -174,11 +174,20 @@ class SlotEngine:
         return self.pool(pats, method)
 
     # ---- helpers -------------------------------------------------------------------------------
+    _NP = {torch.int32: np.int32, torch.float32: np.float32}
+
     def _vec(self, v, B, dtype):
+        """Per-slot parameter vector on the device.  Host values go through a pinned staging tensor and an ASYNCHRONOUS
+        copy: a pageable-memory copy would make the host wait for every kernel already queued on the stream, i.e.
+        serialise the host's preparation of batch i+1 with the GPU's work on batch i (torch's pinned-memory cache
+        recycles the staging block only after the copy has completed)."""
         if isinstance(v, torch.Tensor):
             return v.to(device=self.device, dtype=dtype).contiguous()
-        a = np.array(np.broadcast_to(np.asarray(v), (B,)))     # writable copy (torch.from_numpy needs one)
-        return torch.from_numpy(a).to(device=self.device, dtype=dtype)
+        a = np.array(np.broadcast_to(np.asarray(v), (B,)), dtype=self._NP.get(dtype))     # typed, writable copy
+        t = torch.from_numpy(a)
+        if t.numel() and t.dtype == dtype:
+            return t.pin_memory().to(device=self.device, non_blocking=True)
+        return t.to(device=self.device, dtype=dtype)
 
     def _slots(self, B, model_id, doppler_hz, snr_db, pattern_id, slot0, seed, qpsk=False):
         keep = (self._vec(model_id, B, torch.int32), self._vec(doppler_hz, B, torch.float32),
