@@ -799,7 +799,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 
-template <bool GROUPED>
+// CL2 (opt-in, B2C_DENSE_CLUSTER=1): launched as clusters of two CTAs that share a pair of W row tiles and take adjacent
+// column tiles.  Each CTA fetches ONE of the two W tiles per stage and multicasts it into both CTAs' rings
+// (cp.async.bulk ... .multicast::cluster), so a stage costs an SM 32 KB of L2 reads for W instead of 64 KB.  A ring slot is reused once BOTH CTAs' MMAs have released it: the commits are multicast
+// to both CTAs' empty barriers (count 2).  The grouped tile order is pair-major with an even column-tile count per group.
+template <bool GROUPED, bool CL2 = false>
 __global__ void __launch_bounds__(TA_THREADS, 1) dense_tc_ta_kernel(const float *__restrict__ prepared, int np,
                                                                    const float2 *__restrict__ in, float *__restrict__ out,
                                                                    int64_t ncols, int64_t ld,
@@ -817,12 +821,13 @@ __global__ void __launch_bounds__(TA_THREADS, 1) dense_tc_ta_kernel(const float 
 #pragma unroll
     for (int i = 0; i < MAX_GROUPS; ++i)
       if (i < gt.ngroups - 1 && tile >= gt.tile_end[i]) g = i + 1;
-    int begin = 0, pairs = 1;
+    int begin = 0, pairs = 1, end = 0;
     long long col0 = 0;
 #pragma unroll
     for (int i = 0; i < MAX_GROUPS; ++i) {
       if (i == g) {
         begin = i ? gt.tile_end[i - 1] : 0;
+        end = gt.tile_end[i];
         pairs = gt.tiles_m[i];                      // here: PAIRS of W row tiles
         np = gt.np[i];
         col0 = gt.col0[i];
@@ -831,11 +836,19 @@ __global__ void __launch_bounds__(TA_THREADS, 1) dense_tc_ta_kernel(const float 
       }
     }
     const int local = tile - begin;
-    tile_n = local / pairs;
-    pair = local - tile_n * pairs;
+    if constexpr (CL2) {                            // pair-major: the two CTAs of a cluster differ in the column tile only
+      const int ntn = (end - begin) / pairs;
+      pair = local / ntn;
+      tile_n = local - pair * ntn;
+    } else {
+      tile_n = local / pairs;
+      pair = local - tile_n * pairs;
+    }
     in += col0 * ld;
     out += 2 * col0 * ld;
   }
+  uint32_t crank = 0;
+  if constexpr (CL2) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
   const int kreal = 2 * np;                                   // K and the output rows are both the 2 np real indices
   const int nstages = (kreal + TC_BK - 1) / TC_BK;
   const int tiles_w = (kreal + TC_BM - 1) / TC_BM;
@@ -852,13 +865,17 @@ __global__ void __launch_bounds__(TA_THREADS, 1) dense_tc_ta_kernel(const float 
     for (int b = 0; b < TA_NST; ++b) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;\n" ::"r"(smem_u32(&full_a[b])));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&full_b[b])));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&empty[b])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&empty[b])), "r"(CL2 ? 2u : 1u));
     }
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&acc_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if constexpr (CL2) {      // the peer's barriers exist before anything of ours can land on them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  }
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = tmem_base_sm;
 
@@ -874,21 +891,26 @@ __global__ void __launch_bounds__(TA_THREADS, 1) dense_tc_ta_kernel(const float 
         const uint32_t sB = s0 + b * TA_STAGE;
 #pragma unroll
         for (int kk = 0; kk < TC_BK / 8; ++kk) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h == 0 || has2) {
-              const uint32_t bh = sB + h * (2 * TC_TILE_A), bl = bh + TC_TILE_A;
-              const uint64_t dBh = umma_desc(bh + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
-              const uint64_t dBl = umma_desc(bl + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
-              const uint32_t d = tmem + TA_COL_D + (uint32_t)h * 128u;
-              // same three products in the same order as the SS kernels (W hi x hi, W hi x lo, W lo x hi)
-              umma_tf32_ts(d, aA + kk * 8, dBh, (st | kk) != 0);
-              umma_tf32_ts(d, aA + 32 + kk * 8, dBh, 1u);
-              umma_tf32_ts(d, aA + kk * 8, dBl, 1u);
-            }
-          }
+          // per accumulator the same three products in the same order as the SS kernels (W hi x hi, W hi x lo, W lo x hi);
+          // the two accumulator halves alternate, so that consecutive MMAs never accumulate into the same TMEM tile
+          const uint32_t b0 = sB, b1 = sB + 2 * TC_TILE_A;
+          const uint64_t dBh0 = umma_desc(b0 + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO), dBl0 = umma_desc(b0 + TC_TILE_A + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+          const uint64_t dBh1 = umma_desc(b1 + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO), dBl1 = umma_desc(b1 + TC_TILE_A + kk * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+          const uint32_t d0 = tmem + TA_COL_D, d1 = d0 + 128u, ah = aA + kk * 8, al = aA + 32 + kk * 8;
+          const uint32_t acc = (st | kk) != 0;
+          umma_tf32_ts(d0, ah, dBh0, acc);
+          if (has2) umma_tf32_ts(d1, ah, dBh1, acc);
+          umma_tf32_ts(d0, al, dBh0, 1u);
+          if (has2) umma_tf32_ts(d1, al, dBh1, 1u);
+          umma_tf32_ts(d0, ah, dBl0, 1u);
+          if (has2) umma_tf32_ts(d1, ah, dBl1, 1u);
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&empty[b])) : "memory");
+        if constexpr (CL2)     // the slot is free once BOTH CTAs have read it (each multicasts W tiles into both rings)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                           smem_u32(&empty[b])), "h"((uint16_t)3)
+                       : "memory");
+        else
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&empty[b])) : "memory");
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&acc_bar)) : "memory");
     }
@@ -901,11 +923,22 @@ __global__ void __launch_bounds__(TA_THREADS, 1) dense_tc_ta_kernel(const float 
         if (st >= TA_NST) mbar_wait(smem_u32(&empty[b]), (uint32_t)(st / TA_NST - 1) & 1u);
         const uint32_t bar = smem_u32(&full_b[b]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-        for (int h = 0; h < (has2 ? 2 : 1); ++h)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                           s0 + b * TA_STAGE + h * (2 * TC_TILE_A)),
-                       "l"(prep + ((int64_t)(tm0 + h) * nstages + st) * (2 * TC_TILE_A)), "r"(2u * TC_TILE_A), "r"(bar)
-                       : "memory");
+        if constexpr (CL2) {
+          // this CTA fetches W tile h = its cluster rank (rank 0 alone when the pair has one tile) for BOTH CTAs
+          const int h = (int)crank;
+          if (h == 0 || has2)
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                    s0 + b * TA_STAGE + h * (2 * TC_TILE_A)),
+                "l"(prep + ((int64_t)(tm0 + h) * nstages + st) * (2 * TC_TILE_A)), "r"(2u * TC_TILE_A), "r"(bar), "h"((uint16_t)3)
+                : "memory");
+        } else {
+          for (int h = 0; h < (has2 ? 2 : 1); ++h)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                             s0 + b * TA_STAGE + h * (2 * TC_TILE_A)),
+                         "l"(prep + ((int64_t)(tm0 + h) * nstages + st) * (2 * TC_TILE_A)), "r"(2u * TC_TILE_A), "r"(bar)
+                         : "memory");
+        }
       }
     }
   } else {
@@ -998,6 +1031,10 @@ __global__ void __launch_bounds__(TA_THREADS, 1) dense_tc_ta_kernel(const float 
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if constexpr (CL2) {      // neither CTA leaves while the other may still multicast into its ring or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TA_COLS));
 }
 
@@ -1150,6 +1187,10 @@ extern "C" int b2c_dense_apply_grouped(const b2c_dense_group *groups_host, int32
   int tiles = 0;
   bool ta = (ld & 1) == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 && !getenv("B2C_DENSE_SS");
   for (int g = 0; g < ngroups; ++g) ta = ta && ((groups_host[g].col0 * ld) & 1) == 0;
+  // Cluster-of-two form (W tiles multicast into both CTAs' rings): measured 221-223 TFLOP/s useful against 228-229 for
+  // independent CTAs on 32768 columns -- it takes L2 throughput from 39 % to 32 % but the kernel is not L2-bound (it runs
+  // at 0.94 of the TF32 rate cuBLAS reaches on the same box), so it is opt-in: B2C_DENSE_CLUSTER=1.
+  const bool cl2 = ta && getenv("B2C_DENSE_CLUSTER") != nullptr;
   for (int g = 0; g < ngroups; ++g) {
     const b2c_dense_group &q = groups_host[g];
     B2C_REQUIRE(q.prepared && q.np >= 1 && q.ncols >= 0 && q.col0 >= 0 && ld >= q.np, B2C_E_ARG,
@@ -1160,7 +1201,8 @@ extern "C" int b2c_dense_apply_grouped(const b2c_dense_group *groups_host, int32
     int tm, nst;
     prep_dims(q.np, q.np, 1, tm, nst);
     if (ta) tm = (tm + 1) / 2;                     // TS kernel: a CTA takes a PAIR of W row tiles x 128 columns
-    const int64_t tn = ta ? (q.ncols + TA_BM - 1) / TA_BM : (q.ncols + T2_BN - 1) / T2_BN;
+    int64_t tn = ta ? (q.ncols + TA_BM - 1) / TA_BM : (q.ncols + T2_BN - 1) / T2_BN;
+    if (ta && cl2) tn = (tn + 1) & ~1ll;           // clusters of two adjacent column tiles (a padding tile computes nothing)
     B2C_REQUIRE(tiles + tm * tn < (1ll << 30), B2C_E_UNSUPPORTED, "b2c_dense_apply_grouped: too many tiles");
     const int i = gt.ngroups++;
     tiles += (int)(tm * tn);
@@ -1172,6 +1214,24 @@ extern "C" int b2c_dense_apply_grouped(const b2c_dense_group *groups_host, int32
     gt.prepared[i] = static_cast<const float *>(q.prepared);
   }
   if (tiles == 0) return B2C_OK;
+  if (ta && cl2) {
+    B2C_CUDA((set_max_smem<dense_tc_ta_kernel<true, true>>(TA_SMEM)));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles);
+    cfg.blockDim = dim3(TA_THREADS);
+    cfg.dynamicSmemBytes = TA_SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2C_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_ta_kernel<true, true>, (const float *)nullptr, 0, reinterpret_cast<const float2 *>(in), out,
+                                (int64_t)0, ld, gt));
+    return B2C_OK;
+  }
   if (ta) {
     B2C_CUDA((set_max_smem<dense_tc_ta_kernel<true>>(TA_SMEM)));
     dense_tc_ta_kernel<true><<<(unsigned)tiles, TA_THREADS, TA_SMEM, (cudaStream_t)stream>>>(nullptr, 0, reinterpret_cast<const float2 *>(in), out,

@@ -429,6 +429,15 @@ def test_batched_dense_wiener_pipeline_on_reference_draws(engines):
     assert max(errs) < RTOL
     assert_close_elementwise(H_mm[:, :, 0], d["H_mmse_tx0"])
     assert relerr(out["H_ls"][0, :, :, 0].cpu().numpy(), g["H_ls_tx0"]) < RTOL          # LS part untouched
+    # the opt-in cluster form of the GEMM (W tiles multicast between two CTAs): same products, same accumulation order
+    os.environ["B2C_DENSE_CLUSTER"] = "1"
+    try:
+        out_cl = eng.run(1, eng.models.index("ETU"), float(g["doppler_hz"]), snr, 0, pool, inject=inject_from_golden(eng, g),
+                         mmse="dense", wiener=bank)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["B2C_DENSE_CLUSTER"]
+    assert torch.equal(out_cl["H_mmse"], out["H_mmse"])
     st = out["stats"][0].cpu().numpy()[:, 1].sum(axis=0)
     n = g["channel"].size
     assert abs(db(st[1] / n / (st[2] / n + 1e-12)) - d["metrics_mmse"][2]) < DB_TOL     # dense MMSE NMSE
