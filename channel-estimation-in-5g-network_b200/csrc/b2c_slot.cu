@@ -24,12 +24,13 @@ constexpr int WIDE_PITCH = 600;     // padded row pitch of the wide-store kernel
 // evaluated only at the samples :301-302 consumes) and the AWGN scale of :337-340.
 // One CTA per slot.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GAIN_THREADS)
+__global__ void __launch_bounds__(GAIN_THREADS, 4)
 tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj, int has_inj,
                  float2 *__restrict__ gains, float *__restrict__ noise_std) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *osc = reinterpret_cast<float2 *>(smem_raw);   // [link][20] (phase turns, turns/symbol)
   __shared__ double dred[GAIN_THREADS / 32];
+  __shared__ uint32_t ltab[MAXT * B2C_MAX_ANT * B2C_MAX_ANT];   // link -> t | tx << 8 | rx << 16 | path << 24
 
   const int64_t b = blockIdx.x;
   const int m = slots.model_id[b];
@@ -41,12 +42,20 @@ tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj,
   const PhiloxKey key = make_key(slots.seed, slots.slot0 + b);
   const int nlinks = ntaps * ntx * nrx;                       // link = (tap, tx, rx)
 
+  // The (tap, tx, rx, path) decomposition of a link costs runtime integer divisions: done once per link here, read back
+  // from shared memory by the three stages below (they were ~45 % of stage 1's instructions).
+  for (int link = threadIdx.x; link < nlinks; link += blockDim.x) {
+    const int t = link / (ntx * nrx), rem = link - t * (ntx * nrx);
+    const int tx = rem / nrx, rx = rem - tx * nrx;
+    ltab[link] = (uint32_t)t | ((uint32_t)tx << 8) | ((uint32_t)rx << 16) | ((uint32_t)tap_path[t] << 24);
+  }
+  __syncthreads();
+
   // stage 1: one (phase, per-symbol phase step) pair per oscillator
   for (int i = threadIdx.x; i < nlinks * (NOSC / 2); i += blockDim.x) {
-    int link = i / (NOSC / 2), pr = i - link * (NOSC / 2);
-    int t = link / (ntx * nrx), rem = link - t * (ntx * nrx);
-    int tx = rem / nrx, rx = rem - tx * nrx;
-    int p = tap_path[t];
+    const int link = i / (NOSC / 2), pr = i - link * (NOSC / 2);
+    const uint32_t lt = ltab[link];
+    const int tx = (lt >> 8) & 0xff, rx = (lt >> 16) & 0xff, p = lt >> 24;
     float ua0, up0, ua1, up1;
     if (has_inj) {
       const float *ju = inj.jakes_u + ((((int64_t)b * inj.p_max + p) * ntx + tx) * nrx + rx) * (2 * NOSC);
@@ -73,9 +82,11 @@ tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj,
   const int nout = nrx * nsym * ntx * MAXT;
   for (int o = threadIdx.x; o < nout; o += blockDim.x)
     if ((o % MAXT) >= ntaps) gout[o] = make_float2(0.f, 0.f);
-  // Two threads per link, ten oscillators each.  exp(j 2 pi (phase + s step)) advances from symbol to symbol
-  // by one complex rotation, so an oscillator costs two sincos and nsym-1 complex multiplies instead of nsym
-  // sincos (rounding grows by <= ~1e-7 per step; the parity bound is 1e-4).
+  // Two threads per link, ten oscillators each, held as FIVE PAIRS in structure-of-arrays form: zr = (Re z_a, Re z_b),
+  // zi = (Im z_a, Im z_b).  exp(j 2 pi (phase + s step)) advances from symbol to symbol by one complex rotation
+  // (rounding grows by <= ~1e-7 per step; the parity bound is 1e-4), which in this form is four packed operations per
+  // pair with no operand splats; the symbol loop is outermost, so the only state is the 5 x (z, w) pairs.
+  constexpr int NP2 = NOSC / 4;                                 // oscillator pairs per thread
   const int nwork = nlinks * 2;
   const bool small_step = fabsf(fdT) <= 0.1f;                   // per-symbol Doppler rotation below 0.1 turn (fd <= 1.4 kHz)
   for (int base = 0; base < nwork; base += blockDim.x) {       // warp-uniform trip count (shuffles below)
@@ -83,43 +94,53 @@ tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj,
     const bool valid = i < nwork;
     const int link = valid ? i >> 1 : 0, q = i & 1;
     const float2 *oc = osc + link * NOSC + q * (NOSC / 2);
-    float2 acc[B2C_MAX_SYM];
+    float2 zr[NP2], zi[NP2], wr[NP2], wi[NP2], nwi[NP2];
 #pragma unroll
-    for (int s = 0; s < B2C_MAX_SYM; ++s) acc[s] = make_float2(0.f, 0.f);
-    if (valid) {
-#pragma unroll 2
-      for (int n = 0; n < NOSC / 2; ++n) {
-        const float2 pd = oc[n];
+    for (int n = 0; n < NP2; ++n) {
+      float zc[2], zs[2], wc[2], ws[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 pd = valid ? oc[2 * n + h] : make_float2(0.f, 0.f);
         // the start phase takes the SFU sincos (its 4e-7 error enters once); the per-symbol rotation w is applied
-        // nsym times, so it gets the full-precision sincospi
-        float2 z = cis_turns(pd.x), w;
+        // nsym times, so it gets a full-precision evaluation
+        const float2 z = cis_turns(pd.x);
+        zc[h] = valid ? z.x : 0.f;
+        zs[h] = valid ? z.y : 0.f;
         if (small_step) {
           // |x| = 2 pi |step| <= 0.63 rad: Taylor to x^9 / x^8 (truncation < 2e-9), cheaper than the general routine
           const float x = 6.283185307179586f * pd.y, x2 = x * x;
-          w.y = x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.0f);
-          w.x = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
+          ws[h] = x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.0f);
+          wc[h] = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
         } else {
-          sincospif(2.0f * pd.y, &w.y, &w.x);
-        }
-        const float2 wj = make_float2(-w.y, w.x);          // j w:  z w = z.x * w + z.y * (j w), two packed FMAs
-#pragma unroll
-        for (int s = 0; s < B2C_MAX_SYM; ++s) {
-          if (s < nsym) {
-            acc[s] = __fadd2_rn(acc[s], z);
-            z = __ffma2_rn(make_float2(z.x, z.x), w, __fmul2_rn(make_float2(z.y, z.y), wj));
-          }
+          sincospif(2.0f * pd.y, &ws[h], &wc[h]);
         }
       }
+      zr[n] = make_float2(zc[0], zc[1]);
+      zi[n] = make_float2(zs[0], zs[1]);
+      wr[n] = make_float2(wc[0], wc[1]);
+      wi[n] = make_float2(ws[0], ws[1]);
+      nwi[n] = make_float2(-ws[0], -ws[1]);
     }
-    const int t = link / (ntx * nrx), rem = link - t * (ntx * nrx);
-    const int tx = rem / nrx, rx = rem - tx * nrx;
+    const uint32_t lt = ltab[link];
+    const int t = lt & 0xff, tx = (lt >> 8) & 0xff, rx = (lt >> 16) & 0xff;
     const float a = tap_amp[t];
+    float2 *go = gout + ((rx * nsym) * ntx + tx) * MAXT + t;     // + s * ntx * MAXT
+    for (int s = 0; s < nsym; ++s) {                             // nsym is uniform: no divergence around the shuffles
+      float2 sr = zr[0], si = zi[0];
 #pragma unroll
-    for (int s = 0; s < B2C_MAX_SYM; ++s) {
-      if (s < nsym) {                                          // nsym is uniform: no divergence around the shuffles
-        const float ar = acc[s].x + __shfl_xor_sync(0xffffffffu, acc[s].x, 1);
-        const float ai = acc[s].y + __shfl_xor_sync(0xffffffffu, acc[s].y, 1);
-        if (valid && (s & 1) == q) gout[((rx * nsym + s) * ntx + tx) * MAXT + t] = make_float2(a * ar, a * ai);
+      for (int n = 1; n < NP2; ++n) {
+        sr = __fadd2_rn(sr, zr[n]);
+        si = __fadd2_rn(si, zi[n]);
+      }
+      float re = sr.x + sr.y, im = si.x + si.y;
+      re += __shfl_xor_sync(0xffffffffu, re, 1);                 // the other half of this link's oscillators
+      im += __shfl_xor_sync(0xffffffffu, im, 1);
+      if (valid && (s & 1) == q) go[s * ntx * MAXT] = make_float2(a * re, a * im);
+#pragma unroll
+      for (int n = 0; n < NP2; ++n) {                            // z <- z w:  (zr wr - zi wi, zr wi + zi wr)
+        const float2 pr_ = __fmul2_rn(zr[n], wr[n]), pi_ = __fmul2_rn(zr[n], wi[n]);
+        zr[n] = __ffma2_rn(zi[n], nwi[n], pr_);
+        zi[n] = __ffma2_rn(zi[n], wr[n], pi_);
       }
     }
   }
@@ -127,31 +148,36 @@ tap_gains_kernel(b2c_geom g, b2c_profiles prof, b2c_slots slots, b2c_inject inj,
 
   // stage 3: mean |sum_tx H x|^2 over the slot as the quadratic form gs^H C gs (|x| = 1,
   // same grid on every TX, :402-404), then noise_std of :338-340.  Tiny, done in double.
+  // Items run over (row = rx * nsym + s, tap) with the tap axis padded to MAXT: shifts instead of divisions by ntaps.
   float2 *gs = osc;   // reuse: [rx*nsym + s][MAXT] sum over tx
-  for (int i = threadIdx.x; i < nrx * nsym * ntaps; i += blockDim.x) {    // surviving taps only
-    int t = i % ntaps, rs = i / ntaps;
-    float sr = 0.f, si = 0.f;
-    for (int tx = 0; tx < ntx; ++tx) {
-      float2 v = gout[(rs * ntx + tx) * MAXT + t];
-      sr += v.x;
-      si += v.y;
+  for (int i = threadIdx.x; i < nrx * nsym * MAXT; i += blockDim.x) {
+    const int t = i & (MAXT - 1), rs = i / MAXT;
+    if (t < ntaps) {                                            // surviving taps only
+      float sr = 0.f, si = 0.f;
+      for (int tx = 0; tx < ntx; ++tx) {
+        float2 v = gout[(rs * ntx + tx) * MAXT + t];
+        sr += v.x;
+        si += v.y;
+      }
+      gs[i] = make_float2(sr, si);
     }
-    gs[rs * MAXT + t] = make_float2(sr, si);
   }
   __syncthreads();
   const float2 *corr = reinterpret_cast<const float2 *>(prof.tap_corr) + m * MAXT * MAXT;
   double part = 0.0;
-  for (int i = threadIdx.x; i < nrx * nsym * ntaps; i += blockDim.x) {
-    int p = i % ntaps, rs = i / ntaps;
-    float2 a = gs[rs * MAXT + p];
-    float accr = 0.f;                 // <= 16 fp32 terms per row; the sum over rows is carried in double
-    for (int q = 0; q < ntaps; ++q) {
-      float2 c = gs[rs * MAXT + q], k = corr[p * MAXT + q];
-      // Re( a * conj(c) * k )
-      float zr = fmaf(a.x, c.x, a.y * c.y), zi = fmaf(a.y, c.x, -a.x * c.y);
-      accr = fmaf(zr, k.x, fmaf(-zi, k.y, accr));
+  for (int i = threadIdx.x; i < nrx * nsym * MAXT; i += blockDim.x) {
+    const int p = i & (MAXT - 1), rs = i / MAXT;
+    if (p < ntaps) {
+      float2 a = gs[rs * MAXT + p];
+      float accr = 0.f;                 // <= 16 fp32 terms per row; the sum over rows is carried in double
+      for (int q = 0; q < ntaps; ++q) {
+        float2 c = gs[rs * MAXT + q], k = corr[p * MAXT + q];
+        // Re( a * conj(c) * k )
+        float zr_ = fmaf(a.x, c.x, a.y * c.y), zi_ = fmaf(a.y, c.x, -a.x * c.y);
+        accr = fmaf(zr_, k.x, fmaf(-zi_, k.y, accr));
+      }
+      part += (double)accr;
     }
-    part += (double)accr;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
