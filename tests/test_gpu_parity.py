@@ -1099,6 +1099,13 @@ def test_c_abi_status_codes_and_empty_inputs(engines):
     assert L.b2c_equalize(ref(g), 1, None, P(z), P(z), 1e-8, 0, None) == E_ARG and "null" in msg()
     assert L.b2c_mmse_dense(None, 4, P(z), P(z), 1, 4, None) == E_ARG
     assert L.b2c_count_bit_errors(P(bits), None, 8, P(bits), None) == E_ARG
+    assert L.b2c_dense_apply_grouped(None, 1, P(z), P(z), 4, None) == E_ARG
+    grp = (_b2c.DenseGroup * 1)(_b2c.DenseGroup(z.data_ptr(), 0, 4, 4))
+    assert L.b2c_dense_apply_grouped(grp, 33, P(z), P(bits), 4, None) == E_UNSUPPORTED and "33" in msg()     # at most 32 groups per call
+    assert L.b2c_dense_apply_grouped(grp, 1, P(z), P(z), 4, None) == E_ARG                                    # in-place
+    assert L.b2c_dense_apply_grouped(grp, 0, P(z), P(bits), 4, None) == 0                                     # no groups: no-op
+    assert L.b2c_tdl_circular(ref(g), ref(eng.prof), None, 1, P(z), P(z), P(z), None) == E_ARG
+    assert L.b2c_bit_errors_per_slot(ref(g), ref(eng.random_pool([0.05], seed=1).struct), None, 1, P(bits), P(bits), 2, P(bits), None) == E_ARG
     # geometry outside the compiled limits: even bin count, too many symbols, too many antennas
     for bad in (Geom(14, 600, 2, 2, 1024, 72, 7.1e-5), Geom(17, 599, 2, 2, 1024, 72, 7.1e-5), Geom(14, 599, 9, 2, 1024, 72, 7.1e-5)):
         assert L.b2c_tap_gains(ref(bad), ref(eng.prof), ref(eng._slots(1, 0, 10.0, 10.0, 0, 0, 1)[0]), None, 1, P(z), P(z), None) == E_UNSUPPORTED
