@@ -513,12 +513,9 @@ def run_b200(args, rank, world, local_rank):
         else:
             # the job's slots [0, e2e_total) are CLAIMED chunk by chunk (atomic add on the rendezvous store): the GPUs of a box
             # feed host memory at different rates, a fixed shard would leave the fast links idle while the slow ones finish
-            store = dist.distributed_c10d._get_default_store()
+            from host_pipeline import store_claimer
+            claim = store_claimer(dist.distributed_c10d._get_default_store(), e2e_total, "b2c_e2e_next")
             par_np = np.stack([np.asarray(v, np.float32) for v in par])
-
-            def claim(k):
-                first = store.add("b2c_e2e_next", k) - k
-                return int(first) if first < e2e_total else None
 
             def params_of(first, k):
                 k = min(k, e2e_total - first)

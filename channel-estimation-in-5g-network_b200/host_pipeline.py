@@ -54,6 +54,16 @@ def bind_to_gpu_numa_node(device_index):
         return None
 
 
+def store_claimer(store, total, key="b2c_next_slot"):
+    """claim(n) for HostPipeline.run_dynamic on top of a torch.distributed store (TCPStore / the default rendezvous
+    store): an atomic add hands every caller, on any rank, a fresh range [first, first + n) of the job's `total` slots;
+    None once the job is exhausted (the last range may be shorter: clip with `total`)."""
+    def claim(n):
+        first = store.add(key, int(n)) - int(n)
+        return int(first) if first < total else None
+    return claim
+
+
 class HostPipeline:
     """Slots in, NumPy arrays out: per-slot parameters from pinned host memory, results in pinned host memory.
 
