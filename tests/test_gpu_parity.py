@@ -697,6 +697,37 @@ def test_other_geometries_generic_path(ntx, nrx, nsym, useful, model):
     assert torch.allclose(k3["stats"], out["stats"], rtol=1e-4)
 
 
+@pytest.mark.parametrize("ntx,nrx,nsym,useful,want", [(3, 2, 7, 300, ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats")),
+                                                        (4, 4, 14, 600, ("H_true", "rx", "tx", "H_ls", "stats")),
+                                                        (2, 2, 14, 600, ("H_true", "rx", "tx"))])
+def test_host_pipeline_other_geometries_and_output_sets(ntx, nrx, nsym, useful, want):
+    """HostPipeline's slab layout on a grid the wide kernels do not take (7 x 299, 3 TX: contiguous rows, generic kernel),
+    in dataset mode (no H_mmse: what generate_sample returns) and simulate-only: same arrays as SlotEngine.run, ragged tail."""
+    from engine import SlotEngine
+    from host_pipeline import HostPipeline
+    cfg = {"ofdm": {"fft_size": 1024, "cp_length": 72, "num_symbols": nsym, "useful_subcarriers": useful,
+                    "subcarrier_spacing": 15000}, "mimo": {"num_tx_antennas": ntx, "num_rx_antennas": nrx}}
+    eng = SlotEngine(cfg)
+    est = "H_ls" in want
+    pool = eng.random_pool([0.08], seed=5) if est else None
+    n = 21
+    snr = np.linspace(0, 20, n).astype(np.float32)
+    ref = eng.run(n, 1, 60.0, snr, 0, pool, slot0=40, seed=3, want=want)
+    for compact in (False, True):
+        hp = HostPipeline(eng, pool, chunk=8, want=want, compact=compact)
+        assert hp.pitch == (600 if (useful == 600 and ntx in (1, 2, 4, 8)) else eng.nsc)
+        got = {}
+
+        def consume(first, cnt, host):
+            for k, v in host.items():
+                got.setdefault(k, []).append(np.array(v[:cnt]))
+        assert hp.run(np.full(n, 1), np.full(n, 60.0), snr, np.zeros(n), slot0=40, seed=3, consume=consume) == n
+        for k in want:
+            host = np.concatenate(got[k])
+            assert host.shape == tuple(ref[k].shape), (k, host.shape)
+            assert np.abs(host - ref[k].cpu().numpy()).max() <= 2e-6 * max(1.0, float(ref[k].abs().max())), (k, compact)
+
+
 def test_compact_layout_and_host_pipeline(engines):
     """compact=True writes the tx-replicated arrays once; expanded views equal the full layout.  The
     host-buffer pipeline (pinned memory, double-buffered D2H) hands back the same arrays."""
