@@ -49,7 +49,7 @@ WORKLOADS = {
                         desc=f"SISO EPA 10 Hz, FFT 1024/CP 72, 10% pilots, {_SNR_TXT}, simulate+LS(linear)+MMSE(default)"),
     "c2_2x2_eva": dict(ntx=2, nrx=2, models=["EVA"], dopplers=[50.0], densities=[0.10], mmse="default", want=ALL,
                        desc=f"2x2 EVA 50 Hz, FFT 1024/CP 72, 10% pilots, {_SNR_TXT}, simulate+LS(linear)+MMSE(default)"),
-    "c2_2x2_eva_dense": dict(ntx=2, nrx=2, models=["EVA"], dopplers=[50.0], densities=[0.10], mmse="dense", want=ALL,
+    "c2_2x2_eva_dense": dict(ntx=2, nrx=2, models=["EVA"], dopplers=[50.0], densities=[0.10], mmse="dense", want=ALL, batch=18944,
                              desc=f"2x2 EVA 50 Hz, FFT 1024/CP 72, 10% pilots, {_SNR_TXT}, simulate+LS(linear)+MMSE(known-covariance "
                                   "Wiener filter W = R (R + s2 I)^-1, one 838 x 838 W per SNR)"),
     "c3_4x4_etu": dict(ntx=4, nrx=4, models=["ETU"], dopplers=[200.0], densities=[0.10], mmse="default", want=ALL,
@@ -652,8 +652,9 @@ def main():
                     help="--impl reference: wall-clock budget in seconds; the step loop stops early rather than overrun it")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_4x4_etu", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=4144,
-                    help="slots per launch per GPU (4144 x 4 rx CTAs = 56 full waves of 296 resident CTAs on 148 SMs)")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="slots per launch per GPU.  Default 4144 (x 4 rx CTAs = 56 full waves of 296 resident CTAs on 148 SMs); "
+                         "c2_2x2_eva_dense: 18944 (37888 slot CTAs = 128 full waves; 8 SNR groups x 37 column tiles x 7 W tile pairs = 14 full GEMM waves)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--patterns", type=int, default=64, help="pilot patterns per density in the pool (the reference draws one per sample)")
     ap.add_argument("--pitch", type=int, default=600, choices=[599, 600],
@@ -673,6 +674,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.batch is None:
+        args.batch = WORKLOADS[args.workload].get("batch", 4144)
     if args.steps is None:
         args.steps = 50 if args.impl == "b200" else 6
     if args.warmup is None:

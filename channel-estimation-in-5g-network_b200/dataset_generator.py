@@ -166,10 +166,12 @@ class ChannelEstimationDataset:
             self._pool = self.engine.random_pool(self._lists()[3], self.patterns_per_density, seed=self.seed)
         return self._pool
 
-    def generate_batch(self, count: int, slot0: int = 0, want=("H_true", "rx", "tx", "H_ls"), out=None, ws=None, pitch=None):
+    def generate_batch(self, count: int, slot0: int = 0, want=("H_true", "rx", "tx", "H_ls"), out=None, ws=None, pitch=None,
+                       **run_kwargs):
         """`count` slots starting at global sample index slot0, Philox mode, all on the device.
         Returns (dict of CUDA tensors, dict of per-slot parameter index arrays).  pitch=600: row-padded
-        throughput layout (tensors are 599-wide views), see SlotEngine.run."""
+        throughput layout (tensors are 599-wide views), see SlotEngine.run.  Further keyword arguments go to
+        SlotEngine.run (compact=True, mmse="dense" + wiener=WienerBank for the known-covariance MMSE, qpsk=True)."""
         eng = self.engine
         models, dopplers, snrs, dens = self._lists()
         mi, di, si, pi = philox_param_choice(self.seed, slot0, count, (len(models), len(dopplers), len(snrs), len(dens)))
@@ -177,7 +179,8 @@ class ChannelEstimationDataset:
         pid = pi * self.patterns_per_density + (np.arange(slot0, slot0 + count) % self.patterns_per_density)
         model_id = np.array([eng.models.index(str(m).upper()) for m in models], dtype=np.int32)[mi]
         res = eng.run(count, model_id, np.asarray(dopplers, dtype=np.float32)[di], np.asarray(snrs, dtype=np.float32)[si],
-                      pid.astype(np.int32), self.pattern_pool(), slot0=slot0, seed=self.seed, want=want, out=out, ws=ws, pitch=pitch)
+                      pid.astype(np.int32), self.pattern_pool(), slot0=slot0, seed=self.seed, want=want, out=out, ws=ws, pitch=pitch,
+                      **run_kwargs)
         return res, {"model": mi, "doppler": di, "snr": si, "density": pi, "pattern": pid}
 
     def generate_feature_batch(self, count: int, slot0: int = 0, layout: str = "last", normalize: bool = True,
@@ -224,11 +227,13 @@ class ChannelEstimationDataset:
 
 
 def sharded_statistics(config: Dict, total_slots: int, rank: int = 0, world_size: int = 1, batch: int = 8192,
-                       seed: int = 42, bin_by: str = "snr", want_arrays=(), on_batch=None, dataset: Optional[ChannelEstimationDataset] = None):
+                       seed: int = 42, bin_by: str = "snr", want_arrays=(), on_batch=None, dataset: Optional[ChannelEstimationDataset] = None,
+                       **run_kwargs):
     """Multi-GPU dataset statistics: rank r simulates + estimates global samples
     [r*N/R, (r+1)*N/R) in batches and folds MSE/NMSE into per-bin float64 accumulators on its
     GPU; the caller all-reduces the returned [nbins, 14] tensor (see reduce_bins).  Philox keyed
-    by the global sample index makes the result independent of world_size."""
+    by the global sample index makes the result independent of world_size.  run_kwargs go to SlotEngine.run
+    (e.g. mmse="dense", wiener=WienerBank: statistics of the known-covariance MMSE estimator)."""
     ds = dataset if dataset is not None else ChannelEstimationDataset(config, rng='philox', seed=seed)
     eng = ds.engine
     models, dopplers, snrs, dens = ds._lists()
@@ -246,7 +251,7 @@ def sharded_statistics(config: Dict, total_slots: int, rank: int = 0, world_size
             # (wide-store kernel); callers see 599-wide views
             wide = all(k in want for k in ("H_true", "rx", "tx", "H_ls"))
             out, ws = eng.alloc_outputs(n, want, pitch=600 if (wide and eng.nsc == 599 and eng.nsym % 2 == 0 and eng.ntx in (1, 2, 4, 8)) else None), eng.workspace(n)
-        res, par = ds.generate_batch(n, pos, want=want, out=out, ws=ws)
+        res, par = ds.generate_batch(n, pos, want=want, out=out, ws=ws, **run_kwargs)
         eng.stats_bins(res["stats"], par[bin_by].astype(np.int32), nbins, bins, snr_db=np.asarray(snrs, np.float32)[par["snr"]])
         if on_batch is not None:
             on_batch(pos, res, par)

@@ -344,6 +344,31 @@ def test_reference_test_scripts_run_against_the_drop_in(tmp_path):
         assert PKG in probe.stdout, probe.stdout
 
 
+def test_sharded_statistics_with_the_dense_wiener_estimator():
+    """sharded_statistics(..., mmse="dense", wiener=bank): the per-SNR MMSE columns of the bins come from the
+    known-covariance estimator; sharding over two emulated ranks reproduces the single-rank bins."""
+    import torch
+    import dataset_generator as dg
+    from engine import WienerBank
+    cfg = full_config(2, 2)
+    cfg.update({"channel": {"models": ["EVA"], "doppler_hz": [50], "carrier_freq": 2.0e9}, "pilots": {"density": [0.02]},
+                "simulation": {"snr_range": [0, 10, 20]}})
+    ds = dg.ChannelEstimationDataset(cfg, rng='philox', seed=9)
+    pool = ds.pattern_pool()
+    idx = pool.pilot_indices[0]
+    ps, pk = idx // 599, idx % 599
+    R = 0.4 * np.exp(-np.abs(ps[:, None] - ps[None, :]) / 20.0 - np.abs(pk[:, None] - pk[None, :]) / 60.0) * np.exp(1j * 2 * np.pi * (pk[:, None] - pk[None, :]) * 3 / 1024)
+    bank = WienerBank(ds.engine, pool, {0: R}, [0, 10, 20])
+    one = dg.sharded_statistics(cfg, 48, 0, 1, batch=20, seed=9, dataset=ds, want_arrays=("H_true", "H_ls", "H_mmse"), mmse="dense", wiener=bank)
+    two = sum(dg.sharded_statistics(cfg, 48, r, 2, batch=20, seed=9, dataset=ds, want_arrays=("H_true", "H_ls", "H_mmse"), mmse="dense", wiener=bank)
+              for r in range(2))
+    base = dg.sharded_statistics(cfg, 48, 0, 1, batch=20, seed=9, dataset=ds)
+    torch.cuda.synchronize()
+    assert torch.allclose(one, two, rtol=1e-12) and one[:, 0].sum().item() == 48
+    assert torch.allclose(one[:, [1, 3]], base[:, [1, 3]], rtol=1e-5)          # the LS columns do not depend on the MMSE mode
+    assert not torch.allclose(one[:, 4], base[:, 4], rtol=1e-3)                # the MMSE columns do
+
+
 def test_pilot_density_sweep():
     """run_phase8 PilotOptimizer.analyze_pilot_density: per-(density, SNR) pair-(0,0) NMSE mean/std/dB."""
     import torch
