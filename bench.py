@@ -446,16 +446,17 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- the same metric through the public API (dataset_generator.sharded_statistics), device resident ----------------
     value_api = None
-    if not args.no_api and not dense:
+    if not args.no_api:
         ds = ChannelEstimationDataset(cfg, rng='philox', seed=args.seed, patterns_per_density=ppd)
         ds._pool = pool
         api_slots = max(B, min(slots_total // world, 40 * B))
         arrays = tuple(k for k in want if k != "stats")
-        sharded_statistics(cfg, 2 * B, 0, 1, batch=B, seed=args.seed, want_arrays=arrays, dataset=ds)      # warm-up
+        kw = dict(mmse="dense", wiener=bank) if dense else {}      # (the grouping by SNR is then redone per batch: SNRs are drawn per slot)
+        sharded_statistics(cfg, 2 * B, 0, 1, batch=B, seed=args.seed, want_arrays=arrays, dataset=ds, **kw)      # warm-up
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        api_bins = sharded_statistics(cfg, api_slots * world, rank, world, batch=B, seed=args.seed, want_arrays=arrays, dataset=ds)
+        api_bins = sharded_statistics(cfg, api_slots * world, rank, world, batch=B, seed=args.seed, want_arrays=arrays, dataset=ds, **kw)
         if world > 1:
             dist.all_reduce(api_bins)
         b.record()

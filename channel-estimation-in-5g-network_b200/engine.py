@@ -98,9 +98,10 @@ class WienerBank:
         (pattern, SNR) group and group g = order[starts[g]:starts[g+1]] using the filter keys[g]."""
         pid = np.asarray(pattern_id).astype(np.int64)
         snr = np.asarray(snr_db, dtype=np.float64)
-        uniq, inv = np.unique(np.stack([pid.astype(np.float64), snr], axis=1), axis=0, return_inverse=True)
+        snr_vals, snr_idx = np.unique(snr, return_inverse=True)               # 1-D uniques: cheap on the host path of every batch
+        code, inv = np.unique(pid * len(snr_vals) + snr_idx.reshape(-1), return_inverse=True)
         inv = inv.reshape(-1)
-        keys = [(int(u[0]), float(u[1])) for u in uniq]
+        keys = [(int(c // len(snr_vals)), float(snr_vals[c % len(snr_vals)])) for c in code]
         for k in keys:
             if k not in self.prepared:
                 raise KeyError(f"no Wiener matrix for pattern {k[0]} at {k[1]} dB in this bank")
@@ -119,7 +120,7 @@ class WienerBank:
         nrx = engine.nrx
         plan = DenseBatchPlan()
         plan.B, plan.keys = B, keys
-        plan.col = torch.from_numpy((rank * nrx).astype(np.int32)).to(engine.device)
+        plan.col = torch.from_numpy((rank * nrx).astype(np.int32)).pin_memory().to(engine.device, non_blocking=True)
         plan.groups = (DenseGroup * len(keys))()
         for gi, key in enumerate(keys):
             W = self.prepared[key]
