@@ -607,6 +607,32 @@ def test_pilot_sweep_ber_curves():
     assert res['methods']['LS'][10][0.10]['ber'] <= res['methods']['LS'][10][0.02]['ber'] + 5e-3     # more pilots do not hurt
 
 
+@pytest.mark.parametrize("ntx,nrx", [(4, 4), (2, 2), (1, 1), (8, 2)])
+def test_register_blocked_statistics_kernel(ntx, nrx, engines):
+    """Statistics-only sweeps run slot2_kernel (160 threads, two mirror pairs = four bins per thread): same Philox
+    counters and per-bin arithmetic as the 320-thread wide kernel, so the per-slot sums agree to the rounding of the
+    partial-sum grouping (four bins per thread instead of two) with both that kernel and the full pipeline."""
+    eng = engines(ntx, nrx)
+    pool = eng.random_pool([0.10, 0.03], seed=13)
+    B = 9
+    pid = np.arange(B, dtype=np.int32) % 2
+    mid = np.array([0, 1, 2, 2, 1, 0, 2, 1, 0], np.int32)                         # mixed profiles: 5 / 8 / 9 taps
+    fd = np.array([10, 50, 100, 200, 70, 30, 150, 5, 90], np.float32)
+    snr = np.linspace(-5, 30, B).astype(np.float32)
+    kw = dict(model_id=mid, doppler_hz=fd, snr_db=snr, pattern_id=pid, pool=pool, slot0=31337, seed=5)
+    got = eng.run(B, want=("stats",), **kw)["stats"]
+    os.environ["B2C_NO_SLOT2"] = "1"
+    try:
+        ref = eng.run(B, want=("stats",), **kw)["stats"]
+    finally:
+        del os.environ["B2C_NO_SLOT2"]
+    full = eng.run(B, pitch=600, **kw)["stats"]
+    torch.cuda.synchronize()
+    assert torch.allclose(got, ref, rtol=2e-6, atol=0)
+    assert torch.allclose(got, full, rtol=2e-6 if ntx < 4 else 2e-5, atol=0)
+    assert not torch.equal(got, torch.zeros_like(got))
+
+
 def test_error_reporting(engines):
     import _b2c
     eng = engines(2, 2)
