@@ -52,6 +52,11 @@ WORKLOADS = {
     "c2_2x2_eva_dense": dict(ntx=2, nrx=2, models=["EVA"], dopplers=[50.0], densities=[0.10], mmse="dense", want=ALL, batch=18944,
                              desc=f"2x2 EVA 50 Hz, FFT 1024/CP 72, 10% pilots, {_SNR_TXT}, simulate+LS(linear)+MMSE(known-covariance "
                                   "Wiener filter W = R (R + s2 I)^-1, one 838 x 838 W per SNR)"),
+    "c2_2x2_eva_dense_stats": dict(ntx=2, nrx=2, models=["EVA"], dopplers=[50.0], densities=[0.10], mmse="dense", want=("stats",),
+                                   batch=18944,
+                                   desc=f"2x2 EVA 50 Hz, FFT 1024/CP 72, 10% pilots, {_SNR_TXT}, simulate+LS(linear)+MMSE(known-covariance "
+                                        "Wiener filter, one 838 x 838 W per SNR), per-SNR MSE / NMSE curves only (no array leaves the SM: "
+                                        "slot kernel -> grouped GEMM -> b2c_dense_score)"),
     "c3_4x4_etu": dict(ntx=4, nrx=4, models=["ETU"], dopplers=[200.0], densities=[0.10], mmse="default", want=ALL,
                        desc=f"4x4 ETU 200 Hz, FFT 1024/CP 72, 10% pilots, {_SNR_TXT}, simulate+LS(linear)+MMSE(default)"),
     "c4_sweep": dict(ntx=4, nrx=4, models=["EVA"], dopplers=[50.0], densities=[0.01 * d for d in range(1, 11)], mmse="default",
@@ -63,7 +68,7 @@ WORKLOADS = {
                      desc="4x4 mixed EPA/EVA/ETU x Doppler [10, 50, 100, 200] Hz x SNR [-5..30] dB x pilot density [5, 10] %, every "
                           "parameter drawn per slot (Philox stream 3), dataset arrays of generate_sample (H_true, rx, tx, H_ls) + statistics"),
 }
-CPU_WORKLOAD = {"c2_2x2_eva_dense": "c2_2x2_eva", "c4_sweep": "c3_4x4_etu", "c5_mixed": "c3_4x4_etu"}   # cost-equivalent CPU samples
+CPU_WORKLOAD = {"c2_2x2_eva_dense": "c2_2x2_eva", "c2_2x2_eva_dense_stats": "c2_2x2_eva", "c4_sweep": "c3_4x4_etu", "c5_mixed": "c3_4x4_etu"}   # cost-equivalent CPU samples
 
 
 def slot_bytes(ntx, nrx, nsym=14, nsc=599, compact=False, want=ALL):
@@ -318,7 +323,7 @@ def run_b200(args, rank, world, local_rank):
         if dense:
             eng.run(B, model_id, doppler, snr, pattern, pool, slot0=gslot, seed=args.seed, out=outs[buf], ws=wss[buf],
                     mmse="dense", wiener=bank, dense_plan=dplan)
-            launches[0] += 4                         # K1a, slot kernel, one grouped GEMM (8 SNR groups), K3
+            launches[0] += 4                         # K1a, slot kernel, one grouped GEMM (8 SNR groups), K3 / b2c_dense_score
         else:
             eng.run(B, model_id, doppler, snr, pattern, pool, slot0=gslot, seed=args.seed, out=outs[buf], ws=wss[buf],
                     compact=compact)
@@ -383,7 +388,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- dominant kernel alone, CUDA events on its stream, over rotating buffers (right after the timed region) --------
     L = _b2c.lib()
-    from _b2c import Slots, check, dptr, ref, rows_ptr, stream_ptr
+    from _b2c import PilotIO, Slots, check, dptr, ref, rows_ptr, stream_ptr
     P = _b2c.row_pitch(outs[0]["H_true"]) if "H_true" in outs[0] else eng.nsc
     g_out = eng._with_pitch(eng.geom, P)
     kev = []
@@ -391,13 +396,14 @@ def run_b200(args, rank, world, local_rank):
         o, w = outs[i % NBUF], wss[i % NBUF]
         sl = Slots(base + (n + i) * B, args.seed, model_id.data_ptr(), doppler.data_ptr(), snr.data_ptr(), pattern.data_ptr())
         check(L.b2c_tap_gains(ref(eng.geom), ref(eng.prof), ref(sl), None, B, dptr(w["gains"], "c64"), dptr(w["noise_std"], "f32"), stream_ptr()))
+        pio = PilotIO(w["hp"].data_ptr(), dplan.col.data_ptr(), w["hp"].shape[1]) if dense else None    # as the dense pass launches it
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         check(L.b2c_slot_pipeline(ref(g_out), ref(eng.prof), ref(pool.struct), ref(sl), None, B, dptr(w["gains"], "c64"),
                                   dptr(w["noise_std"], "f32"), rows_ptr(o.get("H_true"), P, True), rows_ptr(o.get("rx"), P, True),
                                   rows_ptr(o.get("tx"), P, True), rows_ptr(o.get("H_ls"), P, True),
                                   None if dense else rows_ptr(o.get("H_mmse"), P, True), dptr(o["stats"], "f64"),
-                                  int(compact), None, stream_ptr()))
+                                  int(compact), ref(pio), stream_ptr()))
         b.record()
         if i >= 2:
             kev.append((a, b))
@@ -424,6 +430,18 @@ def run_b200(args, rank, world, local_rank):
         g_ms = statistics.mean(a.elapsed_time(b) for a, b in evs[2:])
         useful = 8.0 * npil * npil * ncols / (g_ms * 1e-3) / 1e12
         tensor = {"gemm_ms": g_ms, "columns": ncols, "np": npil, "useful_tflops": useful, "issued_tf32_tflops": 3 * useful}
+        if stats_only:      # the scoring pass alone (CFR regenerated from the gains, filtered pilots interpolated, error sums)
+            sl = Slots(base, args.seed, model_id.data_ptr(), doppler.data_ptr(), snr.data_ptr(), pattern.data_ptr())
+            evs = []
+            for i in range(10):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                check(L.b2c_dense_score(ref(eng.geom), ref(eng.prof), ref(pool.struct), ref(sl), B, dptr(wss[0]["gains"], "c64"),
+                                        dptr(hm, "c64"), dptr(dplan.col, "i32"), hp.shape[1], dptr(outs[0]["stats"], "f64"), stream_ptr()))
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            tensor["score_ms"] = statistics.mean(a.elapsed_time(b) for a, b in evs[2:])
         # a measured TF32 peak of this box (library matmul, measurement only -- not on the product path): 8192^3, best of 8
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = True
@@ -572,8 +590,8 @@ def run_b200(args, rank, world, local_rank):
                 traffic = ent["dram_bytes_per_slot"] * B
                 traffic_note = (f"static: dram__bytes_read + dram__bytes_write per slot from the ncu capture {ent.get('capture', '?')} "
                                 f"(profiles/), x {B} slots; not re-measured in this run")
-        kname = "slot_kernel<%d, ..., 599, FAST, pitch %s%s%s>" % (ntx, P, ", compact" if compact else "",
-                                                                   ", store-free (statistics only)" if stats_only else "")
+        kname = ("slot2_kernel<%d, EST, store-free> (register-blocked, statistics only)" % ntx if stats_only else
+                 "slot_kernel<%d, ..., 599, FAST, pitch %s%s>" % (ntx, P, ", compact" if compact else ""))
         share = k_ms * lps * args.steps / ms
         if stats_only:
             roof = {"bound": "issue", "kernel": kname, "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,

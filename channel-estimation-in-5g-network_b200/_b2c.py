@@ -18,7 +18,7 @@ EXPORTS = ["b2c_last_error_string", "b2c_abi_version", "b2c_tap_gains", "b2c_slo
            "b2c_ls_interp", "b2c_pilot_vectors", "b2c_mmse_dense", "b2c_dense_real_apply", "b2c_stats_bins",
            "b2c_ofdm_modulate", "b2c_ofdm_demodulate", "b2c_apply_channel", "b2c_tdl_full", "b2c_tdl_circular", "b2c_equalize",
            "b2c_qam_modulate", "b2c_qam_demodulate", "b2c_count_bit_errors", "b2c_bit_errors_per_slot", "b2c_pair00_moments", "b2c_pair00_errors", "b2c_count_nonfinite", "b2c_dense_prepared_bytes", "b2c_dense_prepare",
-           "b2c_dense_apply_prepared", "b2c_dense_apply_grouped", "b2c_abs_diff_sum",
+           "b2c_dense_apply_prepared", "b2c_dense_apply_grouped", "b2c_dense_score", "b2c_abs_diff_sum",
            "b2c_ml_features"]
 
 
@@ -100,6 +100,7 @@ def lib():
             "b2c_dense_prepare": [P, I32, I32, I32, P, P],
             "b2c_dense_apply_prepared": [P, I32, I32, I32, P, P, I64, I64, I64, P],
             "b2c_dense_apply_grouped": [P, I32, P, P, I64, P],
+            "b2c_dense_score": [P, P, P, P, I64, P, P, P, I64, P, P],
             "b2c_ml_features": [P, P, P, I64, P, P, P, I64, I32, I32, P, P, P, P],
         }
         L.b2c_dense_prepared_bytes.argtypes = [I32, I32, I32]

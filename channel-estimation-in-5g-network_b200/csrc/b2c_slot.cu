@@ -1003,7 +1003,11 @@ __device__ __forceinline__ void slot_body_wide2(const SlotArgs &a, const SlotCtx
   }
 }
 
-template <int NTX, bool EST, bool STORE, bool COMPACT>
+// SCORE (dense statistics): the second pass of the array-free dense-Wiener pipeline.  The pilot phase is replaced by
+// loading this (slot, rx)'s FILTERED pilot vector (row hp_col[b] + rx of a.hp_out, here an input) into shared memory;
+// the body regenerates the true CFR from the tap gains, interpolates the filtered pilots and takes the error sums, of
+// which only the MMSE fields (stats[..., 1]) are written -- no resource-grid array ever reaches HBM.
+template <int NTX, bool EST, bool STORE, bool COMPACT, bool SCORE = false>
 __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_constant__ SlotArgs a) {
   constexpr int WIDE = WIDE_PITCH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1019,7 +1023,7 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
   c.rx = blockIdx.x - (int)c.b * nrx;
   c.m = a.slots.model_id[c.b];
   c.ntaps = a.prof.ntaps[c.m];
-  c.sigma = a.noise_std[c.b];
+  c.sigma = SCORE ? 0.f : a.noise_std[c.b];
   c.key = make_key(a.slots.seed, a.slots.slot0 + c.b);
   c.gsp = gsp;
   c.hp = hp;
@@ -1029,8 +1033,16 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
 
   const float2 *gin = a.gains + (c.b * nrx + c.rx) * (int64_t)(nsym * ntx * MAXT);
   for (int i = threadIdx.x; i < nsym * ntx * MAXT; i += SLOT2_THREADS) gsp[i] = __ldg(gin + i);
+  if (SCORE) {
+    c.pid = a.slots.pattern_id[c.b];
+    c.alpha = 1.f;                     // the filtered pilots are interpolated as they are
+    const int np = a.pat.npilots[c.pid];
+    const float2 *hm = a.hp_out + ((a.hp_col ? (int64_t)a.hp_col[c.b] : c.b * nrx) + c.rx) * a.hp_ld;
+    for (int i = threadIdx.x; i < np; i += SLOT2_THREADS) hp[i] = __ldg(hm + i);
+    if (threadIdx.x == 0) hp[a.pat.np_max] = make_float2(0.f, 0.f);
+  }
   __syncthreads();
-  if (EST) {
+  if (EST && !SCORE) {
     for (int i = threadIdx.x; i < nsym * MAXT; i += SLOT2_THREADS) {
       int s = i / MAXT, t = i - s * MAXT;
       float sr = 0.f, si = 0.f;
@@ -1049,16 +1061,16 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
   for (int q = 0; q < 2; ++q) st[q][0] = st[q][1] = st[q][2] = make_float2(0.f, 0.f);
 
   if (c.ntaps <= 5) {
-    if (EST) pilot_phase<5, 599, SLOT2_THREADS>(a, c, gs, hp, red);
+    if (EST && !SCORE) pilot_phase<5, 599, SLOT2_THREADS>(a, c, gs, hp, red);
     slot_body_wide2<5, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
   } else if (c.ntaps <= 8) {
-    if (EST) pilot_phase<8, 599, SLOT2_THREADS>(a, c, gs, hp, red);
+    if (EST && !SCORE) pilot_phase<8, 599, SLOT2_THREADS>(a, c, gs, hp, red);
     slot_body_wide2<8, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
   } else if (c.ntaps <= 9) {
-    if (EST) pilot_phase<9, 599, SLOT2_THREADS>(a, c, gs, hp, red);
+    if (EST && !SCORE) pilot_phase<9, 599, SLOT2_THREADS>(a, c, gs, hp, red);
     slot_body_wide2<9, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
   } else {
-    if (EST) pilot_phase<MAXT, 599, SLOT2_THREADS>(a, c, gs, hp, red);
+    if (EST && !SCORE) pilot_phase<MAXT, 599, SLOT2_THREADS>(a, c, gs, hp, red);
     slot_body_wide2<MAXT, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
   }
 
@@ -1089,21 +1101,21 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
         double v;
         if (j == 2) v = q ? P : P0;
         else v = q ? P - 2.0 * cc * T + n * cc * cc * U : P0 - 2.0 * cc * T0 + cc * cc * U;
-        a.stats[(c.b * nrx + c.rx) * 6 + threadIdx.x] = v;
+        if (!SCORE || j == 1) a.stats[(c.b * nrx + c.rx) * 6 + threadIdx.x] = v;
       }
     } else if (threadIdx.x < 6) {
       double acc = 0.0;
       for (int w = 0; w < SLOT2_THREADS / 32; ++w) acc += (double)ssm[w][threadIdx.x];
-      a.stats[(c.b * nrx + c.rx) * 6 + threadIdx.x] = acc;
+      if (!SCORE || threadIdx.x % 3 == 1) a.stats[(c.b * nrx + c.rx) * 6 + threadIdx.x] = acc;
     }
   }
 }
 
-template <int NTX, bool EST, bool STORE, bool COMPACT>
+template <int NTX, bool EST, bool STORE, bool COMPACT, bool SCORE = false>
 static int launch_slot2(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
   if (EST) smem += 16 + 8 * SLOT2_THREADS * sizeof(uint4);      // plan-entry staging: 2 buffers x 4 entries per thread
-  if (smem > 48 * 1024) B2C_CUDA((set_max_smem<slot2_kernel<NTX, EST, STORE, COMPACT>>(smem)));
-  slot2_kernel<NTX, EST, STORE, COMPACT><<<(unsigned)(B * a.g.nrx), SLOT2_THREADS, smem, stream>>>(a);
+  if (smem > 48 * 1024) B2C_CUDA((set_max_smem<slot2_kernel<NTX, EST, STORE, COMPACT, SCORE>>(smem)));
+  slot2_kernel<NTX, EST, STORE, COMPACT, SCORE><<<(unsigned)(B * a.g.nrx), SLOT2_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
 }
@@ -1257,4 +1269,37 @@ extern "C" int b2c_slot_pipeline(const b2c_geom *g, const b2c_profiles *prof, co
   B2C_REQUIRE(smem <= 100 * 1024, B2C_E_UNSUPPORTED, "b2c_slot_pipeline: %zu B shared memory needed", smem);
   return est ? launch_slot_ntx<true>(a, B, smem, (cudaStream_t)stream)
              : launch_slot_ntx<false>(a, B, smem, (cudaStream_t)stream);
+}
+
+extern "C" int b2c_dense_score(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat,
+                               const b2c_slots *slots, int64_t B, const float *gains, const float *hm,
+                               const int32_t *hm_col, int64_t hm_ld, double *stats, void *stream) {
+  B2C_REQUIRE(g && prof && pat && slots && gains && hm && stats, B2C_E_ARG, "b2c_dense_score: null argument");
+  if (int rc = check_geom(g)) return rc;
+  B2C_REQUIRE(B >= 0 && B * g->nrx < (1ll << 31), B2C_E_ARG, "b2c_dense_score: B=%lld out of range", (long long)B);
+  B2C_REQUIRE(pat->plan && pat->npilots && slots->pattern_id && slots->model_id, B2C_E_ARG,
+              "b2c_dense_score: pattern pool / per-slot ids missing");
+  B2C_REQUIRE(hm_ld >= pat->np_max && pat->np_max <= 65534, B2C_E_ARG, "b2c_dense_score: hm_ld=%lld < np_max=%d",
+              (long long)hm_ld, pat->np_max);
+  const int ntx = g->ntx;
+  B2C_REQUIRE(g->nsc == 599 && (g->nsym & 1) == 0 && (ntx == 1 || ntx == 2 || ntx == 4 || ntx == 8), B2C_E_UNSUPPORTED,
+              "b2c_dense_score: needs the default grid (599 bins, even nsym) and ntx in {1, 2, 4, 8}");
+  if (B == 0) return B2C_OK;
+  SlotArgs a = {};
+  a.g = *g;
+  a.prof = *prof;
+  a.pat = *pat;
+  a.slots = *slots;
+  a.gains = reinterpret_cast<const float2 *>(gains);
+  a.stats = stats;
+  a.hp_out = const_cast<float2 *>(reinterpret_cast<const float2 *>(hm));   // read only in SCORE mode
+  a.hp_col = hm_col;
+  a.hp_ld = hm_ld;
+  const size_t smem = slot_smem_bytes(g, pat->np_max);
+  B2C_REQUIRE(smem <= 100 * 1024, B2C_E_UNSUPPORTED, "b2c_dense_score: %zu B shared memory needed", smem);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ntx == 1) return launch_slot2<1, true, false, false, true>(a, B, smem, st);
+  if (ntx == 2) return launch_slot2<2, true, false, false, true>(a, B, smem, st);
+  if (ntx == 4) return launch_slot2<4, true, false, false, true>(a, B, smem, st);
+  return launch_slot2<8, true, false, false, true>(a, B, smem, st);
 }

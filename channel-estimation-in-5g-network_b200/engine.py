@@ -255,6 +255,7 @@ class SlotEngine:
         if mmse not in ("default", "dense"):
             raise ValueError(f"Unknown mmse mode: {mmse}")
         dense = mmse == "dense" and any(k in (out if out is not None else want) for k in ("H_mmse", "stats"))
+        score_only = False
         if dense:
             if wiener is None or pool is None:
                 raise ValueError('mmse="dense" needs a WienerBank and its PatternPool')
@@ -262,7 +263,12 @@ class SlotEngine:
                 raise ValueError('mmse="dense" writes H_mmse in the full layout')
             if dense_plan is None and (isinstance(pattern_id, torch.Tensor) or isinstance(snr_db, torch.Tensor)):
                 raise ValueError('mmse="dense" groups slots by (pattern, SNR) on the host: pass host values or a dense_plan')
-            if out is None:
+            req = out if out is not None else want
+            # statistics only: the array-free form (slot kernel -> GEMM -> b2c_dense_score); nothing but the pilot vectors
+            # and the per-slot sums is written to HBM
+            score_only = not any(k in req for k in ("H_true", "rx", "tx", "H_ls", "H_mmse")) and self.nsc == 599 \
+                and self.nsym % 2 == 0 and self.ntx in (1, 2, 4, 8) and inject is None
+            if out is None and not score_only:
                 want = tuple(want) + tuple(k for k in ("H_true", "H_ls") if k not in want)   # K3 scores against H_true
         if out is None:
             out = self.alloc_outputs(B, want, compact, pitch)
@@ -283,7 +289,7 @@ class SlotEngine:
         g = self._with_pitch(self.geom, P)
         pio = None
         if dense:
-            if "H_true" not in out:
+            if "H_true" not in out and not score_only:
                 raise ValueError('mmse="dense" needs H_true among the outputs (the MMSE error sums are taken against it)')
             if dense_plan is None:
                 dense_plan = wiener.plan_batch(self, pattern_id, snr_db, B)
@@ -311,11 +317,18 @@ class SlotEngine:
                 n = min(32, ng - g0)
                 check(L.b2c_dense_apply_grouped(C.byref(dense_plan.groups, g0 * C.sizeof(DenseGroup)), n, dptr(hp, "c64"), dptr(hm, "c64"),
                                                 ld, stream_ptr()), "b2c_dense_apply_grouped")
-            # K3, mode 2: interpolate the filtered pilots into H_mmse, MMSE error sums into stats[..., 1]
-            check(L.b2c_ls_interp(ref(g), ref(pool.struct), keep[3].data_ptr(), None, B, None, None, 0, dptr(hm, "c64"), 2,
-                                  rows_ptr(out["H_true"], P) if "stats" in out else None, None,
-                                  rows_ptr(out.get("H_mmse"), P, True), None, dptr(out.get("stats"), "f64", True),
-                                  dptr(col, "i32"), ld, stream_ptr()), "b2c_ls_interp")
+            if score_only:
+                # second pass of the statistics-only form: true CFR regenerated from the gains, filtered pilots interpolated,
+                # MMSE error sums into stats[..., 1]
+                check(L.b2c_dense_score(ref(self.geom), ref(self.prof), ref(pool.struct), ref(slots), B, dptr(ws["gains"], "c64"),
+                                        dptr(hm, "c64"), dptr(col, "i32"), ld, dptr(out["stats"], "f64"), stream_ptr()),
+                      "b2c_dense_score")
+            else:
+                # K3, mode 2: interpolate the filtered pilots into H_mmse, MMSE error sums into stats[..., 1]
+                check(L.b2c_ls_interp(ref(g), ref(pool.struct), keep[3].data_ptr(), None, B, None, None, 0, dptr(hm, "c64"), 2,
+                                      rows_ptr(out["H_true"], P) if "stats" in out else None, None,
+                                      rows_ptr(out.get("H_mmse"), P, True), None, dptr(out.get("stats"), "f64", True),
+                                      dptr(col, "i32"), ld, stream_ptr()), "b2c_ls_interp")
             keep = keep + (dense_plan,)
         out["_keepalive"] = (keep, keep_inj, ws)
         return out

@@ -252,6 +252,19 @@ typedef struct b2c_dense_group {
 int b2c_dense_apply_grouped(const b2c_dense_group *groups_host, int32_t ngroups, const float *in, float *out, int64_t ld,
                             void *stream);
 
+/* Dense statistics, second pass.  For evaluation runs that want only the error statistics of the dense Wiener estimate
+ * (the MSE / NMSE-versus-SNR curves of evaluate_estimator, src/baseline_estimators.py:326-337, with
+ * MMSEEstimator(channel_cov=...) as the estimator) no resource-grid array has to exist in HBM at all:
+ *   b2c_slot_pipeline(stats + pilots_out, no arrays)  ->  b2c_dense_apply_grouped  ->  b2c_dense_score.
+ * This entry regenerates the true CFR of every (slot, rx) from the tap gains exactly as the slot kernel does,
+ * interpolates the FILTERED pilot vector hm (row hm_col[b] + rx of [.][hm_ld], or b * nrx + rx when hm_col is NULL)
+ * through the pattern's plan and writes sum |H_mmse - H_true|^2 into stats[b][rx][q][1] (q = 0: pair (rx, 0), q = 1:
+ * all tx); the other fields of stats are left as the first pass wrote them.  Default grid only (599 bins, even nsym,
+ * ntx in {1, 2, 4, 8}); gains as b2c_tap_gains wrote them for the same batch.                                     */
+int b2c_dense_score(const b2c_geom *g, const b2c_profiles *prof, const b2c_patterns *pat, const b2c_slots *slots,
+                    int64_t B, const float *gains, const float *hm, const int32_t *hm_col, int64_t hm_ld,
+                    double *stats, void *stream);
+
 /* K5.  Fold per-slot statistics into per-bin float64 accumulators (deterministic order).
  * Replaces the per-sample evaluate_estimator / compute_nmse + list aggregation of
  * src/baseline_estimators.py:326-337 and run_phase8_pilot_optimization.py:32-37,186-206.

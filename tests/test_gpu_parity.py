@@ -503,6 +503,43 @@ def test_batched_dense_wiener_pipeline_groups(pitch, engines):
         assert (one[:, :n] - hm_grouped[rows, :n]).abs().max().item() <= 2e-6 * one[:, :n].abs().max().item(), key
 
 
+@pytest.mark.parametrize("ntx,nrx,model", [(1, 1, "EPA"), (2, 2, "EVA"), (4, 4, "ETU"), (4, 2, "EVA")])
+def test_dense_wiener_statistics_without_arrays(ntx, nrx, model, engines):
+    """run(mmse="dense", want=("stats",)): slot kernel (statistics + pilot vectors) -> grouped GEMM -> b2c_dense_score,
+    no resource-grid array in HBM.  The per-slot sums must equal those of the array-writing dense pipeline (which is
+    checked against the reference above): the LS / power fields come from the same arithmetic, the MMSE field from the
+    same filtered pilots interpolated against the regenerated CFR."""
+    from engine import WienerBank
+    eng = engines(ntx, nrx)
+    pool = eng.random_pool([0.05, 0.02, 0.1], seed=4)
+    snrs = [-5.0, 10.0, 25.0]
+    bank = WienerBank(eng, pool, {i: model_cov(pool.pilot_indices[i]) for i in range(3)}, snrs)
+    B = 37
+    rng = np.random.default_rng(8)
+    pid = rng.integers(0, 3, B).astype(np.int32)
+    snr = np.asarray(snrs, np.float32)[rng.integers(0, 3, B)]
+    args = dict(model_id=eng.models.index(model), doppler_hz=80.0, snr_db=snr, pattern_id=pid, pool=pool, slot0=977, seed=3,
+                mmse="dense", wiener=bank)
+    full = eng.run(B, **args)
+    lean = eng.run(B, want=("stats",), **args)
+    torch.cuda.synchronize()
+    assert set(k for k in lean if not k.startswith("_")) == {"stats"}
+    a, b = full["stats"].cpu().numpy(), lean["stats"].cpu().numpy()
+    worst = np.abs(b / a - 1).max(axis=(0, 1, 2))
+    diag(test="dense_score", case=f"{ntx}x{nrx}_{model}", worst_ls=worst[0], worst_mmse=worst[1], worst_pow=worst[2])
+    assert worst.max() < 2e-5
+    # against float64 on the array run's own outputs: sum |H_mmse - H_true|^2 over all tx of one rx
+    Hm, Ht = full["H_mmse"].cpu().numpy().astype(np.complex128), full["H_true"].cpu().numpy().astype(np.complex128)
+    e = (np.abs(Hm - Ht) ** 2).sum(axis=(1, 3, 4))                                     # [B, nrx]
+    assert np.abs(b[:, :, 1, 1] / e - 1).max() < 2e-5
+    # a prebuilt plan with device-resident parameters takes the same route
+    plan = bank.plan_batch(eng, pid, snr, B)
+    dev = dict(args, snr_db=torch.from_numpy(snr).to(eng.device), pattern_id=torch.from_numpy(pid).to(eng.device))
+    again = eng.run(B, want=("stats",), dense_plan=plan, **dev)
+    torch.cuda.synchronize()
+    assert torch.equal(again["stats"], lean["stats"])
+
+
 @pytest.mark.parametrize("model,fd,ntx,nrx", [("EPA", 10.0, 1, 1), ("EVA", 50.0, 2, 2), ("ETU", 200.0, 4, 4)])
 def test_time_domain_path_lands_on_the_frequency_domain_grid(model, fd, ntx, nrx, engines):
     """modulate (K2) -> per-symbol circular TDL convolution with the K1a tap gains -> demodulate (K2) reproduces the
@@ -1163,6 +1200,13 @@ def test_c_abi_status_codes_and_empty_inputs(engines):
     assert L.b2c_dense_apply_grouped(grp, 0, P(z), P(bits), 4, None) == 0                                     # no groups: no-op
     assert L.b2c_tdl_circular(ref(g), ref(eng.prof), None, 1, P(z), P(z), P(z), None) == E_ARG
     assert L.b2c_bit_errors_per_slot(ref(g), ref(eng.random_pool([0.05], seed=1).struct), None, 1, P(bits), P(bits), 2, P(bits), None) == E_ARG
+    pool1 = eng.random_pool([0.05], seed=1)
+    sl = eng._slots(1, 0, 10.0, 10.0, 0, 0, 1)[0]
+    assert L.b2c_dense_score(ref(g), ref(eng.prof), ref(pool1.struct), ref(sl), 1, P(z), None, None, 2048, P(z), None) == E_ARG
+    assert L.b2c_dense_score(ref(g), ref(eng.prof), ref(pool1.struct), ref(sl), 1, P(z), P(z), None, 4, P(z), None) == E_ARG and "np_max" in msg()
+    g3 = Geom(14, 599, 3, 2, 1024, 72, 7.1e-5)
+    assert L.b2c_dense_score(ref(g3), ref(eng.prof), ref(pool1.struct), ref(sl), 1, P(z), P(z), None, 2048, P(z), None) == E_UNSUPPORTED
+    assert L.b2c_dense_score(ref(g), ref(eng.prof), ref(pool1.struct), ref(sl), 0, P(z), P(z), None, 2048, P(z), None) == 0
     # geometry outside the compiled limits: even bin count, too many symbols, too many antennas
     for bad in (Geom(14, 600, 2, 2, 1024, 72, 7.1e-5), Geom(17, 599, 2, 2, 1024, 72, 7.1e-5), Geom(14, 599, 9, 2, 1024, 72, 7.1e-5)):
         assert L.b2c_tap_gains(ref(bad), ref(eng.prof), ref(eng._slots(1, 0, 10.0, 10.0, 0, 0, 1)[0]), None, 1, P(z), P(z), None) == E_UNSUPPORTED
