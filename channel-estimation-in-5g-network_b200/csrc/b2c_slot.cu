@@ -223,6 +223,8 @@ struct SlotCtx {
   const float2 *gsp;   // smem [nsym][ntx][MAXT] tap gains of this rx
   const float2 *hp;    // smem [np] LS estimates at the pilots
   uint4 *pstage;       // smem [2][2][SLOT_THREADS] plan-entry staging of the wide kernel (16-byte aligned)
+  uint64_t *pbar;      // smem [PLAN_RING] mbarriers of the bulk-staged plan ring (slot2 kernel)
+  int *pcnt;           // smem [PLAN_RING] warps that have taken their entries out of a ring slot
 };
 
 // Symbol and noise draws for resource element (s, k) of this CTA's rx antenna (layout in b2c.h:
@@ -507,9 +509,19 @@ __device__ __forceinline__ void slot_body(const SlotArgs &a, const SlotCtx &c, f
 // ntx >= 4: the wide kernel takes the error sums over all tx from the tx-summed CFR instead of per-tx differences
 __host__ __device__ constexpr bool wide_fold(int ntx) { return ntx >= 4; }
 
+// Bulk-staged plan rows (see slot_body_wide2 for the scheme)
+constexpr int PLAN_ROW = 600;       // entries per row of the bulk-staged plan ring: 599 bins + the all-outside entry
+constexpr int PLAN_RING = 4;        // rows in the ring: a row is fetched PLAN_RING symbols before it is used
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+
 // COMPACT: the tx-replicated outputs are written once, in rx's row layout: H_ls / H_mmse [B][nsym][nrx][PITCH] and
 // tx [B][nsym][PITCH] (1 945 552 unique bytes per 4x4 slot instead of 3 756 928).
-template <int T, int NTX, bool EST, int PITCH, bool STORE, bool COMPACT>
+template <int T, int NTX, bool EST, int PITCH, bool STORE, bool COMPACT, bool BULK = false>
 __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx &c, float2 (&st)[2][3]) {
   constexpr int NSC = 599, HALF = 300;
   const int nsym = a.g.nsym, nrx = a.g.nrx;
@@ -568,7 +580,17 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ps_s + slot * PS_SLOT) : "memory");
     return v;
   };
-  if (EST) stage_plan(0);
+  // BULK: plan rows arrive by cp.async.bulk in a ring of PLAN_RING rows (started by the kernel before the pilot phase).  Every
+  // lane loads entry 300 + t and entry 299 - t (both conflict-free: 32 consecutive entries per warp) and takes K / S from
+  // them by parity; entry 599 of a ring row is the all-outside entry (idle lanes, the missing bin).
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(c.pstage), bars = (uint32_t)__cvta_generic_to_shared(c.pbar);
+  const uint32_t oA = ((act && kp < NSC) ? kp : NSC) * 16u, oB = (act ? km : NSC) * 16u;
+  auto ring_ld = [&](uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+  };
+  if (EST && !BULK) stage_plan(0);
   auto xchg = [](float2 v) {     // value of this lane's S bin -> the neighbour that stores it as K+1
     return make_float2(__shfl_xor_sync(0xffffffffu, v.x, 1), __shfl_xor_sync(0xffffffffu, v.y, 1));
   };
@@ -578,7 +600,18 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
     for (int j = 0; j < 2; ++j) {
       const int s = s2 + j;
       float2 lK = zero2, lS = zero2;
-      if (EST) {
+      int ring_old = 0;
+      if (EST && BULK) {
+        const int rb = s & (PLAN_RING - 1);
+        while (!mbar_try_wait(bars + rb * 8, (uint32_t)(s / PLAN_RING) & 1u)) {}
+        const uint4 eA = ring_ld(ring + rb * PLAN_ROW * 16u + oA), eB = ring_ld(ring + rb * PLAN_ROW * 16u + oB);
+        if (s + PLAN_RING < nsym && (t_ & 31) == 0) ring_old = atomicAdd(c.pcnt + rb, 1);      // see slot_body_wide2
+        const uint4 eK = make_uint4(odd ? eB.x : eA.x, odd ? eB.y : eA.y, odd ? eB.z : eA.z, odd ? eB.w : eA.w);
+        const uint4 eS = make_uint4(odd ? eA.x : eB.x, odd ? eA.y : eB.y, odd ? eA.z : eB.z, odd ? eA.w : eB.w);
+        lK = plan_apply(plan_decode(eK), c.hp);
+        lS = plan_apply(plan_decode(eS), c.hp);
+      }
+      if (EST && !BULK) {
         oPK += dPK;
         oPS += dPS;
         stage_plan(j ^ 1);                                   // next symbol's entries (s2 is even: buffer = s & 1 = j)
@@ -656,6 +689,14 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
         st[1][1] = __ffma2_rn(lK, lK, st[1][1]);
         st[1][1] = __ffma2_rn(lS, lS, st[1][1]);
       }
+      if (EST && BULK && s + PLAN_RING < nsym && (t_ & 31) == 0 && ring_old == SLOT_THREADS / 32 - 1) {
+        // last warp out of this ring slot: refill it with the row PLAN_RING symbols ahead
+        const int rb = s & (PLAN_RING - 1);
+        c.pcnt[rb] = 0;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bars + rb * 8), "r"(NSC * 16u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(ring + rb * PLAN_ROW * 16u),
+                     "l"(plan + (s + PLAN_RING) * NSC), "r"(NSC * 16u), "r"(bars + rb * 8) : "memory");
+      }
       if (!STORE) {
         gps += NTX * MAXT;
         continue;
@@ -686,7 +727,30 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
   }
 }
 
-template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE, bool STORE = true, bool COMPACT = false>
+// One thread: barriers, counters, the all-outside entry of every ring row, and the first PLAN_RING plan rows on their way.
+__device__ __forceinline__ void plan_ring_start(const SlotArgs &a, const SlotCtx &c) {
+  const int nsym = a.g.nsym;
+  const uint4 *plan = reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * (nsym * 599 + 1);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(c.pstage), bars = (uint32_t)__cvta_generic_to_shared(c.pbar);
+  const uint4 outside = __ldg(plan + nsym * 599);
+#pragma unroll
+  for (int b = 0; b < PLAN_RING; ++b) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bars + b * 8));
+    c.pstage[b * PLAN_ROW + 599] = outside;
+    c.pcnt[b] = 0;
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+#pragma unroll
+  for (int b = 0; b < PLAN_RING; ++b) {
+    if (b < nsym) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bars + b * 8), "r"(599u * 16u) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(ring + b * PLAN_ROW * 16u),
+                   "l"(plan + b * 599), "r"(599u * 16u), "r"(bars + b * 8) : "memory");
+    }
+  }
+}
+
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE, bool STORE = true, bool COMPACT = false, bool BULK = false>
 __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nsc = NSC ? NSC : a.g.nsc;
@@ -696,6 +760,8 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   float2 *hp = gs + nsym * MAXT;                                      // [np_max + 1], last = 0
   __shared__ float red[33];
   __shared__ float ssm[SLOT_THREADS / 32][6];
+  __shared__ __align__(8) uint64_t pbar[PLAN_RING];
+  __shared__ int pcnt[PLAN_RING];
 
   SlotCtx c;
   c.b = blockIdx.x / nrx;
@@ -707,8 +773,11 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   c.gsp = gsp;
   c.hp = hp;
   c.pstage = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(hp + (EST ? a.pat.np_max + 1 : 0)) + 15) & ~(uintptr_t)15);
+  c.pbar = pbar;
+  c.pcnt = pcnt;
   c.alpha = 0.f;
-  c.pid = 0;
+  c.pid = EST ? a.slots.pattern_id[c.b] : 0;
+  if (WIDE != 0 && EST && BULK && threadIdx.x == 0) plan_ring_start(a, c);
 
   const float2 *gin = a.gains + (c.b * nrx + c.rx) * (int64_t)(nsym * ntx * MAXT);
   for (int i = threadIdx.x; i < nsym * ntx * MAXT; i += SLOT_THREADS) {
@@ -730,7 +799,6 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
       gs[i] = make_float2(sr, si);
     }
     __syncthreads();
-    c.pid = a.slots.pattern_id[c.b];
   }
 
   float2 st[2][3];   // packed (re^2, im^2) sums: [0] tx 0 (antenna pair (rx, 0)), [1] tx >= 1
@@ -739,22 +807,22 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
 
   if (c.ntaps <= 5) {
     if (EST) pilot_phase<5, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<5, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<5, NTX, EST, WIDE, STORE, COMPACT, BULK>(a, c, st);
     else slot_body<5, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else if (c.ntaps <= 8) {
     if (EST) pilot_phase<8, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<8, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<8, NTX, EST, WIDE, STORE, COMPACT, BULK>(a, c, st);
     else slot_body<8, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else if (c.ntaps <= 9) {
     if (EST) pilot_phase<9, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<9, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<9, NTX, EST, WIDE, STORE, COMPACT, BULK>(a, c, st);
     else slot_body<9, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
   else {
     if (EST) pilot_phase<MAXT, NSC>(a, c, gs, hp, red);
-    if constexpr (WIDE) slot_body_wide<MAXT, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
+    if constexpr (WIDE) slot_body_wide<MAXT, NTX, EST, WIDE, STORE, COMPACT, BULK>(a, c, st);
     else slot_body<MAXT, NTX, EXACT, EST, NSC, FAST>(a, c, st);
   }
 
@@ -810,7 +878,11 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
 // is spread over four bins.  Same Philox counters (bin +-f draws from lane f-1), same operation order per bin:
 // bit-identical to slot_body_wide.  t = 149: f2 = 300 has no +f bin (element 599 is the padding element, written as 0).
 constexpr int SLOT2_THREADS = 160;
-template <int T, int NTX, bool EST, int PITCH, bool STORE, bool COMPACT>
+// BULK: the plan rows of a symbol (599 contiguous 16-byte entries) are brought into a two-row shared-memory ring by
+// cp.async.bulk (one instruction of one thread per symbol, completion on an mbarrier) instead of one cp.async per entry
+// and thread: the copy engine writes shared memory without passing through the LSU data pipe, which was the first limiter
+// of the statistics kernels (ncu: 83-92 % busy, about a third of its wavefronts the per-thread staging copies).
+template <int T, int NTX, bool EST, int PITCH, bool STORE, bool COMPACT, bool BULK = false>
 __device__ __forceinline__ void slot_body_wide2(const SlotArgs &a, const SlotCtx &c, float2 (&st)[2][3]) {
   constexpr int NSC = 599, HALF = 300;
   const int nsym = a.g.nsym, nrx = a.g.nrx;
@@ -871,14 +943,53 @@ __device__ __forceinline__ void slot_body_wide2(const SlotArgs &a, const SlotCtx
     return v;
   };
   auto st16 = [](float2 *p, float2 lo, float2 hi) { __stcs(reinterpret_cast<float4 *>(p), make_float4(lo.x, lo.y, hi.x, hi.y)); };
-  if (EST) stage_plan(0);
+  // bulk form: ring of PLAN_RING rows of PLAN_ROW entries; entry 599 of each row is the all-outside entry (idle lanes / the
+  // missing bin); this thread's four entries sit at fixed positions of a row
+  constexpr uint32_t ROW_BYTES = NSC * sizeof(uint4);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(c.pstage), bars = (uint32_t)__cvta_generic_to_shared(c.pbar);
+  // thread t reads the adjacent entries (kp, kp + 1) and (km, km + 1): with every thread loading the lower entry first a
+  // quarter-warp would touch 8 entries 32 bytes apart (two per bank group); threads 4..7 of every eight load the UPPER
+  // entry first instead, which makes the eight 16-byte accesses of a quarter-warp fall into eight different bank groups
+  const bool swp = (t_ >> 2) & 1;
+  const uint32_t eraw[4] = {(act ? kp : NSC) * 16u, (vp2 ? kp + 1 : NSC) * 16u, (act ? km : NSC) * 16u, (act ? km + 1 : NSC) * 16u};
+  const uint32_t eo[4] = {swp ? eraw[1] : eraw[0], swp ? eraw[0] : eraw[1], swp ? eraw[3] : eraw[2], swp ? eraw[2] : eraw[3]};
+  auto fetch_row = [&](int row, int buf) {           // one thread: row `row` of the plan -> ring[buf]
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bars + buf * 8), "r"(ROW_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(ring + buf * PLAN_ROW * 16u),
+                 "l"(plan + row * NSC), "r"(ROW_BYTES), "r"(bars + buf * 8) : "memory");
+  };
+  auto ring_entry = [&](int buf, int q) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring + buf * PLAN_ROW * 16u + eo[q]) : "memory");
+    return v;
+  };
+  // (bulk form: the kernel has initialised the barriers and started rows 0 and 1 before the pilot phase)
+  if (EST && !BULK) stage_plan(0);
   uint4 ws1 = make_uint4(0, 0, 0, 0), ws2 = ws1;
   for (int s2 = 0; s2 < nsym; s2 += 2) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int s = s2 + j;
       float2 lp1 = zero2, lp2 = zero2, lm2 = zero2, lm1 = zero2;      // LS estimates at +f1, +f2, -f2, -f1
-      if (EST) {
+      int ring_old = 0;
+      if (EST && BULK) {
+        // row s sits in ring[s % PLAN_RING], its (s / PLAN_RING)-th fill
+        const int rb = s & (PLAN_RING - 1);
+        while (!mbar_try_wait(bars + rb * 8, (uint32_t)(s / PLAN_RING) & 1u)) {}
+        const uint4 r0 = ring_entry(rb, 0), r1 = ring_entry(rb, 1), r2 = ring_entry(rb, 2), r3 = ring_entry(rb, 3);
+        auto sel4 = [](bool c, uint4 x, uint4 y) { return make_uint4(c ? x.x : y.x, c ? x.y : y.y, c ? x.z : y.z, c ? x.w : y.w); };
+        const uint4 e0 = sel4(swp, r1, r0), e1 = sel4(swp, r0, r1), e2 = sel4(swp, r3, r2), e3 = sel4(swp, r2, r3);
+        // the ring slot is free once every warp holds its entries: the warps count themselves off on a shared-memory counter
+        // and whichever comes last refills the slot with row s + PLAN_RING at the END of its symbol (the atomic's return
+        // value is not needed before, so nobody waits for anybody; the copy has PLAN_RING - 1 symbols of work to land under).
+        // A warp cannot count itself twice on one slot: its next visit (symbol s + PLAN_RING) waits for this very refill.
+        if (s + PLAN_RING < nsym && (t_ & 31) == 0) ring_old = atomicAdd(c.pcnt + rb, 1);
+        lp1 = plan_apply(plan_decode(e0), c.hp);
+        lp2 = plan_apply(plan_decode(e1), c.hp);
+        lm2 = plan_apply(plan_decode(e2), c.hp);
+        lm1 = plan_apply(plan_decode(e3), c.hp);
+      }
+      if (EST && !BULK) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) oP[q] += dP[q];
         stage_plan(j ^ 1);
@@ -965,6 +1076,10 @@ __device__ __forceinline__ void slot_body_wide2(const SlotArgs &a, const SlotCtx
         st[1][1] = __ffma2_rn(lm2, lm2, st[1][1]);
         st[1][1] = __ffma2_rn(lm1, lm1, st[1][1]);
       }
+      if (EST && BULK && s + PLAN_RING < nsym && (t_ & 31) == 0 && ring_old == SLOT2_THREADS / 32 - 1) {
+        c.pcnt[s & (PLAN_RING - 1)] = 0;
+        fetch_row(s + PLAN_RING, s & (PLAN_RING - 1));
+      }
       if (!STORE) {
         gps += NTX * MAXT;
         continue;
@@ -1007,7 +1122,7 @@ __device__ __forceinline__ void slot_body_wide2(const SlotArgs &a, const SlotCtx
 // loading this (slot, rx)'s FILTERED pilot vector (row hp_col[b] + rx of a.hp_out, here an input) into shared memory;
 // the body regenerates the true CFR from the tap gains, interpolates the filtered pilots and takes the error sums, of
 // which only the MMSE fields (stats[..., 1]) are written -- no resource-grid array ever reaches HBM.
-template <int NTX, bool EST, bool STORE, bool COMPACT, bool SCORE = false>
+template <int NTX, bool EST, bool STORE, bool COMPACT, bool SCORE = false, bool BULK = false>
 __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_constant__ SlotArgs a) {
   constexpr int WIDE = WIDE_PITCH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1017,6 +1132,8 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
   float2 *hp = gs + nsym * MAXT;                                      // [np_max + 1], last = 0
   __shared__ float red[33];
   __shared__ float ssm[SLOT2_THREADS / 32][6];
+  __shared__ __align__(8) uint64_t pbar[PLAN_RING];
+  __shared__ int pcnt[PLAN_RING];
 
   SlotCtx c;
   c.b = blockIdx.x / nrx;
@@ -1028,13 +1145,18 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
   c.gsp = gsp;
   c.hp = hp;
   c.pstage = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(hp + (EST ? a.pat.np_max + 1 : 0)) + 15) & ~(uintptr_t)15);
+  c.pbar = pbar;
+  c.pcnt = pcnt;
   c.alpha = 0.f;
   c.pid = 0;
 
   const float2 *gin = a.gains + (c.b * nrx + c.rx) * (int64_t)(nsym * ntx * MAXT);
+  if (EST) c.pid = a.slots.pattern_id[c.b];
+  // plan ring: barriers, the all-outside entries and the first rows on their way before anything else happens (they land
+  // under the gain staging and the pilot phase)
+  if (EST && BULK && threadIdx.x == 0) plan_ring_start(a, c);
   for (int i = threadIdx.x; i < nsym * ntx * MAXT; i += SLOT2_THREADS) gsp[i] = __ldg(gin + i);
   if (SCORE) {
-    c.pid = a.slots.pattern_id[c.b];
     c.alpha = 1.f;                     // the filtered pilots are interpolated as they are
     const int np = a.pat.npilots[c.pid];
     const float2 *hm = a.hp_out + ((a.hp_col ? (int64_t)a.hp_col[c.b] : c.b * nrx) + c.rx) * a.hp_ld;
@@ -1054,7 +1176,6 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
       gs[i] = make_float2(sr, si);
     }
     __syncthreads();
-    c.pid = a.slots.pattern_id[c.b];
   }
   float2 st[2][3];
 #pragma unroll
@@ -1062,16 +1183,16 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
 
   if (c.ntaps <= 5) {
     if (EST && !SCORE) pilot_phase<5, 599, SLOT2_THREADS>(a, c, gs, hp, red);
-    slot_body_wide2<5, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
+    slot_body_wide2<5, NTX, EST, WIDE, STORE, COMPACT, BULK>(a, c, st);
   } else if (c.ntaps <= 8) {
     if (EST && !SCORE) pilot_phase<8, 599, SLOT2_THREADS>(a, c, gs, hp, red);
-    slot_body_wide2<8, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
+    slot_body_wide2<8, NTX, EST, WIDE, STORE, COMPACT, BULK>(a, c, st);
   } else if (c.ntaps <= 9) {
     if (EST && !SCORE) pilot_phase<9, 599, SLOT2_THREADS>(a, c, gs, hp, red);
-    slot_body_wide2<9, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
+    slot_body_wide2<9, NTX, EST, WIDE, STORE, COMPACT, BULK>(a, c, st);
   } else {
     if (EST && !SCORE) pilot_phase<MAXT, 599, SLOT2_THREADS>(a, c, gs, hp, red);
-    slot_body_wide2<MAXT, NTX, EST, WIDE, STORE, COMPACT>(a, c, st);
+    slot_body_wide2<MAXT, NTX, EST, WIDE, STORE, COMPACT, BULK>(a, c, st);
   }
 
   if (EST && a.stats) {
@@ -1111,13 +1232,25 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
   }
 }
 
-template <int NTX, bool EST, bool STORE, bool COMPACT, bool SCORE = false>
-static int launch_slot2(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
-  if (EST) smem += 16 + 8 * SLOT2_THREADS * sizeof(uint4);      // plan-entry staging: 2 buffers x 4 entries per thread
-  if (smem > 48 * 1024) B2C_CUDA((set_max_smem<slot2_kernel<NTX, EST, STORE, COMPACT, SCORE>>(smem)));
-  slot2_kernel<NTX, EST, STORE, COMPACT, SCORE><<<(unsigned)(B * a.g.nrx), SLOT2_THREADS, smem, stream>>>(a);
+template <int NTX, bool EST, bool STORE, bool COMPACT, bool SCORE = false, bool BULK = false>
+static int launch_slot2_form(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
+  // plan staging: 2 buffers x 4 entries per thread, or (bulk) a ring of PLAN_RING rows of PLAN_ROW entries
+  if (EST) smem += 16 + (BULK ? PLAN_RING * PLAN_ROW : 8 * SLOT2_THREADS) * sizeof(uint4);
+  if (smem > 48 * 1024) B2C_CUDA((set_max_smem<slot2_kernel<NTX, EST, STORE, COMPACT, SCORE, BULK>>(smem)));
+  slot2_kernel<NTX, EST, STORE, COMPACT, SCORE, BULK><<<(unsigned)(B * a.g.nrx), SLOT2_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
+}
+template <int NTX, bool EST, bool STORE, bool COMPACT, bool SCORE = false>
+static int launch_slot2(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
+  // Plan rows by bulk copy into the shared-memory ring: the default of the scoring pass, where it is worth 16 % (2x2, 18 944
+  // slots: 1.14 ms against 1.36 ms; its L1 data pipe was 92 % busy).  The first pass spends a third of its time in the pilot
+  // phase and is latency-bound at 15 warps per SM, not pipe-bound: there the bulk form measured -3 % (4x4) to +1 % (2x2), so it
+  // keeps the per-thread cp.async staging.  B2C_PLAN_BULK=1 / 0 forces either form for both (tests, A/B runs).
+  const char *e = getenv("B2C_PLAN_BULK");
+  const bool bulk = e ? e[0] != '0' : SCORE;
+  if (EST && !STORE && bulk) return launch_slot2_form<NTX, EST, STORE, COMPACT, SCORE, true>(a, B, smem, stream);
+  return launch_slot2_form<NTX, EST, STORE, COMPACT, SCORE, false>(a, B, smem, stream);
 }
 
 static size_t slot_smem_bytes(const b2c_geom *g, int np_max) {
@@ -1125,14 +1258,23 @@ static size_t slot_smem_bytes(const b2c_geom *g, int np_max) {
          (size_t)(np_max + 1) * sizeof(float2);
 }
 
-template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0, bool STORE = true, bool COMPACT = false>
-static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
-  auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT>;
-  if (WIDE && EST) smem += 16 + 4 * SLOT_THREADS * sizeof(uint4);      // plan-entry staging (+ alignment slack)
-  if (smem > 48 * 1024) B2C_CUDA((set_max_smem<slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT>>(smem)));
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0, bool STORE = true, bool COMPACT = false, bool BULK = false>
+static int launch_slot_form(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
+  auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT, BULK>;
+  // plan-entry staging (+ alignment slack): per-thread slots, or the ring of bulk-copied rows
+  if (WIDE && EST) smem += 16 + (BULK ? PLAN_RING * PLAN_ROW : 4 * SLOT_THREADS) * sizeof(uint4);
+  if (smem > 48 * 1024) B2C_CUDA((set_max_smem<slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT, BULK>>(smem)));
   kern<<<(unsigned)(B * a.g.nrx), SLOT_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
   return B2C_OK;
+}
+template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0, bool STORE = true, bool COMPACT = false>
+static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
+  if constexpr (WIDE != 0 && EST && STORE) {
+    const char *e = getenv("B2C_PLAN_BULK");        // storing wide kernels: bulk-copied plan rows on request (A/B runs)
+    if (e && e[0] != '0') return launch_slot_form<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT, true>(a, B, smem, stream);
+  }
+  return launch_slot_form<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT, false>(a, B, smem, stream);
 }
 
 // Fast path: the throughput configuration -- default grid (599 used bins), power-of-two TX count,

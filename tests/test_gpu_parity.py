@@ -538,6 +538,14 @@ def test_dense_wiener_statistics_without_arrays(ntx, nrx, model, engines):
     again = eng.run(B, want=("stats",), dense_plan=plan, **dev)
     torch.cuda.synchronize()
     assert torch.equal(again["stats"], lean["stats"])
+    # the scoring pass with per-thread plan staging instead of the bulk-copied row ring: same bits
+    os.environ["B2C_PLAN_BULK"] = "0"
+    try:
+        per_thread = eng.run(B, want=("stats",), dense_plan=plan, **dev)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["B2C_PLAN_BULK"]
+    assert torch.equal(per_thread["stats"], lean["stats"])
 
 
 @pytest.mark.parametrize("model,fd,ntx,nrx", [("EPA", 10.0, 1, 1), ("EVA", 50.0, 2, 2), ("ETU", 200.0, 4, 4)])
@@ -644,6 +652,29 @@ def test_pilot_sweep_ber_curves():
     assert res['methods']['LS'][10][0.10]['ber'] <= res['methods']['LS'][10][0.02]['ber'] + 5e-3     # more pilots do not hurt
 
 
+@pytest.mark.parametrize("ntx,nrx,compact", [(4, 4, False), (4, 4, True), (2, 2, False), (1, 2, True)])
+def test_wide_kernel_with_bulk_copied_plan_rows(ntx, nrx, compact, engines):
+    """B2C_PLAN_BULK=1 makes the wide-store slot kernel take its interpolation plan rows from a shared-memory ring filled by
+    cp.async.bulk instead of per-thread cp.async staging: same entries, same arithmetic -- every output bit-identical, over
+    several waves of CTAs and mixed profiles / patterns."""
+    eng = engines(ntx, nrx)
+    pool = eng.random_pool([0.10, 0.03], seed=21)
+    B = 700
+    rng = np.random.default_rng(2)
+    kw = dict(model_id=rng.integers(0, 3, B).astype(np.int32), doppler_hz=rng.uniform(5, 200, B).astype(np.float32),
+              snr_db=rng.uniform(-5, 30, B).astype(np.float32), pattern_id=rng.integers(0, 2, B).astype(np.int32), pool=pool,
+              slot0=5150, seed=8, pitch=600, compact=compact)
+    ref = eng.run(B, **kw)
+    os.environ["B2C_PLAN_BULK"] = "1"
+    try:
+        got = eng.run(B, **kw)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["B2C_PLAN_BULK"]
+    for k in ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"):
+        assert torch.equal(got[k], ref[k]), k
+
+
 @pytest.mark.parametrize("ntx,nrx", [(4, 4), (2, 2), (1, 1), (8, 2)])
 def test_register_blocked_statistics_kernel(ntx, nrx, engines):
     """Statistics-only sweeps run slot2_kernel (160 threads, two mirror pairs = four bins per thread): same Philox
@@ -664,7 +695,20 @@ def test_register_blocked_statistics_kernel(ntx, nrx, engines):
     finally:
         del os.environ["B2C_NO_SLOT2"]
     full = eng.run(B, pitch=600, **kw)["stats"]
+    # plan rows by bulk copy (B2C_PLAN_BULK=1; the scoring pass's default) against the per-thread cp.async staging: same entries, same arithmetic, same bits --
+    # on a batch large enough for several waves of CTAs (ring reuse, barrier races would show as differing sums)
+    Bb = 1200
+    kwb = dict(model_id=np.resize(mid, Bb), doppler_hz=np.resize(fd, Bb), snr_db=np.resize(snr, Bb), pattern_id=np.resize(pid, Bb),
+               pool=pool, slot0=99, seed=5)
+    forms = []
+    for flag in ("1", "0"):
+        os.environ["B2C_PLAN_BULK"] = flag
+        try:
+            forms.append(eng.run(Bb, want=("stats",), **kwb)["stats"])
+        finally:
+            del os.environ["B2C_PLAN_BULK"]
     torch.cuda.synchronize()
+    assert torch.equal(forms[0], forms[1])
     assert torch.allclose(got, ref, rtol=2e-6, atol=0)
     assert torch.allclose(got, full, rtol=2e-6 if ntx < 4 else 2e-5, atol=0)
     assert not torch.equal(got, torch.zeros_like(got))
