@@ -222,9 +222,8 @@ struct SlotCtx {
   PhiloxKey key;
   const float2 *gsp;   // smem [nsym][ntx][MAXT] tap gains of this rx
   const float2 *hp;    // smem [np] LS estimates at the pilots
-  uint4 *pstage;       // smem [2][2][SLOT_THREADS] plan-entry staging of the wide kernel (16-byte aligned)
-  uint64_t *pbar;      // smem [PLAN_RING] mbarriers of the bulk-staged plan ring (slot2 kernel)
-  int *pcnt;           // smem [PLAN_RING] warps that have taken their entries out of a ring slot
+  uint4 *pstage;       // smem, 16-byte aligned: [2][2][SLOT_THREADS] per-thread plan-entry staging of the wide kernels, or the
+                       // bulk-copied ring (PLAN_RING rows of PLAN_ROW entries, then its mbarriers and warp counters)
 };
 
 // Symbol and noise draws for resource element (s, k) of this CTA's rx antenna (layout in b2c.h:
@@ -512,6 +511,28 @@ __host__ __device__ constexpr bool wide_fold(int ntx) { return ntx >= 4; }
 // Bulk-staged plan rows (see slot_body_wide2 for the scheme)
 constexpr int PLAN_ROW = 600;       // entries per row of the bulk-staged plan ring: 599 bins + the all-outside entry
 constexpr int PLAN_RING = 4;        // rows in the ring: a row is fetched PLAN_RING symbols before it is used
+// The ring's mbarriers and warp counters live right behind its rows in dynamic shared memory and are addressed, like the rows,
+// by 32-bit shared-window offsets from ONE base register (static __shared__ objects reached through generic pointers made
+// the compiler re-derive the window base from SR_CgaCtaId inside the loop: an S2R with its latency twice per symbol).
+constexpr uint32_t PLAN_RING_BYTES = PLAN_RING * PLAN_ROW * 16u + PLAN_RING * 8u + PLAN_RING * 4u;
+__device__ __forceinline__ uint32_t ring_row(uint32_t ring, int b) { return ring + (uint32_t)b * (PLAN_ROW * 16u); }
+__device__ __forceinline__ uint32_t ring_bar(uint32_t ring, int b) { return ring + PLAN_RING * PLAN_ROW * 16u + (uint32_t)b * 8u; }
+__device__ __forceinline__ uint32_t ring_cnt(uint32_t ring, int b) { return ring + PLAN_RING * PLAN_ROW * 16u + PLAN_RING * 8u + (uint32_t)b * 4u; }
+__device__ __forceinline__ void ring_fetch(uint32_t ring, int b, const uint4 *src) {       // one thread: 599 entries -> ring row b
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(ring_bar(ring, b)), "r"(599u * 16u) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(ring_row(ring, b)), "l"(src),
+               "r"(599u * 16u), "r"(ring_bar(ring, b)) : "memory");
+}
+__device__ __forceinline__ int ring_count_in(uint32_t ring, int b) {                         // returns the count before this warp
+  int old;
+  // inc, not add: ptxas turns a predicated atom.add into a warp-aggregated one (VOTE, S2R lane id / lane mask, SHFL) although
+  // only one lane runs it -- two S2R per symbol showed up as 6-7 % of the kernel's stall samples
+  asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;\n" : "=r"(old) : "r"(ring_cnt(ring, b)) : "memory");
+  return old;
+}
+__device__ __forceinline__ void ring_count_reset(uint32_t ring, int b) {
+  asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(ring_cnt(ring, b)), "r"(0) : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
@@ -583,7 +604,7 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
   // BULK: plan rows arrive by cp.async.bulk in a ring of PLAN_RING rows (started by the kernel before the pilot phase).  Every
   // lane loads entry 300 + t and entry 299 - t (both conflict-free: 32 consecutive entries per warp) and takes K / S from
   // them by parity; entry 599 of a ring row is the all-outside entry (idle lanes, the missing bin).
-  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(c.pstage), bars = (uint32_t)__cvta_generic_to_shared(c.pbar);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(c.pstage);
   const uint32_t oA = ((act && kp < NSC) ? kp : NSC) * 16u, oB = (act ? km : NSC) * 16u;
   auto ring_ld = [&](uint32_t addr) {
     uint4 v;
@@ -603,9 +624,9 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
       int ring_old = 0;
       if (EST && BULK) {
         const int rb = s & (PLAN_RING - 1);
-        while (!mbar_try_wait(bars + rb * 8, (uint32_t)(s / PLAN_RING) & 1u)) {}
-        const uint4 eA = ring_ld(ring + rb * PLAN_ROW * 16u + oA), eB = ring_ld(ring + rb * PLAN_ROW * 16u + oB);
-        if (s + PLAN_RING < nsym && (t_ & 31) == 0) ring_old = atomicAdd(c.pcnt + rb, 1);      // see slot_body_wide2
+        while (!mbar_try_wait(ring_bar(ring, rb), (uint32_t)(s / PLAN_RING) & 1u)) {}
+        const uint4 eA = ring_ld(ring_row(ring, rb) + oA), eB = ring_ld(ring_row(ring, rb) + oB);
+        if (s + PLAN_RING < nsym && (t_ & 31) == 0) ring_old = ring_count_in(ring, rb);      // see slot_body_wide2
         const uint4 eK = make_uint4(odd ? eB.x : eA.x, odd ? eB.y : eA.y, odd ? eB.z : eA.z, odd ? eB.w : eA.w);
         const uint4 eS = make_uint4(odd ? eA.x : eB.x, odd ? eA.y : eB.y, odd ? eA.z : eB.z, odd ? eA.w : eB.w);
         lK = plan_apply(plan_decode(eK), c.hp);
@@ -692,10 +713,8 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
       if (EST && BULK && s + PLAN_RING < nsym && (t_ & 31) == 0 && ring_old == SLOT_THREADS / 32 - 1) {
         // last warp out of this ring slot: refill it with the row PLAN_RING symbols ahead
         const int rb = s & (PLAN_RING - 1);
-        c.pcnt[rb] = 0;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bars + rb * 8), "r"(NSC * 16u) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(ring + rb * PLAN_ROW * 16u),
-                     "l"(plan + (s + PLAN_RING) * NSC), "r"(NSC * 16u), "r"(bars + rb * 8) : "memory");
+        ring_count_reset(ring, rb);
+        ring_fetch(ring, rb, plan + (s + PLAN_RING) * NSC);
       }
       if (!STORE) {
         gps += NTX * MAXT;
@@ -731,23 +750,19 @@ __device__ __forceinline__ void slot_body_wide(const SlotArgs &a, const SlotCtx 
 __device__ __forceinline__ void plan_ring_start(const SlotArgs &a, const SlotCtx &c) {
   const int nsym = a.g.nsym;
   const uint4 *plan = reinterpret_cast<const uint4 *>(a.pat.plan) + (int64_t)c.pid * (nsym * 599 + 1);
-  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(c.pstage), bars = (uint32_t)__cvta_generic_to_shared(c.pbar);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(c.pstage);
   const uint4 outside = __ldg(plan + nsym * 599);
 #pragma unroll
   for (int b = 0; b < PLAN_RING; ++b) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bars + b * 8));
-    c.pstage[b * PLAN_ROW + 599] = outside;
-    c.pcnt[b] = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(ring_bar(ring, b)));
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(ring_row(ring, b) + 599u * 16u), "r"(outside.x), "r"(outside.y), "r"(outside.z),
+                 "r"(outside.w) : "memory");
+    ring_count_reset(ring, b);
   }
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 #pragma unroll
-  for (int b = 0; b < PLAN_RING; ++b) {
-    if (b < nsym) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bars + b * 8), "r"(599u * 16u) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(ring + b * PLAN_ROW * 16u),
-                   "l"(plan + b * 599), "r"(599u * 16u), "r"(bars + b * 8) : "memory");
-    }
-  }
+  for (int b = 0; b < PLAN_RING; ++b)
+    if (b < nsym) ring_fetch(ring, b, plan + b * 599);
 }
 
 template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE, bool STORE = true, bool COMPACT = false, bool BULK = false>
@@ -760,8 +775,6 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   float2 *hp = gs + nsym * MAXT;                                      // [np_max + 1], last = 0
   __shared__ float red[33];
   __shared__ float ssm[SLOT_THREADS / 32][6];
-  __shared__ __align__(8) uint64_t pbar[PLAN_RING];
-  __shared__ int pcnt[PLAN_RING];
 
   SlotCtx c;
   c.b = blockIdx.x / nrx;
@@ -773,8 +786,6 @@ __global__ void __launch_bounds__(SLOT_THREADS, 2) slot_kernel(SlotArgs a) {
   c.gsp = gsp;
   c.hp = hp;
   c.pstage = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(hp + (EST ? a.pat.np_max + 1 : 0)) + 15) & ~(uintptr_t)15);
-  c.pbar = pbar;
-  c.pcnt = pcnt;
   c.alpha = 0.f;
   c.pid = EST ? a.slots.pattern_id[c.b] : 0;
   if (WIDE != 0 && EST && BULK && threadIdx.x == 0) plan_ring_start(a, c);
@@ -945,22 +956,16 @@ __device__ __forceinline__ void slot_body_wide2(const SlotArgs &a, const SlotCtx
   auto st16 = [](float2 *p, float2 lo, float2 hi) { __stcs(reinterpret_cast<float4 *>(p), make_float4(lo.x, lo.y, hi.x, hi.y)); };
   // bulk form: ring of PLAN_RING rows of PLAN_ROW entries; entry 599 of each row is the all-outside entry (idle lanes / the
   // missing bin); this thread's four entries sit at fixed positions of a row
-  constexpr uint32_t ROW_BYTES = NSC * sizeof(uint4);
-  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(c.pstage), bars = (uint32_t)__cvta_generic_to_shared(c.pbar);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(c.pstage);
   // thread t reads the adjacent entries (kp, kp + 1) and (km, km + 1): with every thread loading the lower entry first a
   // quarter-warp would touch 8 entries 32 bytes apart (two per bank group); threads 4..7 of every eight load the UPPER
   // entry first instead, which makes the eight 16-byte accesses of a quarter-warp fall into eight different bank groups
   const bool swp = (t_ >> 2) & 1;
   const uint32_t eraw[4] = {(act ? kp : NSC) * 16u, (vp2 ? kp + 1 : NSC) * 16u, (act ? km : NSC) * 16u, (act ? km + 1 : NSC) * 16u};
   const uint32_t eo[4] = {swp ? eraw[1] : eraw[0], swp ? eraw[0] : eraw[1], swp ? eraw[3] : eraw[2], swp ? eraw[2] : eraw[3]};
-  auto fetch_row = [&](int row, int buf) {           // one thread: row `row` of the plan -> ring[buf]
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bars + buf * 8), "r"(ROW_BYTES) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(ring + buf * PLAN_ROW * 16u),
-                 "l"(plan + row * NSC), "r"(ROW_BYTES), "r"(bars + buf * 8) : "memory");
-  };
   auto ring_entry = [&](int buf, int q) {
     uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring + buf * PLAN_ROW * 16u + eo[q]) : "memory");
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_row(ring, buf) + eo[q]) : "memory");
     return v;
   };
   // (bulk form: the kernel has initialised the barriers and started rows 0 and 1 before the pilot phase)
@@ -975,7 +980,7 @@ __device__ __forceinline__ void slot_body_wide2(const SlotArgs &a, const SlotCtx
       if (EST && BULK) {
         // row s sits in ring[s % PLAN_RING], its (s / PLAN_RING)-th fill
         const int rb = s & (PLAN_RING - 1);
-        while (!mbar_try_wait(bars + rb * 8, (uint32_t)(s / PLAN_RING) & 1u)) {}
+        while (!mbar_try_wait(ring_bar(ring, rb), (uint32_t)(s / PLAN_RING) & 1u)) {}
         const uint4 r0 = ring_entry(rb, 0), r1 = ring_entry(rb, 1), r2 = ring_entry(rb, 2), r3 = ring_entry(rb, 3);
         auto sel4 = [](bool c, uint4 x, uint4 y) { return make_uint4(c ? x.x : y.x, c ? x.y : y.y, c ? x.z : y.z, c ? x.w : y.w); };
         const uint4 e0 = sel4(swp, r1, r0), e1 = sel4(swp, r0, r1), e2 = sel4(swp, r3, r2), e3 = sel4(swp, r2, r3);
@@ -983,7 +988,7 @@ __device__ __forceinline__ void slot_body_wide2(const SlotArgs &a, const SlotCtx
         // and whichever comes last refills the slot with row s + PLAN_RING at the END of its symbol (the atomic's return
         // value is not needed before, so nobody waits for anybody; the copy has PLAN_RING - 1 symbols of work to land under).
         // A warp cannot count itself twice on one slot: its next visit (symbol s + PLAN_RING) waits for this very refill.
-        if (s + PLAN_RING < nsym && (t_ & 31) == 0) ring_old = atomicAdd(c.pcnt + rb, 1);
+        if (s + PLAN_RING < nsym && (t_ & 31) == 0) ring_old = ring_count_in(ring, rb);
         lp1 = plan_apply(plan_decode(e0), c.hp);
         lp2 = plan_apply(plan_decode(e1), c.hp);
         lm2 = plan_apply(plan_decode(e2), c.hp);
@@ -1077,8 +1082,8 @@ __device__ __forceinline__ void slot_body_wide2(const SlotArgs &a, const SlotCtx
         st[1][1] = __ffma2_rn(lm1, lm1, st[1][1]);
       }
       if (EST && BULK && s + PLAN_RING < nsym && (t_ & 31) == 0 && ring_old == SLOT2_THREADS / 32 - 1) {
-        c.pcnt[s & (PLAN_RING - 1)] = 0;
-        fetch_row(s + PLAN_RING, s & (PLAN_RING - 1));
+        ring_count_reset(ring, s & (PLAN_RING - 1));
+        ring_fetch(ring, s & (PLAN_RING - 1), plan + (s + PLAN_RING) * NSC);
       }
       if (!STORE) {
         gps += NTX * MAXT;
@@ -1132,8 +1137,6 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
   float2 *hp = gs + nsym * MAXT;                                      // [np_max + 1], last = 0
   __shared__ float red[33];
   __shared__ float ssm[SLOT2_THREADS / 32][6];
-  __shared__ __align__(8) uint64_t pbar[PLAN_RING];
-  __shared__ int pcnt[PLAN_RING];
 
   SlotCtx c;
   c.b = blockIdx.x / nrx;
@@ -1145,8 +1148,6 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
   c.gsp = gsp;
   c.hp = hp;
   c.pstage = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(hp + (EST ? a.pat.np_max + 1 : 0)) + 15) & ~(uintptr_t)15);
-  c.pbar = pbar;
-  c.pcnt = pcnt;
   c.alpha = 0.f;
   c.pid = 0;
 
@@ -1235,7 +1236,7 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
 template <int NTX, bool EST, bool STORE, bool COMPACT, bool SCORE = false, bool BULK = false>
 static int launch_slot2_form(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
   // plan staging: 2 buffers x 4 entries per thread, or (bulk) a ring of PLAN_RING rows of PLAN_ROW entries
-  if (EST) smem += 16 + (BULK ? PLAN_RING * PLAN_ROW : 8 * SLOT2_THREADS) * sizeof(uint4);
+  if (EST) smem += 16 + (BULK ? PLAN_RING_BYTES : 8 * SLOT2_THREADS * sizeof(uint4));
   if (smem > 48 * 1024) B2C_CUDA((set_max_smem<slot2_kernel<NTX, EST, STORE, COMPACT, SCORE, BULK>>(smem)));
   slot2_kernel<NTX, EST, STORE, COMPACT, SCORE, BULK><<<(unsigned)(B * a.g.nrx), SLOT2_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
@@ -1243,12 +1244,12 @@ static int launch_slot2_form(const SlotArgs &a, int64_t B, size_t smem, cudaStre
 }
 template <int NTX, bool EST, bool STORE, bool COMPACT, bool SCORE = false>
 static int launch_slot2(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
-  // Plan rows by bulk copy into the shared-memory ring: the default of the scoring pass, where it is worth 16 % (2x2, 18 944
-  // slots: 1.14 ms against 1.36 ms; its L1 data pipe was 92 % busy).  The first pass spends a third of its time in the pilot
-  // phase and is latency-bound at 15 warps per SM, not pipe-bound: there the bulk form measured -3 % (4x4) to +1 % (2x2), so it
-  // keeps the per-thread cp.async staging.  B2C_PLAN_BULK=1 / 0 forces either form for both (tests, A/B runs).
+  // Plan rows by bulk copy into the shared-memory ring, measured against the per-thread cp.async staging (2x2, 18 944 slots):
+  // scoring pass 1.10 ms against 1.35 ms (its L1 data pipe was 92 % busy), first pass 1.74 against 1.81 ms.  The 4x4 first pass
+  // spends its time in the pilot phase and the tx loop, latency-bound at 15 warps per SM: 0.883 against 0.875 ms per 4144
+  // slots, so ntx >= 4 keeps the per-thread form there.  B2C_PLAN_BULK=1 / 0 forces either form (tests, A/B runs).
   const char *e = getenv("B2C_PLAN_BULK");
-  const bool bulk = e ? e[0] != '0' : SCORE;
+  const bool bulk = e ? e[0] != '0' : (SCORE || NTX <= 2);
   if (EST && !STORE && bulk) return launch_slot2_form<NTX, EST, STORE, COMPACT, SCORE, true>(a, B, smem, stream);
   return launch_slot2_form<NTX, EST, STORE, COMPACT, SCORE, false>(a, B, smem, stream);
 }
@@ -1262,7 +1263,7 @@ template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0, bool 
 static int launch_slot_form(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
   auto kern = slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT, BULK>;
   // plan-entry staging (+ alignment slack): per-thread slots, or the ring of bulk-copied rows
-  if (WIDE && EST) smem += 16 + (BULK ? PLAN_RING * PLAN_ROW : 4 * SLOT_THREADS) * sizeof(uint4);
+  if (WIDE && EST) smem += 16 + (BULK ? PLAN_RING_BYTES : 4 * SLOT_THREADS * sizeof(uint4));
   if (smem > 48 * 1024) B2C_CUDA((set_max_smem<slot_kernel<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT, BULK>>(smem)));
   kern<<<(unsigned)(B * a.g.nrx), SLOT_THREADS, smem, stream>>>(a);
   B2C_CUDA(cudaGetLastError());
@@ -1271,8 +1272,11 @@ static int launch_slot_form(const SlotArgs &a, int64_t B, size_t smem, cudaStrea
 template <int NTX, bool EXACT, bool EST, int NSC, bool FAST, int WIDE = 0, bool STORE = true, bool COMPACT = false>
 static int launch_slot(const SlotArgs &a, int64_t B, size_t smem, cudaStream_t stream) {
   if constexpr (WIDE != 0 && EST && STORE) {
-    const char *e = getenv("B2C_PLAN_BULK");        // storing wide kernels: bulk-copied plan rows on request (A/B runs)
-    if (e && e[0] != '0') return launch_slot_form<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT, true>(a, B, smem, stream);
+    // storing wide kernels: plan rows by bulk copy into the shared-memory ring (measured against the per-thread cp.async
+    // staging on one box: full layout 2.56 vs 2.68 ms per 4144 4x4 slots = 0.93 vs 0.89 of the HBM peak, c5 dataset mode
+    // +3.9 %, 2x2 +2.9 %, compact +1.3 %; bit-identical outputs).  B2C_PLAN_BULK=0 selects the per-thread form.
+    const char *e = getenv("B2C_PLAN_BULK");
+    if (!(e && e[0] == '0')) return launch_slot_form<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT, true>(a, B, smem, stream);
   }
   return launch_slot_form<NTX, EXACT, EST, NSC, FAST, WIDE, STORE, COMPACT, false>(a, B, smem, stream);
 }

@@ -654,8 +654,8 @@ def test_pilot_sweep_ber_curves():
 
 @pytest.mark.parametrize("ntx,nrx,compact", [(4, 4, False), (4, 4, True), (2, 2, False), (1, 2, True)])
 def test_wide_kernel_with_bulk_copied_plan_rows(ntx, nrx, compact, engines):
-    """B2C_PLAN_BULK=1 makes the wide-store slot kernel take its interpolation plan rows from a shared-memory ring filled by
-    cp.async.bulk instead of per-thread cp.async staging: same entries, same arithmetic -- every output bit-identical, over
+    """The wide-store slot kernel takes its interpolation plan rows from a shared-memory ring filled by cp.async.bulk
+    (default; B2C_PLAN_BULK=0 selects the older per-thread cp.async staging): same entries, same arithmetic -- every output bit-identical, over
     several waves of CTAs and mixed profiles / patterns."""
     eng = engines(ntx, nrx)
     pool = eng.random_pool([0.10, 0.03], seed=21)
@@ -664,15 +664,18 @@ def test_wide_kernel_with_bulk_copied_plan_rows(ntx, nrx, compact, engines):
     kw = dict(model_id=rng.integers(0, 3, B).astype(np.int32), doppler_hz=rng.uniform(5, 200, B).astype(np.float32),
               snr_db=rng.uniform(-5, 30, B).astype(np.float32), pattern_id=rng.integers(0, 2, B).astype(np.int32), pool=pool,
               slot0=5150, seed=8, pitch=600, compact=compact)
-    ref = eng.run(B, **kw)
-    os.environ["B2C_PLAN_BULK"] = "1"
-    try:
-        got = eng.run(B, **kw)
-        torch.cuda.synchronize()
-    finally:
-        del os.environ["B2C_PLAN_BULK"]
+    res = []
+    for flag in ("0", "1"):
+        os.environ["B2C_PLAN_BULK"] = flag
+        try:
+            res.append(eng.run(B, **kw))
+            torch.cuda.synchronize()
+        finally:
+            del os.environ["B2C_PLAN_BULK"]
+    dflt = eng.run(B, **kw)
+    torch.cuda.synchronize()
     for k in ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"):
-        assert torch.equal(got[k], ref[k]), k
+        assert torch.equal(res[0][k], res[1][k]) and torch.equal(dflt[k], res[1][k]), k
 
 
 @pytest.mark.parametrize("ntx,nrx", [(4, 4), (2, 2), (1, 1), (8, 2)])
