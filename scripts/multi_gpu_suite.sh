@@ -8,11 +8,13 @@ run() {
   if [ "$N" = 1 ]; then python "$@"; else
     python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) "$@"; fi
 }
-for spec in "c3_4x4_etu full" "c3_4x4_etu compact" "c2_2x2_eva_dense full" "c4_sweep full" "c5_mixed full" "c5_mixed compact" "c2_2x2_eva full" "c1_siso_epa full"; do
-  set -- $spec
+# SUITE="workload:layout ..." restricts the list (default: every workload); NO_PCIE=1 skips the copy probe
+SUITE=${SUITE:-"c3_4x4_etu:full c3_4x4_etu:compact c2_2x2_eva_dense:full c2_2x2_eva_dense_stats:full c4_sweep:full c5_mixed:full c5_mixed:compact c2_2x2_eva:full c1_siso_epa:full"}
+for spec in $SUITE; do
+  set -- ${spec%%:*} ${spec##*:}
   run bench.py --gpus "$N" --steps "$STEPS" --no-cpu-baseline --workload "$1" --layout "$2" --patterns 16 2> "$OUT/scale_${N}_$1_$2.err" | tail -1 >> "$OUT/scale_$N.jsonl"
 done
-run scripts/pcie_d2h_probe.py 2> "$OUT/pcie_$N.err" | tail -1 > "$OUT/pcie_$N.json"
+[ -z "$NO_PCIE" ] && run scripts/pcie_d2h_probe.py 2> "$OUT/pcie_$N.err" | tail -1 > "$OUT/pcie_$N.json"
 python - "$OUT/scale_$N.jsonl" <<'PY'
 import json, sys
 for line in open(sys.argv[1]):
@@ -23,4 +25,4 @@ for line in open(sys.argv[1]):
     except Exception as e:
         print("ERR", e, line[:200])
 PY
-cat "$OUT/pcie_$N.json"
+[ -z "$NO_PCIE" ] && cat "$OUT/pcie_$N.json"; true
