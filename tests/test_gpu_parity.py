@@ -678,6 +678,46 @@ def test_wide_kernel_with_bulk_copied_plan_rows(ntx, nrx, compact, engines):
         assert torch.equal(res[0][k], res[1][k]) and torch.equal(dflt[k], res[1][k]), k
 
 
+@pytest.mark.parametrize("nsym", [2, 6, 16])
+def test_wide_kernels_on_short_and_long_slots(nsym):
+    """599 bins with 2 / 6 / 16 symbols per slot: fewer symbols than the plan ring has rows, a partial second lap, the
+    compiled maximum.  The wide-store kernel (pitch 600), the statistics kernel and the dense scoring pass must agree with
+    the generic contiguous-row kernel (the one the oracle parity tests above pin) and with their per-thread staging forms."""
+    from engine import SlotEngine, WienerBank
+    cfg = {"ofdm": {"fft_size": 1024, "cp_length": 72, "num_symbols": nsym, "useful_subcarriers": 600, "subcarrier_spacing": 15000},
+           "mimo": {"num_tx_antennas": 2, "num_rx_antennas": 2}}
+    eng = SlotEngine(cfg)
+    pool = eng.random_pool([0.08], seed=3)
+    B = 300
+    rng = np.random.default_rng(nsym)
+    snrs = [0.0, 15.0]
+    snr = np.asarray(snrs, np.float32)[rng.integers(0, 2, B)]
+    kw = dict(model_id=rng.integers(0, 3, B).astype(np.int32), doppler_hz=rng.uniform(5, 200, B).astype(np.float32), snr_db=snr,
+              pattern_id=0, pool=pool, slot0=12, seed=4)
+    generic = eng.run(B, **kw)
+    wide = eng.run(B, pitch=600, **kw)
+    stats_only = eng.run(B, want=("stats",), **kw)
+    idx = pool.pilot_indices[0]
+    bank = WienerBank(eng, pool, {0: model_cov(idx)}, snrs)
+    dense = eng.run(B, mmse="dense", wiener=bank, **kw)
+    lean = eng.run(B, mmse="dense", wiener=bank, want=("stats",), **kw)
+    torch.cuda.synchronize()
+    for k in ("H_true", "rx", "tx", "H_ls", "H_mmse"):
+        assert relerr(wide[k].cpu().numpy(), generic[k].cpu().numpy()) < 2e-6, k
+    assert torch.allclose(wide["stats"], generic["stats"], rtol=2e-5) and torch.allclose(stats_only["stats"], generic["stats"], rtol=2e-5)
+    assert torch.allclose(lean["stats"], dense["stats"], rtol=2e-5)
+    os.environ["B2C_PLAN_BULK"] = "0"
+    try:
+        wide0 = eng.run(B, pitch=600, **kw)
+        lean0 = eng.run(B, mmse="dense", wiener=bank, want=("stats",), **kw)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["B2C_PLAN_BULK"]
+    for k in ("H_true", "rx", "tx", "H_ls", "H_mmse", "stats"):
+        assert torch.equal(wide0[k], wide[k]), k
+    assert torch.equal(lean0["stats"], lean["stats"])
+
+
 @pytest.mark.parametrize("ntx,nrx", [(4, 4), (2, 2), (1, 1), (8, 2)])
 def test_register_blocked_statistics_kernel(ntx, nrx, engines):
     """Statistics-only sweeps run slot2_kernel (160 threads, two mirror pairs = four bins per thread): same Philox
