@@ -1159,7 +1159,9 @@ __global__ void __launch_bounds__(SLOT2_THREADS, 3) slot2_kernel(const __grid_co
   for (int i = threadIdx.x; i < nsym * ntx * MAXT; i += SLOT2_THREADS) gsp[i] = __ldg(gin + i);
   if (SCORE) {
     c.alpha = 1.f;                     // the filtered pilots are interpolated as they are
-    const int np = a.pat.npilots[c.pid];
+    // the whole row (np_max entries; ld >= np_max): the plan only refers to the pattern's first npilots entries, and not
+    // waiting for npilots[pid] takes one dependent round trip out of the prologue
+    const int np = a.pat.np_max;
     const float2 *hm = a.hp_out + ((a.hp_col ? (int64_t)a.hp_col[c.b] : c.b * nrx) + c.rx) * a.hp_ld;
     for (int i = threadIdx.x; i < np; i += SLOT2_THREADS) hp[i] = __ldg(hm + i);
     if (threadIdx.x == 0) hp[a.pat.np_max] = make_float2(0.f, 0.f);
